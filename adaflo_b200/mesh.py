@@ -1,0 +1,379 @@
+"""Synthetic hexahedral box meshes with Taylor-Hood Q2/Q1 DoF spaces.
+
+This module stands in for the host side that deal.II / p4est own in the
+reference (mesh, DoF numbering, constraints, partition).  It produces exactly
+the arrays a deal.II adaptor would extract from ``MatrixFree`` and hand to the
+C ABI (``include/adaflo_b200.h``): per-cell node index lists with Dirichlet
+flag bits, hanging-node masks, geometry in compressed form and the ghost
+exchange plan of the vector partitioner.
+
+Reference conventions restated here (no reference code is used):
+  * velocity FE = FESystem(FE_Q(QGaussLobatto(3)), dim), pressure FE = FE_Q(1)
+    or FE_Q_DG0(1)                      -- source/navier_stokes.cc:92-106
+  * quadrature QGauss(3) for the coupled operator, QGauss(2) for the pressure
+    sub-operators                       -- source/navier_stokes.cc:447-448
+  * cell-local DoF order is lexicographic (x fastest) -- MatrixFree's
+    ``lexicographic_numbering``         -- SURVEY.md 8(c) item (1)
+  * mesh partition: contiguous ranges of cells per rank, interface DoFs owned
+    by the lower rank (p4est/deal.II rule) -- tests/beltrami.cc:196,209
+
+Device vector layout chosen by this framework (not the reference's):
+velocity vectors are node-major with the ``dim`` components interleaved
+(``u[node*3 + c]``), so that one 32-bit node index serves three DoFs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FLAG_SHIFT = 29
+NODE_MASK = (1 << FLAG_SHIFT) - 1
+
+
+# --------------------------------------------------------------------------
+# 1-D building blocks
+# --------------------------------------------------------------------------
+def gauss_legendre_01(n: int):
+    """Gauss-Legendre points/weights on [0,1] (deal.II ``QGauss<1>(n)``)."""
+    x, w = np.polynomial.legendre.leggauss(n)
+    # polish with two Newton steps in long double for last-bit reproducibility
+    x = x.astype(np.longdouble)
+    for _ in range(2):
+        p0 = np.ones_like(x)
+        p1 = x.copy()
+        for k in range(2, n + 1):
+            p0, p1 = p1, ((2 * k - 1) * x * p1 - (k - 1) * p0) / k
+        dp = n * (x * p1 - p0) / (x * x - 1)
+        x = x - p1 / dp
+    p0 = np.ones_like(x)
+    p1 = x.copy()
+    for k in range(2, n + 1):
+        p0, p1 = p1, ((2 * k - 1) * x * p1 - (k - 1) * p0) / k
+    dp = n * (x * p1 - p0) / (x * x - 1)
+    w = 2.0 / ((1 - x * x) * dp * dp)
+    return np.asarray(0.5 * (x + 1), dtype=np.float64), np.asarray(0.5 * w, dtype=np.float64)
+
+
+def gauss_lobatto_01(n: int):
+    """Gauss-Lobatto points on [0,1] (support points of FE_Q(degree n-1))."""
+    if n == 2:
+        return np.array([0.0, 1.0])
+    if n == 3:
+        return np.array([0.0, 0.5, 1.0])
+    # interior points = roots of P'_{n-1}
+    k = n - 1
+    c = np.zeros(k + 1)
+    c[k] = 1
+    r = np.polynomial.legendre.Legendre(c).deriv().roots()
+    x = np.concatenate([[-1.0], np.sort(r.real), [1.0]])
+    return 0.5 * (x + 1)
+
+
+def lagrange_values(nodes: np.ndarray, x: np.ndarray):
+    """Values and first derivatives of the Lagrange basis on ``nodes`` at ``x``.
+
+    Returns (V, D) with V[q, i] = l_i(x_q), D[q, i] = l_i'(x_q).
+    """
+    nodes = np.asarray(nodes, dtype=np.longdouble)
+    x = np.asarray(x, dtype=np.longdouble)
+    n = len(nodes)
+    V = np.ones((len(x), n), dtype=np.longdouble)
+    D = np.zeros((len(x), n), dtype=np.longdouble)
+    for i in range(n):
+        denom = np.longdouble(1)
+        for j in range(n):
+            if j != i:
+                denom *= nodes[i] - nodes[j]
+        for q in range(len(x)):
+            val = np.longdouble(1)
+            for j in range(n):
+                if j != i:
+                    val *= x[q] - nodes[j]
+            der = np.longdouble(0)
+            for m in range(n):
+                if m == i:
+                    continue
+                t = np.longdouble(1)
+                for j in range(n):
+                    if j != i and j != m:
+                        t *= x[q] - nodes[j]
+                der += t
+            V[q, i] = val / denom
+            D[q, i] = der / denom
+    return np.asarray(V, dtype=np.float64), np.asarray(D, dtype=np.float64)
+
+
+# --------------------------------------------------------------------------
+# DoF space description (what the C ABI's space_upload consumes)
+# --------------------------------------------------------------------------
+class DofSpace:
+    """One DoF space of one rank: local numbering = owned nodes, then ghosts."""
+
+    def __init__(self, name, n_comp, nodes_per_cell):
+        self.name = name
+        self.n_comp = n_comp
+        self.nodes_per_cell = nodes_per_cell
+        self.n_owned = 0          # nodes
+        self.n_ghost = 0          # nodes
+        self.cell_nodes = None    # [n_cells, nodes_per_cell] uint32 local node index (no flags)
+        self.dirichlet = None     # [n_local, n_comp] bool
+        self.coords = None        # [n_local, 3] float64 support points
+        self.global_ids = None    # [n_local] int64 global node id (partition independent)
+        # ghost exchange plan: lists of (peer, local indices)
+        self.send = []            # owned nodes that peer ghosts: (peer, idx int64[])
+        self.recv = []            # (peer, first ghost local index, count)
+        # hanging nodes (None on conforming meshes)
+        self.hanging_mask = None  # [n_cells] uint32 refinement configuration
+        self.n_dg0 = 0            # FE_Q_DG0: number of element-constant dofs (owned, appended)
+
+    @property
+    def n_local(self):
+        return self.n_owned + self.n_ghost
+
+    @property
+    def n_dofs_owned(self):
+        return self.n_owned * self.n_comp
+
+    @property
+    def n_dofs_local(self):
+        return self.n_local * self.n_comp
+
+    def encoded_cell_nodes(self):
+        """cell->node list with the per-component Dirichlet flags in bits 29..31."""
+        idx = self.cell_nodes.astype(np.uint32)
+        assert self.n_local <= NODE_MASK
+        flags = np.zeros(self.n_local, dtype=np.uint32)
+        for c in range(self.n_comp):
+            flags |= (self.dirichlet[:, c].astype(np.uint32) << np.uint32(FLAG_SHIFT + c))
+        return idx | flags[self.cell_nodes]
+
+    def constrained_dofs(self):
+        """Locally owned constrained dof indices (vector entries), sorted.
+
+        Mirrors ``MatrixFree::get_constrained_dofs`` used at
+        source/navier_stokes_matrix.cc:250-255.
+        """
+        d = self.dirichlet[: self.n_owned].reshape(-1)
+        return np.nonzero(d)[0].astype(np.uint32)
+
+
+class BoxMesh:
+    """Uniform Cartesian box of n = (nx, ny, nz) hexahedra, z-slab partition.
+
+    ``rank``/``nranks`` select the slab; ``deform`` (callable X->x with
+    jacobian) switches the geometry to the general per-quadrature-point path.
+    """
+
+    def __init__(self, n, lower=(-1.0, -1.0, -1.0), upper=(1.0, 1.0, 1.0),
+                 rank=0, nranks=1, dirichlet_faces=(0, 1, 2, 3, 4, 5),
+                 augmented=False, build_coords=True):
+        self.dim = 3
+        self.n = tuple(int(v) for v in n)
+        self.lower = np.asarray(lower, dtype=np.float64)
+        self.upper = np.asarray(upper, dtype=np.float64)
+        self.h = (self.upper - self.lower) / np.asarray(self.n, dtype=np.float64)
+        self.rank, self.nranks = rank, nranks
+        self.augmented = augmented
+        nx, ny, nz = self.n
+        assert nz >= nranks
+        # contiguous z-slabs (cells are lexicographic, so a slab is a contiguous cell range)
+        bounds = [(nz * r) // nranks for r in range(nranks + 1)]
+        self.z0, self.z1 = bounds[rank], bounds[rank + 1]
+        self.n_cells = nx * ny * (self.z1 - self.z0)
+        self.n_cells_global = nx * ny * nz
+        self.u = self._build_space("u", 2, 3, dirichlet_faces, build_coords)
+        self.p = self._build_space("p", 1, 1, (), build_coords)
+        if augmented:
+            self._append_dg0()
+
+    # ---------------------------------------------------------------- spaces
+    def _build_space(self, name, k, n_comp, dirichlet_faces, build_coords):
+        nx, ny, nz = self.n
+        NX, NY, NZ = k * nx + 1, k * ny + 1, k * nz + 1
+        z0, z1 = self.z0, self.z1
+        # owned node planes: interface plane belongs to the lower rank
+        zp0 = 0 if self.rank == 0 else k * z0 + 1
+        zp1 = k * z1                     # inclusive
+        n_planes = zp1 - zp0 + 1
+        plane = NX * NY
+        sp = DofSpace(name, n_comp, (k + 1) ** 3)
+        sp.grid = (NX, NY, NZ)
+        sp.n_owned = plane * n_planes
+        sp.n_ghost = plane if self.rank > 0 else 0
+        sp.n_owned_global = NX * NY * NZ
+
+        # local index of a global node (ix,iy,iz): owned -> lexicographic in owned range;
+        # ghost plane (iz == k*z0, rank>0) -> appended
+        def local_index(ix, iy, iz):
+            owned = (iz - zp0) * plane + iy * NX + ix
+            ghost = sp.n_owned + iy * NX + ix
+            return np.where(iz >= zp0, owned, ghost)
+
+        # cells, lexicographic x fastest
+        cz, cy, cx = np.meshgrid(np.arange(z0, z1), np.arange(ny), np.arange(nx), indexing="ij")
+        cx, cy, cz = cx.reshape(-1), cy.reshape(-1), cz.reshape(-1)
+        a = np.arange(k + 1)
+        lz, ly, lx = np.meshgrid(a, a, a, indexing="ij")
+        lx, ly, lz = lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)
+        gx = k * cx[:, None] + lx[None, :]
+        gy = k * cy[:, None] + ly[None, :]
+        gz = k * cz[:, None] + lz[None, :]
+        sp.cell_nodes = local_index(gx, gy, gz).astype(np.uint32)
+        self.cell_coords = np.stack([cx, cy, cz], axis=1)
+
+        # global ids / coords / Dirichlet flags of local nodes
+        iz_o, iy_o, ix_o = np.meshgrid(np.arange(zp0, zp1 + 1), np.arange(NY), np.arange(NX), indexing="ij")
+        ix_l, iy_l, iz_l = ix_o.reshape(-1), iy_o.reshape(-1), iz_o.reshape(-1)
+        if sp.n_ghost:
+            iy_g, ix_g = np.meshgrid(np.arange(NY), np.arange(NX), indexing="ij")
+            ix_l = np.concatenate([ix_l, ix_g.reshape(-1)])
+            iy_l = np.concatenate([iy_l, iy_g.reshape(-1)])
+            iz_l = np.concatenate([iz_l, np.full(plane, k * z0)])
+        sp.global_ids = (ix_l + NX * (iy_l + NY * iz_l)).astype(np.int64)
+        if build_coords:
+            # FE_Q support points: Gauss-Lobatto inside each cell (equidistant for k<=2)
+            assert k <= 2
+            sp.coords = np.stack([self.lower[0] + self.h[0] * ix_l / k,
+                                  self.lower[1] + self.h[1] * iy_l / k,
+                                  self.lower[2] + self.h[2] * iz_l / k], axis=1)
+        on_face = [ix_l == 0, ix_l == NX - 1, iy_l == 0, iy_l == NY - 1, iz_l == 0, iz_l == NZ - 1]
+        d = np.zeros(len(ix_l), dtype=bool)
+        for f in dirichlet_faces:
+            d |= on_face[f]
+        sp.dirichlet = np.repeat(d[:, None], n_comp, axis=1)
+
+        # ghost exchange plan (slab partition: one peer below, one above)
+        if self.rank > 0:
+            sp.recv.append((self.rank - 1, sp.n_owned, plane))
+        if self.rank < self.nranks - 1:
+            top = (zp1 - zp0) * plane + np.arange(plane, dtype=np.int64)
+            sp.send.append((self.rank + 1, top))
+        return sp
+
+    def _append_dg0(self):
+        """FE_Q_DG0(1): one element-constant pressure dof per cell, appended to
+        the owned range (source/navier_stokes.cc:98-106)."""
+        sp = self.p
+        # re-number: owned Q1 nodes, owned DG0 dofs, ghosts
+        n_q1_owned = sp.n_owned
+        shift = self.n_cells
+        cn = sp.cell_nodes.astype(np.int64)
+        cn = np.where(cn >= n_q1_owned, cn + shift, cn)
+        dg = n_q1_owned + np.arange(self.n_cells, dtype=np.int64)
+        sp.cell_nodes = np.concatenate([cn, dg[:, None]], axis=1).astype(np.uint32)
+        sp.nodes_per_cell = 9
+        sp.n_dg0 = self.n_cells
+        sp.n_q1_owned = n_q1_owned
+        # global ids: DG0 dofs numbered after all Q1 nodes
+        nx, ny = self.n[0], self.n[1]
+        cell_gid = sp.n_owned_global + (self.cell_coords[:, 0] + nx * (self.cell_coords[:, 1] + ny * self.cell_coords[:, 2]))
+        sp.global_ids = np.concatenate([sp.global_ids[:n_q1_owned], cell_gid, sp.global_ids[n_q1_owned:]])
+        ctr = self.lower[None, :] + self.h[None, :] * (self.cell_coords + 0.5)
+        if sp.coords is not None:
+            sp.coords = np.concatenate([sp.coords[:n_q1_owned], ctr, sp.coords[n_q1_owned:]])
+        sp.dirichlet = np.concatenate([sp.dirichlet[:n_q1_owned], np.zeros((self.n_cells, 1), bool),
+                                       sp.dirichlet[n_q1_owned:]])
+        sp.n_owned = n_q1_owned + self.n_cells
+        sp.recv = [(peer, first + shift, cnt) for (peer, first, cnt) in sp.recv]
+
+    # -------------------------------------------------------------- geometry
+    def cartesian_geometry(self):
+        """Compressed Cartesian geometry: one table row (1/hx,1/hy,1/hz,det) and a
+        per-cell row index (MatrixFree detects box meshes as Cartesian,
+        source/navier_stokes.cc:60-63 / SURVEY appendix A)."""
+        table = np.array([[1.0 / self.h[0], 1.0 / self.h[1], 1.0 / self.h[2], np.prod(self.h)]])
+        index = np.zeros(self.n_cells, dtype=np.uint32)
+        return table, index
+
+    def general_geometry(self, n_q_1d=3, deform=None):
+        """Per-quadrature-point inverse Jacobian K[f][e]=d xi_f/d x_e and JxW.
+
+        Returns invJ [n_cells, n_q, 3, 3] and JxW [n_cells, n_q]; ``deform`` is
+        ``(X) -> (x, dx/dX)`` on physical box coordinates (identity if None).
+        """
+        qp, qw = gauss_legendre_01(n_q_1d)
+        qz, qy, qx = np.meshgrid(np.arange(n_q_1d), np.arange(n_q_1d), np.arange(n_q_1d), indexing="ij")
+        qx, qy, qz = qx.reshape(-1), qy.reshape(-1), qz.reshape(-1)
+        w = qw[qx] * qw[qy] * qw[qz]
+        xi = np.stack([qp[qx], qp[qy], qp[qz]], axis=1)                        # [nq,3]
+        X = self.lower[None, None, :] + self.h[None, None, :] * (self.cell_coords[:, None, :] + xi[None, :, :])
+        nq = len(w)
+        J = np.zeros((self.n_cells, nq, 3, 3))
+        if deform is None:
+            for d in range(3):
+                J[:, :, d, d] = self.h[d]
+        else:
+            _, F = deform(X.reshape(-1, 3))                                   # F[e][f] = dx_e/dX_f
+            J = F.reshape(self.n_cells, nq, 3, 3) * self.h[None, None, None, :]  # dx_e/dxi_f
+        det = np.linalg.det(J)
+        K = np.linalg.inv(J)                                                  # K[f][e] = dxi_f/dx_e
+        return np.ascontiguousarray(K), det * w[None, :]
+
+    def quadrature_points(self, n_q_1d=3, deform=None):
+        qp, _ = gauss_legendre_01(n_q_1d)
+        qz, qy, qx = np.meshgrid(np.arange(n_q_1d), np.arange(n_q_1d), np.arange(n_q_1d), indexing="ij")
+        xi = np.stack([qp[qx.reshape(-1)], qp[qy.reshape(-1)], qp[qz.reshape(-1)]], axis=1)
+        X = self.lower[None, None, :] + self.h[None, None, :] * (self.cell_coords[:, None, :] + xi[None, :, :])
+        if deform is not None:
+            x, _ = deform(X.reshape(-1, 3))
+            X = x.reshape(X.shape)
+        return X
+
+
+def sine_deformation(amplitude=0.05):
+    """Smooth invertible deformation of the box used to force the general-geometry path."""
+    def deform(X):
+        x = X.copy()
+        F = np.zeros((X.shape[0], 3, 3))
+        for d in range(3):
+            F[:, d, d] = 1.0
+        s = np.sin(np.pi * X)
+        c = np.cos(np.pi * X) * np.pi
+        # x_e += A * sin(pi X_{e+1}) * sin(pi X_{e+2})
+        for e in range(3):
+            a, b = (e + 1) % 3, (e + 2) % 3
+            x[:, e] += amplitude * s[:, a] * s[:, b]
+            F[:, e, a] += amplitude * c[:, a] * s[:, b]
+            F[:, e, b] += amplitude * s[:, a] * c[:, b]
+        return x, F
+    return deform
+
+
+# --------------------------------------------------------------------------
+# deterministic, partition independent test vectors
+# --------------------------------------------------------------------------
+def seeded_uniform(global_ids: np.ndarray, n_comp: int, seed: int):
+    """U(-1,1) values keyed by global dof id (counter based, so any partition
+    reproduces the same global vector) -- SURVEY.md 8(d) 'Synthetic inputs'."""
+    gid = (global_ids[:, None].astype(np.uint64) * np.uint64(n_comp) + np.arange(n_comp, dtype=np.uint64)[None, :])
+    x = gid.reshape(-1) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+    # splitmix64
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
+
+
+def beltrami_velocity(x: np.ndarray, t=0.0, nu=1.0):
+    """Ethier-Steinman Beltrami flow, the analytic field of tests/beltrami.cc:82-115."""
+    a = 0.25 * np.pi
+    d = 2.0 * a
+    X, Y, Z = x[..., 0], x[..., 1], x[..., 2]
+    e = np.exp(-nu * d * d * t)
+    u0 = -a * (np.exp(a * X) * np.sin(a * Y + d * Z) + np.exp(a * Z) * np.cos(a * X + d * Y)) * e
+    u1 = -a * (np.exp(a * Y) * np.sin(a * Z + d * X) + np.exp(a * X) * np.cos(a * Y + d * Z)) * e
+    u2 = -a * (np.exp(a * Z) * np.sin(a * X + d * Y) + np.exp(a * Y) * np.cos(a * Z + d * X)) * e
+    return np.stack([u0, u1, u2], axis=-1)
+
+
+def beltrami_pressure(x: np.ndarray, t=0.0, nu=1.0):
+    """Pressure of the Beltrami flow, tests/beltrami.cc:140-160."""
+    a = 0.25 * np.pi
+    d = 2.0 * a
+    X, Y, Z = x[..., 0], x[..., 1], x[..., 2]
+    val = -a * a * 0.5 * (np.exp(2 * a * X) + np.exp(2 * a * Y) + np.exp(2 * a * Z)
+                          + 2 * np.sin(a * X + d * Y) * np.cos(a * Z + d * X) * np.exp(a * (Y + Z))
+                          + 2 * np.sin(a * Y + d * Z) * np.cos(a * X + d * Y) * np.exp(a * (Z + X))
+                          + 2 * np.sin(a * Z + d * X) * np.cos(a * Y + d * Z) * np.exp(a * (X + Y)))
+    return val * np.exp(-2 * nu * d * d * t)

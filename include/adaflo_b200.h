@@ -1,0 +1,272 @@
+/* adaflo_b200.h -- C ABI of the B200-native matrix-free operator library.
+ *
+ * This is the drop-in boundary for ONE hot path of kronbichler/adaflo: the
+ * matrix-free operator application.  The reference has no
+ * FFI; its boundary is a set of duck-typed C++ operator classes handed to
+ * deal.II solver templates.  Every entry point below cites the reference
+ * interface (file:line under the adaflo source tree) it replaces.  A thin C++
+ * class with the reference's own method names sits on top of this ABI in
+ * include/adaflo_b200/navier_stokes_matrix.h; INTEGRATION.md shows the deal.II
+ * side adaptor.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure;
+ *    adaflo_b200_last_error() returns a thread-local message.
+ *  - "host" pointers are read during the call and may be freed afterwards;
+ *    "dev" pointers are CUDA device pointers owned by the caller.  The library
+ *    never frees caller memory and never retains vector pointers across calls
+ *    (exception: adaflo_b200_ns_set_old_solutions, which mirrors the reference
+ *    constructor holding references to solution_old / solution_old_old).
+ *  - there is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with ADAFLO_B200_ERR_CUDA.
+ *
+ * Vector layout (device): a DoF space with C components stores entry
+ * (node, c) at index node*C + c; local vectors hold the owned nodes first and
+ * the ghost nodes after them (deal.II LinearAlgebra::distributed::Vector
+ * layout).  Velocity: C = dim; pressure and level set: C = 1.
+ */
+#ifndef ADAFLO_B200_H
+#define ADAFLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADAFLO_B200_OK 0
+#define ADAFLO_B200_ERR_ARG 1
+#define ADAFLO_B200_ERR_CUDA 2
+#define ADAFLO_B200_ERR_UNSUPPORTED 3 /* reference: AssertThrow(.., ExcNotImplemented()) navier_stokes_matrix.cc:68,82 */
+#define ADAFLO_B200_ERR_STATE 4       /* reference: Assert(matrix_free != 0, ExcNotInitialized()) navier_stokes_matrix.cc:228 */
+#define ADAFLO_B200_ERR_COMM 5
+
+/* per-component Dirichlet flags live in the top bits of each cell->node index */
+#define ADAFLO_B200_FLAG_SHIFT 29u
+#define ADAFLO_B200_NODE_MASK 0x1FFFFFFFu
+
+typedef struct adaflo_b200_ctx_s *adaflo_b200_ctx_t;
+typedef struct adaflo_b200_mf_s *adaflo_b200_mf_t;
+typedef struct adaflo_b200_ns_s *adaflo_b200_ns_t;
+
+const char *adaflo_b200_last_error(void);
+const char *adaflo_b200_version(void);
+
+/* ------------------------------------------------------------------ context
+ * One context per rank/GPU.  `stream` is a cudaStream_t (NULL = default
+ * stream).  Replaces the MPI communicator + TBB scheduler that deal.II's
+ * MatrixFree owns in the reference (source/navier_stokes.cc:414-451). */
+int adaflo_b200_ctx_create(adaflo_b200_ctx_t *out, int device, void *stream);
+int adaflo_b200_ctx_destroy(adaflo_b200_ctx_t ctx);
+int adaflo_b200_ctx_set_stream(adaflo_b200_ctx_t ctx, void *stream);
+int adaflo_b200_ctx_synchronize(adaflo_b200_ctx_t ctx);
+/* Multi-GPU: NCCL communicator owned by the library (replaces deal.II's
+ * Utilities::MPI::Partitioner point-to-point exchange).  Rank 0
+ * obtains the 128-byte id, the caller broadcasts it out of band. */
+int adaflo_b200_comm_unique_id(unsigned char id[128]);
+int adaflo_b200_ctx_init_comm(adaflo_b200_ctx_t ctx, const unsigned char id[128], int rank, int nranks);
+
+/* -------------------------------------------------- matrix-free data mirror
+ * Device mirror of dealii::MatrixFree<dim,double> as adaflo configures it
+ * (source/navier_stokes.cc:414-451, source/two_phase_base.cc:239-273): a list
+ * of DoF spaces (dof handler + constraints) and a list of quadratures with the
+ * cell geometry evaluated on them. */
+enum adaflo_b200_fe_kind {
+  ADAFLO_B200_FE_Q = 0,        /* FE_Q(QGaussLobatto(degree+1)), possibly vector valued */
+  ADAFLO_B200_FE_Q_DG0 = 1,    /* FE_Q_DG0(degree): +1 element-constant dof, last in the cell list */
+  ADAFLO_B200_FE_Q_ISO_Q1 = 2  /* FE_Q_iso_Q1(degree subdivisions) (level set) */
+};
+
+typedef struct {
+  int32_t peer;           /* rank */
+  uint32_t n_send;        /* owned nodes this peer ghosts */
+  const uint32_t *send;   /* host: local node indices, [n_send] */
+  uint32_t recv_first;    /* first local ghost node filled by this peer */
+  uint32_t n_recv;        /* contiguous range */
+} adaflo_b200_exchange;
+
+typedef struct {
+  int32_t fe_kind;        /* enum adaflo_b200_fe_kind */
+  int32_t degree;
+  int32_t n_components;   /* dim for velocity, 1 otherwise */
+  uint32_t n_owned_nodes;
+  uint32_t n_ghost_nodes;
+  uint32_t nodes_per_cell;
+  /* host [n_cells][nodes_per_cell]: local node index, lexicographic within the
+   * cell (x fastest), bit (29+c) set if component c of that node is constrained
+   * to zero by a homogeneous Dirichlet constraint (read as 0, never written):
+   * the semantics of FEEvaluation::read_dof_values / distribute_local_to_global
+   * on constrained dofs. */
+  const uint32_t *cell_nodes;
+  /* host [n_cells] or NULL: refinement configuration of cells with hanging
+   * faces/edges (bit layout documented in DESIGN.md); on such faces the cell
+   * list holds the coarse neighbour's nodes */
+  const uint32_t *hanging_masks;
+  /* locally owned constrained vector entries (MatrixFree::get_constrained_dofs,
+   * used at navier_stokes_matrix.cc:250-255) */
+  uint32_t n_constrained;
+  const uint32_t *constrained_dofs;
+  int32_t n_exchange;
+  const adaflo_b200_exchange *exchange;
+} adaflo_b200_space_desc;
+
+enum adaflo_b200_geometry_type {
+  ADAFLO_B200_GEOM_CARTESIAN = 0, /* table rows of 4: 1/hx, 1/hy, 1/hz, |J| */
+  ADAFLO_B200_GEOM_AFFINE = 1,    /* table rows of 10: K[f][e] = d xi_f / d x_e (9), |J| */
+  ADAFLO_B200_GEOM_GENERAL = 2    /* per quadrature point */
+};
+
+typedef struct {
+  int32_t n_q_1d;            /* QGauss(n_q_1d) per direction */
+  int32_t geometry_type;
+  uint32_t n_table_rows;     /* cartesian / affine */
+  const double *table;       /* host */
+  const uint32_t *cell_row;  /* host [n_cells] row of each cell (deal.II compresses equal Jacobians) */
+  const double *inv_jacobian;/* general, host [n_cells][9][n_q], entry f*3+e = d xi_f/d x_e */
+  const double *jxw;         /* general, host [n_cells][n_q] */
+} adaflo_b200_quad_desc;
+
+typedef struct {
+  int32_t dim;               /* 3 (2 is not implemented yet) */
+  uint32_t n_cells;          /* locally owned cells */
+  int32_t n_spaces;
+  const adaflo_b200_space_desc *spaces;
+  int32_t n_quads;
+  const adaflo_b200_quad_desc *quads;
+} adaflo_b200_mf_desc;
+
+int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *desc, adaflo_b200_mf_t *out);
+int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf);
+/* vector sizes: MatrixFree::initialize_dof_vector */
+int adaflo_b200_mf_vector_size(adaflo_b200_mf_t mf, int space, uint64_t *n_owned_entries, uint64_t *n_local_entries);
+/* LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) */
+int adaflo_b200_mf_update_ghost_values(adaflo_b200_mf_t mf, int space, double *vec_dev);
+int adaflo_b200_mf_compress_add(adaflo_b200_mf_t mf, int space, double *vec_dev);
+
+/* ------------------------------------------------------- NavierStokesMatrix
+ * Enumerations and PODs mirror adaflo::FlowParameters
+ * (include/adaflo/parameters.h:54-86) and adaflo::TimeStepping
+ * (include/adaflo/time_stepping.h:240-295). */
+enum adaflo_b200_physical_type {
+  ADAFLO_B200_INCOMPRESSIBLE = 0,
+  ADAFLO_B200_INCOMPRESSIBLE_STATIONARY = 1,
+  ADAFLO_B200_STOKES = 2
+};
+enum adaflo_b200_linearization {
+  ADAFLO_B200_COUPLED_IMPLICIT_NEWTON = 0,
+  ADAFLO_B200_COUPLED_IMPLICIT_PICARD = 1,
+  ADAFLO_B200_COUPLED_VELOCITY_SEMI_IMPLICIT = 2,
+  ADAFLO_B200_COUPLED_VELOCITY_EXPLICIT = 3,
+  ADAFLO_B200_PROJECTION = 4
+};
+
+typedef struct {
+  int32_t physical_type;
+  int32_t linearization;
+  int32_t augmented_taylor_hood;
+  int32_t variable_coefficients; /* density_diff != 0 || viscosity_diff != 0, navier_stokes_matrix.cc:97-98 */
+  double density;
+  double viscosity;
+  double damping;                /* already sign-flipped as parameters.cc:466-467 does */
+  double tau_grad_div;
+  double beta_convective_term_momentum_balance;
+} adaflo_b200_flow_params;
+
+typedef struct {
+  double weight;          /* TimeStepping::weight()         */
+  double weight_old;      /* TimeStepping::weight_old()     */
+  double weight_old_old;  /* TimeStepping::weight_old_old() */
+  double tau1;            /* TimeStepping::tau1(); tau2 must be 0 (navier_stokes_matrix.cc:629) */
+  double extrapolate_old;     /* factors of TimeStepping::extrapolate, time_stepping.h:290-295 */
+  double extrapolate_old_old;
+} adaflo_b200_time_weights;
+
+/* NavierStokesMatrix(parameters, dof_index_u, dof_index_p, quad_index_u,
+ * quad_index_p, ..) + initialize(matrix_free, time_stepping,
+ * pressure_average_fix): navier_stokes_matrix.cc:43-60,85-169.  Allocates the
+ * per-quadrature-point coefficient arrays and builds the pressure null-space
+ * vectors (mode 0: constants; mode 1: DG0 constants). */
+int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaflo_b200_flow_params *prm,
+                          int dof_index_u, int dof_index_p, int quad_index_u, int quad_index_p,
+                          int pressure_average_fix, adaflo_b200_ns_t *out);
+int adaflo_b200_ns_destroy(adaflo_b200_ns_t ns); /* NavierStokesMatrix::clear, :173-187 */
+int adaflo_b200_ns_set_flow_params(adaflo_b200_ns_t ns, const adaflo_b200_flow_params *prm);
+int adaflo_b200_ns_set_time_weights(adaflo_b200_ns_t ns, const adaflo_b200_time_weights *w);
+/* the references to solution_old / solution_old_old held by the constructor
+ * (velocity blocks only are read, navier_stokes_matrix.cc:677,682) */
+int adaflo_b200_ns_set_old_solutions(adaflo_b200_ns_t ns, const double *old_u_dev, const double *old_old_u_dev);
+
+/* vmult(dst, src): navier_stokes_matrix.cc:221-262.  dst = A src including the
+ * constrained-row fix-up and the pressure mean projection.  Ghost exchange is
+ * done inside when a communicator was set. */
+int adaflo_b200_ns_vmult(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+/* the algebraic transpose of vmult (no counterpart in the reference) */
+int adaflo_b200_ns_Tvmult(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+/* residual(system_rhs, src, user_rhs): navier_stokes_matrix.cc:266-293.
+ * system_rhs is read-modify-write (the caller preloads const_rhs, navier_stokes.cc:784);
+ * writes the linearization point consumed by vmult. */
+int adaflo_b200_ns_residual(adaflo_b200_ns_t ns, double *rhs_u, double *rhs_p, const double *src_u, const double *src_p,
+                            const double *user_rhs_u, const double *user_rhs_p);
+/* velocity_vmult: :337-382 ; divergence_vmult_add: :300-332 (adds, no zeroing);
+ * pressure_{poisson,mass,convdiff}_vmult: :386-483 */
+int adaflo_b200_ns_velocity_vmult(adaflo_b200_ns_t ns, double *dst_u, const double *src_u);
+int adaflo_b200_ns_divergence_vmult_add(adaflo_b200_ns_t ns, double *dst_p, const double *src_u, int weight_by_viscosity);
+int adaflo_b200_ns_pressure_poisson_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p);
+int adaflo_b200_ns_pressure_mass_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p);
+int adaflo_b200_ns_pressure_convdiff_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p);
+/* diagonal of the velocity block / of the coupled operator ("diagonal
+ * computation" has no reference routine beyond the pressure-mass row sum; this is
+ * the exact diagonal of vmult, tested against unit-vector products) */
+int adaflo_b200_ns_compute_diagonal(adaflo_b200_ns_t ns, double *diag_u, double *diag_p);
+/* fix_linearization_point: :1144-1152 (snapshot used by velocity_vmult & co.) */
+int adaflo_b200_ns_fix_linearization_point(adaflo_b200_ns_t ns);
+/* apply_pressure_average_projection / apply_pressure_shift: :191-217 */
+int adaflo_b200_ns_apply_pressure_average_projection(adaflo_b200_ns_t ns, double *p_dev);
+int adaflo_b200_ns_apply_pressure_shift(adaflo_b200_ns_t ns, double shift, double *p_dev);
+/* begin_densities / begin_viscosities / begin_damping_coeff /
+ * begin_linearized_velocities (navier_stokes_matrix.h:162-178,293-395): raw
+ * device pointers into the coefficient arrays other components write.
+ * Layouts: rho/mu/damping [n_cells][n_q]; linearized [n_cells][12][n_q] with
+ * rows 0..2 = u_d, row 3+3d+e = d u_d / d x_e. */
+enum adaflo_b200_coefficient {
+  ADAFLO_B200_COEF_DENSITY = 0,
+  ADAFLO_B200_COEF_VISCOSITY = 1,
+  ADAFLO_B200_COEF_DAMPING = 2,
+  ADAFLO_B200_COEF_LINEARIZED_VELOCITY = 3
+};
+int adaflo_b200_ns_coefficient_ptr(adaflo_b200_ns_t ns, int which, double **dev_ptr, uint64_t *n_doubles);
+/* pressure null-space data built by initialize (:110-168): device pointers */
+int adaflo_b200_ns_nullspace(adaflo_b200_ns_t ns, int mode, const double **modes, const double **weights, double *inverse_weight);
+/* get_matvec_statistics: :1194-1206 (count, accumulated seconds; resets) */
+int adaflo_b200_ns_get_matvec_statistics(adaflo_b200_ns_t ns, uint64_t *count, double *seconds);
+
+/* End-to-end variant with HOST vectors (what a deal.II adaptor that keeps host
+ * vectors authoritative calls, SURVEY 8(b) "mirror per call"): H2D of src, vmult,
+ * D2H of dst on the context stream, synchronous on return. */
+int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *dst_p_host,
+                              const double *src_u_host, const double *src_p_host);
+
+/* ------------------------------------------------- Krylov-step vector kernels
+ * The deal.II vector operations the solvers call between two vmults
+ *  and adaflo's DiagonalPreconditioner
+ * (source/diagonal_preconditioner.cc:38-124), as bandwidth-bound fused kernels.
+ * n counts doubles; results of reductions land in result_dev (device) and are
+ * all-reduced over the communicator if one is set. */
+int adaflo_b200_vec_set(adaflo_b200_ctx_t ctx, double *x, double value, uint64_t n);
+int adaflo_b200_vec_axpy(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, uint64_t n);            /* y += a x */
+int adaflo_b200_vec_sadd(adaflo_b200_ctx_t ctx, double *y, double s, double a, const double *x, uint64_t n);  /* y = s y + a x */
+int adaflo_b200_vec_scale(adaflo_b200_ctx_t ctx, double *y, const double *scaling, uint64_t n);               /* y *= scaling */
+int adaflo_b200_vec_dot(adaflo_b200_ctx_t ctx, const double *x, const double *y, uint64_t n, double *result_host);
+/* k dots of one vector against k others in one pass (GMRES Gram-Schmidt) */
+int adaflo_b200_vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *ys, int k, uint64_t n, double *results_host);
+/* add_and_dot: y += a x ; returns y . z   (deal.II Vector::add_and_dot, used by SolverCG) */
+int adaflo_b200_vec_add_and_dot(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, const double *z, uint64_t n, double *result_host);
+/* DiagonalPreconditioner::reinit (guarded inverse, :38-60) and ::vmult (:99-124) */
+int adaflo_b200_jacobi_reinit(adaflo_b200_ctx_t ctx, double *inv_diag, const double *diag, uint64_t n);
+int adaflo_b200_jacobi_vmult(adaflo_b200_ctx_t ctx, double *dst, const double *src, const double *inv_diag, uint64_t n, int n_blocks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADAFLO_B200_H */

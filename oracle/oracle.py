@@ -1,0 +1,279 @@
+"""ctypes front end of the CPU oracle (oracle/ns_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of ns_oracle.c.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The operator-level logic composed here (zeroing,
+constrained rows, mean projection, coefficient rules of the pressure
+sub-operators) restates source/navier_stokes_matrix.cc:85-483.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+OP_VMULT, OP_RESIDUAL, OP_VMULT_VELOCITY = 0, 1, 2
+INCOMPRESSIBLE, STATIONARY, STOKES = 0, 1, 2
+NEWTON, PICARD, SEMI_IMPLICIT, EXPLICIT, PROJECTION = 0, 1, 2, 3, 4
+
+
+class _Mesh(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("n_q_1d", C.c_int32), ("u_degree", C.c_int32), ("p_degree", C.c_int32),
+                ("p_dg0", C.c_int32), ("pad_", C.c_int32),
+                ("u_ptr", C.c_void_p), ("u_idx", C.c_void_p), ("u_w", C.c_void_p),
+                ("p_ptr", C.c_void_p), ("p_idx", C.c_void_p), ("p_w", C.c_void_p),
+                ("u_constrained", C.c_void_p), ("p_constrained", C.c_void_p),
+                ("inv_jac", C.c_void_p), ("jxw", C.c_void_p)]
+
+
+class FlowParams(C.Structure):
+    _fields_ = [("physical_type", C.c_int32), ("linearization", C.c_int32), ("augmented_taylor_hood", C.c_int32),
+                ("variable_coefficients", C.c_int32), ("density", C.c_double), ("viscosity", C.c_double),
+                ("damping", C.c_double), ("tau_grad_div", C.c_double), ("beta", C.c_double)]
+
+
+class TimeWeights(C.Structure):
+    _fields_ = [("weight", C.c_double), ("weight_old", C.c_double), ("weight_old_old", C.c_double),
+                ("tau1", C.c_double), ("extrapolate_old", C.c_double), ("extrapolate_old_old", C.c_double)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = os.path.join(_HERE, "ns_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"])
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.oracle_l2_error.restype = C.c_double
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def gauss01(n):
+    x = np.zeros(n)
+    w = np.zeros(n)
+    lib().oracle_gauss01(n, _p(x), _p(w))
+    return x, w
+
+
+def shape_1d(degree, nq):
+    v = np.zeros((nq, degree + 1))
+    d = np.zeros((nq, degree + 1))
+    lib().oracle_shape_1d(degree, nq, _p(v), _p(d))
+    return v, d
+
+
+class OracleMesh:
+    """Uncompressed mesh description for the oracle, built from a BoxMesh-like
+    object (spaces with cell_nodes / dirichlet, general geometry arrays)."""
+
+    def __init__(self, mesh, n_q_1d=3, deform=None, u_lists=None, p_lists=None):
+        self.mesh = mesh
+        self.n_q_1d = n_q_1d
+        nc = mesh.n_cells
+        u, p = mesh.u, mesh.p
+        self.p_dg0 = 1 if getattr(p, "n_dg0", 0) else 0
+        # velocity gather lists: row = cell*81 + c*27 + n  ->  entry node*3 + c
+        if u_lists is None:
+            cn = u.cell_nodes.astype(np.int64)
+            idx = (cn[:, None, :] * 3 + np.arange(3)[None, :, None]).reshape(-1)
+            self.u_idx = np.ascontiguousarray(idx)
+            self.u_ptr = np.arange(len(idx) + 1, dtype=np.int64)
+            self.u_w = np.ones(len(idx))
+        else:
+            self.u_ptr, self.u_idx, self.u_w = u_lists
+        if p_lists is None:
+            idx = p.cell_nodes.astype(np.int64).reshape(-1)
+            self.p_idx = np.ascontiguousarray(idx)
+            self.p_ptr = np.arange(len(idx) + 1, dtype=np.int64)
+            self.p_w = np.ones(len(idx))
+        else:
+            self.p_ptr, self.p_idx, self.p_w = p_lists
+        self.u_con = np.ascontiguousarray(u.dirichlet.reshape(-1).astype(np.uint8))
+        self.p_con = np.ascontiguousarray(p.dirichlet.reshape(-1).astype(np.uint8))
+        K, jxw = mesh.general_geometry(n_q_1d, deform)
+        self.inv_jac = np.ascontiguousarray(K)
+        self.jxw = np.ascontiguousarray(jxw)
+        self.c = _Mesh(nc, n_q_1d, 2, 1, self.p_dg0, 0, _p(self.u_ptr), _p(self.u_idx), _p(self.u_w),
+                       _p(self.p_ptr), _p(self.p_idx), _p(self.p_w), _p(self.u_con), _p(self.p_con),
+                       _p(self.inv_jac), _p(self.jxw))
+        self.n_q = n_q_1d ** 3
+
+
+class OracleNavierStokesMatrix:
+    """CPU restatement of adaflo::NavierStokesMatrix<3> for one rank (no ghosts
+    exchange: use with nranks == 1, or exchange by hand in the gloo tests)."""
+
+    def __init__(self, mesh, prm: FlowParams, tw: TimeWeights, deform=None, pressure_average_fix=True,
+                 u_lists=None, p_lists=None):
+        self.mesh = mesh
+        self.prm = prm
+        self.tw = tw
+        self.mu = OracleMesh(mesh, 3, deform, u_lists, p_lists)   # quad_index_u: QGauss(3)
+        self.mp = OracleMesh(mesh, 2, deform, u_lists, p_lists)   # quad_index_p: QGauss(2)
+        nc, nq = mesh.n_cells, 27
+        self.n_u = mesh.u.n_dofs_local
+        self.n_p = mesh.p.n_dofs_local
+        self.lin = np.zeros((nc, 12, nq))
+        self.rho = self.muq = self.damp = None
+        if prm.variable_coefficients:
+            # initialize(): navier_stokes_matrix.cc:100-106
+            self.rho = np.full((nc, nq), prm.density)
+            self.muq = np.full((nc, nq), prm.viscosity)
+            self.damp = np.zeros((nc, nq))
+        self.old_u = np.zeros(self.n_u)
+        self.old_old_u = np.zeros(self.n_u)
+        self.lin_prec = None
+        # pressure null-space data, navier_stokes_matrix.cc:110-168
+        self.modes = [None, None]
+        self.mode_weights = [None, None]
+        self.inv_weights = [0.0, 0.0]
+        if pressure_average_fix or prm.augmented_taylor_hood:
+            pres_mass = np.zeros(self.n_p)
+            lib().oracle_pressure_op(C.byref(self.mp.c), 2, None, 0, None, _p(pres_mass))
+            n_own = mesh.p.n_owned
+            n_dg0 = getattr(mesh.p, "n_dg0", 0)
+            is_dg0 = np.zeros(self.n_p, bool)
+            if n_dg0:
+                is_dg0[mesh.p.n_q1_owned:mesh.p.n_q1_owned + n_dg0] = True
+            const_modes = [~is_dg0, is_dg0] if n_dg0 else [np.ones(self.n_p, bool), None]
+            for mode in range(2):
+                if mode == 0 and not pressure_average_fix:
+                    continue
+                if mode == 1 and not prm.augmented_taylor_hood:
+                    continue
+                m = np.zeros(self.n_p)
+                w = np.zeros(self.n_p)
+                sel = const_modes[mode].copy()
+                sel[n_own:] = False
+                m[sel] = 1.0
+                w[sel] = pres_mass[sel]
+                m[mesh.p.dirichlet.reshape(-1)] = 0.0
+                self.modes[mode] = m
+                self.mode_weights[mode] = w
+                self.inv_weights[mode] = 1.0 / float(m[:n_own] @ w[:n_own])
+
+    # ------------------------------------------------------------------ helpers
+    def _loop(self, op, src_u, src_p, dst_u, dst_p):
+        lib().oracle_ns_cell_loop(C.byref(self.mu.c), C.byref(self.prm), C.byref(self.tw), op, _p(src_u), _p(src_p),
+                                  _p(self.old_u), _p(self.old_old_u), _p(dst_u), _p(dst_p), _p(self.lin),
+                                  _p(self.rho), _p(self.muq), _p(self.damp))
+
+    def apply_pressure_average_projection(self, p):
+        """navier_stokes_matrix.cc:191-205"""
+        if self.prm.linearization != PROJECTION and self.prm.physical_type != STATIONARY:
+            n_own = self.mesh.p.n_owned
+            for mode in range(2):
+                if self.mode_weights[mode] is not None:
+                    product = float(self.mode_weights[mode][:n_own] @ p[:n_own])
+                    p += (-product * self.inv_weights[mode]) * self.modes[mode]
+
+    # --------------------------------------------------------------- operators
+    def vmult(self, src_u, src_p):
+        """navier_stokes_matrix.cc:221-262"""
+        dst_u = np.zeros(self.n_u)
+        dst_p = np.zeros(self.n_p)
+        self._loop(OP_VMULT, src_u, src_p, dst_u, dst_p)
+        cu = self.mesh.u.constrained_dofs()
+        cp = self.mesh.p.constrained_dofs()
+        dst_u[cu] = src_u[cu]
+        dst_p[cp] = -src_p[cp]
+        self.apply_pressure_average_projection(dst_p)
+        return dst_u, dst_p
+
+    def residual(self, rhs_u, rhs_p, src_u, src_p, user_u, user_p):
+        """navier_stokes_matrix.cc:266-293 (rhs is read-modify-write)"""
+        self._loop(OP_RESIDUAL, src_u, src_p, rhs_u, rhs_p)
+        rhs_u *= -1.0
+        rhs_u += user_u
+        rhs_p *= -1.0
+        rhs_p += user_p
+
+    def velocity_vmult(self, src_u):
+        """navier_stokes_matrix.cc:337-382"""
+        dst_u = np.zeros(self.n_u)
+        lin_keep = self.lin
+        if self.lin_prec is not None:
+            self.lin = self.lin_prec
+        self._loop(OP_VMULT_VELOCITY, src_u, None, dst_u, None)
+        self.lin = lin_keep
+        cu = self.mesh.u.constrained_dofs()
+        dst_u[cu] = src_u[cu]
+        return dst_u
+
+    def fix_linearization_point(self):
+        self.lin_prec = self.lin.copy()
+
+    def divergence_vmult_add(self, dst_p, src_u, weight_by_viscosity=False):
+        """navier_stokes_matrix.cc:300-332"""
+        lib().oracle_ns_divergence(C.byref(self.mu.c), C.byref(self.prm), int(weight_by_viscosity), _p(src_u),
+                                   _p(dst_p), _p(self.muq))
+
+    def _mu_center(self):
+        # begin_viscosities(cell)[n_q_points(0)/2]: the centre point of QGauss(3)^3
+        return self.muq[:, 27 // 2] if self.muq is not None else np.full(self.mesh.n_cells, self.prm.viscosity)
+
+    def pressure_mass_vmult(self, src_p):
+        """navier_stokes_matrix.cc:421-455, kernel :1036-1071"""
+        if self.prm.linearization == PROJECTION or self.prm.physical_type == STATIONARY:
+            coeff = np.ones(self.mesh.n_cells)
+        else:
+            coeff = 1.0 / (self._mu_center() + self.prm.tau_grad_div)
+        coeff = np.ascontiguousarray(coeff)
+        dst = np.zeros(self.n_p)
+        lib().oracle_pressure_op(C.byref(self.mp.c), 0, _p(coeff), 0, _p(src_p), _p(dst))
+        cp = self.mesh.p.constrained_dofs()
+        dst[cp] = src_p[cp]
+        if self.mode_weights[1] is not None and self.prm.linearization != PROJECTION:
+            n_own = self.mesh.p.n_owned
+            w = float(self.mode_weights[1][:n_own] @ dst[:n_own])
+            dst += (-w * self.inv_weights[1]) * self.modes[1]
+        return dst
+
+    def pressure_poisson_vmult(self, src_p):
+        """navier_stokes_matrix.cc:386-417, kernel :965-1032"""
+        var = self.rho is not None and self.prm.linearization != PROJECTION
+        dst = np.zeros(self.n_p)
+        if var and self.prm.physical_type != STATIONARY:
+            coeff = np.ascontiguousarray(1.0 / (self.tw.weight * self.rho))
+            lib().oracle_pressure_op(C.byref(self.mu.c), 1, _p(coeff), 1, _p(src_p), _p(dst))
+        else:
+            if var:
+                rho = self.rho[:, 27 // 2]
+            else:
+                rho = np.full(self.mesh.n_cells, min(self.prm.density, self.prm.density + getattr(self, "density_diff", 0.0)))
+            coeff = np.ones(self.mesh.n_cells) if self.prm.physical_type == STATIONARY else 1.0 / (self.tw.weight * rho)
+            coeff = np.ascontiguousarray(coeff)
+            lib().oracle_pressure_op(C.byref(self.mp.c), 1, _p(coeff), 0, _p(src_p), _p(dst))
+        cp = self.mesh.p.constrained_dofs()
+        dst[cp] = src_p[cp]
+        return dst
+
+    def pressure_convdiff_vmult(self, src_p):
+        """navier_stokes_matrix.cc:459-483, kernel :1099-1140 (diffusive part only)"""
+        coeff = np.ascontiguousarray(self._mu_center())
+        dst = np.zeros(self.n_p)
+        lib().oracle_pressure_op(C.byref(self.mu.c), 1, _p(coeff), 0, _p(src_p), _p(dst))
+        cp = self.mesh.p.constrained_dofs()
+        dst[cp] = src_p[cp]
+        return dst
+
+    def l2_error(self, n_comp, vec, exact_q, n_q_1d=3, deform=None):
+        om = self.mu if n_q_1d == 3 else OracleMesh(self.mesh, n_q_1d, deform)
+        exact_q = np.ascontiguousarray(exact_q)
+        return lib().oracle_l2_error(C.byref(om.c), n_comp, _p(vec), _p(exact_q))
