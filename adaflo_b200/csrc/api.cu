@@ -1,0 +1,819 @@
+// api.cu -- the C ABI of libadaflo_b200.so (include/adaflo_b200.h): handle
+// management, uploads, and the operator-level logic of NavierStokesMatrix
+// (source/navier_stokes_matrix.cc:85-483) around the cell kernels.
+#include <chrono>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace ab200 {
+
+static thread_local std::string g_error;
+void set_error(const std::string &msg) { g_error = msg; }
+int fail(int code, const std::string &msg)
+{
+  g_error = msg;
+  return code;
+}
+
+template <typename T>
+static int upload(T **dev, const T *host, size_t n, cudaStream_t s)
+{
+  *dev = nullptr;
+  if (n == 0) return 0;
+  AB_CUDA(cudaMalloc((void **)dev, n * sizeof(T)));
+  if (host) AB_CUDA(cudaMemcpyAsync(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice, s));
+  return 0;
+}
+
+static void free_dev(void *p)
+{
+  if (p) cudaFree(p);
+}
+
+static int mode_of(const adaflo_b200_flow_params &p)
+{
+  if (p.physical_type == ADAFLO_B200_STOKES) return MODE_STOKES;
+  switch (p.linearization) {
+    case ADAFLO_B200_COUPLED_IMPLICIT_NEWTON: return MODE_NEWTON;
+    case ADAFLO_B200_COUPLED_VELOCITY_EXPLICIT: return MODE_NOCONV;
+    default: return MODE_PICARD;
+  }
+}
+
+static void fill_geometry(NSArgs &a, const Quad &q)
+{
+  a.geom_row = q.cell_row;
+  a.geom_table = q.table;
+  a.inv_jac = q.inv_jac;
+  a.jxw = q.jxw;
+}
+
+static void fill_geometry(PArgs &a, const Quad &q)
+{
+  a.geom_row = q.cell_row;
+  a.geom_table = q.table;
+  a.inv_jac = q.inv_jac;
+  a.jxw = q.jxw;
+  a.geom = q.geometry_type;
+}
+
+static NSArgs make_args(adaflo_b200_ns_t ns, bool use_prec)
+{
+  adaflo_b200_mf_t mf = ns->mf;
+  NSArgs a{};
+  a.n_cells = mf->n_cells;
+  a.np_cell = (int)mf->spaces[ns->dof_p].nodes_per_cell;
+  a.cell_u = mf->spaces[ns->dof_u].cell_nodes;
+  a.cell_p = mf->spaces[ns->dof_p].cell_nodes;
+  const bool prec = use_prec && ns->lin_prec;
+  a.lin = prec ? ns->lin_prec : ns->lin;
+  a.rho = (use_prec && ns->rho_prec) ? ns->rho_prec : ns->rho;
+  a.mu = (use_prec && ns->mu_prec) ? ns->mu_prec : ns->mu;
+  a.damp = (use_prec && ns->damp_prec) ? ns->damp_prec : ns->damp;
+  fill_geometry(a, mf->quads[ns->quad_u]);
+  const auto &p = ns->prm;
+  const auto &t = ns->tw;
+  a.gamma = p.physical_type == ADAFLO_B200_INCOMPRESSIBLE ? t.weight : 0.0;  // :621-623
+  a.w_old = t.weight_old;
+  a.w_oo = t.weight_old_old;
+  a.tau1 = t.tau1;
+  a.beta = p.beta_convective_term_momentum_balance;
+  a.rho0 = p.density;
+  a.mu0 = p.viscosity;
+  a.damp0 = p.damping;
+  a.tau_gd = p.tau_grad_div;
+  a.ex_old = t.extrapolate_old;
+  a.ex_oo = t.extrapolate_old_old;
+  a.linearization = p.linearization;
+  a.physical_type = p.physical_type;
+  a.skip_p_test = p.linearization == ADAFLO_B200_PROJECTION;
+  return a;
+}
+
+static int launch_cells(adaflo_b200_ns_t ns, const NSArgs &a, bool with_p)
+{
+  const Quad &q = ns->mf->quads[ns->quad_u];
+  const int mode = mode_of(ns->prm);
+  cudaStream_t s = ns->ctx->stream;
+  switch (q.geometry_type) {
+    case ADAFLO_B200_GEOM_CARTESIAN: return launch_ns_vmult_cartesian(a, with_p, mode, ns->var, s);
+    case ADAFLO_B200_GEOM_AFFINE: return launch_ns_vmult_affine(a, with_p, mode, ns->var, s);
+    default: return launch_ns_vmult_general(a, with_p, mode, ns->var, s);
+  }
+}
+
+static bool projection_active(const adaflo_b200_ns_t ns)
+{
+  // navier_stokes_matrix.cc:196-197
+  return ns->prm.linearization != ADAFLO_B200_PROJECTION && ns->prm.physical_type != ADAFLO_B200_INCOMPRESSIBLE_STATIONARY;
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" {
+
+const char *adaflo_b200_last_error(void) { return g_error.c_str(); }
+const char *adaflo_b200_version(void) { return "adaflo_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------ context
+int adaflo_b200_ctx_create(adaflo_b200_ctx_t *out, int device, void *stream)
+{
+  if (!out) return fail(ADAFLO_B200_ERR_ARG, "ctx_create: null output");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(ADAFLO_B200_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(ADAFLO_B200_ERR_ARG, "ctx_create: bad device ordinal");
+  AB_CUDA(cudaSetDevice(device));
+  adaflo_b200_ctx_t c = new (std::nothrow) adaflo_b200_ctx_s();
+  if (!c) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");
+  c->device = device;
+  c->stream = (cudaStream_t)stream;
+  c->comm_stream = nullptr;
+  c->nccl_comm = nullptr;
+  c->rank = 0;
+  c->nranks = 1;
+  AB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  c->red_capacity = 64 + (size_t)8 * c->sm_count * 8 + 64;
+  AB_CUDA(cudaMalloc((void **)&c->red_dev, c->red_capacity * sizeof(double)));
+  AB_CUDA(cudaMallocHost((void **)&c->red_host, 64 * sizeof(double)));
+  AB_CUDA(cudaEventCreate(&c->ev_a));
+  AB_CUDA(cudaEventCreate(&c->ev_b));
+  *out = c;
+  return 0;
+}
+
+int adaflo_b200_ctx_destroy(adaflo_b200_ctx_t ctx)
+{
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  comm_destroy(ctx);
+  free_dev(ctx->red_dev);
+  if (ctx->red_host) cudaFreeHost(ctx->red_host);
+  cudaEventDestroy(ctx->ev_a);
+  cudaEventDestroy(ctx->ev_b);
+  delete ctx;
+  return 0;
+}
+
+int adaflo_b200_ctx_set_stream(adaflo_b200_ctx_t ctx, void *stream)
+{
+  if (!ctx) return fail(ADAFLO_B200_ERR_ARG, "null context");
+  ctx->stream = (cudaStream_t)stream;
+  return 0;
+}
+
+int adaflo_b200_ctx_synchronize(adaflo_b200_ctx_t ctx)
+{
+  if (!ctx) return fail(ADAFLO_B200_ERR_ARG, "null context");
+  AB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int adaflo_b200_comm_unique_id(unsigned char id[128]) { return comm_unique_id(id); }
+
+int adaflo_b200_ctx_init_comm(adaflo_b200_ctx_t ctx, const unsigned char id[128], int rank, int nranks)
+{
+  if (!ctx) return fail(ADAFLO_B200_ERR_ARG, "null context");
+  if (nranks <= 1) {
+    ctx->rank = 0;
+    ctx->nranks = 1;
+    return 0;
+  }
+  return comm_init(ctx, id, rank, nranks);
+}
+
+// ------------------------------------------------------------- matrix-free
+int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, adaflo_b200_mf_t *out)
+{
+  if (!ctx || !d || !out) return fail(ADAFLO_B200_ERR_ARG, "mf_create: null argument");
+  if (d->dim != 3) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "mf_create: only dim == 3 is implemented");
+  AB_CUDA(cudaSetDevice(ctx->device));
+  adaflo_b200_mf_t mf = new (std::nothrow) adaflo_b200_mf_s();
+  if (!mf) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");
+  mf->ctx = ctx;
+  mf->dim = d->dim;
+  mf->n_cells = d->n_cells;
+  cudaStream_t s = ctx->stream;
+  for (int i = 0; i < d->n_spaces; ++i) {
+    const adaflo_b200_space_desc &sd = d->spaces[i];
+    Space sp{};
+    sp.fe_kind = sd.fe_kind;
+    sp.degree = sd.degree;
+    sp.n_comp = sd.n_components;
+    sp.n_owned_nodes = sd.n_owned_nodes;
+    sp.n_ghost_nodes = sd.n_ghost_nodes;
+    sp.nodes_per_cell = sd.nodes_per_cell;
+    if (sd.n_components < 1 || sd.n_components > 3) return fail(ADAFLO_B200_ERR_ARG, "mf_create: n_components must be 1..3");
+    if ((uint64_t)sd.n_owned_nodes + sd.n_ghost_nodes > ADAFLO_B200_NODE_MASK)
+      return fail(ADAFLO_B200_ERR_ARG, "mf_create: more than 2^29 nodes per rank");
+    AB_CHECK(upload(&sp.cell_nodes, sd.cell_nodes, (size_t)d->n_cells * sd.nodes_per_cell, s));
+    if (sd.hanging_masks) AB_CHECK(upload(&sp.hanging_masks, sd.hanging_masks, (size_t)d->n_cells, s));
+    sp.n_constrained = sd.n_constrained;
+    AB_CHECK(upload(&sp.constrained, sd.constrained_dofs, (size_t)sd.n_constrained, s));
+    if (sd.fe_kind == ADAFLO_B200_FE_Q_DG0) {
+      sp.dg0_dofs.resize(d->n_cells);
+      for (uint32_t c = 0; c < d->n_cells; ++c)
+        sp.dg0_dofs[c] = sd.cell_nodes[(size_t)c * sd.nodes_per_cell + sd.nodes_per_cell - 1] & ADAFLO_B200_NODE_MASK;
+    }
+    for (int e = 0; e < sd.n_exchange; ++e) {
+      const adaflo_b200_exchange &xd = sd.exchange[e];
+      Exchange x{};
+      x.peer = xd.peer;
+      x.n_send = xd.n_send;
+      x.recv_first = xd.recv_first;
+      x.n_recv = xd.n_recv;
+      AB_CHECK(upload(&x.send_dev, xd.send, (size_t)xd.n_send, s));
+      if (xd.n_send) AB_CUDA(cudaMalloc((void **)&x.send_buf, sizeof(double) * (size_t)xd.n_send * sd.n_components));
+      sp.exchange.push_back(x);
+    }
+    mf->spaces.push_back(sp);
+  }
+  for (int i = 0; i < d->n_quads; ++i) {
+    const adaflo_b200_quad_desc &qd = d->quads[i];
+    Quad q{};
+    q.n_q_1d = qd.n_q_1d;
+    q.geometry_type = qd.geometry_type;
+    q.n_rows = qd.n_table_rows;
+    const size_t nq = (size_t)qd.n_q_1d * qd.n_q_1d * qd.n_q_1d;
+    if (qd.geometry_type == ADAFLO_B200_GEOM_GENERAL) {
+      if (!qd.inv_jacobian || !qd.jxw) return fail(ADAFLO_B200_ERR_ARG, "mf_create: general geometry needs inv_jacobian and jxw");
+      AB_CHECK(upload(&q.inv_jac, qd.inv_jacobian, (size_t)d->n_cells * 9 * nq, s));
+      AB_CHECK(upload(&q.jxw, qd.jxw, (size_t)d->n_cells * nq, s));
+    } else {
+      const int w = qd.geometry_type == ADAFLO_B200_GEOM_CARTESIAN ? 4 : 10;
+      if (!qd.table || !qd.cell_row) return fail(ADAFLO_B200_ERR_ARG, "mf_create: compressed geometry needs table and cell_row");
+      AB_CHECK(upload(&q.table, qd.table, (size_t)qd.n_table_rows * w, s));
+      AB_CHECK(upload(&q.cell_row, qd.cell_row, (size_t)d->n_cells, s));
+    }
+    mf->quads.push_back(q);
+  }
+  AB_CUDA(cudaStreamSynchronize(s));  // host arrays may be freed by the caller now
+  *out = mf;
+  return 0;
+}
+
+int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf)
+{
+  if (!mf) return 0;
+  cudaSetDevice(mf->ctx->device);
+  for (Space &sp : mf->spaces) {
+    free_dev(sp.cell_nodes);
+    free_dev(sp.hanging_masks);
+    free_dev(sp.constrained);
+    for (Exchange &x : sp.exchange) {
+      free_dev(x.send_dev);
+      free_dev(x.send_buf);
+    }
+  }
+  for (Quad &q : mf->quads) {
+    free_dev(q.table);
+    free_dev(q.cell_row);
+    free_dev(q.inv_jac);
+    free_dev(q.jxw);
+  }
+  delete mf;
+  return 0;
+}
+
+int adaflo_b200_mf_vector_size(adaflo_b200_mf_t mf, int space, uint64_t *n_owned, uint64_t *n_local)
+{
+  if (!mf || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "mf_vector_size: bad argument");
+  if (n_owned) *n_owned = mf->spaces[space].n_owned_entries();
+  if (n_local) *n_local = mf->spaces[space].n_local_entries();
+  return 0;
+}
+
+int adaflo_b200_mf_update_ghost_values(adaflo_b200_mf_t mf, int space, double *vec)
+{
+  if (!mf || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "update_ghost_values: bad argument");
+  return comm_update_ghosts(mf, space, vec);
+}
+
+int adaflo_b200_mf_compress_add(adaflo_b200_mf_t mf, int space, double *vec)
+{
+  if (!mf || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "compress_add: bad argument");
+  return comm_compress_add(mf, space, vec);
+}
+
+// ------------------------------------------------------- NavierStokesMatrix
+int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaflo_b200_flow_params *prm, int dof_u, int dof_p,
+                          int quad_u, int quad_p, int pressure_average_fix, adaflo_b200_ns_t *out)
+{
+  if (!ctx || !mf || !prm || !out) return fail(ADAFLO_B200_ERR_ARG, "ns_create: null argument");
+  const int ns_ = (int)mf->spaces.size(), nq_ = (int)mf->quads.size();
+  if (dof_u < 0 || dof_u >= ns_ || dof_p < 0 || dof_p >= ns_ || quad_u < 0 || quad_u >= nq_ || quad_p < 0 || quad_p >= nq_)
+    return fail(ADAFLO_B200_ERR_ARG, "ns_create: dof/quad index out of range");
+  const Space &su = mf->spaces[dof_u], &sp = mf->spaces[dof_p];
+  // EXPAND_OPERATIONS, navier_stokes_matrix.cc:64-82: the reference dispatches pressure degree 1..5;
+  // this library implements degree_p == 1 (Q2/Q1 and Q2/(Q1+DG0))
+  if (su.degree != 2 || su.n_comp != 3 || su.nodes_per_cell != 27 || sp.degree != 1 || sp.n_comp != 1 ||
+      !(sp.nodes_per_cell == 8 || sp.nodes_per_cell == 9) || mf->quads[quad_u].n_q_1d != 3 || mf->quads[quad_p].n_q_1d != 2)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: only 3-D Taylor-Hood Q2/Q1(+DG0) with QGauss(3)/QGauss(2) is implemented");
+  if (su.hanging_masks || sp.hanging_masks)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: hanging-node masks are not implemented yet");
+  AB_CUDA(cudaSetDevice(ctx->device));
+  adaflo_b200_ns_t ns = new (std::nothrow) adaflo_b200_ns_s();
+  if (!ns) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");
+  std::memset((void *)ns, 0, sizeof(*ns));
+  ns->ctx = ctx;
+  ns->mf = mf;
+  ns->prm = *prm;
+  ns->tw = adaflo_b200_time_weights{1.0, -1.0, 0.0, 1.0, 1.0, 0.0};
+  ns->dof_u = dof_u;
+  ns->dof_p = dof_p;
+  ns->quad_u = quad_u;
+  ns->quad_p = quad_p;
+  ns->n_q = 27;
+  ns->var = prm->density_diff != 0 || prm->viscosity_diff != 0;  // :97-98
+  cudaStream_t s = ctx->stream;
+  const size_t size = (size_t)mf->n_cells * ns->n_q;
+  if (ns->var) {  // :100-106
+    AB_CUDA(cudaMalloc((void **)&ns->rho, size * sizeof(double)));
+    AB_CUDA(cudaMalloc((void **)&ns->mu, size * sizeof(double)));
+    AB_CUDA(cudaMalloc((void **)&ns->damp, size * sizeof(double)));
+    AB_CHECK(vec_set(s, ns->rho, prm->density, size));
+    AB_CHECK(vec_set(s, ns->mu, prm->viscosity, size));
+    AB_CHECK(vec_set(s, ns->damp, 0.0, size));
+  }
+  if (prm->linearization != ADAFLO_B200_COUPLED_VELOCITY_EXPLICIT) {  // :107-108
+    AB_CUDA(cudaMalloc((void **)&ns->lin, size * 12 * sizeof(double)));
+    AB_CUDA(cudaMemsetAsync(ns->lin, 0, size * 12 * sizeof(double), s));
+  }
+  const uint64_t n_p_local = sp.n_local_entries(), n_p_owned = sp.n_owned_entries();
+  AB_CUDA(cudaMalloc((void **)&ns->tmp_p, (n_p_local + 1) * sizeof(double)));
+
+  // pressure null space, :110-168
+  if (pressure_average_fix || prm->augmented_taylor_hood) {
+    double *pres_mass = ns->tmp_p;
+    AB_CUDA(cudaMemsetAsync(pres_mass, 0, n_p_local * sizeof(double), s));
+    PArgs pa{};
+    pa.n_cells = mf->n_cells;
+    pa.np_cell = (int)sp.nodes_per_cell;
+    pa.cell_p = sp.cell_nodes;
+    pa.dst = pres_mass;
+    pa.c0 = 1.0;
+    fill_geometry(pa, mf->quads[quad_p]);
+    AB_CHECK(launch_pressure_op(pa, 2, 2, s));
+    AB_CHECK(comm_compress_add(mf, dof_p, pres_mass));
+    std::vector<double> pm(n_p_local), m(n_p_local), w(n_p_local);
+    AB_CUDA(cudaMemcpyAsync(pm.data(), pres_mass, n_p_local * sizeof(double), cudaMemcpyDeviceToHost, s));
+    std::vector<uint32_t> con(sp.n_constrained);
+    if (sp.n_constrained)
+      AB_CUDA(cudaMemcpyAsync(con.data(), sp.constrained, sp.n_constrained * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(cudaStreamSynchronize(s));
+    std::vector<char> is_dg0(n_p_local, 0);
+    for (uint32_t dof : sp.dg0_dofs) is_dg0[dof] = 1;
+    for (int mode = 0; mode < 2; ++mode) {
+      if (mode == 0 && !pressure_average_fix) continue;
+      if (mode == 1 && !prm->augmented_taylor_hood) continue;
+      if (mode == 1 && sp.fe_kind != ADAFLO_B200_FE_Q_DG0)
+        return fail(ADAFLO_B200_ERR_ARG, "ns_create: augmented_taylor_hood requires an FE_Q_DG0 pressure space");
+      std::fill(m.begin(), m.end(), 0.0);
+      std::fill(w.begin(), w.end(), 0.0);
+      for (uint64_t i = 0; i < n_p_owned; ++i)
+        if ((mode == 1) == (is_dg0[i] != 0)) {
+          m[i] = 1.0;
+          w[i] = pm[i];
+        }
+      for (uint32_t c : con) m[c] = 0.0;  // :159-163
+      AB_CHECK(upload(&ns->modes[mode], m.data(), n_p_local, s));
+      AB_CHECK(upload(&ns->mode_weights[mode], w.data(), n_p_local, s));
+      const double *ys[1] = {ns->mode_weights[mode]};
+      double dot = 0;
+      AB_CHECK(vec_multi_dot(ctx, ns->modes[mode], ys, 1, n_p_owned, &dot, true));
+      ns->inv_weights[mode] = 1.0 / dot;  // :165-166
+      ns->has_mode[mode] = true;
+    }
+  }
+  AB_CUDA(cudaStreamSynchronize(s));
+  *out = ns;
+  return 0;
+}
+
+int adaflo_b200_ns_destroy(adaflo_b200_ns_t ns)
+{
+  if (!ns) return 0;
+  cudaSetDevice(ns->ctx->device);
+  cudaStreamSynchronize(ns->ctx->stream);
+  void *ptrs[] = {ns->lin, ns->rho, ns->mu, ns->damp, ns->lin_prec, ns->rho_prec, ns->mu_prec, ns->damp_prec, ns->modes[0],
+                  ns->modes[1], ns->mode_weights[0], ns->mode_weights[1], ns->stage_u[0], ns->stage_u[1], ns->stage_p[0],
+                  ns->stage_p[1], ns->tmp_p};
+  for (void *p : ptrs) free_dev(p);
+  delete ns;
+  return 0;
+}
+
+int adaflo_b200_ns_set_flow_params(adaflo_b200_ns_t ns, const adaflo_b200_flow_params *prm)
+{
+  if (!ns || !prm) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  const bool var = prm->density_diff != 0 || prm->viscosity_diff != 0;
+  if (var != ns->var) return fail(ADAFLO_B200_ERR_STATE, "set_flow_params: cannot change the variable-coefficient mode after create");
+  if (prm->linearization != ADAFLO_B200_COUPLED_VELOCITY_EXPLICIT && !ns->lin)
+    return fail(ADAFLO_B200_ERR_STATE, "set_flow_params: linearization storage was not allocated at create");
+  ns->prm = *prm;
+  return 0;
+}
+
+int adaflo_b200_ns_set_time_weights(adaflo_b200_ns_t ns, const adaflo_b200_time_weights *w)
+{
+  if (!ns || !w) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  ns->tw = *w;
+  return 0;
+}
+
+int adaflo_b200_ns_set_old_solutions(adaflo_b200_ns_t ns, const double *old_u, const double *old_old_u)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  ns->old_u = old_u;
+  ns->old_old_u = old_old_u;
+  return 0;
+}
+
+static int stats_begin(adaflo_b200_ns_t ns, std::chrono::steady_clock::time_point &t0)
+{
+  t0 = std::chrono::steady_clock::now();
+  (void)ns;
+  return 0;
+}
+
+static void stats_end(adaflo_b200_ns_t ns, const std::chrono::steady_clock::time_point &t0)
+{
+  // matvec_timer semantics (:227,260-261): host wall time of the call.  Launches are
+  // asynchronous; the time of the last call is completed by the next synchronising call.
+  ns->matvec_count++;
+  ns->matvec_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const double *src_u, const double *src_p, bool transpose)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "vmult: operator not initialised");
+  if (!dst_u || !dst_p || !src_u || !src_p) return fail(ADAFLO_B200_ERR_ARG, "vmult: null vector");
+  adaflo_b200_mf_t mf = ns->mf;
+  adaflo_b200_ctx_t ctx = ns->ctx;
+  cudaStream_t s = ctx->stream;
+  const Space &su = mf->spaces[ns->dof_u], &sp = mf->spaces[ns->dof_p];
+  const int mode = mode_of(ns->prm);
+  if ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin) return fail(ADAFLO_B200_ERR_STATE, "vmult: no linearization storage");
+  std::chrono::steady_clock::time_point t0;
+  stats_begin(ns, t0);
+  const double *in_p = src_p;
+  if (transpose && projection_active(ns) && (ns->has_mode[0] || ns->has_mode[1])) {
+    // (P1 P0)^T = P0^T P1^T applied to the pressure source
+    AB_CUDA(cudaMemcpyAsync(ns->tmp_p, src_p, sp.n_local_entries() * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    for (int m = 1; m >= 0; --m)
+      if (ns->has_mode[m])
+        AB_CHECK(vec_project(ctx, ns->tmp_p, ns->modes[m], ns->mode_weights[m], ns->inv_weights[m], sp.n_owned_entries(),
+                             sp.n_local_entries()));
+    in_p = ns->tmp_p;
+  }
+  // cell_loop: ghost import of src, cells, compress(add) of dst (:236-242)
+  if (ctx->nranks > 1) {
+    AB_CHECK(comm_update_ghosts(mf, ns->dof_u, const_cast<double *>(src_u)));
+    AB_CHECK(comm_update_ghosts(mf, ns->dof_p, const_cast<double *>(in_p)));
+  }
+  AB_CUDA(cudaMemsetAsync(dst_u, 0, su.n_local_entries() * sizeof(double), s));  // dst = 0, :229
+  AB_CUDA(cudaMemsetAsync(dst_p, 0, sp.n_local_entries() * sizeof(double), s));
+  NSArgs a = make_args(ns, false);
+  a.src_u = src_u;
+  a.src_p = in_p;
+  a.dst_u = dst_u;
+  a.dst_p = dst_p;
+  a.transpose = transpose ? 1 : 0;
+  AB_CHECK(launch_cells(ns, a, true));
+  if (ctx->nranks > 1) {
+    AB_CHECK(comm_compress_add(mf, ns->dof_u, dst_u));
+    AB_CHECK(comm_compress_add(mf, ns->dof_p, dst_p));
+  }
+  // constrained rows, :247-256
+  AB_CHECK(vec_copy_indexed(s, dst_u, src_u, su.constrained, su.n_constrained, 1.0));
+  AB_CHECK(vec_copy_indexed(s, dst_p, in_p, sp.constrained, sp.n_constrained, -1.0));
+  if (!transpose && projection_active(ns))  // :258
+    for (int m = 0; m < 2; ++m)
+      if (ns->has_mode[m])
+        AB_CHECK(vec_project(ctx, dst_p, ns->mode_weights[m], ns->modes[m], ns->inv_weights[m], sp.n_owned_entries(),
+                             sp.n_local_entries()));
+  stats_end(ns, t0);
+  return 0;
+}
+
+int adaflo_b200_ns_vmult(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+{
+  return vmult_impl(ns, dst_u, dst_p, src_u, src_p, false);
+}
+
+int adaflo_b200_ns_Tvmult(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const double *src_u, const double *src_p)
+{
+  return vmult_impl(ns, dst_u, dst_p, src_u, src_p, true);
+}
+
+int adaflo_b200_ns_residual(adaflo_b200_ns_t ns, double *rhs_u, double *rhs_p, const double *src_u, const double *src_p,
+                            const double *user_u, const double *user_p)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "residual: operator not initialised");
+  if (!rhs_u || !rhs_p || !src_u || !src_p || !user_u || !user_p) return fail(ADAFLO_B200_ERR_ARG, "residual: null vector");
+  adaflo_b200_mf_t mf = ns->mf;
+  adaflo_b200_ctx_t ctx = ns->ctx;
+  cudaStream_t s = ctx->stream;
+  const Space &su = mf->spaces[ns->dof_u], &sp = mf->spaces[ns->dof_p];
+  const bool needs_old = ns->prm.physical_type == ADAFLO_B200_INCOMPRESSIBLE;
+  if (needs_old && (!ns->old_u || !ns->old_old_u)) return fail(ADAFLO_B200_ERR_STATE, "residual: old solutions not set");
+  if (ns->prm.physical_type != ADAFLO_B200_STOKES && ns->prm.linearization != ADAFLO_B200_COUPLED_VELOCITY_EXPLICIT && !ns->lin)
+    return fail(ADAFLO_B200_ERR_STATE, "residual: no linearization storage");
+  if (ctx->nranks > 1) {
+    AB_CHECK(comm_update_ghosts(mf, ns->dof_u, const_cast<double *>(src_u)));
+    AB_CHECK(comm_update_ghosts(mf, ns->dof_p, const_cast<double *>(src_p)));
+    if (needs_old) {
+      AB_CHECK(comm_update_ghosts(mf, ns->dof_u, const_cast<double *>(ns->old_u)));
+      AB_CHECK(comm_update_ghosts(mf, ns->dof_u, const_cast<double *>(ns->old_old_u)));
+    }
+    // ghost part of the accumulation target must start from zero
+    if (su.n_ghost_nodes) AB_CUDA(cudaMemsetAsync(rhs_u + su.n_owned_entries(), 0, sizeof(double) * su.n_ghost_nodes * su.n_comp, s));
+    if (sp.n_ghost_nodes) AB_CUDA(cudaMemsetAsync(rhs_p + sp.n_owned_entries(), 0, sizeof(double) * sp.n_ghost_nodes * sp.n_comp, s));
+  }
+  NSArgs a = make_args(ns, false);
+  a.src_u = src_u;
+  a.src_p = src_p;
+  a.old_u = ns->old_u;
+  a.old_old_u = ns->old_old_u;
+  a.dst_u = rhs_u;
+  a.dst_p = rhs_p;
+  AB_CHECK(launch_ns_residual(a, mf->quads[ns->quad_u].geometry_type, ns->var, s));
+  if (ctx->nranks > 1) {
+    AB_CHECK(comm_compress_add(mf, ns->dof_u, rhs_u));
+    AB_CHECK(comm_compress_add(mf, ns->dof_p, rhs_p));
+  }
+  // system_rhs.sadd(-1., 1., user_rhs), :292
+  AB_CHECK(vec_sadd(s, rhs_u, -1.0, 1.0, user_u, su.n_owned_entries()));
+  AB_CHECK(vec_sadd(s, rhs_p, -1.0, 1.0, user_p, sp.n_owned_entries()));
+  return 0;
+}
+
+int adaflo_b200_ns_velocity_vmult(adaflo_b200_ns_t ns, double *dst_u, const double *src_u)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "velocity_vmult: operator not initialised");
+  if (!dst_u || !src_u) return fail(ADAFLO_B200_ERR_ARG, "velocity_vmult: null vector");
+  adaflo_b200_mf_t mf = ns->mf;
+  cudaStream_t s = ns->ctx->stream;
+  const Space &su = mf->spaces[ns->dof_u];
+  if (ns->ctx->nranks > 1) AB_CHECK(comm_update_ghosts(mf, ns->dof_u, const_cast<double *>(src_u)));
+  AB_CUDA(cudaMemsetAsync(dst_u, 0, su.n_local_entries() * sizeof(double), s));
+  NSArgs a = make_args(ns, true);  // preconditioner snapshot if present, :349-355
+  a.src_u = src_u;
+  a.dst_u = dst_u;
+  AB_CHECK(launch_cells(ns, a, false));
+  if (ns->ctx->nranks > 1) AB_CHECK(comm_compress_add(mf, ns->dof_u, dst_u));
+  AB_CHECK(vec_copy_indexed(s, dst_u, src_u, su.constrained, su.n_constrained, 1.0));  // :377-381
+  return 0;
+}
+
+int adaflo_b200_ns_divergence_vmult_add(adaflo_b200_ns_t ns, double *dst_p, const double *src_u, int weight_by_viscosity)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "divergence_vmult_add: operator not initialised");
+  if (!dst_p || !src_u) return fail(ADAFLO_B200_ERR_ARG, "divergence_vmult_add: null vector");
+  adaflo_b200_mf_t mf = ns->mf;
+  cudaStream_t s = ns->ctx->stream;
+  const Space &sp = mf->spaces[ns->dof_p];
+  if (ns->ctx->nranks > 1) {
+    AB_CHECK(comm_update_ghosts(mf, ns->dof_u, const_cast<double *>(src_u)));
+    if (sp.n_ghost_nodes) AB_CUDA(cudaMemsetAsync(dst_p + sp.n_owned_entries(), 0, sizeof(double) * sp.n_ghost_nodes, s));
+  }
+  PArgs pa{};
+  pa.n_cells = mf->n_cells;
+  pa.np_cell = (int)sp.nodes_per_cell;
+  pa.cell_u = mf->spaces[ns->dof_u].cell_nodes;
+  pa.cell_p = sp.cell_nodes;
+  pa.src = src_u;
+  pa.dst = dst_p;
+  pa.resolve = ns->prm.linearization != ADAFLO_B200_PROJECTION;  // :940-943
+  pa.c0 = ns->prm.viscosity;
+  pa.coeff_q = (weight_by_viscosity && ns->var) ? ns->mu : nullptr;  // :948-953
+  fill_geometry(pa, mf->quads[ns->quad_u]);
+  AB_CHECK(launch_divergence(pa, weight_by_viscosity != 0, s));
+  if (ns->ctx->nranks > 1) AB_CHECK(comm_compress_add(mf, ns->dof_p, dst_p));
+  return 0;
+}
+
+static int pressure_common(adaflo_b200_ns_t ns, double *dst_p, const double *src_p, PArgs &pa, int kind, int quad)
+{
+  adaflo_b200_mf_t mf = ns->mf;
+  cudaStream_t s = ns->ctx->stream;
+  const Space &sp = mf->spaces[ns->dof_p];
+  if (ns->ctx->nranks > 1) AB_CHECK(comm_update_ghosts(mf, ns->dof_p, const_cast<double *>(src_p)));
+  AB_CUDA(cudaMemsetAsync(dst_p, 0, sp.n_local_entries() * sizeof(double), s));
+  pa.n_cells = mf->n_cells;
+  pa.np_cell = (int)sp.nodes_per_cell;
+  pa.cell_p = sp.cell_nodes;
+  pa.src = src_p;
+  pa.dst = dst_p;
+  fill_geometry(pa, mf->quads[quad]);
+  AB_CHECK(launch_pressure_op(pa, kind, mf->quads[quad].n_q_1d, s));
+  if (ns->ctx->nranks > 1) AB_CHECK(comm_compress_add(mf, ns->dof_p, dst_p));
+  AB_CHECK(vec_copy_indexed(s, dst_p, src_p, sp.constrained, sp.n_constrained, 1.0));
+  return 0;
+}
+
+int adaflo_b200_ns_pressure_mass_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_mass_vmult: operator not initialised");
+  if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_mass_vmult: null vector");
+  PArgs pa{};
+  const auto &p = ns->prm;
+  if (p.linearization == ADAFLO_B200_PROJECTION || p.physical_type == ADAFLO_B200_INCOMPRESSIBLE_STATIONARY) {
+    pa.coeff_mode = 0;
+    pa.c0 = 1.0;  // :1059-1062
+  } else if (ns->var) {
+    pa.coeff_mode = 1;
+    pa.coeff_q = ns->mu_prec ? ns->mu_prec : ns->mu;  // :430-431
+    pa.c1 = p.tau_grad_div;
+  } else {
+    pa.coeff_mode = 0;
+    pa.c0 = 1.0 / (p.viscosity + p.tau_grad_div);  // :1063
+  }
+  AB_CHECK(pressure_common(ns, dst_p, src_p, pa, 0, ns->quad_p));
+  if (ns->has_mode[1] && p.linearization != ADAFLO_B200_PROJECTION) {  // :449-454
+    const Space &sp = ns->mf->spaces[ns->dof_p];
+    AB_CHECK(vec_project(ns->ctx, dst_p, ns->mode_weights[1], ns->modes[1], ns->inv_weights[1], sp.n_owned_entries(),
+                         sp.n_local_entries()));
+  }
+  return 0;
+}
+
+int adaflo_b200_ns_pressure_poisson_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_poisson_vmult: operator not initialised");
+  if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_poisson_vmult: null vector");
+  PArgs pa{};
+  const auto &p = ns->prm;
+  const bool var = ns->var && p.linearization != ADAFLO_B200_PROJECTION;  // :975-977
+  const double *rho = ns->rho_prec ? ns->rho_prec : ns->rho;             // :398-399
+  const bool stationary = p.physical_type == ADAFLO_B200_INCOMPRESSIBLE_STATIONARY;
+  int quad = ns->quad_p;
+  if (var && !stationary) {  // :979-1001
+    pa.coeff_mode = 2;
+    pa.coeff_q = rho;
+    pa.c0 = ns->tw.weight;
+    quad = ns->quad_u;
+  } else if (stationary) {
+    pa.coeff_mode = 0;
+    pa.c0 = 1.0;  // :1020-1022
+  } else if (var) {
+    pa.coeff_mode = 3;
+    pa.coeff_q = rho;
+    pa.c0 = ns->tw.weight;
+  } else {
+    pa.coeff_mode = 0;
+    const double rho_value = p.density < p.density + p.density_diff ? p.density : p.density + p.density_diff;  // :1017-1019
+    pa.c0 = 1.0 / (ns->tw.weight * rho_value);
+  }
+  return pressure_common(ns, dst_p, src_p, pa, 1, quad);
+}
+
+int adaflo_b200_ns_pressure_convdiff_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_convdiff_vmult: operator not initialised");
+  if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_convdiff_vmult: null vector");
+  if (!ns->lin) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "pressure_convdiff_vmult needs linearized velocities (:1111)");
+  PArgs pa{};
+  if (ns->var) {
+    pa.coeff_mode = 4;
+    pa.coeff_q = ns->mu;
+  } else {
+    pa.coeff_mode = 0;
+    pa.c0 = ns->prm.viscosity;
+  }
+  return pressure_common(ns, dst_p, src_p, pa, 1, ns->quad_u);
+}
+
+int adaflo_b200_ns_compute_diagonal(adaflo_b200_ns_t ns, double *diag_u, double *diag_p)
+{
+  (void)ns; (void)diag_u; (void)diag_p;
+  return fail(ADAFLO_B200_ERR_UNSUPPORTED, "compute_diagonal is not implemented yet");
+}
+
+int adaflo_b200_ns_fix_linearization_point(adaflo_b200_ns_t ns)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "operator not initialised");
+  cudaStream_t s = ns->ctx->stream;
+  const size_t size = (size_t)ns->mf->n_cells * ns->n_q;
+  struct { double **dst; double *src; size_t n; } items[] = {{&ns->lin_prec, ns->lin, size * 12},
+                                                             {&ns->rho_prec, ns->rho, size},
+                                                             {&ns->mu_prec, ns->mu, size},
+                                                             {&ns->damp_prec, ns->damp, size}};
+  for (auto &it : items) {
+    if (!it.src) continue;
+    if (!*it.dst) AB_CUDA(cudaMalloc((void **)it.dst, it.n * sizeof(double)));
+    AB_CUDA(cudaMemcpyAsync(*it.dst, it.src, it.n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+int adaflo_b200_ns_apply_pressure_average_projection(adaflo_b200_ns_t ns, double *p)
+{
+  if (!ns || !p) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  if (!projection_active(ns)) return 0;
+  const Space &sp = ns->mf->spaces[ns->dof_p];
+  for (int m = 0; m < 2; ++m)
+    if (ns->has_mode[m])
+      AB_CHECK(vec_project(ns->ctx, p, ns->mode_weights[m], ns->modes[m], ns->inv_weights[m], sp.n_owned_entries(), sp.n_local_entries()));
+  return 0;
+}
+
+int adaflo_b200_ns_apply_pressure_shift(adaflo_b200_ns_t ns, double shift, double *p)
+{
+  if (!ns || !p) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  if (!ns->has_mode[0]) return fail(ADAFLO_B200_ERR_STATE, "apply_pressure_shift: no constant pressure mode (:215)");
+  return vec_axpy(ns->ctx->stream, p, shift, ns->modes[0], ns->mf->spaces[ns->dof_p].n_local_entries());
+}
+
+int adaflo_b200_ns_coefficient_ptr(adaflo_b200_ns_t ns, int which, double **dev_ptr, uint64_t *n)
+{
+  if (!ns || !dev_ptr) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  const uint64_t size = (uint64_t)ns->mf->n_cells * ns->n_q;
+  double *p = nullptr;
+  uint64_t cnt = size;
+  switch (which) {
+    case ADAFLO_B200_COEF_DENSITY: p = ns->rho; break;
+    case ADAFLO_B200_COEF_VISCOSITY: p = ns->mu; break;
+    case ADAFLO_B200_COEF_DAMPING: p = ns->damp; break;
+    case ADAFLO_B200_COEF_LINEARIZED_VELOCITY: p = ns->lin; cnt = size * 12; break;
+    default: return fail(ADAFLO_B200_ERR_ARG, "coefficient_ptr: unknown coefficient");
+  }
+  *dev_ptr = p;
+  if (n) *n = p ? cnt : 0;
+  return 0;
+}
+
+int adaflo_b200_ns_nullspace(adaflo_b200_ns_t ns, int mode, const double **modes, const double **weights, double *inv)
+{
+  if (!ns || mode < 0 || mode > 1) return fail(ADAFLO_B200_ERR_ARG, "nullspace: bad argument");
+  if (modes) *modes = ns->modes[mode];
+  if (weights) *weights = ns->mode_weights[mode];
+  if (inv) *inv = ns->inv_weights[mode];
+  return 0;
+}
+
+int adaflo_b200_ns_get_matvec_statistics(adaflo_b200_ns_t ns, uint64_t *count, double *seconds)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CUDA(cudaStreamSynchronize(ns->ctx->stream));
+  if (count) *count = ns->matvec_count;
+  if (seconds) *seconds = ns->matvec_seconds;
+  ns->matvec_count = 0;  // :1203-1204
+  ns->matvec_seconds = 0;
+  return 0;
+}
+
+int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *dst_p_host, const double *src_u_host,
+                              const double *src_p_host)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "vmult_host: operator not initialised");
+  if (!dst_u_host || !dst_p_host || !src_u_host || !src_p_host) return fail(ADAFLO_B200_ERR_ARG, "vmult_host: null vector");
+  cudaStream_t s = ns->ctx->stream;
+  const Space &su = ns->mf->spaces[ns->dof_u], &sp = ns->mf->spaces[ns->dof_p];
+  const size_t nu = su.n_local_entries(), np = sp.n_local_entries();
+  for (int i = 0; i < 2; ++i) {
+    if (!ns->stage_u[i]) AB_CUDA(cudaMalloc((void **)&ns->stage_u[i], nu * sizeof(double)));
+    if (!ns->stage_p[i]) AB_CUDA(cudaMalloc((void **)&ns->stage_p[i], np * sizeof(double)));
+  }
+  AB_CUDA(cudaMemcpyAsync(ns->stage_u[0], src_u_host, su.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+  AB_CUDA(cudaMemcpyAsync(ns->stage_p[0], src_p_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+  AB_CHECK(vmult_impl(ns, ns->stage_u[1], ns->stage_p[1], ns->stage_u[0], ns->stage_p[0], false));
+  AB_CUDA(cudaMemcpyAsync(dst_u_host, ns->stage_u[1], su.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  AB_CUDA(cudaMemcpyAsync(dst_p_host, ns->stage_p[1], sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  AB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// ------------------------------------------------- Krylov-step vector kernels
+int adaflo_b200_vec_set(adaflo_b200_ctx_t ctx, double *x, double v, uint64_t n) { return vec_set(ctx->stream, x, v, n); }
+int adaflo_b200_vec_axpy(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, uint64_t n) { return vec_axpy(ctx->stream, y, a, x, n); }
+int adaflo_b200_vec_sadd(adaflo_b200_ctx_t ctx, double *y, double sc, double a, const double *x, uint64_t n)
+{
+  return vec_sadd(ctx->stream, y, sc, a, x, n);
+}
+int adaflo_b200_vec_scale(adaflo_b200_ctx_t ctx, double *y, const double *sc, uint64_t n) { return vec_scale(ctx->stream, y, sc, n); }
+int adaflo_b200_vec_dot(adaflo_b200_ctx_t ctx, const double *x, const double *y, uint64_t n, double *result_host)
+{
+  const double *ys[1] = {y};
+  return vec_multi_dot(ctx, x, ys, 1, n, result_host, true);
+}
+int adaflo_b200_vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *ys, int k, uint64_t n, double *results_host)
+{
+  return vec_multi_dot(ctx, x, ys, k, n, results_host, true);
+}
+int adaflo_b200_vec_add_and_dot(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, const double *z, uint64_t n, double *result_host)
+{
+  return vec_add_and_dot(ctx, y, a, x, z, n, result_host);
+}
+int adaflo_b200_jacobi_reinit(adaflo_b200_ctx_t ctx, double *inv_diag, const double *diag, uint64_t n) { return jacobi_reinit(ctx, inv_diag, diag, n); }
+int adaflo_b200_jacobi_vmult(adaflo_b200_ctx_t ctx, double *dst, const double *src, const double *inv_diag, uint64_t n, int n_blocks)
+{
+  return jacobi_vmult(ctx->stream, dst, src, inv_diag, n, n_blocks);
+}
+
+}  // extern "C"

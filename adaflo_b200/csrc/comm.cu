@@ -1,0 +1,150 @@
+// comm.cu -- ghost exchange and scalar all-reduce over NCCL (NVLink 5 / NVSwitch).
+//
+// Replaces deal.II's Utilities::MPI::Partitioner point-to-point exchange inside
+// MatrixFree::cell_loop and the MPI_Allreduce of Vector::operator* (SURVEY 2.3
+// "Communication call sites").  NCCL is bound lazily with dlopen so that a
+// single-GPU process needs no NCCL at all; inside a PyTorch process the already
+// loaded libnccl.so.2 is reused.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace ab200 {
+
+namespace {
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+int load_nccl()
+{
+  if (g_nccl.handle) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) return fail(ADAFLO_B200_ERR_COMM, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define AB_SYM(field, name)                                                                  \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.handle, name);                                    \
+  if (!g_nccl.field) return fail(ADAFLO_B200_ERR_COMM, std::string("missing NCCL symbol ") + name);
+  AB_SYM(GetUniqueId, "ncclGetUniqueId")
+  AB_SYM(CommInitRank, "ncclCommInitRank")
+  AB_SYM(CommDestroy, "ncclCommDestroy")
+  AB_SYM(GroupStart, "ncclGroupStart")
+  AB_SYM(GroupEnd, "ncclGroupEnd")
+  AB_SYM(Send, "ncclSend")
+  AB_SYM(Recv, "ncclRecv")
+  AB_SYM(AllReduce, "ncclAllReduce")
+  AB_SYM(GetErrorString, "ncclGetErrorString")
+#undef AB_SYM
+  return 0;
+}
+}  // namespace
+
+#define AB_NCCL(expr)                                                                                    \
+  do {                                                                                                   \
+    ncclResult_t r__ = (expr);                                                                           \
+    if (r__ != ncclSuccess)                                                                              \
+      return fail(ADAFLO_B200_ERR_COMM, std::string(#expr) + ": " + g_nccl.GetErrorString(r__));         \
+  } while (0)
+
+int comm_unique_id(unsigned char id[128])
+{
+  AB_CHECK(load_nccl());
+  ncclUniqueId uid;
+  AB_NCCL(g_nccl.GetUniqueId(&uid));
+  static_assert(sizeof(uid) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id, &uid, 128);
+  return 0;
+}
+
+int comm_init(adaflo_b200_ctx_t ctx, const unsigned char id[128], int rank, int nranks)
+{
+  AB_CHECK(load_nccl());
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, 128);
+  ncclComm_t comm;
+  AB_CUDA(cudaSetDevice(ctx->device));
+  AB_NCCL(g_nccl.CommInitRank(&comm, nranks, uid, rank));
+  ctx->nccl_comm = comm;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return 0;
+}
+
+int comm_destroy(adaflo_b200_ctx_t ctx)
+{
+  if (ctx->nccl_comm) {
+    g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+  }
+  return 0;
+}
+
+int comm_allreduce(adaflo_b200_ctx_t ctx, double *dev, int k, int op_max)
+{
+  if (ctx->nranks <= 1) return 0;
+  if (!ctx->nccl_comm) return fail(ADAFLO_B200_ERR_STATE, "communicator not initialised");
+  AB_NCCL(g_nccl.AllReduce(dev, dev, (size_t)k, ncclDouble, op_max ? ncclMax : ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  return 0;
+}
+
+// owner -> ghost import (LinearAlgebra::distributed::Vector::update_ghost_values)
+int comm_update_ghosts(adaflo_b200_mf_t mf, int space, double *vec)
+{
+  adaflo_b200_ctx_t ctx = mf->ctx;
+  Space &sp = mf->spaces[space];
+  if (sp.exchange.empty() || ctx->nranks <= 1) return 0;
+  if (!ctx->nccl_comm) return fail(ADAFLO_B200_ERR_STATE, "communicator not initialised");
+  for (Exchange &e : sp.exchange)
+    if (e.n_send) AB_CHECK(vec_pack(ctx->stream, e.send_buf, vec, e.send_dev, e.n_send, sp.n_comp));
+  AB_NCCL(g_nccl.GroupStart());
+  for (Exchange &e : sp.exchange) {
+    if (e.n_send)
+      AB_NCCL(g_nccl.Send(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    if (e.n_recv)
+      AB_NCCL(g_nccl.Recv(vec + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
+                          (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  }
+  AB_NCCL(g_nccl.GroupEnd());
+  return 0;
+}
+
+// ghost -> owner accumulation (Vector::compress(VectorOperation::add)); ghost entries are zeroed afterwards
+int comm_compress_add(adaflo_b200_mf_t mf, int space, double *vec)
+{
+  adaflo_b200_ctx_t ctx = mf->ctx;
+  Space &sp = mf->spaces[space];
+  if (sp.exchange.empty() || ctx->nranks <= 1) return 0;
+  if (!ctx->nccl_comm) return fail(ADAFLO_B200_ERR_STATE, "communicator not initialised");
+  AB_NCCL(g_nccl.GroupStart());
+  for (Exchange &e : sp.exchange) {
+    if (e.n_recv)
+      AB_NCCL(g_nccl.Send(vec + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
+                          (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    if (e.n_send)
+      AB_NCCL(g_nccl.Recv(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  }
+  AB_NCCL(g_nccl.GroupEnd());
+  for (Exchange &e : sp.exchange)
+    if (e.n_send) AB_CHECK(vec_unpack_add(ctx->stream, vec, e.send_buf, e.send_dev, e.n_send, sp.n_comp));
+  if (sp.n_ghost_nodes)
+    AB_CUDA(cudaMemsetAsync(vec + sp.n_owned_entries(), 0, sizeof(double) * (size_t)sp.n_ghost_nodes * sp.n_comp, ctx->stream));
+  return 0;
+}
+
+}  // namespace ab200

@@ -1,0 +1,198 @@
+// common.cuh -- internal declarations shared by the translation units of
+// libadaflo_b200.so.  Not part of the public ABI (include/adaflo_b200.h is).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/adaflo_b200.h"
+
+namespace ab200 {
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define AB_CUDA(expr)                                                                                  \
+  do {                                                                                                 \
+    cudaError_t e__ = (expr);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return ::ab200::fail(ADAFLO_B200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define AB_CHECK(expr)        \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// ------------------------------------------------------------------ handles
+struct Exchange {
+  int peer;
+  uint32_t n_send;
+  uint32_t *send_dev;  // local node indices
+  uint32_t recv_first;
+  uint32_t n_recv;
+  double *send_buf;    // n_send * n_comp
+  double *recv_buf;    // n_recv * n_comp (compress direction)
+};
+
+struct Space {
+  int fe_kind, degree, n_comp;
+  uint32_t n_owned_nodes, n_ghost_nodes, nodes_per_cell;
+  uint32_t *cell_nodes;      // device [n_cells][nodes_per_cell]
+  uint32_t *hanging_masks;   // device [n_cells] or null
+  uint32_t n_constrained;
+  uint32_t *constrained;     // device
+  std::vector<Exchange> exchange;
+  std::vector<uint32_t> dg0_dofs;  // host: element-constant dofs (FE_Q_DG0)
+  uint64_t n_owned_entries() const { return (uint64_t)n_owned_nodes * n_comp; }
+  uint64_t n_local_entries() const { return (uint64_t)(n_owned_nodes + n_ghost_nodes) * n_comp; }
+};
+
+struct Quad {
+  int n_q_1d, geometry_type;
+  uint32_t n_rows;
+  double *table;       // device
+  uint32_t *cell_row;  // device
+  double *inv_jac;     // device [n_cells][9][n_q]
+  double *jxw;         // device [n_cells][n_q]
+};
+
+}  // namespace ab200
+
+struct adaflo_b200_ctx_s {
+  int device;
+  cudaStream_t stream;
+  cudaStream_t comm_stream;
+  cudaEvent_t ev_a, ev_b;
+  int sm_count;
+  // reductions
+  double *red_dev;     // scratch for block partials / results
+  double *red_host;    // pinned
+  size_t red_capacity; // doubles
+  // communicator
+  void *nccl_comm;
+  int rank, nranks;
+};
+
+struct adaflo_b200_mf_s {
+  adaflo_b200_ctx_t ctx;
+  int dim;
+  uint32_t n_cells;
+  std::vector<ab200::Space> spaces;
+  std::vector<ab200::Quad> quads;
+};
+
+struct adaflo_b200_ns_s {
+  adaflo_b200_ctx_t ctx;
+  adaflo_b200_mf_t mf;
+  adaflo_b200_flow_params prm;
+  adaflo_b200_time_weights tw;
+  int dof_u, dof_p, quad_u, quad_p;
+  int n_q;  // points of quad_u
+  // per-quadrature-point coefficient arrays (owned)
+  double *lin, *rho, *mu, *damp;
+  double *lin_prec, *rho_prec, *mu_prec, *damp_prec;  // fix_linearization_point snapshots
+  const double *old_u, *old_old_u;
+  // pressure null space
+  double *modes[2], *mode_weights[2];
+  double inv_weights[2];
+  bool has_mode[2];
+  // host staging for the *_host entry points
+  double *stage_u[2], *stage_p[2];
+  double *tmp_p;  // scratch pressure vector (Tvmult)
+  bool var;       // variable coefficients in use
+  // statistics
+  uint64_t matvec_count;
+  double matvec_seconds;
+};
+
+namespace ab200 {
+
+// --------------------------------------------------------- kernel arguments
+struct NSArgs {
+  uint32_t n_cells;
+  int np_cell;  // pressure dofs per cell: 8, or 9 with DG0
+  const uint32_t *cell_u;
+  const uint32_t *cell_p;
+  const double *src_u;
+  const double *src_p;
+  const double *old_u;
+  const double *old_old_u;
+  double *dst_u;
+  double *dst_p;
+  double *lin;
+  const double *rho;
+  const double *mu;
+  const double *damp;
+  const uint32_t *geom_row;
+  const double *geom_table;
+  const double *inv_jac;
+  const double *jxw;
+  double gamma, w_old, w_oo, tau1, beta, rho0, mu0, damp0, tau_gd, ex_old, ex_oo;
+  int linearization;  // runtime copy (residual kernel)
+  int physical_type;
+  int transpose;      // Tvmult
+  int skip_p_test;    // linearization == projection: pressure block not integrated (:902-907)
+};
+
+// mode of the convective block in a matrix-vector product
+enum { MODE_STOKES = 0, MODE_NEWTON = 1, MODE_PICARD = 2, MODE_NOCONV = 3 };
+
+int upload_shape_tables(cudaStream_t s);
+
+// launchers (one translation unit per geometry type keeps compile times down)
+int launch_ns_vmult_cartesian(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
+int launch_ns_vmult_affine(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
+int launch_ns_vmult_general(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
+int launch_ns_residual(const NSArgs &a, int geom, bool var, cudaStream_t s);
+
+struct PArgs {
+  uint32_t n_cells;
+  int np_cell;
+  const uint32_t *cell_u;
+  const uint32_t *cell_p;
+  const double *src;
+  double *dst;
+  const double *coeff_q;   // per quadrature point [n_cells][n_q] or null
+  int resolve;             // divergence: read_dof_values (1) or read_dof_values_plain (0)
+  int coeff_mode;          // see pressure_ops.cu
+  double c0, c1;
+  const uint32_t *geom_row;
+  const double *geom_table;
+  const double *inv_jac;
+  const double *jxw;
+  int geom;
+};
+int launch_divergence(const PArgs &a, bool weight_by_viscosity, cudaStream_t s);
+int launch_pressure_op(const PArgs &a, int kind, int n_q_1d, cudaStream_t s);
+
+// vector kernels
+int vec_set(cudaStream_t s, double *x, double v, uint64_t n);
+int vec_axpy(cudaStream_t s, double *y, double a, const double *x, uint64_t n);
+int vec_sadd(cudaStream_t s, double *y, double sc, double a, const double *x, uint64_t n);
+int vec_scale(cudaStream_t s, double *y, const double *sc, uint64_t n);
+int vec_copy_indexed(cudaStream_t s, double *dst, const double *src, const uint32_t *idx, uint32_t n, double sign);
+int vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *ys, int k, uint64_t n, double *results_host,
+                  bool to_host);
+int vec_project(adaflo_b200_ctx_t ctx, double *p, const double *w, const double *mode, double inv_weight, uint64_t n_owned,
+                uint64_t n_local);
+int vec_pack(cudaStream_t s, double *buf, const double *vec, const uint32_t *idx, uint32_t n_nodes, int n_comp);
+int vec_unpack_add(cudaStream_t s, double *vec, const double *buf, const uint32_t *idx, uint32_t n_nodes, int n_comp);
+int vec_add_and_dot(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, const double *z, uint64_t n, double *result_host);
+int jacobi_reinit(adaflo_b200_ctx_t ctx, double *inv, const double *diag, uint64_t n);
+int jacobi_vmult(cudaStream_t s, double *dst, const double *src, const double *inv, uint64_t n, int n_blocks);
+int allreduce_sum_host(adaflo_b200_ctx_t ctx, double *vals, int k);  // via device buffer + NCCL when nranks > 1
+
+// communication (comm.cu)
+int comm_update_ghosts(adaflo_b200_mf_t mf, int space, double *vec);
+int comm_compress_add(adaflo_b200_mf_t mf, int space, double *vec);
+int comm_allreduce(adaflo_b200_ctx_t ctx, double *dev, int k, int op_max);
+int comm_unique_id(unsigned char id[128]);
+int comm_init(adaflo_b200_ctx_t ctx, const unsigned char id[128], int rank, int nranks);
+int comm_destroy(adaflo_b200_ctx_t ctx);
+
+}  // namespace ab200

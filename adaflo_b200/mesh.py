@@ -345,7 +345,7 @@ def seeded_uniform(global_ids: np.ndarray, n_comp: int, seed: int):
     """U(-1,1) values keyed by global dof id (counter based, so any partition
     reproduces the same global vector) -- SURVEY.md 8(d) 'Synthetic inputs'."""
     gid = (global_ids[:, None].astype(np.uint64) * np.uint64(n_comp) + np.arange(n_comp, dtype=np.uint64)[None, :])
-    x = gid.reshape(-1) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+    x = gid.reshape(-1) + np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
     # splitmix64
     x = (x + np.uint64(0x9E3779B97F4A7C15))
     z = x
@@ -377,3 +377,14 @@ def beltrami_pressure(x: np.ndarray, t=0.0, nu=1.0):
                           + 2 * np.sin(a * Y + d * Z) * np.cos(a * X + d * Y) * np.exp(a * (Z + X))
                           + 2 * np.sin(a * Z + d * X) * np.cos(a * Y + d * Z) * np.exp(a * (X + Y)))
     return val * np.exp(-2 * nu * d * d * t)
+
+
+def linear_deformation(shear=0.15):
+    """Affine (constant Jacobian) deformation used to exercise the affine geometry path."""
+    A = np.array([[1.0, shear, 0.5 * shear], [0.0, 1.0 + shear, -shear], [0.25 * shear, 0.0, 1.0]])
+
+    def deform(X):
+        x = X @ A.T
+        F = np.broadcast_to(A, (X.shape[0], 3, 3)).copy()
+        return x, F
+    return deform

@@ -1,0 +1,376 @@
+"""Host-side mirror of the reference's operator interface on top of the C ABI.
+
+Class and method names follow adaflo (include/adaflo/navier_stokes_matrix.h:57-204,
+include/adaflo/diagonal_preconditioner.h) so that tests read like calls into the
+reference.  PyTorch is used for device memory and streams only; every operation
+runs in libadaflo_b200.so (hand-written CUDA) -- there is no PyTorch or CPU
+fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import FlowParams, TimeWeights, check
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+        return C.c_void_p(t.data_ptr())
+    raise TypeError(type(t))
+
+
+def _np(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _DevView:
+    """Wrap a raw device pointer so torch can view it (no ownership)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def device_view(ptr, n, device):
+    return torch.as_tensor(_DevView(ptr, n), device=device)
+
+
+class Context:
+    """One rank / one GPU (adaflo_b200_ctx_t)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = capi.load()
+        if not torch.cuda.is_available():
+            raise capi.AdafloB200Error("no CUDA device: adaflo_b200 has no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device)
+        self.stream = stream
+        h = C.c_void_p()
+        check(self.lib.adaflo_b200_ctx_create(C.byref(h), device, C.c_void_p(stream.cuda_stream)))
+        self.h = h
+        self.rank, self.nranks = 0, 1
+
+    def init_comm(self, rank, nranks, broadcast_bytes):
+        """Create the NCCL communicator; ``broadcast_bytes(bytes|None) -> bytes``
+        distributes rank 0's unique id (e.g. over torch.distributed)."""
+        if nranks <= 1:
+            return
+        idbuf = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(self.lib.adaflo_b200_comm_unique_id(idbuf))
+        data = broadcast_bytes(bytes(idbuf) if rank == 0 else None)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(data)
+        check(self.lib.adaflo_b200_ctx_init_comm(self.h, idbuf, rank, nranks))
+        self.rank, self.nranks = rank, nranks
+
+    def synchronize(self):
+        check(self.lib.adaflo_b200_ctx_synchronize(self.h))
+
+    def close(self):
+        if self.h:
+            self.lib.adaflo_b200_ctx_destroy(self.h)
+            self.h = None
+
+    # ---- vector kernels (deal.II LinearAlgebra::distributed::Vector operations)
+    def axpy(self, y, a, x):
+        check(self.lib.adaflo_b200_vec_axpy(self.h, _ptr(y), a, _ptr(x), y.numel()))
+
+    def sadd(self, y, s, a, x):
+        check(self.lib.adaflo_b200_vec_sadd(self.h, _ptr(y), s, a, _ptr(x), y.numel()))
+
+    def scale(self, y, scaling):
+        check(self.lib.adaflo_b200_vec_scale(self.h, _ptr(y), _ptr(scaling), y.numel()))
+
+    def set(self, x, value):
+        check(self.lib.adaflo_b200_vec_set(self.h, _ptr(x), value, x.numel()))
+
+    def dot(self, x, y, n=None):
+        r = C.c_double()
+        check(self.lib.adaflo_b200_vec_dot(self.h, _ptr(x), _ptr(y), n if n is not None else x.numel(), C.byref(r)))
+        return r.value
+
+    def multi_dot(self, x, ys, n=None):
+        k = len(ys)
+        arr = (C.c_void_p * k)(*[y.data_ptr() for y in ys])
+        res = (C.c_double * k)()
+        check(self.lib.adaflo_b200_vec_multi_dot(self.h, _ptr(x), arr, k, n if n is not None else x.numel(), res))
+        return [res[i] for i in range(k)]
+
+    def add_and_dot(self, y, a, x, z, n=None):
+        r = C.c_double()
+        check(self.lib.adaflo_b200_vec_add_and_dot(self.h, _ptr(y), a, _ptr(x), _ptr(z), n if n is not None else y.numel(), C.byref(r)))
+        return r.value
+
+
+class MatrixFree:
+    """Device mirror of dealii::MatrixFree as adaflo sets it up: dof handlers
+    {0: u, 1: p}, quadratures {0: QGauss(3), 1: QGauss(2)}
+    (source/navier_stokes.cc:414-451)."""
+
+    def __init__(self, ctx: Context, mesh, geometry="cartesian", deform=None):
+        self.ctx = ctx
+        self.mesh = mesh
+        lib = ctx.lib
+        keep = []  # keep numpy arrays alive during the call
+        spaces = (capi.SpaceDesc * 2)()
+        for i, sp in enumerate((mesh.u, mesh.p)):
+            cn = np.ascontiguousarray(sp.encoded_cell_nodes())
+            con = np.ascontiguousarray(sp.constrained_dofs())
+            n_ex = len(sp.send) + len(sp.recv)
+            peers = sorted(set([p for p, _ in sp.send] + [p for p, _, _ in sp.recv]))
+            ex = (capi.Exchange * max(1, len(peers)))()
+            for j, peer in enumerate(peers):
+                send = [idx for p, idx in sp.send if p == peer]
+                recv = [(f, n) for p, f, n in sp.recv if p == peer]
+                ex[j].peer = peer
+                if send:
+                    s = np.ascontiguousarray(send[0].astype(np.uint32))
+                    keep.append(s)
+                    ex[j].n_send = len(s)
+                    ex[j].send = s.ctypes.data
+                if recv:
+                    ex[j].recv_first, ex[j].n_recv = recv[0]
+            keep += [cn, con, ex]
+            d = spaces[i]
+            d.fe_kind = capi.FE_Q_DG0 if getattr(sp, "n_dg0", 0) else capi.FE_Q
+            d.degree = 2 if i == 0 else 1
+            d.n_components = sp.n_comp
+            d.n_owned_nodes = sp.n_owned
+            d.n_ghost_nodes = sp.n_ghost
+            d.nodes_per_cell = sp.nodes_per_cell
+            d.cell_nodes = cn.ctypes.data
+            d.hanging_masks = None
+            d.n_constrained = len(con)
+            d.constrained_dofs = con.ctypes.data if len(con) else None
+            d.n_exchange = len(peers) if n_ex else 0
+            d.exchange = ex
+        quads = (capi.QuadDesc * 2)()
+        for i, nq1 in enumerate((3, 2)):
+            q = quads[i]
+            q.n_q_1d = nq1
+            if geometry == "cartesian":
+                table, row = mesh.cartesian_geometry()
+                q.geometry_type = capi.GEOM_CARTESIAN
+            elif geometry == "affine":
+                K, jxw = mesh.general_geometry(1, deform)   # one point per cell: the affine Jacobian
+                det = jxw[:, 0]                                # weight of the 1-point rule is 1
+                table = np.concatenate([K[:, 0].reshape(-1, 9), det[:, None]], axis=1)
+                row = np.arange(mesh.n_cells, dtype=np.uint32)
+                q.geometry_type = capi.GEOM_AFFINE
+            elif geometry == "general":
+                K, jxw = mesh.general_geometry(nq1, deform)
+                invj = np.ascontiguousarray(K.reshape(mesh.n_cells, nq1 ** 3, 9).transpose(0, 2, 1))
+                jxw = np.ascontiguousarray(jxw)
+                keep += [invj, jxw]
+                q.geometry_type = capi.GEOM_GENERAL
+                q.inv_jacobian = invj.ctypes.data
+                q.jxw = jxw.ctypes.data
+                continue
+            else:
+                raise ValueError(geometry)
+            table = np.ascontiguousarray(table)
+            row = np.ascontiguousarray(row)
+            keep += [table, row]
+            q.n_table_rows = table.shape[0]
+            q.table = table.ctypes.data
+            q.cell_row = row.ctypes.data
+        desc = capi.MFDesc(3, mesh.n_cells, 2, spaces, 2, quads)
+        h = C.c_void_p()
+        check(lib.adaflo_b200_mf_create(ctx.h, C.byref(desc), C.byref(h)))
+        self.h = h
+        del keep
+
+    def initialize_dof_vector(self, space):
+        n_owned, n_local = C.c_uint64(), C.c_uint64()
+        check(self.ctx.lib.adaflo_b200_mf_vector_size(self.h, space, C.byref(n_owned), C.byref(n_local)))
+        return torch.zeros(n_local.value, dtype=torch.float64, device=self.ctx.device)
+
+    def n_owned(self, space):
+        n_owned = C.c_uint64()
+        check(self.ctx.lib.adaflo_b200_mf_vector_size(self.h, space, C.byref(n_owned), None))
+        return n_owned.value
+
+    def update_ghost_values(self, space, vec):
+        check(self.ctx.lib.adaflo_b200_mf_update_ghost_values(self.h, space, _ptr(vec)))
+
+    def compress_add(self, space, vec):
+        check(self.ctx.lib.adaflo_b200_mf_compress_add(self.h, space, _ptr(vec)))
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.adaflo_b200_mf_destroy(self.h)
+            self.h = None
+
+
+class BlockVector:
+    """LinearAlgebra::distributed::BlockVector<double> with blocks (u, p)."""
+
+    def __init__(self, u, p):
+        self.blocks = [u, p]
+
+    def block(self, i):
+        return self.blocks[i]
+
+    @staticmethod
+    def like(mf: MatrixFree):
+        return BlockVector(mf.initialize_dof_vector(0), mf.initialize_dof_vector(1))
+
+
+class NavierStokesMatrix:
+    """adaflo::NavierStokesMatrix<3> (include/adaflo/navier_stokes_matrix.h:57-204)."""
+
+    def __init__(self, parameters: FlowParams, dof_index_u, dof_index_p, quad_index_u, quad_index_p,
+                 solution_old: BlockVector, solution_old_old: BlockVector):
+        self.parameters = parameters
+        self.dof_index_u, self.dof_index_p = dof_index_u, dof_index_p
+        self.quad_index_u, self.quad_index_p = quad_index_u, quad_index_p
+        self.solution_old, self.solution_old_old = solution_old, solution_old_old
+        self.matrix_free = None
+        self.h = None
+
+    def initialize(self, matrix_free: MatrixFree, time_stepping: TimeWeights, pressure_average_fix: bool):
+        self.clear()
+        self.matrix_free = matrix_free
+        self.ctx = matrix_free.ctx
+        self.lib = self.ctx.lib
+        h = C.c_void_p()
+        check(self.lib.adaflo_b200_ns_create(self.ctx.h, matrix_free.h, C.byref(self.parameters), self.dof_index_u,
+                                             self.dof_index_p, self.quad_index_u, self.quad_index_p,
+                                             int(pressure_average_fix), C.byref(h)))
+        self.h = h
+        self.set_time_stepping(time_stepping)
+        if self.solution_old is not None:
+            check(self.lib.adaflo_b200_ns_set_old_solutions(self.h, _ptr(self.solution_old.block(0)),
+                                                            _ptr(self.solution_old_old.block(0))))
+
+    def set_time_stepping(self, time_stepping: TimeWeights):
+        self.time_stepping = time_stepping
+        check(self.lib.adaflo_b200_ns_set_time_weights(self.h, C.byref(time_stepping)))
+
+    def set_parameters(self, parameters: FlowParams):
+        self.parameters = parameters
+        check(self.lib.adaflo_b200_ns_set_flow_params(self.h, C.byref(parameters)))
+
+    def clear(self):
+        if self.h:
+            self.lib.adaflo_b200_ns_destroy(self.h)
+        self.h = None
+        self.matrix_free = None
+
+    def _require(self):
+        if not self.h:
+            raise capi.AdafloB200Error("NavierStokesMatrix not initialized (ExcNotInitialized)")
+
+    def vmult(self, dst: BlockVector, src: BlockVector):
+        self._require()
+        check(self.lib.adaflo_b200_ns_vmult(self.h, _ptr(dst.block(0)), _ptr(dst.block(1)), _ptr(src.block(0)), _ptr(src.block(1))))
+
+    def Tvmult(self, dst: BlockVector, src: BlockVector):
+        self._require()
+        check(self.lib.adaflo_b200_ns_Tvmult(self.h, _ptr(dst.block(0)), _ptr(dst.block(1)), _ptr(src.block(0)), _ptr(src.block(1))))
+
+    def residual(self, system_rhs: BlockVector, src: BlockVector, user_rhs: BlockVector):
+        self._require()
+        check(self.lib.adaflo_b200_ns_residual(self.h, _ptr(system_rhs.block(0)), _ptr(system_rhs.block(1)),
+                                               _ptr(src.block(0)), _ptr(src.block(1)), _ptr(user_rhs.block(0)), _ptr(user_rhs.block(1))))
+
+    def velocity_vmult(self, dst, src):
+        self._require()
+        check(self.lib.adaflo_b200_ns_velocity_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def divergence_vmult_add(self, dst, src, weight_by_viscosity=False):
+        self._require()
+        check(self.lib.adaflo_b200_ns_divergence_vmult_add(self.h, _ptr(dst), _ptr(src), int(weight_by_viscosity)))
+
+    def pressure_poisson_vmult(self, dst, src):
+        self._require()
+        check(self.lib.adaflo_b200_ns_pressure_poisson_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def pressure_mass_vmult(self, dst, src):
+        self._require()
+        check(self.lib.adaflo_b200_ns_pressure_mass_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def pressure_convdiff_vmult(self, dst, src):
+        self._require()
+        check(self.lib.adaflo_b200_ns_pressure_convdiff_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def fix_linearization_point(self):
+        self._require()
+        check(self.lib.adaflo_b200_ns_fix_linearization_point(self.h))
+
+    def apply_pressure_average_projection(self, vector):
+        self._require()
+        check(self.lib.adaflo_b200_ns_apply_pressure_average_projection(self.h, _ptr(vector)))
+
+    def apply_pressure_shift(self, shift, pressure):
+        self._require()
+        check(self.lib.adaflo_b200_ns_apply_pressure_shift(self.h, float(shift), _ptr(pressure)))
+
+    def _coef(self, which):
+        self._require()
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.lib.adaflo_b200_ns_coefficient_ptr(self.h, which, C.byref(p), C.byref(n)))
+        if not p.value:
+            return None
+        return device_view(p.value, n.value, self.ctx.device)
+
+    def begin_densities(self):
+        """[n_cells, 27] view (reference: begin_densities(macro_cell), navier_stokes_matrix.h:162-166)"""
+        t = self._coef(capi.COEF_DENSITY)
+        return None if t is None else t.view(-1, 27)
+
+    def begin_viscosities(self):
+        t = self._coef(capi.COEF_VISCOSITY)
+        return None if t is None else t.view(-1, 27)
+
+    def begin_damping_coeff(self):
+        t = self._coef(capi.COEF_DAMPING)
+        return None if t is None else t.view(-1, 27)
+
+    def begin_linearized_velocities(self):
+        """[n_cells, 12, 27] view: rows 0..2 velocity, 3+3d+e = d u_d / d x_e"""
+        t = self._coef(capi.COEF_LINEARIZED_VELOCITY)
+        return None if t is None else t.view(-1, 12, 27)
+
+    def use_variable_coefficients(self):
+        return self.parameters.density_diff != 0 or self.parameters.viscosity_diff != 0
+
+    def get_matvec_statistics(self):
+        self._require()
+        n, s = C.c_uint64(), C.c_double()
+        check(self.lib.adaflo_b200_ns_get_matvec_statistics(self.h, C.byref(n), C.byref(s)))
+        return s.value, n.value
+
+    def vmult_host(self, dst_u, dst_p, src_u, src_p):
+        """End-to-end call with HOST (pinned) torch tensors or numpy arrays."""
+        self._require()
+
+        def hp(t):
+            return C.c_void_p(t.data_ptr()) if isinstance(t, torch.Tensor) else _np(t)
+        check(self.lib.adaflo_b200_ns_vmult_host(self.h, hp(dst_u), hp(dst_p), hp(src_u), hp(src_p)))
+
+
+class DiagonalPreconditioner:
+    """adaflo::DiagonalPreconditioner<double> (source/diagonal_preconditioner.cc:38-124)."""
+
+    def __init__(self, ctx: Context, diagonal_vector=None):
+        self.ctx = ctx
+        self.inverse_diagonal_vector = None
+        if diagonal_vector is not None:
+            self.reinit(diagonal_vector)
+
+    def reinit(self, diagonal_vector, n_owned=None):
+        self.n = n_owned if n_owned is not None else diagonal_vector.numel()
+        self.inverse_diagonal_vector = torch.zeros_like(diagonal_vector)
+        check(self.ctx.lib.adaflo_b200_jacobi_reinit(self.ctx.h, _ptr(self.inverse_diagonal_vector), _ptr(diagonal_vector), self.n))
+
+    def vmult(self, dst, src, n_blocks=1):
+        check(self.ctx.lib.adaflo_b200_jacobi_vmult(self.ctx.h, _ptr(dst), _ptr(src), _ptr(self.inverse_diagonal_vector), self.n, n_blocks))

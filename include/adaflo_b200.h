@@ -165,9 +165,11 @@ typedef struct {
   int32_t physical_type;
   int32_t linearization;
   int32_t augmented_taylor_hood;
-  int32_t variable_coefficients; /* density_diff != 0 || viscosity_diff != 0, navier_stokes_matrix.cc:97-98 */
+  int32_t reserved;
   double density;
   double viscosity;
+  double density_diff;           /* variable coefficients are used iff density_diff != 0 || viscosity_diff != 0, */
+  double viscosity_diff;         /* navier_stokes_matrix.cc:97-98 */
   double damping;                /* already sign-flipped as parameters.cc:466-467 does */
   double tau_grad_div;
   double beta_convective_term_momentum_balance;

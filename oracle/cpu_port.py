@@ -1,0 +1,64 @@
+"""ctypes front end of oracle/ns_cpu_port.c -- the timed CPU baseline ("port").
+TEST/BENCH INFRASTRUCTURE ONLY (see the header of ns_cpu_port.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class PortArgs(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("layer_cells", C.c_int32), ("cell_u", C.c_void_p), ("cell_p", C.c_void_p),
+                ("inv_h", C.c_double * 3), ("det", C.c_double), ("mode", C.c_int32),
+                ("gamma", C.c_double), ("tau1", C.c_double), ("beta", C.c_double), ("rho", C.c_double),
+                ("mu", C.c_double), ("damping", C.c_double), ("tau_gd", C.c_double), ("lin", C.c_void_p)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libcpu_port.so")
+    src = os.path.join(_HERE, "ns_cpu_port.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"])
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+class CpuPortVmult:
+    """Cell loop of NavierStokesMatrix::vmult on a Cartesian BoxMesh (constant coefficients)."""
+
+    def __init__(self, mesh, mode, gamma, tau1, beta, rho, mu, damping, tau_gd, lin=None):
+        self.mesh = mesh
+        self.cu = np.ascontiguousarray(mesh.u.encoded_cell_nodes())
+        self.cp = np.ascontiguousarray(mesh.p.encoded_cell_nodes())
+        self.lin = None if lin is None else np.ascontiguousarray(lin)
+        a = PortArgs()
+        a.n_cells = mesh.n_cells
+        a.layer_cells = mesh.n[0] * mesh.n[1]
+        a.cell_u = self.cu.ctypes.data
+        a.cell_p = self.cp.ctypes.data
+        for d in range(3):
+            a.inv_h[d] = 1.0 / mesh.h[d]
+        a.det = float(np.prod(mesh.h))
+        a.mode = mode
+        a.gamma, a.tau1, a.beta, a.rho, a.mu, a.damping, a.tau_gd = gamma, tau1, beta, rho, mu, damping, tau_gd
+        a.lin = None if self.lin is None else self.lin.ctypes.data
+        self.args = a
+
+    def cells(self, src_u, src_p, dst_u, dst_p):
+        return lib().port_ns_vmult_cells(C.byref(self.args), src_u.ctypes.data_as(C.c_void_p), src_p.ctypes.data_as(C.c_void_p),
+                                         dst_u.ctypes.data_as(C.c_void_p), dst_p.ctypes.data_as(C.c_void_p))
+
+
+def max_threads():
+    return lib().port_max_threads()

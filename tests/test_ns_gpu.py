@@ -1,0 +1,212 @@
+"""GPU parity: CUDA NavierStokesMatrix (through the C ABI) vs the CPU oracle on the
+same seeded inputs.  Tolerance: 1e-12 relative in the l2 norm (BASELINE.json
+north_star: "match ... within 1e-12 relative (fp64)")."""
+import numpy as np
+import pytest
+import torch
+
+from adaflo_b200 import capi
+from adaflo_b200.mesh import BoxMesh, beltrami_velocity, beltrami_pressure, seeded_uniform
+from adaflo_b200.operators import BlockVector, MatrixFree, NavierStokesMatrix
+from oracle import oracle as orc
+
+from helpers import deformation, flow_params, rel_err, time_weights, variable_coefficients
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def dev(ctx, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+
+
+class Pair:
+    """The oracle and the CUDA operator set up on identical data."""
+
+    def __init__(self, ctx, n=(5, 4, 3), geometry="cartesian", var=False, augmented=False, **kw):
+        self.ctx = ctx
+        self.mesh = mesh = BoxMesh(n, augmented=augmented)
+        deform = deformation(geometry)
+        if var:
+            kw.update(density_diff=9.0, viscosity_diff=0.5)
+        dprm, oprm = flow_params(augmented=augmented, **kw)
+        dtw, otw = time_weights()
+        self.mf = MatrixFree(ctx, mesh, geometry, deform)
+        self.old = BlockVector.like(self.mf)
+        self.old_old = BlockVector.like(self.mf)
+        self.A = NavierStokesMatrix(dprm, 0, 1, 0, 1, self.old, self.old_old)
+        self.A.initialize(self.mf, dtw, True)
+        self.O = orc.OracleNavierStokesMatrix(mesh, oprm, otw, deform, True)
+        self.O.density_diff = kw.get("density_diff", 0.0)
+        if var:
+            rho, mu, damp = variable_coefficients(mesh, deform)
+            self.O.rho[:], self.O.muq[:], self.O.damp[:] = rho, mu, damp
+            self.A.begin_densities().copy_(dev(ctx, rho))
+            self.A.begin_viscosities().copy_(dev(ctx, mu))
+            self.A.begin_damping_coeff().copy_(dev(ctx, damp))
+        # a smooth linearisation point + seeded noise, produced by the residual on both sides
+        m = mesh
+        xu = m.u.coords
+        if deform is not None:
+            xu = deform(xu)[0]
+        self.u_lin = (beltrami_velocity(xu, 0.1).reshape(-1) + 0.1 * seeded_uniform(m.u.global_ids, 3, 7))
+        self.p_lin = seeded_uniform(m.p.global_ids, 1, 8)
+        self.u_old = beltrami_velocity(xu, 0.05).reshape(-1) + 0.05 * seeded_uniform(m.u.global_ids, 3, 9)
+        self.u_oo = beltrami_velocity(xu, 0.0).reshape(-1) + 0.05 * seeded_uniform(m.u.global_ids, 3, 10)
+        self.O.old_u, self.O.old_old_u = self.u_old.copy(), self.u_oo.copy()
+        self.old.block(0).copy_(dev(ctx, self.u_old))
+        self.old_old.block(0).copy_(dev(ctx, self.u_oo))
+
+    def residual_both(self):
+        m = self.mesh
+        cu, cp = seeded_uniform(m.u.global_ids, 3, 21), seeded_uniform(m.p.global_ids, 1, 22)   # const_rhs preload
+        uu, up = seeded_uniform(m.u.global_ids, 3, 23), seeded_uniform(m.p.global_ids, 1, 24)   # user_rhs
+        ru, rp = cu.copy(), cp.copy()
+        self.O.residual(ru, rp, self.u_lin, self.p_lin, uu, up)
+        rhs = BlockVector(dev(self.ctx, cu), dev(self.ctx, cp))
+        self.A.residual(rhs, BlockVector(dev(self.ctx, self.u_lin), dev(self.ctx, self.p_lin)),
+                        BlockVector(dev(self.ctx, uu), dev(self.ctx, up)))
+        return (ru, rp), (rhs.block(0).cpu().numpy(), rhs.block(1).cpu().numpy())
+
+    def vmult_both(self, seed=31):
+        m = self.mesh
+        su, sp = seeded_uniform(m.u.global_ids, 3, seed), seeded_uniform(m.p.global_ids, 1, seed + 1)
+        ou, op = self.O.vmult(su, sp)
+        dst = BlockVector.like(self.mf)
+        dst.block(0).fill_(7.0)  # vmult must overwrite
+        self.A.vmult(dst, BlockVector(dev(self.ctx, su), dev(self.ctx, sp)))
+        return (ou, op), (dst.block(0).cpu().numpy(), dst.block(1).cpu().numpy())
+
+    def close(self):
+        self.A.clear()
+        self.mf.close()
+
+
+@pytest.mark.parametrize("geometry", ["cartesian", "affine", "general"])
+@pytest.mark.parametrize("linearization", [capi.NEWTON, capi.PICARD, capi.SEMI_IMPLICIT, capi.EXPLICIT])
+@pytest.mark.parametrize("var", [False, True])
+def test_residual_then_vmult(ctx, geometry, linearization, var):
+    P = Pair(ctx, geometry=geometry, var=var, linearization=linearization, damping=-0.2, tau_grad_div=0.3)
+    (ru, rp), (gu, gp) = P.residual_both()
+    assert rel_err(gu, ru) < TOL and rel_err(gp, rp) < TOL
+    if linearization != capi.EXPLICIT:
+        lin_gpu = P.A.begin_linearized_velocities().cpu().numpy()
+        rows = 12 if linearization == capi.NEWTON else 4
+        assert rel_err(lin_gpu[:, :rows], P.O.lin[:, :rows]) < TOL
+    (ou, op), (gu, gp) = P.vmult_both()
+    assert rel_err(gu, ou) < TOL and rel_err(gp, op) < TOL
+    P.close()
+
+
+@pytest.mark.parametrize("physical_type", [capi.STOKES, capi.INCOMPRESSIBLE_STATIONARY])
+@pytest.mark.parametrize("geometry", ["cartesian", "general"])
+def test_stokes_and_stationary(ctx, physical_type, geometry):
+    P = Pair(ctx, geometry=geometry, physical_type=physical_type, viscosity=0.7)
+    (ru, rp), (gu, gp) = P.residual_both()
+    assert rel_err(gu, ru) < TOL and rel_err(gp, rp) < TOL
+    (ou, op), (gu, gp) = P.vmult_both()
+    assert rel_err(gu, ou) < TOL and rel_err(gp, op) < TOL
+    P.close()
+
+
+@pytest.mark.parametrize("geometry", ["cartesian", "general"])
+@pytest.mark.parametrize("var", [False, True])
+def test_sub_operators(ctx, geometry, var):
+    """velocity_vmult, divergence_vmult_add, pressure_{mass,poisson,convdiff}_vmult (rows a4-a8)."""
+    P = Pair(ctx, geometry=geometry, var=var, tau_grad_div=0.1)
+    P.residual_both()
+    m = P.mesh
+    su, sp = seeded_uniform(m.u.global_ids, 3, 41), seeded_uniform(m.p.global_ids, 1, 42)
+    P.O.fix_linearization_point()
+    P.A.fix_linearization_point()
+    # velocity block
+    du = P.mf.initialize_dof_vector(0)
+    P.A.velocity_vmult(du, dev(ctx, su))
+    assert rel_err(du.cpu().numpy(), P.O.velocity_vmult(su)) < TOL
+    # divergence adds into dst
+    for wbv in (False, True):
+        pre = seeded_uniform(m.p.global_ids, 1, 43)
+        o = pre.copy()
+        P.O.divergence_vmult_add(o, su, wbv)
+        g = dev(ctx, pre)
+        P.A.divergence_vmult_add(g, dev(ctx, su), wbv)
+        assert rel_err(g.cpu().numpy(), o) < TOL
+    for name in ("pressure_mass_vmult", "pressure_poisson_vmult", "pressure_convdiff_vmult"):
+        g = P.mf.initialize_dof_vector(1)
+        g.fill_(3.0)
+        getattr(P.A, name)(g, dev(ctx, sp))
+        o = getattr(P.O, name)(sp)
+        assert rel_err(g.cpu().numpy(), o) < TOL, name
+    P.close()
+
+
+def test_augmented_taylor_hood(ctx):
+    """Q2/(Q1+DG0) pressure and the second null-space mode."""
+    P = Pair(ctx, n=(4, 4, 3), augmented=True)
+    (ru, rp), (gu, gp) = P.residual_both()
+    assert rel_err(gu, ru) < TOL and rel_err(gp, rp) < TOL
+    (ou, op), (gu, gp) = P.vmult_both()
+    assert rel_err(gu, ou) < TOL and rel_err(gp, op) < TOL
+    g = P.mf.initialize_dof_vector(1)
+    sp = seeded_uniform(P.mesh.p.global_ids, 1, 51)
+    P.A.pressure_mass_vmult(g, dev(ctx, sp))
+    assert rel_err(g.cpu().numpy(), P.O.pressure_mass_vmult(sp)) < TOL
+    P.close()
+
+
+def test_tvmult_is_the_transpose(ctx):
+    """<Tvmult(x), y> == <x, vmult(y)> (no reference Tvmult exists)."""
+    for lin in (capi.NEWTON, capi.PICARD):
+        P = Pair(ctx, geometry="general", var=True, linearization=lin, damping=-0.1)
+        P.residual_both()
+        m = P.mesh
+        x = BlockVector(dev(ctx, seeded_uniform(m.u.global_ids, 3, 61)), dev(ctx, seeded_uniform(m.p.global_ids, 1, 62)))
+        y = BlockVector(dev(ctx, seeded_uniform(m.u.global_ids, 3, 63)), dev(ctx, seeded_uniform(m.p.global_ids, 1, 64)))
+        Ay, Atx = BlockVector.like(P.mf), BlockVector.like(P.mf)
+        P.A.vmult(Ay, y)
+        P.A.Tvmult(Atx, x)
+        lhs = float(Atx.block(0) @ y.block(0) + Atx.block(1) @ y.block(1))
+        rhs = float(x.block(0) @ Ay.block(0) + x.block(1) @ Ay.block(1))
+        assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs), 1.0)
+        P.close()
+
+
+def test_ragged_and_tiny_meshes(ctx):
+    """cell counts that do not fill a warp triple / a block, and the 1-cell mesh."""
+    for n in [(1, 1, 1), (2, 1, 1), (3, 2, 2), (7, 1, 1), (13, 1, 1)]:
+        P = Pair(ctx, n=n)
+        P.residual_both()
+        (ou, op), (gu, gp) = P.vmult_both()
+        assert rel_err(gu, ou) < TOL and rel_err(gp, op) < TOL, n
+        P.close()
+
+
+def test_vmult_is_linear_and_deterministic_enough(ctx):
+    P = Pair(ctx, n=(6, 6, 6))
+    P.residual_both()
+    (_, _), (g1u, g1p) = P.vmult_both(seed=71)
+    (_, _), (g2u, g2p) = P.vmult_both(seed=71)
+    # atomics reorder the adds: repeatability to round-off, not bitwise
+    assert rel_err(g1u, g2u) < 1e-14 and rel_err(g1p, g2p) < 1e-14
+    P.close()
+
+
+def test_uninitialized_operator_fails_loudly(ctx):
+    A = NavierStokesMatrix(flow_params()[0], 0, 1, 0, 1, None, None)
+    with pytest.raises(capi.AdafloB200Error):
+        A.vmult(None, None)
+
+
+def test_host_entry_point_matches_device(ctx):
+    P = Pair(ctx, n=(4, 4, 4))
+    P.residual_both()
+    m = P.mesh
+    su, sp = seeded_uniform(m.u.global_ids, 3, 81), seeded_uniform(m.p.global_ids, 1, 82)
+    ou, op = P.O.vmult(su, sp)
+    hu, hp = torch.from_numpy(su).pin_memory(), torch.from_numpy(sp).pin_memory()
+    du, dp = torch.empty_like(hu).pin_memory(), torch.empty_like(hp).pin_memory()
+    P.A.vmult_host(du, dp, hu, hp)
+    assert rel_err(du.numpy(), ou) < TOL and rel_err(dp.numpy(), op) < TOL
+    s, n = P.A.get_matvec_statistics()
+    assert n == 1 and s >= 0.0
+    P.close()

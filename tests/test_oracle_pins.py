@@ -1,0 +1,136 @@
+"""Pins of the CPU oracle against the reference's own known answers (CPU only).
+
+The reference holds no operator-level golden vectors; what it does
+hold are end-to-end logs and analytic solutions:
+  * tests/beltrami_3d.output:5-7  -- interpolation errors of the Beltrami field on the 16^3 mesh
+  * tests/beltrami_3d.output:13   -- norms of the first nonlinear residual (pure output of
+                                     NavierStokesMatrix::residual + mean projection)
+  * tests/poiseuille.cc:74-112    -- steady Poiseuille flow, exact in the Q2/Q1 space
+plus the defining property vmult == Jacobian of residual, which ties the vmult
+restatement to the pinned residual.
+"""
+import numpy as np
+import pytest
+
+from adaflo_b200 import capi
+from adaflo_b200.mesh import BoxMesh, beltrami_pressure, beltrami_velocity, seeded_uniform, sine_deformation
+from oracle import oracle as orc
+
+from helpers import flow_params, time_weights, variable_coefficients
+
+
+@pytest.fixture(scope="module")
+def beltrami16():
+    mesh = BoxMesh((16, 16, 16))
+    _, oprm = flow_params()  # Newton, beta = 0.5 (skew-symmetric), nu = rho = 1: tests/beltrami_3d.prm
+    dt = 0.05
+    # time step #1 of BDF-2 uses implicit Euler weights and no extrapolation (time_stepping.cc:158-198)
+    tw = orc.TimeWeights(1 / dt, -1 / dt, 0.0, 1.0, 1.0, 0.0)
+    return mesh, orc.OracleNavierStokesMatrix(mesh, oprm, tw), dt
+
+
+def test_dof_counts_match_golden_log(beltrami16):
+    mesh, _, _ = beltrami16
+    # tests/beltrami_3d.output:2-3
+    assert mesh.n_cells == 4096
+    assert mesh.u.n_dofs_owned == 107811 and mesh.p.n_dofs_owned == 4913
+
+
+def test_interpolation_errors_match_golden_log(beltrami16):
+    mesh, ns, _ = beltrami16
+    u0 = beltrami_velocity(mesh.u.coords, 0.0).reshape(-1)
+    p0 = beltrami_pressure(mesh.p.coords, 0.0).reshape(-1)
+    xq = mesh.quadrature_points(4)  # QGauss(v_degree + 2), tests/beltrami.cc:254
+    e_u = ns.l2_error(3, u0, beltrami_velocity(xq, 0.0), n_q_1d=4)
+    e_p = ns.l2_error(1, p0, beltrami_pressure(xq, 0.0)[..., None], n_q_1d=4)
+    # tests/beltrami_3d.output:5 prints 4 significant digits
+    assert f"{e_p:.4g}" == "0.02383"
+    assert f"{e_u:.4g}" == "0.0001993"
+
+
+def test_first_nonlinear_residual_matches_golden_log(beltrami16):
+    mesh, ns, dt = beltrami16
+    u0 = beltrami_velocity(mesh.u.coords, 0.0).reshape(-1)
+    p0 = beltrami_pressure(mesh.p.coords, 0.0).reshape(-1)
+    # init_time_advance (navier_stokes.cc:659-685): solution = extrapolate(cur, old) = cur in step 1,
+    # then Dirichlet values of the new time level (apply_boundary_conditions, :1216-1252)
+    u = u0.copy()
+    d = mesh.u.dirichlet.reshape(-1)
+    u[d] = beltrami_velocity(mesh.u.coords, dt).reshape(-1)[d]
+    ns.old_u, ns.old_old_u = u0.copy(), np.zeros_like(u0)
+    ru, rp = np.zeros(ns.n_u), np.zeros(ns.n_p)          # system_rhs = const_rhs = 0
+    ns.residual(ru, rp, u, p0, np.zeros(ns.n_u), np.zeros(ns.n_p))
+    ns.apply_pressure_average_projection(rp)              # compute_residual, navier_stokes.cc:781-790
+    # tests/beltrami_3d.output:13: "2.590e+00   6.423e-02"
+    assert f"{np.linalg.norm(ru):.3e}" == "2.590e+00"
+    assert f"{np.linalg.norm(rp):.3e}" == "6.423e-02"
+
+
+def test_poiseuille_is_a_discrete_stokes_solution():
+    """u = (0.5/nu)(1-y^2) e_x, p = 2 - x lie in Q2/Q1 (tests/poiseuille.cc:74-112): the Stokes
+    residual vanishes on all rows whose test function does not touch the open boundary."""
+    nu = 0.8
+    mesh = BoxMesh((4, 4, 2), dirichlet_faces=(2, 3, 4, 5))
+    _, oprm = flow_params(physical_type=capi.STOKES, viscosity=nu)
+    _, tw = time_weights()
+    ns = orc.OracleNavierStokesMatrix(mesh, oprm, tw, pressure_average_fix=False)
+    x = mesh.u.coords
+    u = np.zeros((len(x), 3))
+    u[:, 0] = 0.5 / nu * (1 - x[:, 1] ** 2)
+    p = 2.0 - mesh.p.coords[:, 0]
+    ru, rp = np.zeros(ns.n_u), np.zeros(ns.n_p)
+    ns.residual(ru, rp, u.reshape(-1), p, np.zeros(ns.n_u), np.zeros(ns.n_p))
+    interior = (np.abs(np.abs(x[:, 0]) - 1) > 1e-12)       # rows away from the in/outflow faces
+    ru = ru.reshape(-1, 3)
+    assert np.abs(ru[interior]).max() < 1e-12
+    assert np.abs(rp).max() < 1e-12                          # divergence free everywhere
+    # on the open faces the residual is the traction integral -int (p - nu du/dn.n) v.n of the exact solution
+    assert np.abs(ru[~interior]).max() > 1e-3
+
+
+@pytest.mark.parametrize("lin", [capi.NEWTON])
+@pytest.mark.parametrize("var", [False, True])
+def test_vmult_is_the_jacobian_of_the_residual(lin, var):
+    mesh = BoxMesh((3, 3, 2))
+    deform = sine_deformation(0.04)
+    kw = dict(density_diff=9.0, viscosity_diff=0.5) if var else {}
+    _, oprm = flow_params(linearization=lin, damping=-0.2, tau_grad_div=0.3, **kw)
+    _, tw = time_weights()
+    ns = orc.OracleNavierStokesMatrix(mesh, oprm, tw, deform)
+    if var:
+        ns.rho[:], ns.muq[:], ns.damp[:] = variable_coefficients(mesh, deform)
+    u = beltrami_velocity(deform(mesh.u.coords)[0], 0.1).reshape(-1)
+    p = seeded_uniform(mesh.p.global_ids, 1, 3)
+    du = seeded_uniform(mesh.u.global_ids, 3, 4)
+    dp = seeded_uniform(mesh.p.global_ids, 1, 5)
+    # the Jacobian acts on the unconstrained space
+    du[mesh.u.dirichlet.reshape(-1)] = 0.0
+    ns.old_u = seeded_uniform(mesh.u.global_ids, 3, 6)
+    ns.old_old_u = seeded_uniform(mesh.u.global_ids, 3, 7)
+    zero_u, zero_p = np.zeros(ns.n_u), np.zeros(ns.n_p)
+
+    def R(uu, pp):
+        ru, rp = np.zeros(ns.n_u), np.zeros(ns.n_p)
+        ns.residual(ru, rp, uu, pp, zero_u, zero_p)
+        return -ru, -rp       # residual() flips the sign (navier_stokes_matrix.cc:288-292)
+
+    eps = 1e-6
+    rpu, rpp = R(u + eps * du, p + eps * dp)
+    rmu, rmp = R(u - eps * du, p - eps * dp)
+    R(u, p)                   # leaves the linearisation point at (u, p)
+    au, ap = np.zeros(ns.n_u), np.zeros(ns.n_p)
+    ns._loop(orc.OP_VMULT, du, dp, au, ap)
+    fd_u, fd_p = (rpu - rmu) / (2 * eps), (rpp - rmp) / (2 * eps)
+    assert np.linalg.norm(fd_u - au) / np.linalg.norm(au) < 1e-7
+    assert np.linalg.norm(fd_p - ap) / np.linalg.norm(ap) < 1e-7
+
+
+def test_oracle_shape_tables_are_consistent():
+    """partition of unity / derivative sums, and the literals hard-wired in the kernels."""
+    for deg, nq in [(2, 3), (1, 3), (1, 2)]:
+        v, d = orc.shape_1d(deg, nq)
+        assert np.allclose(v.sum(axis=1), 1.0, atol=1e-15) and np.allclose(d.sum(axis=1), 0.0, atol=1e-14)
+    v, d = orc.shape_1d(2, 3)
+    assert v[0, 0] == 0.6872983346207416 and d[0, 1] == 3.0983866769659336
+    x, w = orc.gauss01(3)
+    assert abs(w.sum() - 1) < 1e-15 and w[1] == 0.4444444444444444
