@@ -76,7 +76,8 @@ SYMBOLS = [
     "adaflo_b200_ns_compute_diagonal", "adaflo_b200_ns_fix_linearization_point",
     "adaflo_b200_ns_apply_pressure_average_projection", "adaflo_b200_ns_apply_pressure_shift",
     "adaflo_b200_ns_coefficient_ptr", "adaflo_b200_ns_nullspace", "adaflo_b200_ns_get_matvec_statistics",
-    "adaflo_b200_ns_vmult_host",
+    "adaflo_b200_ns_vmult_host", "adaflo_b200_ns_set_kernel_timing", "adaflo_b200_ns_get_kernel_timing",
+    "adaflo_b200_kernel_launch_count",
     "adaflo_b200_vec_set", "adaflo_b200_vec_axpy", "adaflo_b200_vec_sadd", "adaflo_b200_vec_scale",
     "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_add_and_dot",
     "adaflo_b200_jacobi_reinit", "adaflo_b200_jacobi_vmult",
@@ -131,6 +132,8 @@ def load():
         "adaflo_b200_ns_nullspace": [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(dbl)],
         "adaflo_b200_ns_get_matvec_statistics": [vp, C.POINTER(u64), C.POINTER(dbl)],
         "adaflo_b200_ns_vmult_host": [vp, vp, vp, vp, vp],
+        "adaflo_b200_ns_set_kernel_timing": [vp, i32],
+        "adaflo_b200_ns_get_kernel_timing": [vp, C.POINTER(u64), C.POINTER(dbl)],
         "adaflo_b200_vec_set": [vp, vp, dbl, u64],
         "adaflo_b200_vec_axpy": [vp, vp, dbl, vp, u64],
         "adaflo_b200_vec_sadd": [vp, vp, dbl, dbl, vp, u64],
@@ -145,6 +148,8 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.adaflo_b200_kernel_launch_count.argtypes = []
+    lib.adaflo_b200_kernel_launch_count.restype = C.c_uint64
     _lib = lib
     return lib
 

@@ -10,6 +10,7 @@
 namespace ab200 {
 
 static thread_local std::string g_error;
+unsigned long long g_launches = 0;
 void set_error(const std::string &msg) { g_error = msg; }
 int fail(int code, const std::string &msg)
 {
@@ -404,6 +405,13 @@ int adaflo_b200_ns_destroy(adaflo_b200_ns_t ns)
                   ns->modes[1], ns->mode_weights[0], ns->mode_weights[1], ns->stage_u[0], ns->stage_u[1], ns->stage_p[0],
                   ns->stage_p[1], ns->tmp_p};
   for (void *p : ptrs) free_dev(p);
+  if (ns->kernel_events) {
+    for (auto &e : *ns->kernel_events) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    delete ns->kernel_events;
+  }
   delete ns;
   return 0;
 }
@@ -484,7 +492,17 @@ static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const d
   a.dst_u = dst_u;
   a.dst_p = dst_p;
   a.transpose = transpose ? 1 : 0;
+  if (ns->time_kernel) {
+    if (ns->kernel_events_used == ns->kernel_events->size()) {
+      cudaEvent_t e0, e1;
+      AB_CUDA(cudaEventCreate(&e0));
+      AB_CUDA(cudaEventCreate(&e1));
+      ns->kernel_events->push_back({e0, e1});
+    }
+    AB_CUDA(cudaEventRecord((*ns->kernel_events)[ns->kernel_events_used].first, s));
+  }
   AB_CHECK(launch_cells(ns, a, true));
+  if (ns->time_kernel) AB_CUDA(cudaEventRecord((*ns->kernel_events)[ns->kernel_events_used++].second, s));
   if (ctx->nranks > 1) {
     AB_CHECK(comm_compress_add(mf, ns->dof_u, dst_u));
     AB_CHECK(comm_compress_add(mf, ns->dof_p, dst_p));
@@ -767,6 +785,36 @@ int adaflo_b200_ns_get_matvec_statistics(adaflo_b200_ns_t ns, uint64_t *count, d
   ns->matvec_seconds = 0;
   return 0;
 }
+
+int adaflo_b200_ns_set_kernel_timing(adaflo_b200_ns_t ns, int enable)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  if (!ns->kernel_events) ns->kernel_events = new std::vector<std::pair<cudaEvent_t, cudaEvent_t>>();
+  ns->time_kernel = enable != 0;
+  return 0;
+}
+
+int adaflo_b200_ns_get_kernel_timing(adaflo_b200_ns_t ns, uint64_t *launches, double *seconds)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CUDA(cudaStreamSynchronize(ns->ctx->stream));
+  if (ns->kernel_events) {
+    for (size_t i = 0; i < ns->kernel_events_used; ++i) {
+      float ms = 0;
+      AB_CUDA(cudaEventElapsedTime(&ms, (*ns->kernel_events)[i].first, (*ns->kernel_events)[i].second));
+      ns->kernel_seconds += 1e-3 * ms;
+      ns->kernel_launches++;
+    }
+    ns->kernel_events_used = 0;
+  }
+  if (launches) *launches = ns->kernel_launches;
+  if (seconds) *seconds = ns->kernel_seconds;
+  ns->kernel_launches = 0;
+  ns->kernel_seconds = 0;
+  return 0;
+}
+
+uint64_t adaflo_b200_kernel_launch_count(void) { return (uint64_t)g_launches; }
 
 int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *dst_p_host, const double *src_u_host,
                               const double *src_p_host)

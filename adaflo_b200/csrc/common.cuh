@@ -13,6 +13,8 @@
 namespace ab200 {
 
 void set_error(const std::string &msg);
+extern unsigned long long g_launches;  // kernels launched by this library (bench.py: gpu_launches)
+#define AB_COUNT_LAUNCH() (++::ab200::g_launches)
 int fail(int code, const std::string &msg);
 
 #define AB_CUDA(expr)                                                                                  \
@@ -108,6 +110,12 @@ struct adaflo_b200_ns_s {
   // statistics
   uint64_t matvec_count;
   double matvec_seconds;
+  // optional CUDA-event timing of the cell kernel inside vmult
+  bool time_kernel;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *kernel_events;
+  size_t kernel_events_used;
+  uint64_t kernel_launches;
+  double kernel_seconds;
 };
 
 namespace ab200 {

@@ -547,6 +547,7 @@ int launch_vmult_inst(const NSArgs &a, cudaStream_t s)
   const unsigned grid = (unsigned)((a.n_cells + cells_per_block - 1) / cells_per_block);
   if (grid == 0) return 0;
   kern<<<grid, kWarpsPerBlock * 32, smem, s>>>(a);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }

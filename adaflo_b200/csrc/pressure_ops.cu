@@ -86,6 +86,7 @@ static int launch_div_geom(const PArgs &p, const NSArgs &a, int weight, cudaStre
   }
   if (weight == 0) AB_L(0) else if (weight == 1) AB_L(1) else AB_L(2)
 #undef AB_L
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -276,6 +277,7 @@ int launch_pressure_op(const PArgs &p, int kind, int n_q_1d, cudaStream_t s)
   else if (n_q_1d == 3 && kind == 2) AB_L(3, 2);
   else return fail(ADAFLO_B200_ERR_ARG, "launch_pressure_op: bad variant");
 #undef AB_L
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -86,6 +86,7 @@ int vec_set(cudaStream_t s, double *x, double v, uint64_t n)
     return 0;
   }
   k_set<<<grid_for(n, sm_count_cached()), kVecThreads, 0, s>>>(x, v, n);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -93,6 +94,7 @@ int vec_axpy(cudaStream_t s, double *y, double a, const double *x, uint64_t n)
 {
   if (n == 0) return 0;
   k_axpy<<<grid_for(n, sm_count_cached()), kVecThreads, 0, s>>>(y, a, x, n);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -100,6 +102,7 @@ int vec_sadd(cudaStream_t s, double *y, double sc, double a, const double *x, ui
 {
   if (n == 0) return 0;
   k_sadd<<<grid_for(n, sm_count_cached()), kVecThreads, 0, s>>>(y, sc, a, x, n);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -107,6 +110,7 @@ int vec_scale(cudaStream_t s, double *y, const double *sc, uint64_t n)
 {
   if (n == 0) return 0;
   k_scale<<<grid_for(n, sm_count_cached()), kVecThreads, 0, s>>>(y, sc, n);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -114,6 +118,7 @@ int vec_copy_indexed(cudaStream_t s, double *dst, const double *src, const uint3
 {
   if (n == 0) return 0;
   k_copy_indexed<<<grid_for(n, sm_count_cached(), 1), kVecThreads, 0, s>>>(dst, src, idx, n, sign);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -121,6 +126,7 @@ int vec_pack(cudaStream_t s, double *buf, const double *vec, const uint32_t *idx
 {
   if (n_nodes == 0) return 0;
   k_pack<<<grid_for((uint64_t)n_nodes * n_comp, sm_count_cached(), 1), kVecThreads, 0, s>>>(buf, vec, idx, n_nodes, n_comp);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -128,6 +134,7 @@ int vec_unpack_add(cudaStream_t s, double *vec, const double *buf, const uint32_
 {
   if (n_nodes == 0) return 0;
   k_unpack_add<<<grid_for((uint64_t)n_nodes * n_comp, sm_count_cached(), 1), kVecThreads, 0, s>>>(vec, buf, idx, n_nodes, n_comp);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -239,6 +246,7 @@ static int finish_to_host(adaflo_b200_ctx_t ctx, int k, int n_partial, int op_ma
                           int result_offset = 0)
 {
   k_finish<<<k, kVecThreads, 0, ctx->stream>>>(ctx->red_dev + kResultSlots, n_partial, ctx->red_dev + result_offset, op_max);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   if (ctx->nranks > 1) AB_CHECK(comm_allreduce(ctx, ctx->red_dev + result_offset, k, op_max));
   if (to_host) {
@@ -270,9 +278,11 @@ int vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *y
       case 7: k_multi_dot<7><<<grid, kVecThreads, 0, ctx->stream>>>(x, p, n, partial); break;
       default: k_multi_dot<8><<<grid, kVecThreads, 0, ctx->stream>>>(x, p, n, partial); break;
     }
-    AB_CUDA(cudaGetLastError());
+    AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
     k_finish<<<kk, kVecThreads, 0, ctx->stream>>>(partial, (int)grid, ctx->red_dev + j0, 0);
-    AB_CUDA(cudaGetLastError());
+    AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
   }
   if (ctx->nranks > 1) AB_CHECK(comm_allreduce(ctx, ctx->red_dev, k, 0));
   if (to_host) {
@@ -287,6 +297,7 @@ int vec_add_and_dot(adaflo_b200_ctx_t ctx, double *y, double a, const double *x,
 {
   const unsigned grid = grid_for(n, ctx->sm_count, 8);
   k_add_and_dot<<<grid, kVecThreads, 0, ctx->stream>>>(y, a, x, z, n, ctx->red_dev + kResultSlots);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return finish_to_host(ctx, 1, (int)grid, 0, result_host, true);
 }
@@ -303,6 +314,7 @@ int vec_project(adaflo_b200_ctx_t ctx, double *p, const double *w, const double 
   const double *ys[1] = {p};
   AB_CHECK(vec_multi_dot(ctx, w, ys, 1, n_owned, nullptr, false));
   k_project<<<grid_for(n_local, ctx->sm_count), kVecThreads, 0, ctx->stream>>>(p, mode, ctx->red_dev, inv_weight, n_local);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -321,9 +333,11 @@ int jacobi_reinit(adaflo_b200_ctx_t ctx, double *inv, const double *diag, uint64
 {
   const unsigned grid = grid_for(n, ctx->sm_count, 8);
   k_absmax<<<grid, kVecThreads, 0, ctx->stream>>>(diag, n, ctx->red_dev + kResultSlots);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   AB_CHECK(finish_to_host(ctx, 1, (int)grid, 1, nullptr, false));
   k_jacobi_reinit<<<grid_for(n, ctx->sm_count), kVecThreads, 0, ctx->stream>>>(inv, diag, ctx->red_dev, n);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -342,6 +356,7 @@ int jacobi_vmult(cudaStream_t s, double *dst, const double *src, const double *i
 {
   if (n == 0) return 0;
   k_jacobi<<<grid_for(n, sm_count_cached()), kVecThreads, 0, s>>>(dst, src, inv, n, n_blocks);
+  AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }

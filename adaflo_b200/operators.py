@@ -349,6 +349,17 @@ class NavierStokesMatrix:
         check(self.lib.adaflo_b200_ns_get_matvec_statistics(self.h, C.byref(n), C.byref(s)))
         return s.value, n.value
 
+    def set_kernel_timing(self, enable=True):
+        self._require()
+        check(self.lib.adaflo_b200_ns_set_kernel_timing(self.h, int(enable)))
+
+    def get_kernel_timing(self):
+        """(launches, seconds) of the vmult cell kernel measured with CUDA events; resets."""
+        self._require()
+        n, s = C.c_uint64(), C.c_double()
+        check(self.lib.adaflo_b200_ns_get_kernel_timing(self.h, C.byref(n), C.byref(s)))
+        return n.value, s.value
+
     def vmult_host(self, dst_u, dst_p, src_u, src_p):
         """End-to-end call with HOST (pinned) torch tensors or numpy arrays."""
         self._require()

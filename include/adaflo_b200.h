@@ -243,6 +243,12 @@ int adaflo_b200_ns_nullspace(adaflo_b200_ns_t ns, int mode, const double **modes
 /* get_matvec_statistics: :1194-1206 (count, accumulated seconds; resets) */
 int adaflo_b200_ns_get_matvec_statistics(adaflo_b200_ns_t ns, uint64_t *count, double *seconds);
 
+/* Measurement hooks (bench.py): CUDA-event timing of the dominant cell kernel inside
+ * vmult on the launching stream, and a process-wide count of kernels this library launched. */
+int adaflo_b200_ns_set_kernel_timing(adaflo_b200_ns_t ns, int enable);
+int adaflo_b200_ns_get_kernel_timing(adaflo_b200_ns_t ns, uint64_t *launches, double *seconds);
+uint64_t adaflo_b200_kernel_launch_count(void);
+
 /* End-to-end variant with HOST vectors (what a deal.II adaptor that keeps host
  * vectors authoritative calls, SURVEY 8(b) "mirror per call"): H2D of src, vmult,
  * D2H of dst on the context stream, synchronous on return. */

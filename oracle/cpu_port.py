@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 class PortArgs(C.Structure):
-    _fields_ = [("n_cells", C.c_int32), ("layer_cells", C.c_int32), ("cell_u", C.c_void_p), ("cell_p", C.c_void_p),
+    _fields_ = [("n_cells", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("cell_u", C.c_void_p), ("cell_p", C.c_void_p),
                 ("inv_h", C.c_double * 3), ("det", C.c_double), ("mode", C.c_int32),
                 ("gamma", C.c_double), ("tau1", C.c_double), ("beta", C.c_double), ("rho", C.c_double),
                 ("mu", C.c_double), ("damping", C.c_double), ("tau_gd", C.c_double), ("lin", C.c_void_p)]
@@ -20,7 +20,7 @@ def build(force=False):
     so = os.path.join(_HERE, "libcpu_port.so")
     src = os.path.join(_HERE, "ns_cpu_port.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"])
     return so
 
 
@@ -44,7 +44,7 @@ class CpuPortVmult:
         self.lin = None if lin is None else np.ascontiguousarray(lin)
         a = PortArgs()
         a.n_cells = mesh.n_cells
-        a.layer_cells = mesh.n[0] * mesh.n[1]
+        a.nx, a.ny = mesh.n[0], mesh.n[1]
         a.cell_u = self.cu.ctypes.data
         a.cell_p = self.cp.ctypes.data
         for d in range(3):

@@ -9,9 +9,9 @@
  * cells, constant coefficients, vmult with Stokes / Newton / Picard convection.
  * Validated against the dense oracle (ns_oracle.c) by tests/test_cpu_port.py.
  *
- * Threading: cells are ordered in layers of `layer_cells` cells such that layer L shares
- * dofs only with layers L-1 and L+1 (lexicographic box meshes); even and odd layers are
- * processed in two conflict-free parallel sweeps, so no atomics are needed.
+ * Threading: cells are lexicographic (rows of nx cells along x, ny rows per z-layer); a row
+ * (iy, iz) shares dofs only with the rows (iy+-1, iz+-1), so the four colours (iy%2, iz%2) are
+ * processed in four conflict-free parallel sweeps and no atomics are needed.
  */
 #include <math.h>
 #include <stdint.h>
@@ -24,7 +24,7 @@
 #define FLAG_SHIFT 29
 
 typedef struct {
-  int32_t n_cells, layer_cells;
+  int32_t n_cells, nx, ny; /* cells are lexicographic: rows of nx cells, ny rows per z-layer */
   const uint32_t *cell_u; /* [n_cells][27] with Dirichlet flag bits (same encoding as the C ABI) */
   const uint32_t *cell_p; /* [n_cells][8] */
   double inv_h[3], det;
@@ -39,7 +39,7 @@ static const double NP[3][2] = {{0.8872983346207417, 0.11270166537925831}, {0.5,
 static const double W[3] = {0.2777777777777778, 0.4444444444444444, 0.2777777777777778};
 
 /* apply a 3x3 1-D matrix along direction dir of a 3x3x3 array (transpose: M^T) */
-static inline void apply3(const double M[3][3], int transpose, int dir, const double *in, double *out, int add)
+static inline __attribute__((always_inline)) void apply3(const double M[3][3], int transpose, int dir, const double *in, double *out, int add)
 {
   const int stride = dir == 0 ? 1 : (dir == 1 ? 3 : 9);
   for (int o = 0; o < 9; ++o) {
@@ -155,16 +155,19 @@ static void cell_vmult(const port_args *A, int cell, const double *src_u, const 
 /* dst += cell contributions (dst must be zeroed by the caller); returns the thread count used */
 int port_ns_vmult_cells(const port_args *A, const double *src_u, const double *src_p, double *dst_u, double *dst_p)
 {
-  const int layers = (A->n_cells + A->layer_cells - 1) / A->layer_cells;
+  const int rows = A->n_cells / A->nx, nz = rows / A->ny;
   int threads = 1;
 #ifdef _OPENMP
   threads = omp_get_max_threads();
 #endif
-  for (int colour = 0; colour < 2; ++colour) {
+  for (int colour = 0; colour < 4; ++colour) {
+    const int cy = colour & 1, cz = colour >> 1;
+    const int my = (A->ny - cy + 1) / 2, mz = (nz - cz + 1) / 2;
 #pragma omp parallel for schedule(static)
-    for (int L = colour; L < layers; L += 2) {
-      const int c0 = L * A->layer_cells, c1 = (c0 + A->layer_cells < A->n_cells) ? c0 + A->layer_cells : A->n_cells;
-      for (int cell = c0; cell < c1; ++cell) cell_vmult(A, cell, src_u, src_p, dst_u, dst_p);
+    for (int r = 0; r < my * mz; ++r) {
+      const int iy = cy + 2 * (r % my), iz = cz + 2 * (r / my);
+      const int c0 = (iz * A->ny + iy) * A->nx;
+      for (int cell = c0; cell < c0 + A->nx; ++cell) cell_vmult(A, cell, src_u, src_p, dst_u, dst_p);
     }
   }
   return threads;
