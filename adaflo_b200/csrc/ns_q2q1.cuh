@@ -26,9 +26,9 @@ namespace ab200 {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kCellsPerWarp = 3;
-constexpr int kPS = 12;              // plane stride (doubles) of a 3x3x3 tile
+constexpr int kPS = 9;               // plane stride (doubles): dense 3x3x3 tile
 constexpr int kAS = 3 * kPS;         // one scalar tile
-constexpr int kCellSmem = 10 * kAS + 8;  // 3 arrays x 3 comps + pressure tile, padded: 368 doubles
+constexpr int kCellSmem = 10 * kAS + 13;  // 283 doubles: cell stride = 11 (mod 16) minimises bank conflicts between the 3 cells of a warp
 constexpr int kWarpSmem = kCellsPerWarp * kCellSmem;
 
 // 1-D shape tables (values from the oracle's long-double evaluation, rounded once):
