@@ -68,6 +68,8 @@ static NSArgs make_args(adaflo_b200_ns_t ns, bool use_prec)
   a.np_cell = (int)mf->spaces[ns->dof_p].nodes_per_cell;
   a.cell_u = mf->spaces[ns->dof_u].cell_nodes;
   a.cell_p = mf->spaces[ns->dof_p].cell_nodes;
+  a.cell_u_blk = mf->spaces[ns->dof_u].cell_nodes_blk;
+  a.cell_p_blk = mf->spaces[ns->dof_p].cell_nodes_blk;
   const bool prec = use_prec && ns->lin_prec;
   a.lin = prec ? ns->lin_prec : ns->lin;
   a.rho = (use_prec && ns->rho_prec) ? ns->rho_prec : ns->rho;
@@ -214,6 +216,18 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
       return fail(ADAFLO_B200_ERR_ARG, "mf_create: more than 2^29 nodes per rank");
     AB_CHECK(upload(&sp.cell_nodes, sd.cell_nodes, (size_t)d->n_cells * sd.nodes_per_cell, s));
     if (sd.hanging_masks) AB_CHECK(upload(&sp.hanging_masks, sd.hanging_masks, (size_t)d->n_cells, s));
+    if (sd.nodes_per_cell == 27 || sd.nodes_per_cell == 8 || sd.nodes_per_cell == 9) {
+      // decade-blocked copy for the vmult kernel: lane 3 cw + iz reads in-plane node j of its plane
+      const int n1 = sd.nodes_per_cell == 27 ? 3 : 2, nj = n1 * n1;
+      const size_t ng = n_groups(d->n_cells);
+      std::vector<uint32_t> blk(ng * nj * 30, 0u);
+      for (uint32_t c = 0; c < d->n_cells; ++c)
+        for (int iz = 0; iz < n1; ++iz)
+          for (int j = 0; j < nj; ++j)
+            blk[((size_t)(c / kGroup) * nj + j) * 30 + 3 * (c % kGroup) + iz] = sd.cell_nodes[(size_t)c * sd.nodes_per_cell + iz * nj + j];
+      AB_CHECK(upload(&sp.cell_nodes_blk, blk.data(), blk.size(), s));
+      AB_CUDA(cudaStreamSynchronize(s));
+    }
     sp.n_constrained = sd.n_constrained;
     AB_CHECK(upload(&sp.constrained, sd.constrained_dofs, (size_t)sd.n_constrained, s));
     if (sd.fe_kind == ADAFLO_B200_FE_Q_DG0) {
@@ -243,8 +257,24 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
     const size_t nq = (size_t)qd.n_q_1d * qd.n_q_1d * qd.n_q_1d;
     if (qd.geometry_type == ADAFLO_B200_GEOM_GENERAL) {
       if (!qd.inv_jacobian || !qd.jxw) return fail(ADAFLO_B200_ERR_ARG, "mf_create: general geometry needs inv_jacobian and jxw");
-      AB_CHECK(upload(&q.inv_jac, qd.inv_jacobian, (size_t)d->n_cells * 9 * nq, s));
-      AB_CHECK(upload(&q.jxw, qd.jxw, (size_t)d->n_cells * nq, s));
+      if (qd.n_q_1d == 3) {  // decade blocked (see coef_index)
+        const size_t ng = n_groups(d->n_cells);
+        std::vector<double> kb(ng * 9 * 270, 0.0), jb(ng * 270, 1.0);
+        for (uint32_t c = 0; c < d->n_cells; ++c)
+          for (int qz = 0; qz < 3; ++qz)
+            for (int qy = 0; qy < 3; ++qy)
+              for (int qx = 0; qx < 3; ++qx) {
+                const int qq = qx + 3 * qy + 9 * qz;
+                for (int r = 0; r < 9; ++r) kb[coef_index(c, r, 9, qx, qy, qz)] = qd.inv_jacobian[((size_t)c * 9 + r) * 27 + qq];
+                jb[coef_index(c, 0, 1, qx, qy, qz)] = qd.jxw[(size_t)c * 27 + qq];
+              }
+        AB_CHECK(upload(&q.inv_jac, kb.data(), kb.size(), s));
+        AB_CHECK(upload(&q.jxw, jb.data(), jb.size(), s));
+        AB_CUDA(cudaStreamSynchronize(s));
+      } else {
+        AB_CHECK(upload(&q.inv_jac, qd.inv_jacobian, (size_t)d->n_cells * 9 * nq, s));
+        AB_CHECK(upload(&q.jxw, qd.jxw, (size_t)d->n_cells * nq, s));
+      }
     } else {
       const int w = qd.geometry_type == ADAFLO_B200_GEOM_CARTESIAN ? 4 : 10;
       if (!qd.table || !qd.cell_row) return fail(ADAFLO_B200_ERR_ARG, "mf_create: compressed geometry needs table and cell_row");
@@ -264,6 +294,7 @@ int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf)
   cudaSetDevice(mf->ctx->device);
   for (Space &sp : mf->spaces) {
     free_dev(sp.cell_nodes);
+    free_dev(sp.cell_nodes_blk);
     free_dev(sp.hanging_masks);
     free_dev(sp.constrained);
     for (Exchange &x : sp.exchange) {
@@ -332,7 +363,7 @@ int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   ns->n_q = 27;
   ns->var = prm->density_diff != 0 || prm->viscosity_diff != 0;  // :97-98
   cudaStream_t s = ctx->stream;
-  const size_t size = (size_t)mf->n_cells * ns->n_q;
+  const size_t size = n_groups(mf->n_cells) * 270;  // decade-blocked per-point arrays
   if (ns->var) {  // :100-106
     AB_CUDA(cudaMalloc((void **)&ns->rho, size * sizeof(double)));
     AB_CUDA(cudaMalloc((void **)&ns->mu, size * sizeof(double)));
@@ -717,7 +748,7 @@ int adaflo_b200_ns_fix_linearization_point(adaflo_b200_ns_t ns)
 {
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "operator not initialised");
   cudaStream_t s = ns->ctx->stream;
-  const size_t size = (size_t)ns->mf->n_cells * ns->n_q;
+  const size_t size = n_groups(ns->mf->n_cells) * 270;
   struct { double **dst; double *src; size_t n; } items[] = {{&ns->lin_prec, ns->lin, size * 12},
                                                              {&ns->rho_prec, ns->rho, size},
                                                              {&ns->mu_prec, ns->mu, size},
@@ -751,7 +782,7 @@ int adaflo_b200_ns_apply_pressure_shift(adaflo_b200_ns_t ns, double shift, doubl
 int adaflo_b200_ns_coefficient_ptr(adaflo_b200_ns_t ns, int which, double **dev_ptr, uint64_t *n)
 {
   if (!ns || !dev_ptr) return fail(ADAFLO_B200_ERR_ARG, "null argument");
-  const uint64_t size = (uint64_t)ns->mf->n_cells * ns->n_q;
+  const uint64_t size = (uint64_t)n_groups(ns->mf->n_cells) * 270;
   double *p = nullptr;
   uint64_t cnt = size;
   switch (which) {

@@ -12,6 +12,20 @@
 
 namespace ab200 {
 
+// Per-quadrature-point arrays on QGauss(3) and the cell->node lists used by the vmult kernel
+// are stored "decade blocked": cells are grouped in tens (one warp of the vmult kernel owns a
+// decade, 3 lanes per cell) and the point (qx,qy,qz) of cell 10 g + cw, row r of n_rows, lives at
+//   ((g * n_rows + r) * 9 + 3 qx + qz) * 30 + 3 cw + qy
+// so that the 30 lanes of a warp read 240 contiguous bytes per (row, qx, qz).
+constexpr int kGroup = 10;
+__host__ __device__ inline size_t coef_index(uint32_t cell, int row, int n_rows, int qx, int qy, int qz)
+{
+  const size_t g = cell / kGroup;
+  const int cw = (int)(cell % kGroup);
+  return ((g * n_rows + row) * 9 + (size_t)(3 * qx + qz)) * 30 + 3 * cw + qy;
+}
+inline size_t n_groups(uint32_t n_cells) { return ((size_t)n_cells + kGroup - 1) / kGroup; }
+
 void set_error(const std::string &msg);
 extern unsigned long long g_launches;  // kernels launched by this library (bench.py: gpu_launches)
 #define AB_COUNT_LAUNCH() (++::ab200::g_launches)
@@ -45,6 +59,7 @@ struct Space {
   int fe_kind, degree, n_comp;
   uint32_t n_owned_nodes, n_ghost_nodes, nodes_per_cell;
   uint32_t *cell_nodes;      // device [n_cells][nodes_per_cell]
+  uint32_t *cell_nodes_blk;  // device, decade blocked: u: [g][9 (ix+3iy)][10 cw][3 iz]; p: [g][4 (ix+2iy)][10 cw][3 iz (2 used)]
   uint32_t *hanging_masks;   // device [n_cells] or null
   uint32_t n_constrained;
   uint32_t *constrained;     // device
@@ -59,8 +74,8 @@ struct Quad {
   uint32_t n_rows;
   double *table;       // device
   uint32_t *cell_row;  // device
-  double *inv_jac;     // device [n_cells][9][n_q]
-  double *jxw;         // device [n_cells][n_q]
+  double *inv_jac;     // device; n_q_1d == 3: decade blocked with 9 rows, else [n_cells][9][n_q]
+  double *jxw;         // device; n_q_1d == 3: decade blocked with 1 row, else [n_cells][n_q]
 };
 
 }  // namespace ab200
@@ -126,6 +141,8 @@ struct NSArgs {
   int np_cell;  // pressure dofs per cell: 8, or 9 with DG0
   const uint32_t *cell_u;
   const uint32_t *cell_p;
+  const uint32_t *cell_u_blk;
+  const uint32_t *cell_p_blk;
   const double *src_u;
   const double *src_p;
   const double *old_u;

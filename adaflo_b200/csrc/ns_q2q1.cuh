@@ -281,19 +281,34 @@ struct Geometry {
         for (int e = 0; e < 3; ++e) K[f][e] = row[3 * f + e];
       det = row[9];
     } else {
-      kq = A.inv_jac + (size_t)cell * 9 * 27;
-      jq = A.jxw + (size_t)cell * 27;
+      kq = A.inv_jac;
+      jq = A.jxw;
     }
+    cell_ = cell;
   }
-  // load the point data (general geometry) and return JxW
-  __device__ __forceinline__ double at(int q, double w)
+  uint32_t cell_;
+  // load the point data (general geometry, decade-blocked arrays) and return JxW
+  __device__ __forceinline__ double at(int qx, int qy, int qz, double w)
   {
     if (GEOM == ADAFLO_B200_GEOM_GENERAL) {
 #pragma unroll
       for (int f = 0; f < 3; ++f)
 #pragma unroll
-        for (int e = 0; e < 3; ++e) K[f][e] = __ldg(kq + (3 * f + e) * 27 + q);
-      return __ldg(jq + q);
+        for (int e = 0; e < 3; ++e) K[f][e] = __ldg(kq + coef_index(cell_, 3 * f + e, 9, qx, qy, qz));
+      return __ldg(jq + coef_index(cell_, 0, 1, qx, qy, qz));
+    }
+    return det * w;
+  }
+  // same for the vmult kernel whose lanes are laid out like the blocks: slot = (3 qx + qz) * 30 + lane
+  __device__ __forceinline__ void init_blk(const NSArgs &A, uint32_t cell) { init(A, cell); }
+  __device__ __forceinline__ double at_blk(const NSArgs &A, size_t g, size_t slot, double w)
+  {
+    if (GEOM == ADAFLO_B200_GEOM_GENERAL) {
+#pragma unroll
+      for (int f = 0; f < 3; ++f)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) K[f][e] = __ldg(A.inv_jac + (g * 9 + (3 * f + e)) * 270 + slot);
+      return __ldg(A.jxw + g * 270 + slot);
     }
     return det * w;
   }
@@ -409,11 +424,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) ns_vmult_kernel(const 
 
   // ---- quadrature point loop: points (qx=a, qy, qz=b)
   double tp[3];
-  const double *lin = A.lin + (size_t)cell * 12 * 27;
 #pragma unroll
   for (int qy = 0; qy < 3; ++qy) {
-    const int q = a + 3 * qy + 9 * b;
-    const double jxw = G.at(q, W[a] * W[qy] * W[b]);
+    const double *lin = A.lin + coef_index(cell, 0, 12, a, qy, b);  // row stride 270
+    const double jxw = G.at(a, qy, b, W[a] * W[qy] * W[b]);
+    const size_t q1 = coef_index(cell, 0, 1, a, qy, b);  // rho / mu / damping
     double g[3][3];  // g[d][e] = d u_d / d x_e
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -425,18 +440,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) ns_vmult_kernel(const 
     double Sadd[3][3];  // transposed convection tests the gradient (Tvmult only)
     if (MODE != MODE_STOKES) {
       const double u[3] = {val[0][qy], val[1][qy], val[2][qy]};
-      const double rho = VAR ? __ldg(A.rho + (size_t)cell * 27 + q) : A.rho0;
-      const double damping = VAR ? __ldg(A.damp + (size_t)cell * 27 + q) : A.damp0;
+      const double rho = VAR ? __ldg(A.rho + q1) : A.rho0;
+      const double damping = VAR ? __ldg(A.damp + q1) : A.damp0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) conv[d] = A.gamma * u[d];
       if (MODE == MODE_NEWTON) {
         double lu[3], lg[3][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 27 + q);
+        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
 #pragma unroll
         for (int d = 0; d < 3; ++d)
 #pragma unroll
-          for (int e = 0; e < 3; ++e) lg[d][e] = __ldg(lin + (3 + 3 * d + e) * 27 + q);
+          for (int e = 0; e < 3; ++e) lg[d][e] = __ldg(lin + (3 + 3 * d + e) * 270);
         const double ltr = lg[0][0] + lg[1][1] + lg[2][2];
         if (!TRANSPOSE) {
           const double f1 = A.beta * div, f2 = A.beta * ltr;
@@ -466,8 +481,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) ns_vmult_kernel(const 
       } else if (MODE == MODE_PICARD) {
         double lu[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 27 + q);
-        const double ldiv = __ldg(lin + 3 * 27 + q);
+        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
+        const double ldiv = __ldg(lin + 3 * 270);
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           double res = A.beta * ldiv * u[d];
@@ -484,7 +499,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) ns_vmult_kernel(const 
 #pragma unroll
       for (int d = 0; d < 3; ++d) conv[d] = (conv[d] * rho - damping * u[d]) * jxw;
     }
-    const double tmu = (VAR ? __ldg(A.mu + (size_t)cell * 27 + q) : A.mu0) * A.tau1;
+    const double tmu = (VAR ? __ldg(A.mu + q1) : A.mu0) * A.tau1;
     double S[3][3];
     S[0][1] = S[1][0] = tmu * (g[0][1] + g[1][0]);
     S[0][2] = S[2][0] = tmu * (g[0][2] + g[2][0]);

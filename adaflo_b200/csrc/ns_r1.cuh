@@ -1,0 +1,423 @@
+// ns_r1.cuh -- vmult cell kernel of the 3-D Q2/Q1 Navier-Stokes operator, second design.
+//
+// Profiling of the first design (ns_q2q1.cuh: 9 lanes per cell, line ownership,
+// profiles/r1_a_*) showed the LSU data pipe at 85 % (two thirds of it shared-memory
+// transposes with bank conflicts, one third uncoalesced per-point loads) while HBM sat
+// at 28 %.  This design halves the shared-memory traffic and makes every per-point
+// stream fully coalesced:
+//
+//  * 3 lanes own one cell, a warp owns a "decade" of 10 consecutive cells (30 lanes).
+//  * phase A: lane t owns the node plane iz = t (9 nodes x 3 components in registers) and
+//    runs both in-plane contractions (x and y) in registers; it publishes three tiles
+//    per component (interpolated, d/dx, d/dy) to shared memory.
+//  * phase B: lane t owns the three z-lines (qx = j, qy = t), j = 0..2; per line it reads
+//    the 3 x 9 plane values, contracts in z (values + 3 derivatives at 3 points), applies
+//    the physics and contracts back in z, overwriting the same tile entries.
+//  * phase C: lane t owns node plane t again, transposed in-plane contractions, scatter.
+//    => one shared-memory round trip per direction pair instead of two.
+//  * tile index = k + 3 qx + 33 qy (+9 per array) and a cell stride of 3 (mod 16) doubles
+//    make the bank pair of every access equal to the lane number: conflict free in both
+//    ownership patterns.
+//  * all per-quadrature-point data (linearisation point, rho/mu/damping, Jacobians) and
+//    the cell->node lists are stored decade-blocked, [decade][row][3 qx + qz][30 lanes], so
+//    each warp-level load reads 240 contiguous bytes (see coef_index in common.cuh).
+#pragma once
+
+#include "ns_q2q1.cuh"
+
+namespace ab200 {
+
+constexpr int kR1Warps = 4;                 // warps per block
+constexpr int kR1CompSmem = 93;             // three interleaved tiles of one component
+constexpr int kR1CellSmem = 3 * kR1CompSmem + 18 + 10;  // + pressure tile, padded to 307 = 3 (mod 16)
+constexpr int kR1WarpSmem = kGroup * kR1CellSmem;
+
+__device__ __forceinline__ int r1_idx(int qx, int qy, int k) { return k + 3 * qx + 33 * qy; }
+
+template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
+__global__ void __launch_bounds__(kR1Warps * 32, 2) ns_vmult_r1_kernel(const NSArgs A)
+{
+  AB_TABLES_Q2G3
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cw = lane / 3;
+  const int t = lane - 3 * cw;
+  const size_t g = (size_t)blockIdx.x * kR1Warps + warp;  // decade
+  const size_t cell_l = g * kGroup + cw;
+  const bool active = (lane < 3 * kGroup) && (cell_l < A.n_cells);
+  const unsigned mask = __ballot_sync(0xffffffffu, active);
+  if (!active) return;
+  const uint32_t cell = (uint32_t)cell_l;
+  double *s = smem + warp * kR1WarpSmem + cw * kR1CellSmem;
+  double *sp = s + 3 * kR1CompSmem;
+
+  // ---------------------------------------------------------------- phase A
+  uint32_t node[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) node[j] = __ldg(A.cell_u_blk + (g * 9 + j) * 30 + lane);
+  uint32_t pnode[4] = {0, 0, 0, 0};
+  double p_dg0 = 0;
+  uint32_t dg0_node = 0;
+  if (WITH_P) {
+    if (t < 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pnode[j] = __ldg(A.cell_p_blk + (g * 4 + j) * 30 + lane);
+    }
+    if (A.np_cell == 9) {
+      dg0_node = __ldg(A.cell_p + (size_t)cell * 9 + 8);
+      p_dg0 = A.src_p[dg0_node & ADAFLO_B200_NODE_MASK];
+    }
+  }
+  {
+    double P[3][9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const size_t n = node[j] & ADAFLO_B200_NODE_MASK;
+      const uint32_t flags = node[j] >> ADAFLO_B200_FLAG_SHIFT;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double v = A.src_u[3 * n + c];
+        P[c][j] = ((flags >> c) & 1u) ? 0.0 : v;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double Y[3][3], Yd[3][3];  // [qy][ix]
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double y = 0, yd = 0;
+#pragma unroll
+          for (int m = 0; m < 3; ++m) {
+            y = fma(N[q][m], P[c][3 * m + i], y);
+            yd = fma(D[q][m], P[c][3 * m + i], yd);
+          }
+          Y[q][i] = y;
+          Yd[q][i] = yd;
+        }
+      double *sc = s + c * kR1CompSmem;
+#pragma unroll
+      for (int qy = 0; qy < 3; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < 3; ++qx) {
+          double tv = 0, tx = 0, ty = 0;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            tv = fma(N[qx][i], Y[qy][i], tv);
+            tx = fma(D[qx][i], Y[qy][i], tx);
+            ty = fma(N[qx][i], Yd[qy][i], ty);
+          }
+          sc[0 + r1_idx(qx, qy, t)] = tv;
+          sc[9 + r1_idx(qx, qy, t)] = tx;
+          sc[18 + r1_idx(qx, qy, t)] = ty;
+        }
+    }
+    if (WITH_P && t < 2) {
+      double pl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double v = A.src_p[pnode[j] & ADAFLO_B200_NODE_MASK];
+        pl[j] = (pnode[j] >> ADAFLO_B200_FLAG_SHIFT) ? 0.0 : v;
+      }
+#pragma unroll
+      for (int qy = 0; qy < 3; ++qy) {
+        const double y0 = NP[qy][0] * pl[0] + NP[qy][1] * pl[2];  // ix = 0
+        const double y1 = NP[qy][0] * pl[1] + NP[qy][1] * pl[3];  // ix = 1
+#pragma unroll
+        for (int qx = 0; qx < 3; ++qx) sp[t + 2 * (qx + 3 * qy)] = NP[qx][0] * y0 + NP[qx][1] * y1;
+      }
+    }
+  }
+  __syncwarp(mask);
+
+  // ---------------------------------------------------------------- phase B
+  Geometry<GEOM> G;
+  G.init_blk(A, cell);
+  double dg0_sum = 0;
+  const double wt = (t == 1) ? W[1] : W[0];  // Gauss weight of qy = t
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    double val[3][3], dx[3][3], dy[3][3], dz[3][3];  // [c][qz]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double *sc = s + c * kR1CompSmem + 3 * j + 33 * t;
+      double T[3], Tx[3], Ty[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        T[k] = sc[k];
+        Tx[k] = sc[9 + k];
+        Ty[k] = sc[18 + k];
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        double v = 0, gz = 0, gx = 0, gy = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (MODE != MODE_STOKES) v = fma(N[q][k], T[k], v);
+          gz = fma(D[q][k], T[k], gz);
+          gx = fma(N[q][k], Tx[k], gx);
+          gy = fma(N[q][k], Ty[k], gy);
+        }
+        val[c][q] = v;
+        dx[c][q] = gx;
+        dy[c][q] = gy;
+        dz[c][q] = gz;
+      }
+    }
+    double pv[3] = {0, 0, 0};
+    if (WITH_P) {
+      const double p0 = sp[0 + 2 * (j + 3 * t)], p1 = sp[1 + 2 * (j + 3 * t)];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) pv[q] = NP[q][0] * p0 + NP[q][1] * p1 + p_dg0;
+    }
+    double tp[3];
+    // points (qx = j, qy = t, qz): coefficient slot 3 j + qz of this lane
+    const size_t cbase = (size_t)(3 * j) * 30 + lane;
+#pragma unroll
+    for (int qz = 0; qz < 3; ++qz) {
+      const size_t slot = cbase + (size_t)qz * 30;
+      const double jxw = G.at_blk(A, g, slot, W[j] * W[qz] * wt);
+      double gr[3][3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double r[3] = {dx[d][qz], dy[d][qz], dz[d][qz]};
+        G.to_real(r, gr[d]);
+      }
+      const double div = gr[0][0] + gr[1][1] + gr[2][2];
+      double conv[3] = {0, 0, 0};
+      double Sadd[3][3];
+      if (MODE != MODE_STOKES) {
+        const double u[3] = {val[0][qz], val[1][qz], val[2][qz]};
+        const double rho = VAR ? __ldg(A.rho + g * 270 + slot) : A.rho0;
+        const double damping = VAR ? __ldg(A.damp + g * 270 + slot) : A.damp0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) conv[d] = A.gamma * u[d];
+        const double *lin = A.lin + g * (12 * 270) + slot;
+        if (MODE == MODE_NEWTON) {
+          double lu[3], lg[3][3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) lg[d][e] = __ldg(lin + (3 + 3 * d + e) * 270);
+          const double ltr = lg[0][0] + lg[1][1] + lg[2][2];
+          if (!TRANSPOSE) {
+            const double f1 = A.beta * div, f2 = A.beta * ltr;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              double res = f1 * lu[d] + f2 * u[d];
+#pragma unroll
+              for (int e = 0; e < 3; ++e) res += lu[e] * gr[d][e] + u[e] * lg[d][e];
+              conv[d] += A.tau1 * res;
+            }
+          } else {
+            const double udl = u[0] * lu[0] + u[1] * lu[1] + u[2] * lu[2];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+              double res = A.beta * ltr * u[e];
+#pragma unroll
+              for (int d = 0; d < 3; ++d) res += u[d] * lg[d][e];
+              conv[e] += A.tau1 * res;
+            }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+#pragma unroll
+              for (int e = 0; e < 3; ++e) Sadd[d][e] = A.tau1 * rho * u[d] * lu[e];
+              Sadd[d][d] += A.tau1 * rho * A.beta * udl;
+            }
+          }
+        } else if (MODE == MODE_PICARD) {
+          double lu[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
+          const double ldiv = __ldg(lin + 3 * 270);
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            double res = A.beta * ldiv * u[d];
+            if (!TRANSPOSE) {
+#pragma unroll
+              for (int e = 0; e < 3; ++e) res += lu[e] * gr[d][e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 3; ++e) Sadd[d][e] = A.tau1 * rho * u[d] * lu[e];
+            }
+            conv[d] += A.tau1 * res;
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) conv[d] = (conv[d] * rho - damping * u[d]) * jxw;
+      }
+      const double tmu = (VAR ? __ldg(A.mu + g * 270 + slot) : A.mu0) * A.tau1;
+      double S[3][3];
+      S[0][1] = S[1][0] = tmu * (gr[0][1] + gr[1][0]);
+      S[0][2] = S[2][0] = tmu * (gr[0][2] + gr[2][0]);
+      S[1][2] = S[2][1] = tmu * (gr[1][2] + gr[2][1]);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        S[d][d] = 2. * tmu * gr[d][d] + A.tau_gd * div;
+        if (WITH_P) S[d][d] -= pv[qz];
+      }
+      if (TRANSPOSE && (MODE == MODE_NEWTON || MODE == MODE_PICARD)) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) S[d][e] += Sadd[d][e];
+      }
+      tp[qz] = -div * jxw;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double tr[3];
+        G.to_ref(S[d], jxw, tr);
+        val[d][qz] = conv[d];
+        dx[d][qz] = tr[0];
+        dy[d][qz] = tr[1];
+        dz[d][qz] = tr[2];
+      }
+    }
+    // z contraction back, overwriting this lane's own tile entries
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double *sc = s + c * kR1CompSmem + 3 * j + 33 * t;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        double r = 0, rx = 0, ry = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (MODE != MODE_STOKES) r = fma(N[q][k], val[c][q], r);
+          r = fma(D[q][k], dz[c][q], r);
+          rx = fma(N[q][k], dx[c][q], rx);
+          ry = fma(N[q][k], dy[c][q], ry);
+        }
+        sc[k] = r;
+        sc[9 + k] = rx;
+        sc[18 + k] = ry;
+      }
+    }
+    if (WITH_P) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) sp[k + 2 * (j + 3 * t)] = NP[0][k] * tp[0] + NP[1][k] * tp[1] + NP[2][k] * tp[2];
+      dg0_sum += tp[0] + tp[1] + tp[2];
+    }
+  }
+  __syncwarp(mask);
+
+  // ---------------------------------------------------------------- phase C
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const double *sc = s + c * kR1CompSmem;
+    double Y[3][3], Yd[3][3];  // [qy][ix]
+#pragma unroll
+    for (int qy = 0; qy < 3; ++qy) {
+      double T[3], Tx[3], Ty[3];
+#pragma unroll
+      for (int qx = 0; qx < 3; ++qx) {
+        T[qx] = sc[0 + r1_idx(qx, qy, t)];
+        Tx[qx] = sc[9 + r1_idx(qx, qy, t)];
+        Ty[qx] = sc[18 + r1_idx(qx, qy, t)];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double y = 0, yd = 0;
+#pragma unroll
+        for (int qx = 0; qx < 3; ++qx) {
+          y = fma(N[qx][i], T[qx], y);
+          y = fma(D[qx][i], Tx[qx], y);
+          yd = fma(N[qx][i], Ty[qx], yd);
+        }
+        Y[qy][i] = y;
+        Yd[qy][i] = yd;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double o = 0;
+#pragma unroll
+        for (int qy = 0; qy < 3; ++qy) {
+          o = fma(N[qy][m], Y[qy][i], o);
+          o = fma(D[qy][m], Yd[qy][i], o);
+        }
+        const uint32_t nd = node[3 * m + i];
+        if (!((nd >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) red_add(A.dst_u + 3 * (size_t)(nd & ADAFLO_B200_NODE_MASK) + c, o);
+      }
+  }
+  if (WITH_P && !A.skip_p_test) {
+    if (t < 2) {
+      double y0[3], y1[3];
+#pragma unroll
+      for (int qy = 0; qy < 3; ++qy) {
+        const double a0 = sp[t + 2 * (0 + 3 * qy)], a1 = sp[t + 2 * (1 + 3 * qy)], a2 = sp[t + 2 * (2 + 3 * qy)];
+        y0[qy] = NP[0][0] * a0 + NP[1][0] * a1 + NP[2][0] * a2;
+        y1[qy] = NP[0][1] * a0 + NP[1][1] * a1 + NP[2][1] * a2;
+      }
+      const double o[4] = {NP[0][0] * y0[0] + NP[1][0] * y0[1] + NP[2][0] * y0[2], NP[0][0] * y1[0] + NP[1][0] * y1[1] + NP[2][0] * y1[2],
+                           NP[0][1] * y0[0] + NP[1][1] * y0[1] + NP[2][1] * y0[2], NP[0][1] * y1[0] + NP[1][1] * y1[1] + NP[2][1] * y1[2]};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!(pnode[j] >> ADAFLO_B200_FLAG_SHIFT)) red_add(A.dst_p + (pnode[j] & ADAFLO_B200_NODE_MASK), o[j]);
+    }
+    if (A.np_cell == 9) {
+      double sum = dg0_sum;
+      sum += __shfl_sync(mask, dg0_sum, 3 * cw + (t + 1) % 3) + __shfl_sync(mask, dg0_sum, 3 * cw + (t + 2) % 3);
+      if (t == 0 && !(dg0_node >> ADAFLO_B200_FLAG_SHIFT)) red_add(A.dst_p + (dg0_node & ADAFLO_B200_NODE_MASK), sum);
+    }
+  }
+}
+
+template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
+int launch_vmult_r1_inst(const NSArgs &a, cudaStream_t s)
+{
+  auto kern = ns_vmult_r1_kernel<WITH_P, MODE, GEOM, VAR, TRANSPOSE>;
+  const size_t smem = sizeof(double) * kR1Warps * kR1WarpSmem;
+  static bool configured = false;
+  if (!configured) {
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  const size_t cells_per_block = (size_t)kR1Warps * kGroup;
+  const unsigned grid = (unsigned)((a.n_cells + cells_per_block - 1) / cells_per_block);
+  if (grid == 0) return 0;
+  kern<<<grid, kR1Warps * 32, smem, s>>>(a);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int GEOM>
+int launch_vmult_r1_geom(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s)
+{
+  const bool tr = a.transpose && (mode == MODE_NEWTON || mode == MODE_PICARD);  // other modes are symmetric
+  if (tr) {
+    if (!with_p) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "transposed velocity block not instantiated");
+    if (mode == MODE_NEWTON && !var) return launch_vmult_r1_inst<true, MODE_NEWTON, GEOM, false, true>(a, s);
+    if (mode == MODE_NEWTON && var) return launch_vmult_r1_inst<true, MODE_NEWTON, GEOM, true, true>(a, s);
+    if (mode == MODE_PICARD && !var) return launch_vmult_r1_inst<true, MODE_PICARD, GEOM, false, true>(a, s);
+    return launch_vmult_r1_inst<true, MODE_PICARD, GEOM, true, true>(a, s);
+  }
+#define AB_CASE(P, M, V) \
+  if (with_p == P && mode == M && var == V) return launch_vmult_r1_inst<P, M, GEOM, V, false>(a, s);
+  AB_CASE(true, MODE_STOKES, false)
+  AB_CASE(true, MODE_NEWTON, false)
+  AB_CASE(true, MODE_PICARD, false)
+  AB_CASE(true, MODE_NOCONV, false)
+  AB_CASE(true, MODE_STOKES, true)
+  AB_CASE(true, MODE_NEWTON, true)
+  AB_CASE(true, MODE_PICARD, true)
+  AB_CASE(true, MODE_NOCONV, true)
+  AB_CASE(false, MODE_STOKES, false)
+  AB_CASE(false, MODE_NEWTON, false)
+  AB_CASE(false, MODE_PICARD, false)
+  AB_CASE(false, MODE_NOCONV, false)
+  AB_CASE(false, MODE_STOKES, true)
+  AB_CASE(false, MODE_NEWTON, true)
+  AB_CASE(false, MODE_PICARD, true)
+  AB_CASE(false, MODE_NOCONV, true)
+#undef AB_CASE
+  return fail(ADAFLO_B200_ERR_ARG, "launch_vmult_r1_geom: bad variant");
+}
+
+}  // namespace ab200

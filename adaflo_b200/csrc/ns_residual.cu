@@ -116,11 +116,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
   for (int q = 0; q < 3; ++q) pv[q] += p_dg0;
 
   double tp[3];
-  double *lin = A.lin ? A.lin + (size_t)cell * 12 * 27 : nullptr;
 #pragma unroll
   for (int qy = 0; qy < 3; ++qy) {
-    const int q = a + 3 * qy + 9 * b;
-    const double jxw = G.at(q, W[a] * W[qy] * W[b]);
+    double *lin = A.lin ? A.lin + coef_index(cell, 0, 12, a, qy, b) : nullptr;  // row stride 270
+    const size_t q1 = coef_index(cell, 0, 1, a, qy, b);
+    const double jxw = G.at(a, qy, b, W[a] * W[qy] * W[b]);
     double g[3][3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -157,9 +157,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
 #pragma unroll
             for (int e = 0; e < 3; ++e) res += eu[e] * g[d][e];
             conv[d] += A.tau1 * res;
-            lin[d * 27 + q] = eu[d];
+            lin[d * 270] = eu[d];
           }
-          lin[3 * 27 + q] = ediv;
+          lin[3 * 270] = ediv;
         }
       } else {
 #pragma unroll
@@ -168,22 +168,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
 #pragma unroll
           for (int e = 0; e < 3; ++e) res += u[e] * g[d][e];
           conv[d] += A.tau1 * res;
-          lin[d * 27 + q] = u[d];
+          lin[d * 270] = u[d];
         }
         if (lz == ADAFLO_B200_COUPLED_IMPLICIT_NEWTON) {
 #pragma unroll
           for (int d = 0; d < 3; ++d)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) lin[(3 + 3 * d + e) * 27 + q] = g[d][e];
+            for (int e = 0; e < 3; ++e) lin[(3 + 3 * d + e) * 270] = g[d][e];
         } else
-          lin[3 * 27 + q] = div;
+          lin[3 * 270] = div;
       }
-      const double rho = VAR ? __ldg(A.rho + (size_t)cell * 27 + q) : A.rho0;
-      const double damping = VAR ? __ldg(A.damp + (size_t)cell * 27 + q) : A.damp0;
+      const double rho = VAR ? __ldg(A.rho + q1) : A.rho0;
+      const double damping = VAR ? __ldg(A.damp + q1) : A.damp0;
 #pragma unroll
       for (int d = 0; d < 3; ++d) conv[d] = (conv[d] * rho - damping * u[d]) * jxw;
     }
-    const double tmu = (VAR ? __ldg(A.mu + (size_t)cell * 27 + q) : A.mu0) * A.tau1;
+    const double tmu = (VAR ? __ldg(A.mu + q1) : A.mu0) * A.tau1;
     double S[3][3];
     S[0][1] = S[1][0] = tmu * (g[0][1] + g[1][0]);
     S[0][2] = S[2][0] = tmu * (g[0][2] + g[2][0]);

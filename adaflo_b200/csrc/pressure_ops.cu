@@ -42,8 +42,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) divergence_kernel(cons
   double tp[3];
 #pragma unroll
   for (int qy = 0; qy < 3; ++qy) {
-    const int q = a + 3 * qy + 9 * b;
-    const double jxw = G.at(q, W[a] * W[qy] * W[b]);
+    const double jxw = G.at(a, qy, b, W[a] * W[qy] * W[b]);
     double div = 0;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -52,7 +51,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) divergence_kernel(cons
       G.to_real(r, g);
       div += g[d];
     }
-    const double w = WEIGHT == 0 ? -1.0 : (WEIGHT == 1 ? -P.c0 : -__ldg(P.coeff_q + (size_t)cell * 27 + q));
+    const double w = WEIGHT == 0 ? -1.0 : (WEIGHT == 1 ? -P.c0 : -__ldg(P.coeff_q + coef_index(cell, 0, 1, a, qy, b)));
     tp[qy] = w * div * jxw;
   }
   double outp[2];
@@ -176,9 +175,9 @@ __global__ void __launch_bounds__(128) pressure_kernel(const PArgs P)
     det = row[9];
   }
   double c_cell = P.c0;
-  if (P.coeff_mode == 1) c_cell = 1.0 / (P.coeff_q[(size_t)cell * 27 + 13] + P.c1);
-  if (P.coeff_mode == 3) c_cell = 1.0 / (P.c0 * P.coeff_q[(size_t)cell * 27 + 13]);
-  if (P.coeff_mode == 4) c_cell = P.coeff_q[(size_t)cell * 27 + 13];
+  if (P.coeff_mode == 1) c_cell = 1.0 / (P.coeff_q[coef_index(cell, 0, 1, 1, 1, 1)] + P.c1);
+  if (P.coeff_mode == 3) c_cell = 1.0 / (P.c0 * P.coeff_q[coef_index(cell, 0, 1, 1, 1, 1)]);
+  if (P.coeff_mode == 4) c_cell = P.coeff_q[coef_index(cell, 0, 1, 1, 1, 1)];
 
 #pragma unroll
   for (int qz = 0; qz < NQ1; ++qz)
@@ -192,11 +191,12 @@ __global__ void __launch_bounds__(128) pressure_kernel(const PArgs P)
 #pragma unroll
           for (int f = 0; f < 3; ++f)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) K[f][e] = P.inv_jac[((size_t)cell * 9 + 3 * f + e) * NQ + q];
-          jxw = P.jxw[(size_t)cell * NQ + q];
+            for (int e = 0; e < 3; ++e)
+              K[f][e] = NQ1 == 3 ? P.inv_jac[coef_index(cell, 3 * f + e, 9, qx, qy, qz)] : P.inv_jac[((size_t)cell * 9 + 3 * f + e) * NQ + q];
+          jxw = NQ1 == 3 ? P.jxw[coef_index(cell, 0, 1, qx, qy, qz)] : P.jxw[(size_t)cell * NQ + q];
         } else
           jxw = det * Q1Tables<NQ1>::w(qx) * Q1Tables<NQ1>::w(qy) * Q1Tables<NQ1>::w(qz);
-        const double c = (P.coeff_mode == 2) ? 1.0 / (P.c0 * P.coeff_q[(size_t)cell * 27 + q]) : c_cell;
+        const double c = (P.coeff_mode == 2) ? 1.0 / (P.c0 * P.coeff_q[coef_index(cell, 0, 1, qx, qy, qz)]) : c_cell;
         if (KIND == 0 || KIND == 2) {
           double v = 1.0;
           if (KIND == 0) {

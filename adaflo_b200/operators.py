@@ -322,23 +322,47 @@ class NavierStokesMatrix:
             return None
         return device_view(p.value, n.value, self.ctx.device)
 
+    # Per-quadrature-point coefficient arrays (navier_stokes_matrix.h:162-178,293-395).  On the
+    # device they are decade blocked (adaflo_b200/csrc/common.cuh, coef_index):
+    #   [decade g][row][3 qx + qz][cell in decade][qy]        (n_rows = 1, or 12 for the linearisation)
+    # begin_*() return the raw device views; *_canonical helpers convert to/from the reference
+    # order [cell][row][q], q = qx + 3 qy + 9 qz.
     def begin_densities(self):
-        """[n_cells, 27] view (reference: begin_densities(macro_cell), navier_stokes_matrix.h:162-166)"""
-        t = self._coef(capi.COEF_DENSITY)
-        return None if t is None else t.view(-1, 27)
+        return self._coef(capi.COEF_DENSITY)
 
     def begin_viscosities(self):
-        t = self._coef(capi.COEF_VISCOSITY)
-        return None if t is None else t.view(-1, 27)
+        return self._coef(capi.COEF_VISCOSITY)
 
     def begin_damping_coeff(self):
-        t = self._coef(capi.COEF_DAMPING)
-        return None if t is None else t.view(-1, 27)
+        return self._coef(capi.COEF_DAMPING)
 
     def begin_linearized_velocities(self):
-        """[n_cells, 12, 27] view: rows 0..2 velocity, 3+3d+e = d u_d / d x_e"""
-        t = self._coef(capi.COEF_LINEARIZED_VELOCITY)
-        return None if t is None else t.view(-1, 12, 27)
+        """rows 0..2 velocity, 3+3d+e = d u_d / d x_e"""
+        return self._coef(capi.COEF_LINEARIZED_VELOCITY)
+
+    def to_canonical(self, blocked, n_rows):
+        n_cells = self.matrix_free.mesh.n_cells
+        b = blocked.view(-1, n_rows, 3, 3, 10, 3)             # g, row, qx, qz, cw, qy
+        c = b.permute(0, 4, 1, 3, 5, 2).reshape(-1, n_rows, 27)  # g, cw, row, qz, qy, qx
+        return c[:n_cells]
+
+    def from_canonical(self, canonical, n_rows):
+        n_cells = canonical.shape[0]
+        g = (n_cells + 9) // 10
+        c = torch.zeros(g * 10, n_rows, 27, dtype=torch.float64, device=canonical.device)
+        c[:n_cells] = canonical.reshape(n_cells, n_rows, 27)
+        b = c.view(g, 10, n_rows, 3, 3, 3).permute(0, 2, 5, 3, 1, 4)  # g, row, qx, qz, cw, qy
+        return b.reshape(-1)
+
+    def set_coefficient(self, which, canonical):
+        """which: capi.COEF_*; canonical: [n_cells, 27] (or [n_cells, 12, 27]) device tensor"""
+        n_rows = 12 if which == capi.COEF_LINEARIZED_VELOCITY else 1
+        self._coef(which).copy_(self.from_canonical(canonical, n_rows))
+
+    def get_coefficient(self, which):
+        n_rows = 12 if which == capi.COEF_LINEARIZED_VELOCITY else 1
+        t = self.to_canonical(self._coef(which), n_rows)
+        return t if n_rows == 12 else t.reshape(-1, 27)
 
     def use_variable_coefficients(self):
         return self.parameters.density_diff != 0 or self.parameters.viscosity_diff != 0

@@ -41,9 +41,9 @@ class Pair:
         if var:
             rho, mu, damp = variable_coefficients(mesh, deform)
             self.O.rho[:], self.O.muq[:], self.O.damp[:] = rho, mu, damp
-            self.A.begin_densities().copy_(dev(ctx, rho))
-            self.A.begin_viscosities().copy_(dev(ctx, mu))
-            self.A.begin_damping_coeff().copy_(dev(ctx, damp))
+            self.A.set_coefficient(capi.COEF_DENSITY, dev(ctx, rho))
+            self.A.set_coefficient(capi.COEF_VISCOSITY, dev(ctx, mu))
+            self.A.set_coefficient(capi.COEF_DAMPING, dev(ctx, damp))
         # a smooth linearisation point + seeded noise, produced by the residual on both sides
         m = mesh
         xu = m.u.coords
@@ -90,7 +90,7 @@ def test_residual_then_vmult(ctx, geometry, linearization, var):
     (ru, rp), (gu, gp) = P.residual_both()
     assert rel_err(gu, ru) < TOL and rel_err(gp, rp) < TOL
     if linearization != capi.EXPLICIT:
-        lin_gpu = P.A.begin_linearized_velocities().cpu().numpy()
+        lin_gpu = P.A.get_coefficient(capi.COEF_LINEARIZED_VELOCITY).cpu().numpy()
         rows = 12 if linearization == capi.NEWTON else 4
         assert rel_err(lin_gpu[:, :rows], P.O.lin[:, :rows]) < TOL
     (ou, op), (gu, gp) = P.vmult_both()
