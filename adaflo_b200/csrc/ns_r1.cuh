@@ -27,15 +27,21 @@
 
 namespace ab200 {
 
-constexpr int kR1Warps = 4;                 // warps per block
+constexpr int kR1Warps = 3;                 // warps per block (3 blocks of 3 warps fit the 227 KB shared memory of an SM)
 constexpr int kR1CompSmem = 93;             // three interleaved tiles of one component
 constexpr int kR1CellSmem = 3 * kR1CompSmem + 18 + 10;  // + pressure tile, padded to 307 = 3 (mod 16)
 constexpr int kR1WarpSmem = kGroup * kR1CellSmem;
 
 __device__ __forceinline__ int r1_idx(int qx, int qy, int k) { return k + 3 * qx + 33 * qy; }
 
+// bulk L2 prefetch of a contiguous block (TMA engine, no registers, no LSU wavefronts)
+__device__ __forceinline__ void l2_prefetch(const void *ptr, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
+
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
-__global__ void __launch_bounds__(kR1Warps * 32, 2) ns_vmult_r1_kernel(const NSArgs A)
+__global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSArgs A)
 {
   AB_TABLES_Q2G3
   extern __shared__ double smem[];
@@ -50,6 +56,21 @@ __global__ void __launch_bounds__(kR1Warps * 32, 2) ns_vmult_r1_kernel(const NSA
   const uint32_t cell = (uint32_t)cell_l;
   double *s = smem + warp * kR1WarpSmem + cw * kR1CellSmem;
   double *sp = s + 3 * kR1CompSmem;
+
+  // The per-point streams of this decade are consumed in phase B; ask the L2 for them now so
+  // that their HBM latency overlaps the gather and the in-plane contractions of phase A.
+  if (lane == 0) {
+    if (MODE == MODE_NEWTON || MODE == MODE_PICARD) l2_prefetch(A.lin + g * (12 * 270), (MODE == MODE_NEWTON ? 12 : 4) * 270 * 8);
+    if (VAR) {
+      if (MODE != MODE_STOKES) l2_prefetch(A.rho + g * 270, 270 * 8);
+      if (MODE != MODE_STOKES) l2_prefetch(A.damp + g * 270, 270 * 8);
+      l2_prefetch(A.mu + g * 270, 270 * 8);
+    }
+    if (GEOM == ADAFLO_B200_GEOM_GENERAL) {
+      l2_prefetch(A.inv_jac + g * (9 * 270), 9 * 270 * 8);
+      l2_prefetch(A.jxw + g * 270, 270 * 8);
+    }
+  }
 
   // ---------------------------------------------------------------- phase A
   uint32_t node[9];

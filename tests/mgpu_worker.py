@@ -1,0 +1,111 @@
+"""Worker for the multi-GPU parity test (launched by torchrun, one rank per GPU).
+
+Every rank builds its z-slab of the same global box, runs residual + vmult through the
+C ABI (ghost import / compress(add) / mean projection over NCCL inside the library) and
+compares its owned entries with the single-rank CPU oracle evaluated on the global mesh.
+Exit code 0 = parity within 1e-12.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from adaflo_b200 import capi  # noqa: E402
+from adaflo_b200.mesh import BoxMesh, beltrami_velocity, seeded_uniform  # noqa: E402
+from adaflo_b200.operators import BlockVector, Context, MatrixFree, NavierStokesMatrix  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from helpers import flow_params, time_weights  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
+
+    def bcast(b):
+        obj = [b]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    ctx.init_comm(rank, world, bcast)
+
+    n = (6, 5, 3 * world + 1)
+    mesh = BoxMesh(n, rank=rank, nranks=world)
+    gmesh = BoxMesh(n)
+    dprm, oprm = flow_params(damping=-0.2, tau_grad_div=0.3)
+    dtw, otw = time_weights()
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, old, old_old)
+    A.initialize(mf, dtw, True)
+    O = orc.OracleNavierStokesMatrix(gmesh, oprm, otw)
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+
+    def fields(m, seed_shift=0):
+        u = beltrami_velocity(m.u.coords, 0.1).reshape(-1) + 0.1 * seeded_uniform(m.u.global_ids, 3, 7 + seed_shift)
+        p = seeded_uniform(m.p.global_ids, 1, 8 + seed_shift)
+        return u, p
+
+    def owned(m, sp, vec, ncomp):
+        return vec.reshape(-1, ncomp)[: sp.n_owned]
+
+    def check(name, got_u, got_p, ref_u, ref_p):
+        # compare owned entries against the global oracle vector via global ids
+        gu = ref_u.reshape(-1, 3)[mesh.u.global_ids[: mesh.u.n_owned]]
+        gp = ref_p[mesh.p.global_ids[: mesh.p.n_owned]]
+        eu = np.linalg.norm(owned(mesh, mesh.u, got_u, 3) - gu) / np.linalg.norm(ref_u)
+        ep = np.linalg.norm(got_p[: mesh.p.n_owned] - gp) / np.linalg.norm(ref_p)
+        ok = eu < 1e-12 and ep < 1e-12
+        print(f"[rank {rank}] {name}: rel err u {eu:.2e} p {ep:.2e} {'ok' if ok else 'FAIL'}", flush=True)
+        return ok
+
+    # residual (writes the linearisation point); ghosts of the inputs are imported inside
+    u, p = fields(mesh)
+    Gu, Gp = fields(gmesh)
+    uo, _ = fields(mesh, 10)
+    Guo, _ = fields(gmesh, 10)
+    old.block(0).copy_(dev(uo))
+    old_old.block(0).copy_(dev(uo))
+    O.old_u, O.old_old_u = Guo.copy(), Guo.copy()
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, Gu, Gp, np.zeros(O.n_u), np.zeros(O.n_p))
+    rhs = BlockVector.like(mf)
+    A.residual(rhs, BlockVector(dev(u), dev(p)), BlockVector.like(mf))
+    ok = check("residual", rhs.block(0).cpu().numpy(), rhs.block(1).cpu().numpy(), ru, rp)
+
+    su, sp = seeded_uniform(mesh.u.global_ids, 3, 31), seeded_uniform(mesh.p.global_ids, 1, 32)
+    Gsu, Gsp = seeded_uniform(gmesh.u.global_ids, 3, 31), seeded_uniform(gmesh.p.global_ids, 1, 32)
+    # ghost entries of the source start with garbage: vmult must import them itself
+    su[mesh.u.n_owned * 3:] = 123.0
+    ou, op = O.vmult(Gsu, Gsp)
+    dst = BlockVector.like(mf)
+    A.vmult(dst, BlockVector(dev(su), dev(sp)))
+    ok &= check("vmult", dst.block(0).cpu().numpy(), dst.block(1).cpu().numpy(), ou, op)
+
+    # global dot through the library (all-reduce inside)
+    x = dev(seeded_uniform(mesh.u.global_ids, 3, 41))
+    d = ctx.dot(x, x, mesh.u.n_owned * 3)
+    gx = seeded_uniform(gmesh.u.global_ids, 3, 41)
+    okd = abs(d - float(gx @ gx)) < 1e-11 * float(gx @ gx)
+    print(f"[rank {rank}] dot: {d:.15e} vs {float(gx @ gx):.15e} {'ok' if okd else 'FAIL'}", flush=True)
+    ok &= okd
+
+    flag = torch.tensor([0 if ok else 1], device=ctx.device)
+    dist.all_reduce(flag)
+    A.clear()
+    mf.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(int(flag.item() != 0))
+
+
+if __name__ == "__main__":
+    main()
