@@ -246,8 +246,9 @@ def main():
     value = n_dofs / (ms_per_step * 1e-3)
 
     # ---- e2e: HOST (pinned) vectors through adaflo_b200_ns_vmult_host
-    hu = src.block(0).cpu().pin_memory()
-    hp = src.block(1).cpu().pin_memory()
+    nu_own, np_own = mf.n_owned(0), mf.n_owned(1)
+    hu = src.block(0)[:nu_own].cpu().pin_memory()      # host vectors hold the locally owned range
+    hp = src.block(1)[:np_own].cpu().pin_memory()
     ou, op = torch.empty_like(hu).pin_memory(), torch.empty_like(hp).pin_memory()
     A.vmult_host(ou, op, hu, hp)   # warm-up (allocates staging buffers)
     barrier()
@@ -260,7 +261,6 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_t = float(te[0])
-    nu_own, np_own = mf.n_owned(0), mf.n_owned(1)
     # parity of the two paths (cheap sanity, not timed)
     err = float((ou.to(ctx.device) - dst.block(0)[:nu_own]).norm() / dst.block(0)[:nu_own].norm())
 
@@ -278,7 +278,7 @@ def main():
                        "partition": f"z-slabs x{world}", "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
-                         "kernel": "ns_vmult_kernel<with_p, newton, cartesian>", "kernel_ms": k_avg * 1e3,
+                         "kernel": "ns_vmult_r1_kernel<with_p, newton, cartesian>", "kernel_ms": k_avg * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_dof": B_PER_DOF_N},
             "e2e": {"value": n_dofs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (nu_own + np_own), "d2h_bytes_per_step": 8 * (nu_own + np_own),
                     "ms_per_step": e2e_t * 1e3, "rel_diff_vs_device_path": err},
