@@ -78,6 +78,7 @@ SYMBOLS = [
     "adaflo_b200_ns_coefficient_ptr", "adaflo_b200_ns_nullspace", "adaflo_b200_ns_get_matvec_statistics",
     "adaflo_b200_ns_vmult_host", "adaflo_b200_ns_set_kernel_timing", "adaflo_b200_ns_get_kernel_timing",
     "adaflo_b200_kernel_launch_count",
+    "adaflo_b200_vec_alloc", "adaflo_b200_vec_free", "adaflo_b200_vec_upload", "adaflo_b200_vec_download",
     "adaflo_b200_vec_set", "adaflo_b200_vec_axpy", "adaflo_b200_vec_sadd", "adaflo_b200_vec_scale",
     "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_add_and_dot",
     "adaflo_b200_jacobi_reinit", "adaflo_b200_jacobi_vmult",
@@ -134,6 +135,10 @@ def load():
         "adaflo_b200_ns_vmult_host": [vp, vp, vp, vp, vp],
         "adaflo_b200_ns_set_kernel_timing": [vp, i32],
         "adaflo_b200_ns_get_kernel_timing": [vp, C.POINTER(u64), C.POINTER(dbl)],
+        "adaflo_b200_vec_alloc": [vp, u64, C.POINTER(vp)],
+        "adaflo_b200_vec_free": [vp, vp],
+        "adaflo_b200_vec_upload": [vp, vp, vp, u64],
+        "adaflo_b200_vec_download": [vp, vp, vp, u64],
         "adaflo_b200_vec_set": [vp, vp, dbl, u64],
         "adaflo_b200_vec_axpy": [vp, vp, dbl, vp, u64],
         "adaflo_b200_vec_sadd": [vp, vp, dbl, dbl, vp, u64],

@@ -869,6 +869,39 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
 }
 
 // ------------------------------------------------- Krylov-step vector kernels
+int adaflo_b200_vec_alloc(adaflo_b200_ctx_t ctx, uint64_t n, double **dev_out)
+{
+  if (!ctx || !dev_out) return fail(ADAFLO_B200_ERR_ARG, "vec_alloc: null argument");
+  AB_CUDA(cudaSetDevice(ctx->device));
+  *dev_out = nullptr;
+  if (n == 0) return 0;
+  AB_CUDA(cudaMalloc((void **)dev_out, n * sizeof(double)));
+  AB_CUDA(cudaMemsetAsync(*dev_out, 0, n * sizeof(double), ctx->stream));
+  return 0;
+}
+int adaflo_b200_vec_free(adaflo_b200_ctx_t ctx, double *dev)
+{
+  if (!ctx) return fail(ADAFLO_B200_ERR_ARG, "vec_free: null context");
+  if (dev) {
+    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AB_CUDA(cudaFree(dev));
+  }
+  return 0;
+}
+int adaflo_b200_vec_upload(adaflo_b200_ctx_t ctx, double *dev, const double *host, uint64_t n)
+{
+  if (!ctx || (n && (!dev || !host))) return fail(ADAFLO_B200_ERR_ARG, "vec_upload: null argument");
+  AB_CUDA(cudaMemcpyAsync(dev, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  AB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int adaflo_b200_vec_download(adaflo_b200_ctx_t ctx, double *host, const double *dev, uint64_t n)
+{
+  if (!ctx || (n && (!dev || !host))) return fail(ADAFLO_B200_ERR_ARG, "vec_download: null argument");
+  AB_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  AB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
 int adaflo_b200_vec_set(adaflo_b200_ctx_t ctx, double *x, double v, uint64_t n) { return vec_set(ctx->stream, x, v, n); }
 int adaflo_b200_vec_axpy(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, uint64_t n) { return vec_axpy(ctx->stream, y, a, x, n); }
 int adaflo_b200_vec_sadd(adaflo_b200_ctx_t ctx, double *y, double sc, double a, const double *x, uint64_t n)

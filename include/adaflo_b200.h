@@ -261,6 +261,12 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
  * (source/diagonal_preconditioner.cc:38-124), as bandwidth-bound fused kernels.
  * n counts doubles; results of reductions land in result_dev (device) and are
  * all-reduced over the communicator if one is set. */
+/* device vector storage for host languages without a CUDA runtime binding
+ * (LinearAlgebra::distributed::Vector::reinit / host<->device copies of the adaptor) */
+int adaflo_b200_vec_alloc(adaflo_b200_ctx_t ctx, uint64_t n, double **dev_out);   /* zero initialised */
+int adaflo_b200_vec_free(adaflo_b200_ctx_t ctx, double *dev);
+int adaflo_b200_vec_upload(adaflo_b200_ctx_t ctx, double *dev, const double *host, uint64_t n);   /* synchronous */
+int adaflo_b200_vec_download(adaflo_b200_ctx_t ctx, double *host, const double *dev, uint64_t n); /* synchronous */
 int adaflo_b200_vec_set(adaflo_b200_ctx_t ctx, double *x, double value, uint64_t n);
 int adaflo_b200_vec_axpy(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, uint64_t n);            /* y += a x */
 int adaflo_b200_vec_sadd(adaflo_b200_ctx_t ctx, double *y, double s, double a, const double *x, uint64_t n);  /* y = s y + a x */

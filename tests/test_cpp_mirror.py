@@ -1,0 +1,77 @@
+"""The C++ mirror class (include/adaflo_b200/navier_stokes_matrix.h) driven like the reference
+drives NavierStokesMatrix, checked against the CPU oracle (GPU test; the driver binary is built
+by __graft_entry__.build())."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from adaflo_b200 import capi
+from adaflo_b200.mesh import BoxMesh, beltrami_velocity, seeded_uniform
+from oracle import oracle as orc
+
+from helpers import flow_params, rel_err, time_weights
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRIVER = os.path.join(ROOT, "tests", "cpp", "ns_matrix_driver")
+
+
+def write_dump(path, arrays):
+    with open(path, "wb") as f:
+        for name, a in arrays.items():
+            a = np.ascontiguousarray(a)
+            f.write(struct.pack("<I", len(name)))
+            f.write(name.encode())
+            f.write(struct.pack("<Q", a.nbytes))
+            f.write(a.tobytes())
+
+
+def read_dump(path):
+    out = {}
+    with open(path, "rb") as f:
+        while True:
+            h = f.read(4)
+            if not h:
+                break
+            n = struct.unpack("<I", h)[0]
+            name = f.read(n).decode()
+            nbytes = struct.unpack("<Q", f.read(8))[0]
+            out[name] = np.frombuffer(f.read(nbytes), dtype=np.float64)
+    return out
+
+
+def test_cpp_navier_stokes_matrix_matches_oracle(tmp_path):
+    assert os.path.exists(DRIVER), "build the driver with __graft_entry__.build()"
+    mesh = BoxMesh((5, 4, 3))
+    _, oprm = flow_params(damping=-0.2, tau_grad_div=0.3, viscosity=0.7, density=1.3)
+    _, otw = time_weights()
+    O = orc.OracleNavierStokesMatrix(mesh, oprm, otw)
+    u = beltrami_velocity(mesh.u.coords, 0.1).reshape(-1) + 0.1 * seeded_uniform(mesh.u.global_ids, 3, 7)
+    p = seeded_uniform(mesh.p.global_ids, 1, 8)
+    uo, uoo = seeded_uniform(mesh.u.global_ids, 3, 9), seeded_uniform(mesh.u.global_ids, 3, 10)
+    su, sp = seeded_uniform(mesh.u.global_ids, 3, 11), seeded_uniform(mesh.p.global_ids, 1, 12)
+    table, row = mesh.cartesian_geometry()
+    con = mesh.u.constrained_dofs()
+    write_dump(tmp_path / "in.bin", {
+        "meta": np.array([mesh.n_cells, mesh.u.n_owned, mesh.p.n_owned, len(con)], dtype=np.uint32),
+        "params": np.array([oprm.viscosity, oprm.density, oprm.damping, oprm.tau_grad_div, oprm.beta, otw.weight, otw.weight_old,
+                            otw.weight_old_old, otw.tau1, otw.extrapolate_old, otw.extrapolate_old_old]),
+        "cell_u": mesh.u.encoded_cell_nodes(), "cell_p": mesh.p.encoded_cell_nodes(), "constrained_u": con,
+        "geom_table": table, "geom_row": row, "solution_u": u, "solution_p": p, "old_u": uo, "old_old_u": uoo,
+        "src_u": su, "src_p": sp})
+    r = subprocess.run([DRIVER, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0
+    got = read_dump(tmp_path / "out.bin")
+    O.old_u, O.old_old_u = uo, uoo
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, u, p, np.zeros(O.n_u), np.zeros(O.n_p))
+    O.apply_pressure_average_projection(rp)
+    ou, op = O.vmult(su, sp)
+    assert rel_err(got["residual_u"], ru) < 1e-12 and rel_err(got["residual_p"], rp) < 1e-12
+    assert rel_err(got["vmult_u"], ou) < 1e-12 and rel_err(got["vmult_p"], op) < 1e-12
+    assert abs(got["scalars"][0] - (ou @ su + op @ sp)) < 1e-10 * abs(ou @ su + op @ sp)
+    assert got["scalars"][1] == 1
