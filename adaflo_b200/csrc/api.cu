@@ -2,6 +2,7 @@
 // management, uploads, and the operator-level logic of NavierStokesMatrix
 // (source/navier_stokes_matrix.cc:85-483) around the cell kernels.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 

@@ -51,7 +51,9 @@ __device__ __forceinline__ int tidx(int z, int y, int x) { return z * kPS + y * 
 
 __device__ __forceinline__ void red_add(double *addr, double v)
 {
-  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+  // no "memory" clobber: the destination is never read back by the kernel, and a clobber would
+  // serialise the contraction chains around every scatter
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v));
 }
 
 // ---------------------------------------------------------------- evaluation

@@ -40,6 +40,63 @@ __device__ __forceinline__ void l2_prefetch(const void *ptr, unsigned bytes)
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
 
+// ---------------------------------------------------------------------------
+// Structured 1-D kernels for the Q2 Lagrange basis on {0, 1/2, 1} at the 3 Gauss points.
+// The tables have the rows N[1] = (0, 1, 0), D[1] = (-1, 0, 1) and the symmetries
+// N[2][i] = N[0][2-i], D[2][i] = -D[0][2-i]; written out, a 3x3 apply costs 5-6 flops
+// instead of 9 (IEEE rules forbid the compiler to drop the multiplications by 0 and 1).
+namespace q2 {
+constexpr double a = 0.6872983346207416, b = 0.4, c = -0.08729833462074169;            // N[0][:]
+constexpr double d0 = -2.549193338482967, d1 = 3.0983866769659336, d2 = -0.5491933384829668;  // D[0][:]
+// o = N x
+__device__ __forceinline__ void val(const double x0, const double x1, const double x2, double &o0, double &o1, double &o2)
+{
+  const double t = b * x1;
+  o0 = fma(a, x0, fma(c, x2, t));
+  o1 = x1;
+  o2 = fma(c, x0, fma(a, x2, t));
+}
+// o = D x
+__device__ __forceinline__ void der(const double x0, const double x1, const double x2, double &o0, double &o1, double &o2)
+{
+  const double t = d1 * x1;
+  o0 = fma(d0, x0, fma(d2, x2, t));
+  o1 = x2 - x0;
+  o2 = fma(-d2, x0, fma(-d0, x2, -t));
+}
+// o = N^T i
+__device__ __forceinline__ void val_t(const double i0, const double i1, const double i2, double &o0, double &o1, double &o2)
+{
+  o0 = fma(a, i0, c * i2);
+  o1 = fma(b, i0 + i2, i1);
+  o2 = fma(c, i0, a * i2);
+}
+// o += D^T i
+__device__ __forceinline__ void der_t_add(const double i0, const double i1, const double i2, double &o0, double &o1, double &o2)
+{
+  o0 += fma(d0, i0, fma(-d2, i2, -i1));
+  o1 = fma(d1, i0 - i2, o1);
+  o2 += fma(d2, i0, fma(-d0, i2, i1));
+}
+}  // namespace q2
+
+// pinned (volatile) read-only load: keeps the software prefetch where it is written
+__device__ __forceinline__ double ld_pinned(const double *p)
+{
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+// rows of the linearisation point of quadrature point n = 3 qx + qz of this lane
+template <int MODE>
+__device__ __forceinline__ void load_lin(double (&L)[12], const double *lin_lane, int n)
+{
+  constexpr int rows = MODE == MODE_NEWTON ? 12 : (MODE == MODE_PICARD ? 4 : 0);
+#pragma unroll
+  for (int r = 0; r < rows; ++r) L[r] = ld_pinned(lin_lane + (size_t)r * 270 + n * 30);
+}
+
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
 __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSArgs A)
 {
@@ -72,6 +129,10 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
     }
   }
 
+  const double *lin_lane = A.lin + g * (12 * 270) + lane;
+  Geometry<GEOM> G;  // table row of the cell (two dependent loads): issue before the gather
+  G.init_blk(A, cell);
+
   // ---------------------------------------------------------------- phase A
   uint32_t node[9];
 #pragma unroll
@@ -103,36 +164,26 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      double Y[3][3], Yd[3][3];  // [qy][ix]
+      double Y[3][3], Yd[3][3];  // [qy][ix]: y contraction of the node plane (P index = 3 iy + ix)
 #pragma unroll
-      for (int q = 0; q < 3; ++q)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          double y = 0, yd = 0;
-#pragma unroll
-          for (int m = 0; m < 3; ++m) {
-            y = fma(N[q][m], P[c][3 * m + i], y);
-            yd = fma(D[q][m], P[c][3 * m + i], yd);
-          }
-          Y[q][i] = y;
-          Yd[q][i] = yd;
-        }
+      for (int i = 0; i < 3; ++i) {
+        q2::val(P[c][i], P[c][3 + i], P[c][6 + i], Y[0][i], Y[1][i], Y[2][i]);
+        q2::der(P[c][i], P[c][3 + i], P[c][6 + i], Yd[0][i], Yd[1][i], Yd[2][i]);
+      }
       double *sc = s + c * kR1CompSmem;
 #pragma unroll
-      for (int qy = 0; qy < 3; ++qy)
+      for (int qy = 0; qy < 3; ++qy) {
+        double tv[3], tx[3], ty[3];
+        q2::val(Y[qy][0], Y[qy][1], Y[qy][2], tv[0], tv[1], tv[2]);
+        q2::der(Y[qy][0], Y[qy][1], Y[qy][2], tx[0], tx[1], tx[2]);
+        q2::val(Yd[qy][0], Yd[qy][1], Yd[qy][2], ty[0], ty[1], ty[2]);
 #pragma unroll
         for (int qx = 0; qx < 3; ++qx) {
-          double tv = 0, tx = 0, ty = 0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            tv = fma(N[qx][i], Y[qy][i], tv);
-            tx = fma(D[qx][i], Y[qy][i], tx);
-            ty = fma(N[qx][i], Yd[qy][i], ty);
-          }
-          sc[0 + r1_idx(qx, qy, t)] = tv;
-          sc[9 + r1_idx(qx, qy, t)] = tx;
-          sc[18 + r1_idx(qx, qy, t)] = ty;
+          sc[0 + r1_idx(qx, qy, t)] = tv[qx];
+          sc[9 + r1_idx(qx, qy, t)] = tx[qx];
+          sc[18 + r1_idx(qx, qy, t)] = ty[qx];
         }
+      }
     }
     if (WITH_P && t < 2) {
       double pl[4];
@@ -153,12 +204,16 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   __syncwarp(mask);
 
   // ---------------------------------------------------------------- phase B
-  Geometry<GEOM> G;
-  G.init_blk(A, cell);
   double dg0_sum = 0;
   const double wt = (t == 1) ? W[1] : W[0];  // Gauss weight of qy = t
-#pragma unroll
+  // the line loop stays rolled: a third of the code (instruction cache) and the linearisation
+  // data of a whole line is requested before the shared-memory reads and the z contraction
+#pragma unroll 1
   for (int j = 0; j < 3; ++j) {
+    const double wj = (j == 1) ? W[1] : W[0];
+    double LQ[3][12];
+#pragma unroll
+    for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, 3 * j + qz);
     double val[3][3], dx[3][3], dy[3][3], dz[3][3];  // [c][qz]
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -170,21 +225,10 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
         Tx[k] = sc[9 + k];
         Ty[k] = sc[18 + k];
       }
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        double v = 0, gz = 0, gx = 0, gy = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          if (MODE != MODE_STOKES) v = fma(N[q][k], T[k], v);
-          gz = fma(D[q][k], T[k], gz);
-          gx = fma(N[q][k], Tx[k], gx);
-          gy = fma(N[q][k], Ty[k], gy);
-        }
-        val[c][q] = v;
-        dx[c][q] = gx;
-        dy[c][q] = gy;
-        dz[c][q] = gz;
-      }
+      if (MODE != MODE_STOKES) q2::val(T[0], T[1], T[2], val[c][0], val[c][1], val[c][2]);
+      q2::der(T[0], T[1], T[2], dz[c][0], dz[c][1], dz[c][2]);
+      q2::val(Tx[0], Tx[1], Tx[2], dx[c][0], dx[c][1], dx[c][2]);
+      q2::val(Ty[0], Ty[1], Ty[2], dy[c][0], dy[c][1], dy[c][2]);
     }
     double pv[3] = {0, 0, 0};
     if (WITH_P) {
@@ -198,7 +242,8 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
 #pragma unroll
     for (int qz = 0; qz < 3; ++qz) {
       const size_t slot = cbase + (size_t)qz * 30;
-      const double jxw = G.at_blk(A, g, slot, W[j] * W[qz] * wt);
+      const double(&L)[12] = LQ[qz];
+      const double jxw = G.at_blk(A, g, slot, wj * W[qz] * wt);
       double gr[3][3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
@@ -214,15 +259,14 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
         const double damping = VAR ? __ldg(A.damp + g * 270 + slot) : A.damp0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) conv[d] = A.gamma * u[d];
-        const double *lin = A.lin + g * (12 * 270) + slot;
         if (MODE == MODE_NEWTON) {
           double lu[3], lg[3][3];
 #pragma unroll
-          for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
+          for (int d = 0; d < 3; ++d) lu[d] = L[d];
 #pragma unroll
           for (int d = 0; d < 3; ++d)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) lg[d][e] = __ldg(lin + (3 + 3 * d + e) * 270);
+            for (int e = 0; e < 3; ++e) lg[d][e] = L[3 + 3 * d + e];
           const double ltr = lg[0][0] + lg[1][1] + lg[2][2];
           if (!TRANSPOSE) {
             const double f1 = A.beta * div, f2 = A.beta * ltr;
@@ -252,8 +296,8 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
         } else if (MODE == MODE_PICARD) {
           double lu[3];
 #pragma unroll
-          for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
-          const double ldiv = __ldg(lin + 3 * 270);
+          for (int d = 0; d < 3; ++d) lu[d] = L[d];
+          const double ldiv = L[3];
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             double res = A.beta * ldiv * u[d];
@@ -301,19 +345,16 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       double *sc = s + c * kR1CompSmem + 3 * j + 33 * t;
+      double r[3] = {0, 0, 0}, rx[3], ry[3];
+      if (MODE != MODE_STOKES) q2::val_t(val[c][0], val[c][1], val[c][2], r[0], r[1], r[2]);
+      q2::der_t_add(dz[c][0], dz[c][1], dz[c][2], r[0], r[1], r[2]);
+      q2::val_t(dx[c][0], dx[c][1], dx[c][2], rx[0], rx[1], rx[2]);
+      q2::val_t(dy[c][0], dy[c][1], dy[c][2], ry[0], ry[1], ry[2]);
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        double r = 0, rx = 0, ry = 0;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if (MODE != MODE_STOKES) r = fma(N[q][k], val[c][q], r);
-          r = fma(D[q][k], dz[c][q], r);
-          rx = fma(N[q][k], dx[c][q], rx);
-          ry = fma(N[q][k], dy[c][q], ry);
-        }
-        sc[k] = r;
-        sc[9 + k] = rx;
-        sc[18 + k] = ry;
+        sc[k] = r[k];
+        sc[9 + k] = rx[k];
+        sc[18 + k] = ry[k];
       }
     }
     if (WITH_P) {
@@ -338,32 +379,23 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
         Tx[qx] = sc[9 + r1_idx(qx, qy, t)];
         Ty[qx] = sc[18 + r1_idx(qx, qy, t)];
       }
+      // x contraction back: Y[qy][ix] = N^T T + D^T Tx, Yd[qy][ix] = N^T Ty
+      q2::val_t(T[0], T[1], T[2], Y[qy][0], Y[qy][1], Y[qy][2]);
+      q2::der_t_add(Tx[0], Tx[1], Tx[2], Y[qy][0], Y[qy][1], Y[qy][2]);
+      q2::val_t(Ty[0], Ty[1], Ty[2], Yd[qy][0], Yd[qy][1], Yd[qy][2]);
+    }
+    double o[9];  // o[3 iy + ix] = N^T Y + D^T Yd along y
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double y = 0, yd = 0;
-#pragma unroll
-        for (int qx = 0; qx < 3; ++qx) {
-          y = fma(N[qx][i], T[qx], y);
-          y = fma(D[qx][i], Tx[qx], y);
-          yd = fma(N[qx][i], Ty[qx], yd);
-        }
-        Y[qy][i] = y;
-        Yd[qy][i] = yd;
-      }
+    for (int i = 0; i < 3; ++i) {
+      q2::val_t(Y[0][i], Y[1][i], Y[2][i], o[i], o[3 + i], o[6 + i]);
+      q2::der_t_add(Yd[0][i], Yd[1][i], Yd[2][i], o[i], o[3 + i], o[6 + i]);
     }
 #pragma unroll
-    for (int m = 0; m < 3; ++m)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        double o = 0;
-#pragma unroll
-        for (int qy = 0; qy < 3; ++qy) {
-          o = fma(N[qy][m], Y[qy][i], o);
-          o = fma(D[qy][m], Yd[qy][i], o);
-        }
-        const uint32_t nd = node[3 * m + i];
-        if (!((nd >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) red_add(A.dst_u + 3 * (size_t)(nd & ADAFLO_B200_NODE_MASK) + c, o);
-      }
+    for (int j = 0; j < 9; ++j) {
+      const uint32_t nd = node[j];
+      if (!((nd >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u))
+        red_add(A.dst_u + 3 * (size_t)(nd & ADAFLO_B200_NODE_MASK) + c, o[j]);
+    }
   }
   if (WITH_P && !A.skip_p_test) {
     if (t < 2) {
