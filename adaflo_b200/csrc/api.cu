@@ -71,6 +71,8 @@ static NSArgs make_args(adaflo_b200_ns_t ns, bool use_prec)
   a.cell_p = mf->spaces[ns->dof_p].cell_nodes;
   a.cell_u_blk = mf->spaces[ns->dof_u].cell_nodes_blk;
   a.cell_p_blk = mf->spaces[ns->dof_p].cell_nodes_blk;
+  a.hn_u = mf->spaces[ns->dof_u].hanging_masks;
+  a.hn_p = mf->spaces[ns->dof_p].hanging_masks;
   const bool prec = use_prec && ns->lin_prec;
   a.lin = prec ? ns->lin_prec : ns->lin;
   a.rho = (use_prec && ns->rho_prec) ? ns->rho_prec : ns->rho;
@@ -347,8 +349,8 @@ int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   if (su.degree != 2 || su.n_comp != 3 || su.nodes_per_cell != 27 || sp.degree != 1 || sp.n_comp != 1 ||
       !(sp.nodes_per_cell == 8 || sp.nodes_per_cell == 9) || mf->quads[quad_u].n_q_1d != 3 || mf->quads[quad_p].n_q_1d != 2)
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: only 3-D Taylor-Hood Q2/Q1(+DG0) with QGauss(3)/QGauss(2) is implemented");
-  if (su.hanging_masks || sp.hanging_masks)
-    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: hanging-node masks are not implemented yet");
+  if ((su.hanging_masks != nullptr) != (sp.hanging_masks != nullptr))
+    return fail(ADAFLO_B200_ERR_ARG, "ns_create: hanging-node masks must be given for both spaces or for none");
   AB_CUDA(cudaSetDevice(ctx->device));
   adaflo_b200_ns_t ns = new (std::nothrow) adaflo_b200_ns_s();
   if (!ns) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");
@@ -388,6 +390,7 @@ int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
     pa.n_cells = mf->n_cells;
     pa.np_cell = (int)sp.nodes_per_cell;
     pa.cell_p = sp.cell_nodes;
+    pa.hn_p = sp.hanging_masks;
     pa.dst = pres_mass;
     pa.c0 = 1.0;
     fill_geometry(pa, mf->quads[quad_p]);
@@ -637,6 +640,8 @@ int adaflo_b200_ns_divergence_vmult_add(adaflo_b200_ns_t ns, double *dst_p, cons
   pa.np_cell = (int)sp.nodes_per_cell;
   pa.cell_u = mf->spaces[ns->dof_u].cell_nodes;
   pa.cell_p = sp.cell_nodes;
+  pa.hn_u = mf->spaces[ns->dof_u].hanging_masks;
+  pa.hn_p = sp.hanging_masks;
   pa.src = src_u;
   pa.dst = dst_p;
   pa.resolve = ns->prm.linearization != ADAFLO_B200_PROJECTION;  // :940-943
@@ -658,6 +663,7 @@ static int pressure_common(adaflo_b200_ns_t ns, double *dst_p, const double *src
   pa.n_cells = mf->n_cells;
   pa.np_cell = (int)sp.nodes_per_cell;
   pa.cell_p = sp.cell_nodes;
+  pa.hn_p = sp.hanging_masks;
   pa.src = src_p;
   pa.dst = dst_p;
   fill_geometry(pa, mf->quads[quad]);

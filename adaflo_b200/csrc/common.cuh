@@ -143,6 +143,8 @@ struct NSArgs {
   const uint32_t *cell_p;
   const uint32_t *cell_u_blk;
   const uint32_t *cell_p_blk;
+  const uint32_t *hn_u;  // per-cell refinement masks (null on conforming meshes)
+  const uint32_t *hn_p;
   const double *src_u;
   const double *src_p;
   const double *old_u;
@@ -180,6 +182,8 @@ struct PArgs {
   int np_cell;
   const uint32_t *cell_u;
   const uint32_t *cell_p;
+  const uint32_t *hn_u;
+  const uint32_t *hn_p;
   const double *src;
   double *dst;
   const double *coeff_q;   // per quadrature point [n_cells][n_q] or null

@@ -21,6 +21,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "hanging.cuh"
 
 namespace ab200 {
 
@@ -572,6 +573,7 @@ int launch_vmult_inst(const NSArgs &a, cudaStream_t s)
 template <int GEOM>
 int launch_vmult_geom(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s)
 {
+  if (a.hn_u) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "the v1 vmult kernel has no hanging-node support");
   const bool tr = a.transpose && (mode == MODE_NEWTON || mode == MODE_PICARD);  // other modes are symmetric
   if (tr) {
     if (!with_p) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "transposed velocity block not instantiated");

@@ -23,6 +23,7 @@
 //    each warp-level load reads 240 contiguous bytes (see coef_index in common.cuh).
 #pragma once
 
+#include "hanging.cuh"
 #include "ns_q2q1.cuh"
 
 namespace ab200 {
@@ -97,7 +98,7 @@ __device__ __forceinline__ void load_lin(double (&L)[12], const double *lin_lane
   for (int r = 0; r < rows; ++r) L[r] = ld_pinned(lin_lane + (size_t)r * 270 + n * 30);
 }
 
-template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
+template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
 __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSArgs A)
 {
   AB_TABLES_Q2G3
@@ -132,6 +133,10 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   const double *lin_lane = A.lin + g * (12 * 270) + lane;
   Geometry<GEOM> G;  // table row of the cell (two dependent loads): issue before the gather
   G.init_blk(A, cell);
+  const HnInfo hn(HANGING ? __ldg(A.hn_u + cell) : 0u);
+  const HnInfo hnp(HANGING && WITH_P ? __ldg(A.hn_p + cell) : 0u);
+  const bool hn_z_warp = HANGING && __any_sync(mask, hn.any() && (hn.face(0) || hn.face(1) || hn.edge(2)));
+  const bool hnp_z_warp = HANGING && WITH_P && __any_sync(mask, hnp.any() && (hnp.face(0) || hnp.face(1) || hnp.edge(2)));
 
   // ---------------------------------------------------------------- phase A
   uint32_t node[9];
@@ -162,6 +167,36 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
         P[c][j] = ((flags >> c) & 1u) ? 0.0 : v;
       }
     }
+    if (HANGING) {  // read_dof_values: interpolate the parent's face / edge values onto this cell's nodes
+      if (hn.any()) {
+        // all lines of one direction before the next direction (single lines do not commute)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (hn.line(0, i, t, 3)) {  // x line at iy = i
+#pragma unroll
+            for (int c = 0; c < 3; ++c) hn_q2(hn.sub(0), P[c][3 * i], P[c][3 * i + 1], P[c][3 * i + 2]);
+          }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (hn.line(1, t, i, 3)) {  // y line at ix = i
+#pragma unroll
+            for (int c = 0; c < 3; ++c) hn_q2(hn.sub(1), P[c][i], P[c][3 + i], P[c][6 + i]);
+          }
+      }
+      if (hn_z_warp) {  // z lines live across the 3 lanes of the cell
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const bool need = hn.any() && hn.line(2, j % 3, j / 3, 3);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            double v0 = __shfl_sync(mask, P[c][j], 3 * cw), v1 = __shfl_sync(mask, P[c][j], 3 * cw + 1),
+                   v2 = __shfl_sync(mask, P[c][j], 3 * cw + 2);
+            hn_q2(hn.sub(2), v0, v1, v2);
+            if (need) P[c][j] = t == 0 ? v0 : (t == 1 ? v1 : v2);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       double Y[3][3], Yd[3][3];  // [qy][ix]: y contraction of the node plane (P index = 3 iy + ix)
@@ -185,19 +220,39 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
         }
       }
     }
-    if (WITH_P && t < 2) {
-      double pl[4];
+    if (WITH_P) {
+      double pl[4] = {0, 0, 0, 0};
+      if (t < 2) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double v = A.src_p[pnode[j] & ADAFLO_B200_NODE_MASK];
-        pl[j] = (pnode[j] >> ADAFLO_B200_FLAG_SHIFT) ? 0.0 : v;
+        for (int j = 0; j < 4; ++j) {
+          const double v = A.src_p[pnode[j] & ADAFLO_B200_NODE_MASK];
+          pl[j] = (pnode[j] >> ADAFLO_B200_FLAG_SHIFT) ? 0.0 : v;
+        }
+        if (HANGING && hnp.any()) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (hnp.line(0, i, t, 2)) hn_q1(hnp.sub(0), pl[2 * i], pl[2 * i + 1]);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (hnp.line(1, t, i, 2)) hn_q1(hnp.sub(1), pl[i], pl[2 + i]);
+        }
       }
+      if (hnp_z_warp) {
 #pragma unroll
-      for (int qy = 0; qy < 3; ++qy) {
-        const double y0 = NP[qy][0] * pl[0] + NP[qy][1] * pl[2];  // ix = 0
-        const double y1 = NP[qy][0] * pl[1] + NP[qy][1] * pl[3];  // ix = 1
+        for (int j = 0; j < 4; ++j) {
+          double v0 = __shfl_sync(mask, pl[j], 3 * cw), v1 = __shfl_sync(mask, pl[j], 3 * cw + 1);
+          hn_q1(hnp.sub(2), v0, v1);
+          if (hnp.any() && hnp.line(2, j % 2, j / 2, 2) && t < 2) pl[j] = t == 0 ? v0 : v1;
+        }
+      }
+      if (t < 2) {
 #pragma unroll
-        for (int qx = 0; qx < 3; ++qx) sp[t + 2 * (qx + 3 * qy)] = NP[qx][0] * y0 + NP[qx][1] * y1;
+        for (int qy = 0; qy < 3; ++qy) {
+          const double y0 = NP[qy][0] * pl[0] + NP[qy][1] * pl[2];  // ix = 0
+          const double y1 = NP[qy][0] * pl[1] + NP[qy][1] * pl[3];  // ix = 1
+#pragma unroll
+          for (int qx = 0; qx < 3; ++qx) sp[t + 2 * (qx + 3 * qy)] = NP[qx][0] * y0 + NP[qx][1] * y1;
+        }
       }
     }
   }
@@ -390,6 +445,24 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
       q2::val_t(Y[0][i], Y[1][i], Y[2][i], o[i], o[3 + i], o[6 + i]);
       q2::der_t_add(Yd[0][i], Yd[1][i], Yd[2][i], o[i], o[3 + i], o[6 + i]);
     }
+    if (HANGING) {  // distribute_local_to_global: transposed interpolation onto the parent's nodes
+      if (hn_z_warp) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          double r0 = __shfl_sync(mask, o[j], 3 * cw), r1 = __shfl_sync(mask, o[j], 3 * cw + 1), r2 = __shfl_sync(mask, o[j], 3 * cw + 2);
+          hn_q2_t(hn.sub(2), r0, r1, r2);
+          if (hn.any() && hn.line(2, j % 3, j / 3, 3)) o[j] = t == 0 ? r0 : (t == 1 ? r1 : r2);
+        }
+      }
+      if (hn.any()) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (hn.line(1, t, i, 3)) hn_q2_t(hn.sub(1), o[i], o[3 + i], o[6 + i]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          if (hn.line(0, i, t, 3)) hn_q2_t(hn.sub(0), o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+      }
+    }
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const uint32_t nd = node[j];
@@ -398,6 +471,7 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
     }
   }
   if (WITH_P && !A.skip_p_test) {
+    double o[4] = {0, 0, 0, 0};
     if (t < 2) {
       double y0[3], y1[3];
 #pragma unroll
@@ -406,8 +480,30 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
         y0[qy] = NP[0][0] * a0 + NP[1][0] * a1 + NP[2][0] * a2;
         y1[qy] = NP[0][1] * a0 + NP[1][1] * a1 + NP[2][1] * a2;
       }
-      const double o[4] = {NP[0][0] * y0[0] + NP[1][0] * y0[1] + NP[2][0] * y0[2], NP[0][0] * y1[0] + NP[1][0] * y1[1] + NP[2][0] * y1[2],
-                           NP[0][1] * y0[0] + NP[1][1] * y0[1] + NP[2][1] * y0[2], NP[0][1] * y1[0] + NP[1][1] * y1[1] + NP[2][1] * y1[2]};
+      o[0] = NP[0][0] * y0[0] + NP[1][0] * y0[1] + NP[2][0] * y0[2];
+      o[1] = NP[0][0] * y1[0] + NP[1][0] * y1[1] + NP[2][0] * y1[2];
+      o[2] = NP[0][1] * y0[0] + NP[1][1] * y0[1] + NP[2][1] * y0[2];
+      o[3] = NP[0][1] * y1[0] + NP[1][1] * y1[1] + NP[2][1] * y1[2];
+    }
+    if (HANGING) {
+      if (hnp_z_warp) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double r0 = __shfl_sync(mask, o[j], 3 * cw), r1 = __shfl_sync(mask, o[j], 3 * cw + 1);
+          hn_q1_t(hnp.sub(2), r0, r1);
+          if (hnp.any() && hnp.line(2, j % 2, j / 2, 2) && t < 2) o[j] = t == 0 ? r0 : r1;
+        }
+      }
+      if (hnp.any() && t < 2) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (hnp.line(1, t, i, 2)) hn_q1_t(hnp.sub(1), o[i], o[2 + i]);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          if (hnp.line(0, i, t, 2)) hn_q1_t(hnp.sub(0), o[2 * i], o[2 * i + 1]);
+      }
+    }
+    if (t < 2) {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (!(pnode[j] >> ADAFLO_B200_FLAG_SHIFT)) red_add(A.dst_p + (pnode[j] & ADAFLO_B200_NODE_MASK), o[j]);
@@ -420,10 +516,10 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   }
 }
 
-template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
-int launch_vmult_r1_inst(const NSArgs &a, cudaStream_t s)
+template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
+int launch_vmult_r1_hn(const NSArgs &a, cudaStream_t s)
 {
-  auto kern = ns_vmult_r1_kernel<WITH_P, MODE, GEOM, VAR, TRANSPOSE>;
+  auto kern = ns_vmult_r1_kernel<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>;
   const size_t smem = sizeof(double) * kR1Warps * kR1WarpSmem;
   static bool configured = false;
   if (!configured) {
@@ -438,6 +534,13 @@ int launch_vmult_r1_inst(const NSArgs &a, cudaStream_t s)
   AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
+int launch_vmult_r1_inst(const NSArgs &a, cudaStream_t s)
+{
+  if (a.hn_u) return launch_vmult_r1_hn<WITH_P, MODE, GEOM, VAR, TRANSPOSE, true>(a, s);
+  return launch_vmult_r1_hn<WITH_P, MODE, GEOM, VAR, TRANSPOSE, false>(a, s);
 }
 
 template <int GEOM>

@@ -64,6 +64,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
   double col[3][3];
   uint32_t node[3];
   gather_u(A.cell_u, A.src_u, cell, t9, false, col, node);
+  // hanging nodes: the plain read also needs the interpolated values (the hanging dofs themselves are not stored)
+  const HnInfo hn(A.hn_u ? __ldg(A.hn_u + cell) : 0u), hnp(A.hn_p ? __ldg(A.hn_p + cell) : 0u);
+  const bool hn_warp = A.hn_u && __any_sync(mask, hn.any() || hnp.any());
+  hn_resolve9_u(hn, hn_warp, a, b, 9 * cw, mask, col);
   double pc[2] = {0, 0};
   uint32_t pnode[2] = {0, 0};
   if (a < 2 && b < 2) {
@@ -73,6 +77,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
       pc[k] = A.src_p[pnode[k] & ADAFLO_B200_NODE_MASK];
     }
   }
+  hn_resolve9_p(hnp, hn_warp, a, b, 9 * cw, mask, pc);
   double p_dg0 = 0;
   uint32_t dg0_node = 0;
   if (A.np_cell == 9) {
@@ -101,12 +106,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
     for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int k = 0; k < 3; ++k) cc[c][k] = A.w_old * co[c][k] + A.w_oo * coo[c][k];
+    hn_resolve9_u(hn, hn_warp, a, b, 9 * cw, mask, cc);
     evaluate_u_values(s, a, b, mask, cc, hist);
     if (EXTRAP) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int k = 0; k < 3; ++k) cc[c][k] = A.ex_old * co[c][k] + A.ex_oo * coo[c][k];
+      hn_resolve9_u(hn, hn_warp, a, b, 9 * cw, mask, cc);
       evaluate_u<true>(s, a, b, mask, cc, ev, ex, ey, ez);
     }
   }
@@ -205,10 +212,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
   double out[3][3];
   __syncwarp(mask);
   integrate_u<true>(s, a, b, mask, val, dx, dy, dz, out);
+  hn_distribute9_u(hn, hn_warp, a, b, 9 * cw, mask, out);
   scatter_u(A.dst_u, node, out);
   if (lz != ADAFLO_B200_PROJECTION) {  // :902-907
     double outp[2];
     integrate_p(sp, a, b, mask, tp, outp);
+    hn_distribute9_p(hnp, hn_warp, a, b, 9 * cw, mask, outp);
     if (a < 2 && b < 2) {
 #pragma unroll
       for (int k = 0; k < 2; ++k)

@@ -35,6 +35,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) divergence_kernel(cons
   double col[3][3];
   uint32_t node[3];
   gather_u(P.cell_u, P.src, cell, t9, P.resolve != 0, col, node);
+  const HnInfo hn(P.hn_u ? __ldg(P.hn_u + cell) : 0u), hnp(P.hn_p ? __ldg(P.hn_p + cell) : 0u);
+  const bool hn_warp = P.hn_u && __any_sync(mask, hn.any() || hnp.any());
+  hn_resolve9_u(hn, hn_warp, a, b, 9 * cw, mask, col);
   Geometry<GEOM> G;
   G.init(A, cell);
   double val[3][3], dx[3][3], dy[3][3], dz[3][3];
@@ -56,6 +59,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) divergence_kernel(cons
   }
   double outp[2];
   integrate_p(sp, a, b, mask, tp, outp);
+  hn_distribute9_p(hnp, hn_warp, a, b, 9 * cw, mask, outp);
   if (a < 2 && b < 2) {
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -161,6 +165,25 @@ __global__ void __launch_bounds__(128) pressure_kernel(const PArgs P)
     }
     if (dg0) pl[8] = P.src[pn[8] & ADAFLO_B200_NODE_MASK];
   }
+  const HnInfo hnp(P.hn_p ? __ldg(P.hn_p + cell) : 0u);
+  if (KIND != 2 && hnp.any()) {
+    // all lines of one direction before the next direction (single lines do not commute)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (hnp.line(0, i, j, 2)) hn_q1(hnp.sub(0), pl[2 * i + 4 * j], pl[1 + 2 * i + 4 * j]);   // x line at (iy = i, iz = j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (hnp.line(1, i, j, 2)) hn_q1(hnp.sub(1), pl[j + 4 * i], pl[j + 2 + 4 * i]);           // y line at (iz = i, ix = j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (hnp.line(2, i, j, 2)) hn_q1(hnp.sub(2), pl[i + 2 * j], pl[i + 2 * j + 4]);           // z line at (ix = i, iy = j)
+  }
   // geometry
   double K[3][3] = {{0}}, det = 0;
   if (P.geom == ADAFLO_B200_GEOM_CARTESIAN) {
@@ -258,6 +281,23 @@ __global__ void __launch_bounds__(128) pressure_kernel(const PArgs P)
               }
         }
       }
+  if (hnp.any()) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (hnp.line(2, i, j, 2)) hn_q1_t(hnp.sub(2), out[i + 2 * j], out[i + 2 * j + 4]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (hnp.line(1, i, j, 2)) hn_q1_t(hnp.sub(1), out[j + 4 * i], out[j + 2 + 4 * i]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (hnp.line(0, i, j, 2)) hn_q1_t(hnp.sub(0), out[2 * i + 4 * j], out[1 + 2 * i + 4 * j]);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i)
     if (!(pn[i] >> ADAFLO_B200_FLAG_SHIFT)) red_add(P.dst + (pn[i] & ADAFLO_B200_NODE_MASK), out[i]);

@@ -388,3 +388,234 @@ def linear_deformation(shear=0.15):
         F = np.broadcast_to(A, (X.shape[0], 3, 3)).copy()
         return x, F
     return deform
+
+
+# --------------------------------------------------------------------------
+# two-level meshes with 2:1 hanging nodes (config spurious_currents_ls_3d uses AMR)
+# --------------------------------------------------------------------------
+# Refinement configuration of a cell (adaflo_b200_space_desc.hanging_masks), the information
+# deal.II keeps per cell for its compressed hanging-node scheme: position of the cell in its
+# parent per direction, which of its three outer faces are hanging, and which outer edges are
+# hanging without an adjacent hanging face.
+HN_SUBCELL_X, HN_SUBCELL_Y, HN_SUBCELL_Z = 1, 2, 4
+HN_FACE_X, HN_FACE_Y, HN_FACE_Z = 8, 16, 32
+HN_EDGE_X, HN_EDGE_Y, HN_EDGE_Z = 64, 128, 256
+
+
+class RefinedBoxMesh:
+    """Box of n coarse cells where the coarse cells inside ``refine`` = ((i0,i1),(j0,j1),(k0,k1))
+    are split into 8 children (one level, single rank).  Produces
+
+      * the compressed description the C ABI takes: per-cell node lists in which the slots of a
+        hanging face / edge hold the PARENT's face / edge nodes, plus the per-cell mask;
+      * independently, the plain constraint expansion of every cell-local dof (CSR lists for the
+        oracle), obtained by evaluating the coarse neighbour's Lagrange basis at the hanging node.
+
+    Cells: unrefined coarse cells first (lexicographic), then the children (parent-major)."""
+
+    def __init__(self, n, refine, lower=(-1.0, -1.0, -1.0), upper=(1.0, 1.0, 1.0), dirichlet_faces=(0, 1, 2, 3, 4, 5)):
+        self.dim = 3
+        self.n = tuple(int(v) for v in n)
+        self.lower = np.asarray(lower, dtype=np.float64)
+        self.upper = np.asarray(upper, dtype=np.float64)
+        self.hc = (self.upper - self.lower) / np.asarray(self.n, dtype=np.float64)
+        self.rank, self.nranks = 0, 1
+        nx, ny, nz = self.n
+        refined = np.zeros((nx, ny, nz), dtype=bool)
+        (i0, i1), (j0, j1), (k0, k1) = refine
+        refined[i0:i1, j0:j1, k0:k1] = True
+        self.refined = refined
+        # cells: (level, origin in units of the fine cell size, size in fine cells)
+        cells = []
+        for k in range(nz):
+            for j in range(ny):
+                for i in range(nx):
+                    if not refined[i, j, k]:
+                        cells.append((0, 2 * i, 2 * j, 2 * k, 0, 0, 0))
+        for k in range(nz):
+            for j in range(ny):
+                for i in range(nx):
+                    if refined[i, j, k]:
+                        for c in range(8):
+                            sx, sy, sz = c & 1, (c >> 1) & 1, c >> 2
+                            cells.append((1, 2 * i + sx, 2 * j + sy, 2 * k + sz, sx, sy, sz))
+        self.cells = np.array(cells, dtype=np.int64)
+        self.n_cells = len(cells)
+        self.n_cells_global = self.n_cells
+        self.h_cell = np.where(self.cells[:, 0:1] == 0, self.hc[None, :], 0.5 * self.hc[None, :])
+        self.origin = self.lower[None, :] + 0.5 * self.hc[None, :] * self.cells[:, 1:4]
+        self.u, self.u_lists = self._build_space("u", 2, 3, dirichlet_faces)
+        self.p, self.p_lists = self._build_space("p", 1, 1, ())
+
+    def _is_refined(self, i, j, k):
+        nx, ny, nz = self.n
+        if i < 0 or j < 0 or k < 0 or i >= nx or j >= ny or k >= nz:
+            return None  # outside
+        return bool(self.refined[i, j, k])
+
+    def _build_space(self, name, deg, n_comp, dirichlet_faces):
+        nx, ny, nz = self.n
+        L = 2 * deg                      # lattice steps per coarse cell (fine nodes)
+        NX, NY, NZ = L * nx + 1, L * ny + 1, L * nz + 1
+        n1 = deg + 1
+        npc = n1 ** 3
+        lid = lambda x, y, z: x + NX * (y + NY * z)
+        # lattice points of each cell's nodes
+        step = np.where(self.cells[:, 0] == 0, 2, 1)               # lattice step between nodes of the cell
+        a = np.arange(n1)
+        lz, ly, lx = np.meshgrid(a, a, a, indexing="ij")
+        lx, ly, lz = lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)
+        base = self.cells[:, 1:4] * deg                              # cell origin on the lattice
+        px = base[:, 0:1] + step[:, None] * lx[None, :]
+        py = base[:, 1:2] + step[:, None] * ly[None, :]
+        pz = base[:, 2:3] + step[:, None] * lz[None, :]
+        # a lattice point is hanging if it lies in the closure of an unrefined coarse cell without being its node
+        hanging = np.zeros(NX * NY * NZ, dtype=bool)
+        used = np.zeros(NX * NY * NZ, dtype=bool)
+        used[lid(px, py, pz).reshape(-1)] = True
+        for k in range(nz):
+            for j in range(ny):
+                for i in range(nx):
+                    if self.refined[i, j, k]:
+                        continue
+                    xs, ys, zs = np.meshgrid(np.arange(L * i, L * i + L + 1), np.arange(L * j, L * j + L + 1),
+                                             np.arange(L * k, L * k + L + 1), indexing="ij")
+                    odd = (xs % 2 == 1) | (ys % 2 == 1) | (zs % 2 == 1)
+                    hanging[lid(xs[odd], ys[odd], zs[odd])] = True
+        active = used & ~hanging
+        number = -np.ones(NX * NY * NZ, dtype=np.int64)
+        number[active] = np.arange(active.sum())
+        sp = DofSpace(name, n_comp, npc)
+        sp.n_owned = int(active.sum())
+        sp.n_ghost = 0
+        sp.n_owned_global = sp.n_owned
+        sp.global_ids = np.nonzero(active)[0].astype(np.int64)      # lattice id = partition independent id
+        az, ay, ax = np.unravel_index(sp.global_ids, (NZ, NY, NX))
+        hf = self.hc / L
+        sp.coords = np.stack([self.lower[0] + hf[0] * ax, self.lower[1] + hf[1] * ay, self.lower[2] + hf[2] * az], axis=1)
+        on_face = [ax == 0, ax == NX - 1, ay == 0, ay == NY - 1, az == 0, az == NZ - 1]
+        d = np.zeros(sp.n_owned, dtype=bool)
+        for f in dirichlet_faces:
+            d |= on_face[f]
+        sp.dirichlet = np.repeat(d[:, None], n_comp, axis=1)
+
+        # ---- compressed lists + masks
+        cell_nodes = number[lid(px, py, pz)]                         # -1 on hanging slots
+        masks = np.zeros(self.n_cells, dtype=np.uint32)
+        for c in range(self.n_cells):
+            lvl, ox, oy, oz, sx, sy, sz = self.cells[c]
+            if lvl == 0:
+                continue
+            ci, cj, ck = ox // 2, oy // 2, oz // 2                  # parent coarse cell
+            s = (sx, sy, sz)
+            out = [(-1 if s[d_] == 0 else 1) for d_ in range(3)]    # outward direction of the outer faces
+            nb = lambda dx, dy, dz: self._is_refined(ci + dx, cj + dy, ck + dz)
+            face = [nb(out[0], 0, 0) is False, nb(0, out[1], 0) is False, nb(0, 0, out[2]) is False]
+            # an outer edge along d is hanging if any coarse cell around it is unrefined
+            edge = []
+            for d_ in range(3):
+                e, f = (d_ + 1) % 3, (d_ + 2) % 3
+                off = [0, 0, 0]
+                around = []
+                for se in (0, out[e]):
+                    for sf in (0, out[f]):
+                        off[e], off[f] = se, sf
+                        around.append(nb(*off))
+                edge.append(any(r is False for r in around) and not face[e] and not face[f])
+            m = sx * HN_SUBCELL_X + sy * HN_SUBCELL_Y + sz * HN_SUBCELL_Z
+            m |= face[0] * HN_FACE_X | face[1] * HN_FACE_Y | face[2] * HN_FACE_Z
+            m |= edge[0] * HN_EDGE_X | edge[1] * HN_EDGE_Y | edge[2] * HN_EDGE_Z
+            if not (any(face) or any(edge)):
+                continue
+            masks[c] = m
+            # parent's nodes on the lattice (step 2)
+            pbase = np.array([ci, cj, ck]) * L
+            outer = [0 if s[d_] == 0 else deg for d_ in range(3)]   # local index of the outer face
+            for node in range(npc):
+                l = (node % n1, (node // n1) % n1, node // (n1 * n1))
+                onf = [face[d_] and l[d_] == outer[d_] for d_ in range(3)]
+                one = [edge[d_] and l[(d_ + 1) % 3] == outer[(d_ + 1) % 3] and l[(d_ + 2) % 3] == outer[(d_ + 2) % 3]
+                       for d_ in range(3)]
+                if not (any(onf) or any(one)):
+                    continue
+                # slot holds the parent's node with the same local index on that face / edge; directions
+                # that are not interpolated keep the cell's own lattice position
+                interp_dir = [False, False, False]
+                for d_ in range(3):
+                    if onf[d_]:
+                        interp_dir[(d_ + 1) % 3] = interp_dir[(d_ + 2) % 3] = True
+                    if one[d_]:
+                        interp_dir[d_] = True
+                pos = []
+                for d_ in range(3):
+                    if interp_dir[d_]:
+                        pos.append(pbase[d_] + 2 * l[d_])            # parent's node l[d] along d
+                    else:
+                        pos.append(base[c, d_] + l[d_])              # own position (lies on the parent's boundary)
+                nid = number[lid(pos[0], pos[1], pos[2])]
+                assert nid >= 0, (name, c, node, pos)
+                cell_nodes[c, node] = nid
+        assert cell_nodes.min() >= 0
+        sp.cell_nodes = cell_nodes.astype(np.uint32)
+        sp.hanging_mask = masks
+
+        # ---- independent plain expansion: hanging value = coarse neighbour's interpolant at the point
+        gl = gauss_lobatto_01(n1)
+        ptr = [0]
+        idx, wts = [], []
+        pts = lid(px, py, pz)
+        for c in range(self.n_cells):
+            for comp in range(n_comp):
+                for node in range(npc):
+                    p_l = pts[c, node]
+                    if number[p_l] >= 0:
+                        idx.append(number[p_l] * n_comp + comp)
+                        wts.append(1.0)
+                    else:
+                        x, y, z = px[c, node], py[c, node], pz[c, node]
+                        owner = None
+                        for ci in {(x - 1) // L, min(x // L, nx - 1)}:
+                            for cj in {(y - 1) // L, min(y // L, ny - 1)}:
+                                for ck in {(z - 1) // L, min(z // L, nz - 1)}:
+                                    if self._is_refined(ci, cj, ck) is False and L * ci <= x <= L * ci + L and \
+                                            L * cj <= y <= L * cj + L and L * ck <= z <= L * ck + L:
+                                        owner = (ci, cj, ck)
+                        assert owner is not None
+                        ref = [(x - L * owner[0]) / L, (y - L * owner[1]) / L, (z - L * owner[2]) / L]
+                        V = [lagrange_values(gl, np.array([r]))[0][0] for r in ref]
+                        for kz in range(n1):
+                            for ky in range(n1):
+                                for kx in range(n1):
+                                    w = V[0][kx] * V[1][ky] * V[2][kz]
+                                    if abs(w) > 1e-15:
+                                        q = number[lid(L * owner[0] + 2 * kx, L * owner[1] + 2 * ky, L * owner[2] + 2 * kz)]
+                                        assert q >= 0
+                                        idx.append(q * n_comp + comp)
+                                        wts.append(w)
+                    ptr.append(len(idx))
+        lists = (np.array(ptr, dtype=np.int64), np.array(idx, dtype=np.int64), np.array(wts, dtype=np.float64))
+        return sp, lists
+
+    # ------------------------------------------------------------ geometry
+    def cartesian_geometry(self):
+        table = np.array([[1.0 / self.hc[0], 1.0 / self.hc[1], 1.0 / self.hc[2], np.prod(self.hc)],
+                          [2.0 / self.hc[0], 2.0 / self.hc[1], 2.0 / self.hc[2], np.prod(self.hc) / 8.0]])
+        return table, self.cells[:, 0].astype(np.uint32)
+
+    def general_geometry(self, n_q_1d=3, deform=None):
+        assert deform is None
+        qp, qw = gauss_legendre_01(n_q_1d)
+        qz, qy, qx = np.meshgrid(np.arange(n_q_1d), np.arange(n_q_1d), np.arange(n_q_1d), indexing="ij")
+        w = (qw[qx] * qw[qy] * qw[qz]).reshape(-1)
+        nq = len(w)
+        K = np.zeros((self.n_cells, nq, 3, 3))
+        for d_ in range(3):
+            K[:, :, d_, d_] = 1.0 / self.h_cell[:, d_:d_ + 1]
+        det = np.prod(self.h_cell, axis=1)
+        return np.ascontiguousarray(K), det[:, None] * w[None, :]
+
+    def quadrature_points(self, n_q_1d=3, deform=None):
+        qp, _ = gauss_legendre_01(n_q_1d)
+        qz, qy, qx = np.meshgrid(np.arange(n_q_1d), np.arange(n_q_1d), np.arange(n_q_1d), indexing="ij")
+        xi = np.stack([qp[qx.reshape(-1)], qp[qy.reshape(-1)], qp[qz.reshape(-1)]], axis=1)
+        return self.origin[:, None, :] + self.h_cell[:, None, :] * xi[None, :, :]

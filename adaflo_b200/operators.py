@@ -147,7 +147,13 @@ class MatrixFree:
             d.n_ghost_nodes = sp.n_ghost
             d.nodes_per_cell = sp.nodes_per_cell
             d.cell_nodes = cn.ctypes.data
-            d.hanging_masks = None
+            hm = getattr(sp, "hanging_mask", None)
+            if hm is not None:
+                hm = np.ascontiguousarray(hm.astype(np.uint32))
+                keep.append(hm)
+                d.hanging_masks = hm.ctypes.data
+            else:
+                d.hanging_masks = None
             d.n_constrained = len(con)
             d.constrained_dofs = con.ctypes.data if len(con) else None
             d.n_exchange = len(peers) if n_ex else 0

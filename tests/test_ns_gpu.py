@@ -210,3 +210,68 @@ def test_host_entry_point_matches_device(ctx):
     s, n = P.A.get_matvec_statistics()
     assert n == 1 and s >= 0.0
     P.close()
+
+
+@pytest.mark.parametrize("refine", [((1, 3), (0, 2), (1, 2)), ((0, 1), (0, 1), (0, 1)), ((1, 2), (1, 2), (0, 3))])
+@pytest.mark.parametrize("var", [False, True])
+def test_hanging_nodes(ctx, refine, var):
+    """2:1 refined meshes: in-kernel interpolation (compressed masks) vs the oracle's plain constraint
+    expansion; residual, vmult, Tvmult identity and the sub-block operators."""
+    from adaflo_b200.mesh import RefinedBoxMesh
+    mesh = RefinedBoxMesh((3, 3, 3), refine)
+    kw = dict(density_diff=9.0, viscosity_diff=0.5) if var else {}
+    dprm, oprm = flow_params(damping=-0.2, tau_grad_div=0.3, **kw)
+    dtw, otw = time_weights()
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, old, old_old)
+    A.initialize(mf, dtw, True)
+    O = orc.OracleNavierStokesMatrix(mesh, oprm, otw, None, True, mesh.u_lists, mesh.p_lists)
+    if var:
+        rho, mu, damp = variable_coefficients(mesh)
+        O.rho[:], O.muq[:], O.damp[:] = rho, mu, damp
+        A.set_coefficient(capi.COEF_DENSITY, dev(ctx, rho))
+        A.set_coefficient(capi.COEF_VISCOSITY, dev(ctx, mu))
+        A.set_coefficient(capi.COEF_DAMPING, dev(ctx, damp))
+    m = mesh
+    u = beltrami_velocity(m.u.coords, 0.1).reshape(-1) + 0.1 * seeded_uniform(m.u.global_ids, 3, 7)
+    p = seeded_uniform(m.p.global_ids, 1, 8)
+    uo, uoo = seeded_uniform(m.u.global_ids, 3, 9), seeded_uniform(m.u.global_ids, 3, 10)
+    O.old_u, O.old_old_u = uo.copy(), uoo.copy()
+    old.block(0).copy_(dev(ctx, uo))
+    old_old.block(0).copy_(dev(ctx, uoo))
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, u, p, np.zeros(O.n_u), np.zeros(O.n_p))
+    rhs = BlockVector.like(mf)
+    A.residual(rhs, BlockVector(dev(ctx, u), dev(ctx, p)), BlockVector.like(mf))
+    assert rel_err(rhs.block(0).cpu().numpy(), ru) < TOL and rel_err(rhs.block(1).cpu().numpy(), rp) < TOL
+    su, sp = seeded_uniform(m.u.global_ids, 3, 31), seeded_uniform(m.p.global_ids, 1, 32)
+    ou, op = O.vmult(su, sp)
+    dst = BlockVector.like(mf)
+    src = BlockVector(dev(ctx, su), dev(ctx, sp))
+    A.vmult(dst, src)
+    assert rel_err(dst.block(0).cpu().numpy(), ou) < TOL and rel_err(dst.block(1).cpu().numpy(), op) < TOL
+    # transpose identity
+    y = BlockVector(dev(ctx, seeded_uniform(m.u.global_ids, 3, 63)), dev(ctx, seeded_uniform(m.p.global_ids, 1, 64)))
+    Ay, Atx = BlockVector.like(mf), BlockVector.like(mf)
+    A.vmult(Ay, y)
+    A.Tvmult(Atx, src)
+    lhs = float(Atx.block(0) @ y.block(0) + Atx.block(1) @ y.block(1))
+    rhs_ = float(src.block(0) @ Ay.block(0) + src.block(1) @ Ay.block(1))
+    assert abs(lhs - rhs_) <= 1e-11 * max(abs(lhs), abs(rhs_), 1.0)
+    # sub-block operators
+    du = mf.initialize_dof_vector(0)
+    A.velocity_vmult(du, dev(ctx, su))
+    assert rel_err(du.cpu().numpy(), O.velocity_vmult(su)) < TOL
+    pre = seeded_uniform(m.p.global_ids, 1, 43)
+    o = pre.copy()
+    O.divergence_vmult_add(o, su, var)
+    g = dev(ctx, pre)
+    A.divergence_vmult_add(g, dev(ctx, su), var)
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    for name in ("pressure_mass_vmult", "pressure_poisson_vmult", "pressure_convdiff_vmult"):
+        g = mf.initialize_dof_vector(1)
+        getattr(A, name)(g, dev(ctx, sp))
+        assert rel_err(g.cpu().numpy(), getattr(O, name)(sp)) < TOL, name
+    A.clear()
+    mf.close()
