@@ -49,6 +49,13 @@ class FlowParams(C.Structure):
                 ("beta_convective_term_momentum_balance", C.c_double)]
 
 
+class LSParams(C.Structure):
+    """adaflo_b200_ls_params"""
+    _fields_ = [("dim", C.c_int32), ("concentration_subdivisions", C.c_int32), ("convection_stabilization", C.c_int32),
+                ("reserved", C.c_int32), ("epsilon", C.c_double), ("epsilon_used", C.c_double),
+                ("damping_scale_factor", C.c_double), ("minimal_edge_length", C.c_double)]
+
+
 class TimeWeights(C.Structure):
     """adaflo_b200_time_weights -- the six scalars of adaflo::TimeStepping the kernels read."""
     _fields_ = [("weight", C.c_double), ("weight_old", C.c_double), ("weight_old_old", C.c_double),
@@ -78,6 +85,11 @@ SYMBOLS = [
     "adaflo_b200_ns_coefficient_ptr", "adaflo_b200_ns_nullspace", "adaflo_b200_ns_get_matvec_statistics",
     "adaflo_b200_ns_vmult_host", "adaflo_b200_ns_set_kernel_timing", "adaflo_b200_ns_get_kernel_timing",
     "adaflo_b200_kernel_launch_count",
+    "adaflo_b200_ls_create", "adaflo_b200_ls_destroy", "adaflo_b200_ls_set_time", "adaflo_b200_ls_set_diagonal",
+    "adaflo_b200_ls_mass_diagonal", "adaflo_b200_ls_advance_concentration_vmult", "adaflo_b200_ls_advance_concentration_rhs",
+    "adaflo_b200_ls_compute_normal_vmult", "adaflo_b200_ls_compute_normal_rhs", "adaflo_b200_ls_compute_curvature_vmult",
+    "adaflo_b200_ls_compute_curvature_rhs", "adaflo_b200_ls_curvature_correction", "adaflo_b200_ls_reinitialization_vmult",
+    "adaflo_b200_ls_reinitialization_rhs", "adaflo_b200_ls_pointdata_ptr",
     "adaflo_b200_vec_alloc", "adaflo_b200_vec_free", "adaflo_b200_vec_upload", "adaflo_b200_vec_download",
     "adaflo_b200_vec_set", "adaflo_b200_vec_axpy", "adaflo_b200_vec_sadd", "adaflo_b200_vec_scale",
     "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_add_and_dot",
@@ -135,6 +147,21 @@ def load():
         "adaflo_b200_ns_vmult_host": [vp, vp, vp, vp, vp],
         "adaflo_b200_ns_set_kernel_timing": [vp, i32],
         "adaflo_b200_ns_get_kernel_timing": [vp, C.POINTER(u64), C.POINTER(dbl)],
+        "adaflo_b200_ls_create": [vp, vp, C.POINTER(LSParams), i32, i32, i32, vp, C.POINTER(vp)],
+        "adaflo_b200_ls_destroy": [vp],
+        "adaflo_b200_ls_set_time": [vp, dbl, dbl, dbl, dbl],
+        "adaflo_b200_ls_set_diagonal": [vp, vp],
+        "adaflo_b200_ls_mass_diagonal": [vp, vp],
+        "adaflo_b200_ls_advance_concentration_vmult": [vp, vp, vp],
+        "adaflo_b200_ls_advance_concentration_rhs": [vp, vp, vp, vp, vp, vp],
+        "adaflo_b200_ls_compute_normal_vmult": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "adaflo_b200_ls_compute_normal_rhs": [vp, C.POINTER(vp), vp],
+        "adaflo_b200_ls_compute_curvature_vmult": [vp, vp, vp, i32],
+        "adaflo_b200_ls_compute_curvature_rhs": [vp, vp, C.POINTER(vp)],
+        "adaflo_b200_ls_curvature_correction": [vp, vp, vp],
+        "adaflo_b200_ls_reinitialization_vmult": [vp, vp, vp, i32],
+        "adaflo_b200_ls_reinitialization_rhs": [vp, vp, vp, C.POINTER(vp), i32, i32],
+        "adaflo_b200_ls_pointdata_ptr": [vp, i32, C.POINTER(vp), C.POINTER(u64)],
         "adaflo_b200_vec_alloc": [vp, u64, C.POINTER(vp)],
         "adaflo_b200_vec_free": [vp, vp],
         "adaflo_b200_vec_upload": [vp, vp, vp, u64],

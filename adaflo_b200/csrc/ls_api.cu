@@ -1,0 +1,265 @@
+// ls_api.cu -- C ABI of the level-set operators (include/adaflo_b200.h, "level-set operators"):
+// operator-level logic of LevelSetOKZSolver{AdvanceConcentration, ComputeNormal, ComputeCurvature,
+// Reinitialization}::*_vmult / local_*_rhs around the sub-cell kernels of ls_ops.cu.
+#include <algorithm>
+#include <new>
+
+#include "ls_ops.cuh"
+
+struct adaflo_b200_ls_s {
+  adaflo_b200_ctx_t ctx;
+  adaflo_b200_mf_t mf;
+  adaflo_b200_ls_params prm;
+  int dof_ls, dof_vel, quad_ls;
+  double weight, weight_old, weight_old_old, step_size;
+  double *cell_diameters;      // device
+  double *conv, *normal_q;     // device [cell][sub][3][8]
+  const double *diag;          // not owned
+};
+
+using namespace ab200;
+
+namespace {
+LSArgs base_args(adaflo_b200_ls_t ls)
+{
+  adaflo_b200_mf_t mf = ls->mf;
+  const Space &sp = mf->spaces[ls->dof_ls];
+  const Quad &q = mf->quads[ls->quad_ls];
+  LSArgs a{};
+  a.n_cells = mf->n_cells;
+  a.n_sub = ls->prm.concentration_subdivisions;
+  a.cell_ls = sp.cell_nodes;
+  a.cell_u = ls->dof_vel >= 0 ? mf->spaces[ls->dof_vel].cell_nodes : nullptr;
+  a.geom_row = q.cell_row;
+  a.geom_table = q.table;
+  a.geom = q.geometry_type;
+  a.cell_diameters = ls->cell_diameters;
+  a.gamma = ls->weight;
+  a.w_old = ls->weight_old;
+  a.w_oo = ls->weight_old_old;
+  a.eps_ratio = ls->prm.epsilon_used / ls->prm.epsilon;
+  a.epsilon_used = ls->prm.epsilon_used;
+  const int dim = ls->prm.dim;
+  // reinitialization.cc:65-67
+  a.dtau_inv = std::max(0.95 / (1. / (dim * dim) * ls->prm.minimal_edge_length / ls->prm.concentration_subdivisions), 1. / (5. * ls->step_size));
+  a.n_comp = 1;
+  return a;
+}
+
+int finish_vmult(adaflo_b200_ls_t ls, double *dst, const double *src)
+{
+  const Space &sp = ls->mf->spaces[ls->dof_ls];
+  if (sp.n_constrained) {
+    if (!ls->diag) return fail(ADAFLO_B200_ERR_STATE, "level-set vmult: constrained rows need the preconditioner diagonal (ls_set_diagonal)");
+    AB_CHECK(launch_scaled_copy_indexed(dst, src, ls->diag, sp.constrained, sp.n_constrained, ls->ctx->stream));
+  }
+  return 0;
+}
+
+int zero(adaflo_b200_ls_t ls, double *v)
+{
+  AB_CUDA(cudaMemsetAsync(v, 0, ls->mf->spaces[ls->dof_ls].n_local_entries() * sizeof(double), ls->ctx->stream));
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaflo_b200_ls_params *prm, int dof_ls, int dof_vel,
+                          int quad_ls, const double *cell_diameters_host, adaflo_b200_ls_t *out)
+{
+  if (!ctx || !mf || !prm || !out || !cell_diameters_host) return fail(ADAFLO_B200_ERR_ARG, "ls_create: null argument");
+  if (dof_ls < 0 || dof_ls >= (int)mf->spaces.size() || quad_ls < 0 || quad_ls >= (int)mf->quads.size() || dof_vel >= (int)mf->spaces.size())
+    return fail(ADAFLO_B200_ERR_ARG, "ls_create: dof/quad index out of range");
+  const Space &sp = mf->spaces[dof_ls];
+  const int S = prm->concentration_subdivisions;
+  if (prm->dim != 3 || S < 1 || S > 4 || sp.fe_kind != ADAFLO_B200_FE_Q_ISO_Q1 || sp.degree != S || sp.n_comp != 1 ||
+      sp.nodes_per_cell != (uint32_t)((S + 1) * (S + 1) * (S + 1)) || mf->quads[quad_ls].n_q_1d != 2 * S)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: needs a 3-D FE_Q_iso_Q1(n_sub <= 4) space and the QIterated(QGauss(2), n_sub) quadrature");
+  if (mf->quads[quad_ls].geometry_type == ADAFLO_B200_GEOM_GENERAL)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: general (per-point) geometry is not implemented for the level-set operators");
+  if (sp.hanging_masks) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: hanging nodes are not implemented for the level-set operators");
+  if (prm->convection_stabilization) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: convection_stabilization is not implemented");
+  if (dof_vel >= 0 && (mf->spaces[dof_vel].nodes_per_cell != 27 || mf->spaces[dof_vel].n_comp != 3))
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: the velocity space must be Q2^3");
+  AB_CUDA(cudaSetDevice(ctx->device));
+  adaflo_b200_ls_t ls = new (std::nothrow) adaflo_b200_ls_s();
+  if (!ls) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");
+  ls->ctx = ctx;
+  ls->mf = mf;
+  ls->prm = *prm;
+  ls->dof_ls = dof_ls;
+  ls->dof_vel = dof_vel;
+  ls->quad_ls = quad_ls;
+  ls->weight = 1;
+  ls->weight_old = -1;
+  ls->weight_old_old = 0;
+  ls->step_size = 1;
+  ls->diag = nullptr;
+  const size_t npd = (size_t)mf->n_cells * S * S * S * 24;
+  AB_CUDA(cudaMalloc((void **)&ls->cell_diameters, std::max<size_t>(1, mf->n_cells) * sizeof(double)));
+  AB_CUDA(cudaMemcpyAsync(ls->cell_diameters, cell_diameters_host, mf->n_cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  AB_CUDA(cudaMalloc((void **)&ls->conv, std::max<size_t>(1, npd) * sizeof(double)));
+  AB_CUDA(cudaMalloc((void **)&ls->normal_q, std::max<size_t>(1, npd) * sizeof(double)));
+  AB_CUDA(cudaMemsetAsync(ls->conv, 0, npd * sizeof(double), ctx->stream));
+  AB_CUDA(cudaMemsetAsync(ls->normal_q, 0, npd * sizeof(double), ctx->stream));
+  AB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = ls;
+  return 0;
+}
+
+int adaflo_b200_ls_destroy(adaflo_b200_ls_t ls)
+{
+  if (!ls) return 0;
+  cudaSetDevice(ls->ctx->device);
+  cudaStreamSynchronize(ls->ctx->stream);
+  cudaFree(ls->cell_diameters);
+  cudaFree(ls->conv);
+  cudaFree(ls->normal_q);
+  delete ls;
+  return 0;
+}
+
+int adaflo_b200_ls_set_time(adaflo_b200_ls_t ls, double weight, double weight_old, double weight_old_old, double step_size)
+{
+  if (!ls) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  ls->weight = weight;
+  ls->weight_old = weight_old;
+  ls->weight_old_old = weight_old_old;
+  ls->step_size = step_size;
+  return 0;
+}
+
+int adaflo_b200_ls_set_diagonal(adaflo_b200_ls_t ls, const double *diag)
+{
+  if (!ls) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  ls->diag = diag;
+  return 0;
+}
+
+int adaflo_b200_ls_mass_diagonal(adaflo_b200_ls_t ls, double *diag)
+{
+  if (!ls || !diag) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(zero(ls, diag));
+  LSArgs a = base_args(ls);
+  a.dst[0] = diag;
+  return launch_ls(a, LS_MASS_DIAG, ls->ctx->stream);
+}
+
+int adaflo_b200_ls_advance_concentration_vmult(adaflo_b200_ls_t ls, double *dst, const double *src)
+{
+  if (!ls || !dst || !src) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(zero(ls, dst));
+  LSArgs a = base_args(ls);
+  a.src[0] = src;
+  a.dst[0] = dst;
+  a.pointdata = ls->conv;
+  AB_CHECK(launch_ls(a, LS_ADVECT, ls->ctx->stream));
+  return finish_vmult(ls, dst, src);
+}
+
+int adaflo_b200_ls_advance_concentration_rhs(adaflo_b200_ls_t ls, double *rhs, const double *vel, const double *c, const double *c_old,
+                                             const double *c_old_old)
+{
+  if (!ls || !rhs || !vel || !c || !c_old || !c_old_old) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  if (ls->dof_vel < 0) return fail(ADAFLO_B200_ERR_STATE, "advance_concentration_rhs: no velocity space given at create");
+  LSArgs a = base_args(ls);
+  a.src[0] = c;
+  a.aux[0] = c_old;
+  a.aux[1] = c_old_old;
+  a.vel = vel;
+  a.dst[0] = rhs;
+  a.pointdata = ls->conv;
+  return launch_ls(a, LS_ADVECT_RHS, ls->ctx->stream);
+}
+
+int adaflo_b200_ls_compute_normal_vmult(adaflo_b200_ls_t ls, double *const dst[3], const double *const src[3])
+{
+  if (!ls || !dst || !src) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  LSArgs a = base_args(ls);
+  for (int d = 0; d < 3; ++d) {
+    AB_CHECK(zero(ls, dst[d]));
+    a.src[d] = src[d];
+    a.dst[d] = dst[d];
+  }
+  a.n_comp = 3;
+  a.delta_scale = ls->prm.damping_scale_factor;
+  AB_CHECK(launch_ls(a, LS_DAMPED, ls->ctx->stream));
+  for (int d = 0; d < 3; ++d) AB_CHECK(finish_vmult(ls, dst[d], src[d]));
+  return 0;
+}
+
+int adaflo_b200_ls_compute_normal_rhs(adaflo_b200_ls_t ls, double *const rhs[3], const double *level_set)
+{
+  if (!ls || !rhs || !level_set) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  LSArgs a = base_args(ls);
+  a.src[0] = level_set;
+  for (int d = 0; d < 3; ++d) a.dst[d] = rhs[d];
+  return launch_ls(a, LS_NORMAL_RHS, ls->ctx->stream);
+}
+
+int adaflo_b200_ls_compute_curvature_vmult(adaflo_b200_ls_t ls, double *dst, const double *src, int apply_diffusion)
+{
+  if (!ls || !dst || !src) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(zero(ls, dst));
+  LSArgs a = base_args(ls);
+  a.src[0] = src;
+  a.dst[0] = dst;
+  a.delta_scale = apply_diffusion ? 1.0 : 0.0;
+  AB_CHECK(launch_ls(a, LS_DAMPED, ls->ctx->stream));
+  return finish_vmult(ls, dst, src);
+}
+
+int adaflo_b200_ls_compute_curvature_rhs(adaflo_b200_ls_t ls, double *rhs, const double *const normal[3])
+{
+  if (!ls || !rhs || !normal) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  LSArgs a = base_args(ls);
+  for (int d = 0; d < 3; ++d) a.aux[d] = normal[d];
+  a.dst[0] = rhs;
+  return launch_ls(a, LS_CURV_RHS, ls->ctx->stream);
+}
+
+int adaflo_b200_ls_curvature_correction(adaflo_b200_ls_t ls, double *curvature, const double *level_set)
+{
+  if (!ls || !curvature || !level_set) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  return launch_curvature_correction(curvature, level_set, ls->prm.epsilon_used, ls->prm.dim, ls->mf->spaces[ls->dof_ls].n_owned_entries(),
+                                     ls->ctx->stream);
+}
+
+int adaflo_b200_ls_reinitialization_vmult(adaflo_b200_ls_t ls, double *dst, const double *src, int diffuse_only)
+{
+  if (!ls || !dst || !src) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(zero(ls, dst));
+  LSArgs a = base_args(ls);
+  a.src[0] = src;
+  a.dst[0] = dst;
+  a.pointdata = ls->normal_q;
+  AB_CHECK(launch_ls(a, diffuse_only ? LS_REINIT_DIFFUSE : LS_REINIT, ls->ctx->stream));
+  return finish_vmult(ls, dst, src);
+}
+
+int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const double *solution, const double *const normal[3],
+                                        int diffuse_only, int first_reinit_step)
+{
+  if (!ls || !rhs || !solution) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  if (!diffuse_only && first_reinit_step && !normal) return fail(ADAFLO_B200_ERR_ARG, "reinitialization_rhs: normal field required");
+  LSArgs a = base_args(ls);
+  a.src[0] = solution;
+  if (normal)
+    for (int d = 0; d < 3; ++d) a.aux[d] = normal[d];
+  a.dst[0] = rhs;
+  a.pointdata = ls->normal_q;
+  a.first_step = first_reinit_step;
+  return launch_ls(a, diffuse_only ? LS_REINIT_RHS_DIFFUSE : LS_REINIT_RHS, ls->ctx->stream);
+}
+
+int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_ptr, uint64_t *n)
+{
+  if (!ls || !dev_ptr) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  const int S = ls->prm.concentration_subdivisions;
+  *dev_ptr = which == 0 ? ls->conv : ls->normal_q;
+  if (n) *n = (uint64_t)ls->mf->n_cells * S * S * S * 24;
+  return 0;
+}
+
+}  // extern "C"

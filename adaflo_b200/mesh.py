@@ -186,7 +186,7 @@ class BoxMesh:
             self._append_dg0()
 
     # ---------------------------------------------------------------- spaces
-    def _build_space(self, name, k, n_comp, dirichlet_faces, build_coords):
+    def _build_space(self, name, k, n_comp, dirichlet_faces, build_coords, equidistant=False):
         nx, ny, nz = self.n
         NX, NY, NZ = k * nx + 1, k * ny + 1, k * nz + 1
         z0, z1 = self.z0, self.z1
@@ -231,7 +231,7 @@ class BoxMesh:
         sp.global_ids = (ix_l + NX * (iy_l + NY * iz_l)).astype(np.int64)
         if build_coords:
             # FE_Q support points: Gauss-Lobatto inside each cell (equidistant for k<=2)
-            assert k <= 2
+            assert k <= 2 or equidistant
             sp.coords = np.stack([self.lower[0] + self.h[0] * ix_l / k,
                                   self.lower[1] + self.h[1] * iy_l / k,
                                   self.lower[2] + self.h[2] * iz_l / k], axis=1)
@@ -274,6 +274,18 @@ class BoxMesh:
                                        sp.dirichlet[n_q1_owned:]])
         sp.n_owned = n_q1_owned + self.n_cells
         sp.recv = [(peer, first + shift, cnt) for (peer, first, cnt) in sp.recv]
+
+    def build_ls_space(self, n_sub=3, dirichlet_faces=()):
+        """Level-set space FE_Q_iso_Q1(n_sub) (source/level_set_base.cc:54-60): (n_sub+1)^3 nodes per
+        cell on the uniform (n_sub n + 1)^3 lattice, lexicographic in the cell."""
+        assert self.nranks == 1, "level-set spaces are built for single-rank meshes"
+        self.ls = self._build_space("ls", n_sub, 1, dirichlet_faces, True, equidistant=True)
+        self.ls.n_sub = n_sub
+        return self.ls
+
+    def cell_diameters(self):
+        """compute_cell_diameters (include/adaflo/util.h:47-120): for Cartesian cells the largest edge"""
+        return np.full(self.n_cells, float(self.h.max()))
 
     # -------------------------------------------------------------- geometry
     def cartesian_geometry(self):

@@ -120,8 +120,10 @@ class MatrixFree:
         self.mesh = mesh
         lib = ctx.lib
         keep = []  # keep numpy arrays alive during the call
-        spaces = (capi.SpaceDesc * 2)()
-        for i, sp in enumerate((mesh.u, mesh.p)):
+        ls_space = getattr(mesh, "ls", None)
+        space_list = [mesh.u, mesh.p] + ([ls_space] if ls_space is not None else [])
+        spaces = (capi.SpaceDesc * len(space_list))()
+        for i, sp in enumerate(space_list):
             cn = np.ascontiguousarray(sp.encoded_cell_nodes())
             con = np.ascontiguousarray(sp.constrained_dofs())
             n_ex = len(sp.send) + len(sp.recv)
@@ -140,8 +142,8 @@ class MatrixFree:
                     ex[j].recv_first, ex[j].n_recv = recv[0]
             keep += [cn, con, ex]
             d = spaces[i]
-            d.fe_kind = capi.FE_Q_DG0 if getattr(sp, "n_dg0", 0) else capi.FE_Q
-            d.degree = 2 if i == 0 else 1
+            d.fe_kind = capi.FE_Q_DG0 if getattr(sp, "n_dg0", 0) else (capi.FE_Q_ISO_Q1 if i == 2 else capi.FE_Q)
+            d.degree = 2 if i == 0 else (1 if i == 1 else sp.n_sub)
             d.n_components = sp.n_comp
             d.n_owned_nodes = sp.n_owned
             d.n_ghost_nodes = sp.n_ghost
@@ -158,8 +160,9 @@ class MatrixFree:
             d.constrained_dofs = con.ctypes.data if len(con) else None
             d.n_exchange = len(peers) if n_ex else 0
             d.exchange = ex
-        quads = (capi.QuadDesc * 2)()
-        for i, nq1 in enumerate((3, 2)):
+        quad_sizes = [3, 2] + ([2 * ls_space.n_sub] if ls_space is not None else [])
+        quads = (capi.QuadDesc * len(quad_sizes))()
+        for i, nq1 in enumerate(quad_sizes):
             q = quads[i]
             q.n_q_1d = nq1
             if geometry == "cartesian":
@@ -188,7 +191,7 @@ class MatrixFree:
             q.n_table_rows = table.shape[0]
             q.table = table.ctypes.data
             q.cell_row = row.ctypes.data
-        desc = capi.MFDesc(3, mesh.n_cells, 2, spaces, 2, quads)
+        desc = capi.MFDesc(3, mesh.n_cells, len(space_list), spaces, len(quad_sizes), quads)
         h = C.c_void_p()
         check(lib.adaflo_b200_mf_create(ctx.h, C.byref(desc), C.byref(h)))
         self.h = h
@@ -415,3 +418,86 @@ class DiagonalPreconditioner:
 
     def vmult(self, dst, src, n_blocks=1):
         check(self.ctx.lib.adaflo_b200_jacobi_vmult(self.ctx.h, _ptr(dst), _ptr(src), _ptr(self.inverse_diagonal_vector), self.n, n_blocks))
+
+
+class LevelSetOperators:
+    """The matrix-free operators of adaflo's LevelSetOKZSolver{AdvanceConcentration, ComputeNormal,
+    ComputeCurvature, Reinitialization} (dof handler 2 = level set, quadrature 2 =
+    QIterated(QGauss(2), n_sub): source/two_phase_base.cc:242-271).  Normal fields are lists of three
+    device vectors (the blocks of the reference's BlockVector)."""
+
+    def __init__(self, matrix_free: MatrixFree, parameters: capi.LSParams, cell_diameters, dof_index_ls=2, dof_index_vel=0, quad_index=2):
+        self.matrix_free = matrix_free
+        self.ctx = matrix_free.ctx
+        self.lib = self.ctx.lib
+        self.parameters = parameters
+        cd = np.ascontiguousarray(cell_diameters, dtype=np.float64)
+        h = C.c_void_p()
+        check(self.lib.adaflo_b200_ls_create(self.ctx.h, matrix_free.h, C.byref(parameters), dof_index_ls, dof_index_vel, quad_index,
+                                             _np(cd), C.byref(h)))
+        self.h = h
+        self.dof_index_ls = dof_index_ls
+
+    def close(self):
+        if self.h:
+            self.lib.adaflo_b200_ls_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _blocks(vs):
+        return (C.c_void_p * 3)(*[v.data_ptr() for v in vs])
+
+    def set_time(self, weight, weight_old, weight_old_old, step_size):
+        check(self.lib.adaflo_b200_ls_set_time(self.h, weight, weight_old, weight_old_old, step_size))
+
+    def set_diagonal(self, diag):
+        self._diag = diag
+        check(self.lib.adaflo_b200_ls_set_diagonal(self.h, _ptr(diag)))
+
+    def initialize_mass_matrix_diagonal(self):
+        d = self.matrix_free.initialize_dof_vector(self.dof_index_ls)
+        check(self.lib.adaflo_b200_ls_mass_diagonal(self.h, _ptr(d)))
+        return d
+
+    def advance_concentration_vmult(self, dst, src):
+        check(self.lib.adaflo_b200_ls_advance_concentration_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def advance_concentration_rhs(self, rhs, vel, c, c_old, c_old_old):
+        check(self.lib.adaflo_b200_ls_advance_concentration_rhs(self.h, _ptr(rhs), _ptr(vel), _ptr(c), _ptr(c_old), _ptr(c_old_old)))
+
+    def compute_normal_vmult(self, dst, src):
+        check(self.lib.adaflo_b200_ls_compute_normal_vmult(self.h, self._blocks(dst), self._blocks(src)))
+
+    def compute_normal_rhs(self, rhs, level_set):
+        check(self.lib.adaflo_b200_ls_compute_normal_rhs(self.h, self._blocks(rhs), _ptr(level_set)))
+
+    def compute_curvature_vmult(self, dst, src, apply_diffusion=True):
+        check(self.lib.adaflo_b200_ls_compute_curvature_vmult(self.h, _ptr(dst), _ptr(src), int(apply_diffusion)))
+
+    def compute_curvature_rhs(self, rhs, normal):
+        check(self.lib.adaflo_b200_ls_compute_curvature_rhs(self.h, _ptr(rhs), self._blocks(normal)))
+
+    def curvature_correction(self, curvature, level_set):
+        check(self.lib.adaflo_b200_ls_curvature_correction(self.h, _ptr(curvature), _ptr(level_set)))
+
+    def reinitialization_vmult(self, dst, src, diffuse_only=False):
+        check(self.lib.adaflo_b200_ls_reinitialization_vmult(self.h, _ptr(dst), _ptr(src), int(diffuse_only)))
+
+    def reinitialization_rhs(self, rhs, solution, normal, diffuse_only=False, first_reinit_step=True):
+        blocks = self._blocks(normal) if normal is not None else None
+        check(self.lib.adaflo_b200_ls_reinitialization_rhs(self.h, _ptr(rhs), _ptr(solution), blocks, int(diffuse_only), int(first_reinit_step)))
+
+    def pointdata(self, which):
+        """0: evaluated_convection, 1: evaluated_normal; device view [n_cells, n_sub^3, 3, 8]"""
+        p, n = C.c_void_p(), C.c_uint64()
+        check(self.lib.adaflo_b200_ls_pointdata_ptr(self.h, which, C.byref(p), C.byref(n)))
+        s = self.parameters.concentration_subdivisions
+        return device_view(p.value, n.value, self.ctx.device).view(-1, s ** 3, 3, 8)
+
+    def pointdata_canonical(self, which):
+        """[n_cells, NQ, 3] with q = qx + nq qy + nq^2 qz, the order the oracle uses"""
+        s = self.parameters.concentration_subdivisions
+        t = self.pointdata(which)                               # cell, (sz,sy,sx), comp, (pc,pb,pa)
+        n = t.shape[0]
+        t = t.view(n, s, s, s, 3, 2, 2, 2).permute(0, 1, 5, 2, 6, 3, 7, 4)   # cell, sz,pc, sy,pb, sx,pa, comp
+        return t.reshape(n, (2 * s) ** 3, 3)

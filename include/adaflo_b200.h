@@ -255,6 +255,52 @@ uint64_t adaflo_b200_kernel_launch_count(void);
 int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *dst_p_host,
                               const double *src_u_host, const double *src_p_host);
 
+/* ------------------------------------------------------ level-set operators
+ * The matrix-free operators of LevelSetOKZSolver{AdvanceConcentration, ComputeNormal,
+ * ComputeCurvature, Reinitialization} on FE_Q_iso_Q1(n_sub)
+ * with QIterated(QGauss(2), n_sub); all vectors are device vectors of the level-set space
+ * (normal fields: three block pointers).  Every *_vmult zeroes dst, runs the cell loop and sets
+ * the constrained rows to diag * src (e.g. level_set_okz_reinitialization.cc:227-230). */
+typedef struct adaflo_b200_ls_s *adaflo_b200_ls_t;
+typedef struct {
+  int32_t dim;
+  int32_t concentration_subdivisions; /* n_sub = FE_Q_iso_Q1 degree */
+  int32_t convection_stabilization;   /* must be 0 (the reference default, parameters.cc:360-364) */
+  int32_t reserved;
+  double epsilon;                     /* parameters.epsilon */
+  double epsilon_used;                /* epsilon scaled with the mesh size, as the solver computes it */
+  double damping_scale_factor;        /* LevelSetOKZSolverComputeNormalParameter::damping_scale_factor (4) */
+  double minimal_edge_length;
+} adaflo_b200_ls_params;
+
+int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaflo_b200_ls_params *prm, int dof_index_ls,
+                          int dof_index_vel, int quad_index_ls, const double *cell_diameters_host, adaflo_b200_ls_t *out);
+int adaflo_b200_ls_destroy(adaflo_b200_ls_t ls);
+/* TimeStepping scalars: weight(), weight_old(), weight_old_old() (pass 0 unless BDF-2 and step_no > 1,
+ * advance_concentration.cc:377-380), step_size() */
+int adaflo_b200_ls_set_time(adaflo_b200_ls_t ls, double weight, double weight_old, double weight_old_old, double step_size);
+/* DiagonalPreconditioner::get_vector() used on the constrained rows */
+int adaflo_b200_ls_set_diagonal(adaflo_b200_ls_t ls, const double *diag_dev);
+/* initialize_mass_matrix_diagonal, level_set_okz_preconditioner.h:31-76 */
+int adaflo_b200_ls_mass_diagonal(adaflo_b200_ls_t ls, double *diag_dev);
+/* advance_concentration_vmult :401-480 ; local_advance_concentration_rhs :288-397 (writes evaluated_convection) */
+int adaflo_b200_ls_advance_concentration_vmult(adaflo_b200_ls_t ls, double *dst, const double *src);
+int adaflo_b200_ls_advance_concentration_rhs(adaflo_b200_ls_t ls, double *rhs, const double *vel, const double *c, const double *c_old,
+                                             const double *c_old_old);
+/* compute_normal_vmult :160-183 ; local_compute_normal_rhs :123-156 */
+int adaflo_b200_ls_compute_normal_vmult(adaflo_b200_ls_t ls, double *const dst[3], const double *const src[3]);
+int adaflo_b200_ls_compute_normal_rhs(adaflo_b200_ls_t ls, double *const rhs[3], const double *level_set);
+/* compute_curvature_vmult :263-304 ; local_compute_curvature_rhs :212-259 ; correction :362-377 */
+int adaflo_b200_ls_compute_curvature_vmult(adaflo_b200_ls_t ls, double *dst, const double *src, int apply_diffusion);
+int adaflo_b200_ls_compute_curvature_rhs(adaflo_b200_ls_t ls, double *rhs, const double *const normal[3]);
+int adaflo_b200_ls_curvature_correction(adaflo_b200_ls_t ls, double *curvature, const double *level_set);
+/* reinitialization_vmult :193-231 ; local_reinitialize_rhs :128-189 (freezes the normals when first_reinit_step) */
+int adaflo_b200_ls_reinitialization_vmult(adaflo_b200_ls_t ls, double *dst, const double *src, int diffuse_only);
+int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const double *solution, const double *const normal[3],
+                                        int diffuse_only, int first_reinit_step);
+/* evaluated_convection (which = 0) / evaluated_normal (which = 1): device arrays [cell][sub-cell][3][8 points] */
+int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_ptr, uint64_t *n_doubles);
+
 /* ------------------------------------------------- Krylov-step vector kernels
  * The deal.II vector operations the solvers call between two vmults
  *  and adaflo's DiagonalPreconditioner

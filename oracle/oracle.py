@@ -277,3 +277,111 @@ class OracleNavierStokesMatrix:
         om = self.mu if n_q_1d == 3 else OracleMesh(self.mesh, n_q_1d, deform)
         exact_q = np.ascontiguousarray(exact_q)
         return lib().oracle_l2_error(C.byref(om.c), n_comp, _p(vec), _p(exact_q))
+
+
+# --------------------------------------------------------------------------
+# level-set operators (oracle/ls_oracle.c)
+# --------------------------------------------------------------------------
+class _LSMesh(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("n_sub", C.c_int32), ("cell_nodes", C.c_void_p), ("constrained", C.c_void_p),
+                ("inv_jac", C.c_void_p), ("jxw", C.c_void_p), ("cell_diameters", C.c_void_p)]
+
+
+class LSParams(C.Structure):
+    _fields_ = [("epsilon", C.c_double), ("epsilon_used", C.c_double), ("damping_scale_factor", C.c_double),
+                ("minimal_edge_length", C.c_double), ("step_size", C.c_double), ("dim", C.c_int32), ("pad_", C.c_int32)]
+
+
+_ls_lib = None
+
+
+def ls_lib():
+    global _ls_lib
+    if _ls_lib is None:
+        so = os.path.join(_HERE, "liboracle_ls.so")
+        src = os.path.join(_HERE, "ls_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O2", "-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"])
+        _ls_lib = C.CDLL(so)
+    return _ls_lib
+
+
+def iterated_gauss_geometry(mesh, n_sub, deform=None):
+    """inverse Jacobians and JxW on QIterated(QGauss(2), n_sub) (q = qx + nq qy + nq^2 qz), affine cells"""
+    K1, _ = mesh.general_geometry(1, deform)                   # cell-centre Jacobian (exact for affine cells)
+    nq = (2 * n_sub) ** 3
+    det = 1.0 / np.linalg.det(K1[:, 0])
+    K = np.repeat(K1[:, :1], nq, axis=1)
+    jxw = np.repeat((det / (8.0 * n_sub ** 3))[:, None], nq, axis=1)
+    return np.ascontiguousarray(K), np.ascontiguousarray(jxw)
+
+
+class OracleLevelSet:
+    """Dense CPU restatement of the matrix-free level-set operators on one rank."""
+
+    def __init__(self, mesh, prm: LSParams, deform=None):
+        self.mesh = mesh
+        self.prm = prm
+        ls = mesh.ls
+        self.n_sub = ls.n_sub
+        self.n = ls.n_owned
+        self.NQ = (2 * ls.n_sub) ** 3
+        self.cell_nodes = np.ascontiguousarray(ls.cell_nodes.astype(np.int64))
+        self.con = np.ascontiguousarray(ls.dirichlet.reshape(-1).astype(np.uint8))
+        self.K, self.jxw = iterated_gauss_geometry(mesh, ls.n_sub, deform)
+        self.cd = np.ascontiguousarray(mesh.cell_diameters())
+        self.c = _LSMesh(mesh.n_cells, ls.n_sub, _p(self.cell_nodes), _p(self.con), _p(self.K), _p(self.jxw), _p(self.cd))
+        self.conv = np.zeros((mesh.n_cells, self.NQ, 3))
+        self.normal_q = np.zeros((mesh.n_cells, self.NQ, 3))
+        self.diag = None
+        self.cell_u = np.ascontiguousarray(mesh.u.cell_nodes.astype(np.int64))
+
+    def _constrained_rows(self, dst, src):
+        con = self.mesh.ls.constrained_dofs()
+        if len(con):
+            dst[con] = self.diag[con] * src[con]
+
+    def mass_diagonal(self):
+        d = np.zeros(self.n)
+        ls_lib().ls_oracle_mass_diagonal(C.byref(self.c), _p(d))
+        return d
+
+    def advance_concentration_vmult(self, src, gamma):
+        dst = np.zeros(self.n)
+        ls_lib().ls_oracle_advect(C.byref(self.c), C.c_double(gamma), _p(self.conv), _p(src), _p(dst))
+        self._constrained_rows(dst, src)
+        return dst
+
+    def advance_concentration_rhs(self, rhs, vel, c, c_old, c_oo, gamma, w_old, w_oo):
+        ls_lib().ls_oracle_advect_rhs(C.byref(self.c), _p(self.cell_u), _p(vel), _p(c), _p(c_old), _p(c_oo), C.c_double(gamma),
+                                      C.c_double(w_old), C.c_double(w_oo), _p(rhs), _p(self.conv))
+
+    def _scalar(self, kind, scale, src):
+        dst = np.zeros(self.n)
+        ls_lib().ls_oracle_scalar_op(C.byref(self.c), C.byref(self.prm), kind, C.c_double(scale), _p(self.normal_q), _p(src), _p(dst))
+        self._constrained_rows(dst, src)
+        return dst
+
+    def compute_normal_vmult(self, src):
+        return [self._scalar(0, self.prm.damping_scale_factor, s) for s in src]
+
+    def compute_normal_rhs(self, rhs, level_set):
+        ls_lib().ls_oracle_normal_rhs(C.byref(self.c), _p(level_set), _p(rhs[0]), _p(rhs[1]), _p(rhs[2]))
+
+    def compute_curvature_vmult(self, src, apply_diffusion=True):
+        return self._scalar(0, 1.0 if apply_diffusion else 0.0, src)
+
+    def compute_curvature_rhs(self, rhs, normal):
+        ls_lib().ls_oracle_curvature_rhs(C.byref(self.c), _p(normal[0]), _p(normal[1]), _p(normal[2]), _p(rhs))
+
+    def curvature_correction(self, curvature, level_set):
+        ls_lib().ls_oracle_curvature_correction(C.c_int64(self.n), C.c_double(self.prm.epsilon_used), self.prm.dim, _p(level_set), _p(curvature))
+
+    def reinitialization_vmult(self, src, diffuse_only=False):
+        return self._scalar(2 if diffuse_only else 1, 0.0, src)
+
+    def reinitialization_rhs(self, rhs, solution, normal, diffuse_only=False, first_reinit_step=True):
+        z = np.zeros(self.n)
+        nb = normal if normal is not None else [z, z, z]
+        ls_lib().ls_oracle_reinit_rhs(C.byref(self.c), C.byref(self.prm), int(diffuse_only), int(first_reinit_step), _p(solution),
+                                      _p(nb[0]), _p(nb[1]), _p(nb[2]), _p(self.normal_q), _p(rhs))

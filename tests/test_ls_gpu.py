@@ -1,0 +1,141 @@
+"""GPU parity of the level-set operators vs the dense CPU oracle,
+tolerance 1e-12 relative (fp64)."""
+import numpy as np
+import pytest
+import torch
+
+from adaflo_b200 import capi
+from adaflo_b200.mesh import BoxMesh, beltrami_velocity, seeded_uniform
+from adaflo_b200.operators import LevelSetOperators, MatrixFree
+from oracle import oracle as orc
+
+from helpers import deformation, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def dev(ctx, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+
+
+class LSPair:
+    def __init__(self, ctx, n=(4, 3, 3), n_sub=3, geometry="cartesian", dirichlet_faces=()):
+        self.ctx = ctx
+        self.mesh = mesh = BoxMesh(n, lower=(-1, -1, -1), upper=(1.0, 0.7, 0.5))
+        mesh.build_ls_space(n_sub, dirichlet_faces)
+        deform = deformation(geometry)
+        self.mf = MatrixFree(ctx, mesh, geometry, deform)
+        h_min = float(mesh.h.min())
+        eps, eps_used = 1.5, 1.5 * h_min / n_sub
+        self.dprm = capi.LSParams(3, n_sub, 0, 0, eps, eps_used, 4.0, h_min)
+        self.oprm = orc.LSParams(eps, eps_used, 4.0, h_min, 0.02, 3, 0)
+        cd = mesh.cell_diameters()
+        self.A = LevelSetOperators(self.mf, self.dprm, cd)
+        self.gamma, self.w_old, self.w_oo, self.dt = 75.0, -100.0, 25.0, 0.02
+        self.A.set_time(self.gamma, self.w_old, self.w_oo, self.dt)
+        self.O = orc.OracleLevelSet(mesh, self.oprm, deform)
+        x = mesh.ls.coords if deform is None else deform(mesh.ls.coords)[0]
+        r = np.linalg.norm(x - np.array([0.1, -0.05, -0.2]), axis=1)
+        self.c = -np.tanh((r - 0.45) / (2 * 0.12)) + 0.01 * seeded_uniform(mesh.ls.global_ids, 1, 5)
+        self.n = mesh.ls.n_owned
+        # Jacobi diagonal for constrained rows
+        self.diag = self.O.mass_diagonal()
+        self.O.diag = self.diag
+        self.A.set_diagonal(dev(ctx, self.diag))
+
+    def vec(self, seed):
+        return seeded_uniform(self.mesh.ls.global_ids, 1, seed)
+
+    def close(self):
+        self.A.close()
+        self.mf.close()
+
+
+@pytest.mark.parametrize("geometry", ["cartesian", "affine"])
+@pytest.mark.parametrize("n_sub", [3, 4])
+@pytest.mark.parametrize("dirichlet", [(), (0, 3)])
+def test_level_set_operators(ctx, geometry, n_sub, dirichlet):
+    P = LSPair(ctx, n_sub=n_sub, geometry=geometry, dirichlet_faces=dirichlet)
+    A, O, n = P.A, P.O, P.n
+    # mass diagonal (a18)
+    assert rel_err(A.initialize_mass_matrix_diagonal().cpu().numpy(), P.diag) < TOL
+    # advection: rhs writes the convection velocity, vmult uses it (a11, a12)
+    m = P.mesh
+    vel = beltrami_velocity(m.u.coords, 0.0).reshape(-1) + 0.1 * seeded_uniform(m.u.global_ids, 3, 6)
+    c_old, c_oo = P.c + 0.05 * P.vec(7), P.c + 0.05 * P.vec(8)
+    pre = P.vec(9)
+    o = pre.copy()
+    O.advance_concentration_rhs(o, vel, P.c, c_old, c_oo, P.gamma, P.w_old, P.w_oo)
+    g = dev(ctx, pre)
+    A.advance_concentration_rhs(g, dev(ctx, vel), dev(ctx, P.c), dev(ctx, c_old), dev(ctx, c_oo))
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    assert rel_err(A.pointdata_canonical(0).cpu().numpy(), O.conv) < TOL
+    src = P.vec(10)
+    g = P.mf.initialize_dof_vector(2)
+    g.fill_(5.0)
+    A.advance_concentration_vmult(g, dev(ctx, src))
+    assert rel_err(g.cpu().numpy(), O.advance_concentration_vmult(src, P.gamma)) < TOL
+    # normal (a13)
+    rhs_o = [np.zeros(n) for _ in range(3)]
+    O.compute_normal_rhs(rhs_o, P.c)
+    rhs_g = [P.mf.initialize_dof_vector(2) for _ in range(3)]
+    A.compute_normal_rhs(rhs_g, dev(ctx, P.c))
+    for d in range(3):
+        assert rel_err(rhs_g[d].cpu().numpy(), rhs_o[d]) < TOL
+    nsrc = [P.vec(11 + d) for d in range(3)]
+    ndst = [P.mf.initialize_dof_vector(2) for _ in range(3)]
+    A.compute_normal_vmult(ndst, [dev(ctx, v) for v in nsrc])
+    for d, ref in enumerate(O.compute_normal_vmult(nsrc)):
+        assert rel_err(ndst[d].cpu().numpy(), ref) < TOL
+    # curvature (a14): a smooth normal field = projected gradient stand-in
+    x = m.ls.coords
+    normal = [x[:, d] - [0.1, -0.05, -0.2][d] + 0.02 * P.vec(20 + d) for d in range(3)]
+    normal[0][:5] = 0.0
+    normal[1][:5] = 0.0
+    normal[2][:5] = 1e-3     # |n| <= 1e-2 -> normalised to zero
+    o = np.zeros(n)
+    O.compute_curvature_rhs(o, normal)
+    g = P.mf.initialize_dof_vector(2)
+    A.compute_curvature_rhs(g, [dev(ctx, v) for v in normal])
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    for diff in (True, False):
+        g = P.mf.initialize_dof_vector(2)
+        A.compute_curvature_vmult(g, dev(ctx, src), diff)
+        assert rel_err(g.cpu().numpy(), O.compute_curvature_vmult(src, diff)) < TOL
+    curv = 3.0 * P.vec(30)
+    co = curv.copy()
+    O.curvature_correction(co, P.c)
+    cg = dev(ctx, curv)
+    A.curvature_correction(cg, dev(ctx, P.c))
+    assert rel_err(cg.cpu().numpy(), co) < TOL
+    # reinitialisation (a15): first step freezes the normals, later steps reuse them
+    for first in (True, False):
+        o = np.zeros(n)
+        O.reinitialization_rhs(o, P.c, normal, False, first)
+        g = P.mf.initialize_dof_vector(2)
+        A.reinitialization_rhs(g, dev(ctx, P.c), [dev(ctx, v) for v in normal], False, first)
+        assert rel_err(g.cpu().numpy(), o) < TOL
+    assert rel_err(A.pointdata_canonical(1).cpu().numpy(), O.normal_q) < TOL
+    o = np.zeros(n)
+    O.reinitialization_rhs(o, P.c, None, True, False)
+    g = P.mf.initialize_dof_vector(2)
+    A.reinitialization_rhs(g, dev(ctx, P.c), None, True, False)
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    for diffuse_only in (False, True):
+        g = P.mf.initialize_dof_vector(2)
+        A.reinitialization_vmult(g, dev(ctx, src), diffuse_only)
+        assert rel_err(g.cpu().numpy(), O.reinitialization_vmult(src, diffuse_only)) < TOL
+    P.close()
+
+
+def test_level_set_vmults_are_symmetric_where_the_weak_form_is(ctx):
+    """normal / curvature / reinit operators are symmetric: <A x, y> = <x, A y>"""
+    P = LSPair(ctx)
+    x, y = dev(ctx, P.vec(41)), dev(ctx, P.vec(42))
+    for f in (lambda d, s: P.A.compute_curvature_vmult(d, s, True), lambda d, s: P.A.reinitialization_vmult(d, s, True)):
+        ax, ay = P.mf.initialize_dof_vector(2), P.mf.initialize_dof_vector(2)
+        f(ax, x)
+        f(ay, y)
+        assert abs(float(ax @ y) - float(x @ ay)) < 1e-11 * abs(float(ax @ y))
+    P.close()
