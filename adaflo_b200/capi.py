@@ -89,7 +89,8 @@ SYMBOLS = [
     "adaflo_b200_ls_mass_diagonal", "adaflo_b200_ls_advance_concentration_vmult", "adaflo_b200_ls_advance_concentration_rhs",
     "adaflo_b200_ls_compute_normal_vmult", "adaflo_b200_ls_compute_normal_rhs", "adaflo_b200_ls_compute_curvature_vmult",
     "adaflo_b200_ls_compute_curvature_rhs", "adaflo_b200_ls_curvature_correction", "adaflo_b200_ls_reinitialization_vmult",
-    "adaflo_b200_ls_reinitialization_rhs", "adaflo_b200_ls_pointdata_ptr",
+    "adaflo_b200_ls_reinitialization_rhs", "adaflo_b200_ls_pointdata_ptr", "adaflo_b200_ls_compute_heaviside",
+    "adaflo_b200_ls_compute_force",
     "adaflo_b200_vec_alloc", "adaflo_b200_vec_free", "adaflo_b200_vec_upload", "adaflo_b200_vec_download",
     "adaflo_b200_vec_set", "adaflo_b200_vec_axpy", "adaflo_b200_vec_sadd", "adaflo_b200_vec_scale",
     "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_add_and_dot",
@@ -162,6 +163,8 @@ def load():
         "adaflo_b200_ls_reinitialization_vmult": [vp, vp, vp, i32],
         "adaflo_b200_ls_reinitialization_rhs": [vp, vp, vp, C.POINTER(vp), i32, i32],
         "adaflo_b200_ls_pointdata_ptr": [vp, i32, C.POINTER(vp), C.POINTER(u64)],
+        "adaflo_b200_ls_compute_heaviside": [vp, vp, vp],
+        "adaflo_b200_ls_compute_force": [vp, vp, vp, vp, vp, dbl, dbl, vp],
         "adaflo_b200_vec_alloc": [vp, u64, C.POINTER(vp)],
         "adaflo_b200_vec_free": [vp, vp],
         "adaflo_b200_vec_upload": [vp, vp, vp, u64],

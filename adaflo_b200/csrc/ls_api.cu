@@ -3,6 +3,7 @@
 // Reinitialization}::*_vmult / local_*_rhs around the sub-cell kernels of ls_ops.cu.
 #include <algorithm>
 #include <new>
+#include <vector>
 
 #include "ls_ops.cuh"
 
@@ -15,6 +16,9 @@ struct adaflo_b200_ls_s {
   double *cell_diameters;      // device
   double *conv, *normal_q;     // device [cell][sub][3][8]
   const double *diag;          // not owned
+  uint32_t *last_cell;         // device [n_dofs]: last cell of the cell loop containing the dof (Heaviside)
+  signed char *cell_state;     // device [n_cells]
+  double *interp;              // device [8][N] level set -> pressure interpolation
 };
 
 using namespace ab200;
@@ -103,6 +107,17 @@ int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   AB_CUDA(cudaMalloc((void **)&ls->normal_q, std::max<size_t>(1, npd) * sizeof(double)));
   AB_CUDA(cudaMemsetAsync(ls->conv, 0, npd * sizeof(double), ctx->stream));
   AB_CUDA(cudaMemsetAsync(ls->normal_q, 0, npd * sizeof(double), ctx->stream));
+  {  // Heaviside bookkeeping: the reference loops over cells and the last writer of a shared dof wins
+    const size_t N = sp.nodes_per_cell, n_dofs = sp.n_local_entries();
+    std::vector<uint32_t> cells((size_t)mf->n_cells * N), last(std::max<size_t>(1, n_dofs), 0u);
+    if (!cells.empty()) AB_CUDA(cudaMemcpy(cells.data(), sp.cell_nodes, cells.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (uint32_t c = 0; c < mf->n_cells; ++c)
+      for (size_t i = 0; i < N; ++i) last[cells[c * N + i] & ADAFLO_B200_NODE_MASK] = c;
+    AB_CUDA(cudaMalloc((void **)&ls->last_cell, last.size() * sizeof(uint32_t)));
+    AB_CUDA(cudaMemcpy(ls->last_cell, last.data(), last.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    AB_CUDA(cudaMalloc((void **)&ls->cell_state, std::max<size_t>(1, mf->n_cells)));
+    AB_CUDA(cudaMalloc((void **)&ls->interp, 8 * N * sizeof(double)));
+  }
   AB_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = ls;
   return 0;
@@ -116,6 +131,9 @@ int adaflo_b200_ls_destroy(adaflo_b200_ls_t ls)
   cudaFree(ls->cell_diameters);
   cudaFree(ls->conv);
   cudaFree(ls->normal_q);
+  cudaFree(ls->last_cell);
+  cudaFree(ls->cell_state);
+  cudaFree(ls->interp);
   delete ls;
   return 0;
 }
@@ -251,6 +269,65 @@ int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const 
   a.pointdata = ls->normal_q;
   a.first_step = first_reinit_step;
   return launch_ls(a, diffuse_only ? LS_REINIT_RHS_DIFFUSE : LS_REINIT_RHS, ls->ctx->stream);
+}
+
+int adaflo_b200_ls_compute_heaviside(adaflo_b200_ls_t ls, double *heaviside, const double *level_set)
+{
+  if (!ls || !heaviside || !level_set) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  const Space &sp = ls->mf->spaces[ls->dof_ls];
+  // level_set_okz.cc:516-520: distance scaled by 2 epsilon / concentration_subdivisions
+  const double scale = ls->prm.epsilon * 2. / ls->prm.concentration_subdivisions;
+  return launch_heaviside(sp.cell_nodes, ls->last_cell, ls->cell_state, level_set, heaviside, (int)sp.nodes_per_cell, ls->mf->n_cells,
+                          sp.n_owned_entries(), scale, ls->ctx->stream);
+}
+
+int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, double *dst_u, const double *heaviside, const double *curvature,
+                                 double surface_tension, double gravity, const double *interpolation_host)
+{
+  if (!ls || !ns || !dst_u || !heaviside || !curvature) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  if (ns->mf != ls->mf) return fail(ADAFLO_B200_ERR_ARG, "compute_force: operator and level set must share the MatrixFree data");
+  adaflo_b200_mf_t mf = ls->mf;
+  const Space &sp = mf->spaces[ls->dof_ls], &su = mf->spaces[ns->dof_u];
+  const Quad &q = mf->quads[ns->quad_u];
+  const int S = ls->prm.concentration_subdivisions, n1 = S + 1;
+  ForceArgs f{};
+  f.ns.n_cells = mf->n_cells;
+  f.ns.cell_u = su.cell_nodes;
+  f.ns.hn_u = su.hanging_masks;
+  f.ns.geom_row = q.cell_row;
+  f.ns.geom_table = q.table;
+  f.ns.inv_jac = q.inv_jac;
+  f.ns.jxw = q.jxw;
+  f.ns.dst_u = dst_u;
+  f.cell_ls = sp.cell_nodes;
+  f.n_sub = S;
+  f.heaviside = heaviside;
+  f.curvature = curvature;
+  f.rho_q = ns->var ? ns->rho : nullptr;  // use_variable_parameters, level_set_okz.cc:333-334
+  f.mu_q = ns->var ? ns->mu : nullptr;
+  if (interpolation_host) {
+    AB_CUDA(cudaMemcpyAsync(ls->interp, interpolation_host, 8 * (size_t)n1 * n1 * n1 * sizeof(double), cudaMemcpyHostToDevice, ls->ctx->stream));
+    AB_CUDA(cudaStreamSynchronize(ls->ctx->stream));
+    f.interp = ls->interp;
+  }
+  const double gp[3] = {0.11270166537925831, 0.5, 0.8872983346207417};
+  for (int p = 0; p < 3; ++p) {
+    for (int i = 0; i < 5; ++i) f.hat_v[p][i] = f.hat_d[p][i] = 0;
+    int s = (int)(gp[p] * S);
+    if (s > S - 1) s = S - 1;  // piecewise polynomials are evaluated on the interval [s/S, (s+1)/S)
+    const double xi = gp[p] * S - s;
+    f.hat_v[p][s] = 1 - xi;
+    f.hat_v[p][s + 1] = xi;
+    f.hat_d[p][s] = -(double)S;
+    f.hat_d[p][s + 1] = (double)S;
+  }
+  f.surface_tension = surface_tension;
+  f.gravity = gravity;
+  f.density = ns->prm.density;
+  f.density_diff = ns->prm.density_diff;
+  f.viscosity = ns->prm.viscosity;
+  f.viscosity_diff = ns->prm.viscosity_diff;
+  return launch_ls_force(f, q.geometry_type, ls->ctx->stream);
 }
 
 int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_ptr, uint64_t *n)

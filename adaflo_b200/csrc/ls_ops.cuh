@@ -28,7 +28,21 @@ struct LSArgs {
   int n_comp;
 };
 
+struct ForceArgs {
+  NSArgs ns;                 // geometry, cell_u, hanging masks, dst_u
+  const uint32_t *cell_ls;   // [n_cells][n1^3]
+  int n_sub;
+  const double *heaviside, *curvature;
+  double *rho_q, *mu_q;      // decade blocked, may be null (constant coefficients)
+  const double *interp;      // [8][n1^3] level set -> pressure interpolation or null
+  double hat_v[3][5], hat_d[3][5];  // FE_Q_iso_Q1 hats and derivatives at the 3 Gauss points
+  double surface_tension, gravity, density, density_diff, viscosity, viscosity_diff;
+};
+
 int launch_ls(const LSArgs &a, int op, cudaStream_t s);
+int launch_ls_force(const ForceArgs &f, int geom, cudaStream_t s);
+int launch_heaviside(const uint32_t *cell_ls, const uint32_t *last_cell, signed char *cell_state, const double *c, double *heaviside, int N,
+                     uint32_t n_cells, uint64_t n_dofs, double scale, cudaStream_t s);
 int launch_curvature_correction(double *curv, const double *ls, double eps_used, int dim, uint64_t n, cudaStream_t s);
 int launch_scaled_copy_indexed(double *dst, const double *src, const double *diag, const uint32_t *idx, uint32_t n, cudaStream_t s);
 

@@ -487,6 +487,14 @@ class LevelSetOperators:
         blocks = self._blocks(normal) if normal is not None else None
         check(self.lib.adaflo_b200_ls_reinitialization_rhs(self.h, _ptr(rhs), _ptr(solution), blocks, int(diffuse_only), int(first_reinit_step)))
 
+    def compute_heaviside(self, heaviside, level_set):
+        check(self.lib.adaflo_b200_ls_compute_heaviside(self.h, _ptr(heaviside), _ptr(level_set)))
+
+    def compute_force(self, navier_stokes_matrix, dst_u, heaviside, curvature, surface_tension, gravity, interpolation=None):
+        ip = None if interpolation is None else np.ascontiguousarray(interpolation, dtype=np.float64)
+        check(self.lib.adaflo_b200_ls_compute_force(self.h, navier_stokes_matrix.h, _ptr(dst_u), _ptr(heaviside), _ptr(curvature),
+                                                    float(surface_tension), float(gravity), _np(ip)))
+
     def pointdata(self, which):
         """0: evaluated_convection, 1: evaluated_normal; device view [n_cells, n_sub^3, 3, 8]"""
         p, n = C.c_void_p(), C.c_uint64()

@@ -298,6 +298,15 @@ int adaflo_b200_ls_curvature_correction(adaflo_b200_ls_t ls, double *curvature, 
 int adaflo_b200_ls_reinitialization_vmult(adaflo_b200_ls_t ls, double *dst, const double *src, int diffuse_only);
 int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const double *solution, const double *const normal[3],
                                         int diffuse_only, int first_reinit_step);
+/* LevelSetOKZSolver::compute_heaviside, level_set_okz.cc:479-540 (dof-wise; a dof shared by several cells takes
+ * the value of the last cell in the cell order of the uploaded lists, as the reference's cell loop does) */
+int adaflo_b200_ls_compute_heaviside(adaflo_b200_ls_t ls, double *heaviside, const double *level_set);
+/* LevelSetOKZSolver::local_compute_force, level_set_okz.cc:317-409: dst_u += (v, sigma kappa grad(H) - g rho e_z);
+ * writes rho_q, mu_q of the operator when it uses variable coefficients.  interpolation_host: the
+ * [8][n_ls_dofs_per_cell] matrix interpolation_concentration_pressure (level_set_base.cc:65-137) if
+ * interpolate_grad_onto_pressure, else NULL */
+int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, double *dst_u, const double *heaviside, const double *curvature,
+                                 double surface_tension, double gravity, const double *interpolation_host);
 /* evaluated_convection (which = 0) / evaluated_normal (which = 1): device arrays [cell][sub-cell][3][8 points] */
 int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_ptr, uint64_t *n_doubles);
 

@@ -310,3 +310,84 @@ void ls_oracle_curvature_correction(int64_t n, double epsilon_used, int dim, con
       curvature[i] = 1. / (1. / curvature[i] + distance / (dim - 1));
     }
 }
+
+/* LevelSetOKZSolver::local_compute_force, level_set_okz.cc:317-409, dense.  Geometry arrays on QGauss(3):
+ * inv_jac [n_cells][27][9], jxw [n_cells][27]; cell_u [n_cells][27] velocity nodes (entry = 3 node + comp);
+ * interp: [8][N] level set -> pressure interpolation or NULL. rho_q / mu_q [n_cells][27] written if variable. */
+int ls_oracle_force(int n_cells, int n_sub, const int64_t *cell_ls, const int64_t *cell_u, const uint8_t *u_constrained,
+                    const double *inv_jac, const double *jxw, const double *heaviside, const double *curvature, double sigma,
+                    double gravity, double rho0, double drho, double mu0, double dmu, int variable, const double *interp,
+                    double *dst_u, double *rho_q, double *mu_q)
+{
+  const int n1 = n_sub + 1, N = n1 * n1 * n1;
+  const real s35 = sqrtl(0.6L);
+  const real gp[3] = {0.5L - 0.5L * s35, 0.5L, 0.5L + 0.5L * s35};
+  real hv[3][MAXN1], hd[3][MAXN1], L2[3][3];
+  for (int p = 0; p < 3; ++p) {
+    for (int i = 0; i < n1; ++i) hv[p][i] = hd[p][i] = 0;
+    int s = (int)(gp[p] * n_sub);
+    if (s > n_sub - 1) s = n_sub - 1;
+    const real xi = gp[p] * n_sub - s;
+    hv[p][s] = 1 - xi; hv[p][s + 1] = xi; hd[p][s] = -(real)n_sub; hd[p][s + 1] = (real)n_sub;
+    const real x = gp[p];
+    L2[p][0] = 2 * (x - 0.5L) * (x - 1); L2[p][1] = 4 * x * (1 - x); L2[p][2] = 2 * x * (x - 0.5L);
+  }
+  real *out = malloc(sizeof(real) * 81);
+  for (int cell = 0; cell < n_cells; ++cell) {
+    const int64_t *cl = cell_ls + (int64_t)cell * N;
+    real hp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (interp)
+      for (int i = 0; i < 8; ++i)
+        for (int j = 0; j < N; ++j) hp[i] += (real)interp[i * N + j] * (real)heaviside[cl[j]];
+    for (int i = 0; i < 81; ++i) out[i] = 0;
+    for (int q = 0; q < 27; ++q) {
+      const int qx = q % 3, qy = (q / 3) % 3, qz = q / 9;
+      real H = 0, kap = 0, gr[3] = {0, 0, 0};
+      for (int k = 0; k < n1; ++k)
+        for (int j = 0; j < n1; ++j)
+          for (int i = 0; i < n1; ++i) {
+            const int64_t d = cl[i + n1 * (j + n1 * k)];
+            const real w = hv[qx][i] * hv[qy][j] * hv[qz][k];
+            H += w * (real)heaviside[d];
+            kap += w * (real)curvature[d];
+            gr[0] += hd[qx][i] * hv[qy][j] * hv[qz][k] * (real)heaviside[d];
+            gr[1] += hv[qx][i] * hd[qy][j] * hv[qz][k] * (real)heaviside[d];
+            gr[2] += hv[qx][i] * hv[qy][j] * hd[qz][k] * (real)heaviside[d];
+          }
+      if (interp) {
+        gr[0] = gr[1] = gr[2] = 0;
+        for (int i = 0; i < 8; ++i) {
+          const real vx = (i & 1) ? gp[qx] : 1 - gp[qx], vy = (i & 2) ? gp[qy] : 1 - gp[qy], vz = (i & 4) ? gp[qz] : 1 - gp[qz];
+          gr[0] += ((i & 1) ? 1 : -1) * vy * vz * hp[i];
+          gr[1] += vx * ((i & 2) ? 1 : -1) * vz * hp[i];
+          gr[2] += vx * vy * ((i & 4) ? 1 : -1) * hp[i];
+        }
+      }
+      const double *K = inv_jac + ((int64_t)cell * 27 + q) * 9;
+      const real JxW = jxw[(int64_t)cell * 27 + q];
+      real g[3];
+      for (int e = 0; e < 3; ++e) g[e] = gr[0] * (real)K[e] + gr[1] * (real)K[3 + e] + gr[2] * (real)K[6 + e];
+      real rho = rho0;
+      if (variable) {
+        rho = rho0 + drho * H;
+        rho_q[(int64_t)cell * 27 + q] = (double)rho;
+        mu_q[(int64_t)cell * 27 + q] = (double)(mu0 + dmu * H);
+      }
+      real f[3];
+      for (int d = 0; d < 3; ++d) f[d] = sigma * kap * g[d];
+      f[2] -= gravity * rho;
+      for (int n = 0; n < 27; ++n) {
+        const real phiu = L2[qx][n % 3] * L2[qy][(n / 3) % 3] * L2[qz][n / 9];
+        for (int d = 0; d < 3; ++d) out[d * 27 + n] += phiu * f[d] * JxW;
+      }
+    }
+    for (int n = 0; n < 27; ++n)
+      for (int d = 0; d < 3; ++d) {
+        const int64_t e = 3 * cell_u[(int64_t)cell * 27 + n] + d;
+        if (u_constrained && u_constrained[e]) continue;
+        dst_u[e] += (double)out[d * 27 + n];
+      }
+  }
+  free(out);
+  return 0;
+}

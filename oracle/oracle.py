@@ -385,3 +385,47 @@ class OracleLevelSet:
         nb = normal if normal is not None else [z, z, z]
         ls_lib().ls_oracle_reinit_rhs(C.byref(self.c), C.byref(self.prm), int(diffuse_only), int(first_reinit_step), _p(solution),
                                       _p(nb[0]), _p(nb[1]), _p(nb[2]), _p(self.normal_q), _p(rhs))
+
+
+def discrete_heaviside(x):
+    """include/adaflo/level_set_base.h:122-145"""
+    if x > 0:
+        return 1.0 - discrete_heaviside(-x)
+    if x < -2.0:
+        return 0.0
+    if x < -1.0:
+        return (1. / 8. * (5. * x + x * x) + 1. / 32. * (-3. - 2. * x) * np.sqrt(-7. - 12. * x - 4. * x * x)
+                - 1. / 16 * np.arcsin(np.sqrt(2.) * (x + 3. / 2.)) + 23. / 32. - np.pi / 64.)
+    return (1. / 8. * (3. * x + x * x) - 1. / 32. * (-1. - 2. * x) * np.sqrt(1. - 4. * x - 4. * x * x)
+            + 1. / 16 * np.arcsin(np.sqrt(2.) * (x + 1. / 2.)) + 15. / 32. - np.pi / 64.)
+
+
+def compute_heaviside(cell_nodes, level_set, epsilon, n_sub):
+    """LevelSetOKZSolver::compute_heaviside, source/level_set_okz.cc:479-540 (cell loop, last writer wins)"""
+    cutoff = np.tanh(2.0)
+    H = np.zeros_like(level_set)
+    for nodes in cell_nodes:
+        loc = level_set[nodes]
+        if np.any(np.abs(loc) < cutoff):
+            for i, c in zip(nodes, loc):
+                d = -3.0 if c < -cutoff else (3.0 if c > cutoff else np.log((1 + c) / (1 - c)))
+                H[i] = discrete_heaviside(d * epsilon * 2.0 / n_sub)
+        else:
+            H[nodes] = 0.0 if loc[0] < 0 else 1.0
+    return H
+
+
+def compute_force(mesh, heaviside, curvature, sigma, gravity, rho0, drho, mu0, dmu, variable, interp, dst_u, deform=None):
+    """dense LevelSetOKZSolver::local_compute_force; returns (rho_q, mu_q) [n_cells, 27]"""
+    n_sub = mesh.ls.n_sub
+    K, jxw = mesh.general_geometry(3, deform)
+    K, jxw = np.ascontiguousarray(K), np.ascontiguousarray(jxw)
+    cl = np.ascontiguousarray(mesh.ls.cell_nodes.astype(np.int64))
+    cu = np.ascontiguousarray(mesh.u.cell_nodes.astype(np.int64))
+    ucon = np.ascontiguousarray(mesh.u.dirichlet.reshape(-1).astype(np.uint8))
+    rho_q, mu_q = np.zeros((mesh.n_cells, 27)), np.zeros((mesh.n_cells, 27))
+    ip = None if interp is None else np.ascontiguousarray(interp)
+    ls_lib().ls_oracle_force(mesh.n_cells, n_sub, _p(cl), _p(cu), _p(ucon), _p(K), _p(jxw), _p(heaviside), _p(curvature),
+                             C.c_double(sigma), C.c_double(gravity), C.c_double(rho0), C.c_double(drho), C.c_double(mu0),
+                             C.c_double(dmu), int(variable), _p(ip), _p(dst_u), _p(rho_q), _p(mu_q))
+    return rho_q, mu_q

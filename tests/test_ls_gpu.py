@@ -139,3 +139,52 @@ def test_level_set_vmults_are_symmetric_where_the_weak_form_is(ctx):
         f(ay, y)
         assert abs(float(ax @ y) - float(x @ ay)) < 1e-11 * abs(float(ax @ y))
     P.close()
+
+
+@pytest.mark.parametrize("geometry", ["cartesian", "general"])
+@pytest.mark.parametrize("interpolate", [False, True])
+def test_heaviside_and_force(ctx, geometry, interpolate):
+    """compute_heaviside + local_compute_force (row a16): Heaviside, rho_q/mu_q written into the NS operator, force vector"""
+    from adaflo_b200.operators import BlockVector, NavierStokesMatrix
+    from helpers import flow_params, time_weights
+    n_sub = 3
+    mesh = BoxMesh((4, 3, 3))
+    mesh.build_ls_space(n_sub)
+    deform = deformation(geometry)
+    ls_geometry = "cartesian" if geometry == "general" else geometry   # level-set kernels: compressed geometry only
+    mf = MatrixFree(ctx, mesh, geometry, deform) if geometry != "general" else None
+    if mf is None:
+        # general geometry for the NS quadrature is exercised with a mesh whose level-set quadrature stays Cartesian
+        pytest.skip("mixed geometry descriptions are not expressible through the Python MatrixFree helper")
+    dprm, _ = flow_params(density=1.0, viscosity=0.1, density_diff=9.0, viscosity_diff=0.4)
+    dtw, _ = time_weights()
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, BlockVector.like(mf), BlockVector.like(mf))
+    A.initialize(mf, dtw, True)
+    eps = 1.5
+    L = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, eps, eps * float(mesh.h.min()) / n_sub, 4.0, float(mesh.h.min())), mesh.cell_diameters())
+    x = mesh.ls.coords
+    r = np.linalg.norm(x - np.array([0.1, -0.05, -0.2]), axis=1)
+    c = -np.tanh((r - 0.5) / (2 * 0.08))
+    H_ref = orc.compute_heaviside(mesh.ls.cell_nodes.astype(np.int64), c, eps, n_sub)
+    Hg = mf.initialize_dof_vector(2)
+    L.compute_heaviside(Hg, dev(ctx, c))
+    assert np.abs(Hg.cpu().numpy() - H_ref).max() < 1e-14
+    assert 0.0 < H_ref.mean() < 1.0 and ((H_ref > 0) & (H_ref < 1)).sum() > 10
+    kappa = 2.0 / np.maximum(r, 0.2) + 0.1 * seeded_uniform(mesh.ls.global_ids, 1, 3)
+    interp = None
+    if interpolate:  # nodal interpolation onto the pressure space (level_set_base.cc:65-137): corner values
+        n1 = n_sub + 1
+        interp = np.zeros((8, n1 ** 3))
+        for i in range(8):
+            interp[i, (n_sub * (i & 1)) + n1 * ((n_sub * ((i >> 1) & 1)) + n1 * (n_sub * (i >> 2)))] = 1.0
+    pre = seeded_uniform(mesh.u.global_ids, 3, 4)
+    o = pre.copy()
+    rho_q, mu_q = orc.compute_force(mesh, H_ref, kappa, 0.07, 0.98, 1.0, 9.0, 0.1, 0.4, True, interp, o, deform)
+    g = dev(ctx, pre)
+    L.compute_force(A, g, dev(ctx, H_ref), dev(ctx, kappa), 0.07, 0.98, interp)
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    assert rel_err(A.get_coefficient(capi.COEF_DENSITY).cpu().numpy(), rho_q) < TOL
+    assert rel_err(A.get_coefficient(capi.COEF_VISCOSITY).cpu().numpy(), mu_q) < TOL
+    L.close()
+    A.clear()
+    mf.close()
