@@ -747,8 +747,26 @@ int adaflo_b200_ns_pressure_convdiff_vmult(adaflo_b200_ns_t ns, double *dst_p, c
 
 int adaflo_b200_ns_compute_diagonal(adaflo_b200_ns_t ns, double *diag_u, double *diag_p)
 {
-  (void)ns; (void)diag_u; (void)diag_p;
-  return fail(ADAFLO_B200_ERR_UNSUPPORTED, "compute_diagonal is not implemented yet");
+  // Exact diagonal of vmult.  Velocity block: diag(C^T A_cell C) summed over cells (one unit-source pass per
+  // cell-local slot inside the cell kernel), 1 on constrained rows.  Pressure block: the operator has no
+  // pressure-pressure coupling and the mean projection removes a multiple of (A^T w)_p = 0, so the diagonal is
+  // 0, and -1 on constrained rows (navier_stokes_matrix.cc:247-256).
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "compute_diagonal: operator not initialised");
+  if (!diag_u || !diag_p) return fail(ADAFLO_B200_ERR_ARG, "compute_diagonal: null vector");
+  adaflo_b200_mf_t mf = ns->mf;
+  cudaStream_t s = ns->ctx->stream;
+  const Space &su = mf->spaces[ns->dof_u], &sp = mf->spaces[ns->dof_p];
+  AB_CUDA(cudaMemsetAsync(diag_u, 0, su.n_local_entries() * sizeof(double), s));
+  AB_CUDA(cudaMemsetAsync(diag_p, 0, sp.n_local_entries() * sizeof(double), s));
+  NSArgs a = make_args(ns, false);
+  a.src_u = diag_u;  // not read in diagonal mode
+  a.dst_u = diag_u;
+  a.diag = 1;
+  AB_CHECK(launch_cells(ns, a, false));
+  if (ns->ctx->nranks > 1) AB_CHECK(comm_compress_add(mf, ns->dof_u, diag_u));
+  AB_CHECK(vec_set_indexed(s, diag_u, su.constrained, su.n_constrained, 1.0));
+  AB_CHECK(vec_set_indexed(s, diag_p, sp.constrained, sp.n_constrained, -1.0));
+  return 0;
 }
 
 int adaflo_b200_ns_fix_linearization_point(adaflo_b200_ns_t ns)

@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   const double *lin_lane = A.lin + g * (12 * 270) + lane;
   Geometry<GEOM> G;  // table row of the cell (two dependent loads): issue before the gather
   G.init_blk(A, cell);
-  const HnInfo hn(HANGING ? __ldg(A.hn_u + cell) : 0u);
-  const HnInfo hnp(HANGING && WITH_P ? __ldg(A.hn_p + cell) : 0u);
+  const HnInfo hn((HANGING && A.hn_u) ? __ldg(A.hn_u + cell) : 0u);
+  const HnInfo hnp((HANGING && WITH_P && A.hn_p) ? __ldg(A.hn_p + cell) : 0u);
   const bool hn_z_warp = HANGING && __any_sync(mask, hn.any() && (hn.face(0) || hn.face(1) || hn.edge(2)));
   const bool hnp_z_warp = HANGING && WITH_P && __any_sync(mask, hnp.any() && (hnp.face(0) || hnp.face(1) || hnp.edge(2)));
 
@@ -155,6 +155,15 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
       p_dg0 = A.src_p[dg0_node & ADAFLO_B200_NODE_MASK];
     }
   }
+  // Diagonal mode (compute_diagonal, velocity block only, instantiated with the hanging-node variant):
+  // one pass per cell-local slot with a unit source at that slot; only that slot's result is scattered,
+  // which yields diag(C^T A_cell C) including the hanging-node weights.
+  double dg0_sum = 0;
+  constexpr bool kDiagCapable = HANGING && !WITH_P;
+  const int n_pass = (kDiagCapable && A.diag) ? 81 : 1;
+#pragma unroll 1
+  for (int pass = 0; pass < n_pass; ++pass) {
+  const int dg_c = pass / 27, dg_t = (pass % 27) / 9, dg_j = pass % 9;
   {
     double P[3][9];
 #pragma unroll
@@ -163,7 +172,11 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
       const uint32_t flags = node[j] >> ADAFLO_B200_FLAG_SHIFT;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const double v = A.src_u[3 * n + c];
+        double v;
+        if (kDiagCapable && A.diag)
+          v = (c == dg_c && j == dg_j && t == dg_t) ? 1.0 : 0.0;
+        else
+          v = A.src_u[3 * n + c];
         P[c][j] = ((flags >> c) & 1u) ? 0.0 : v;
       }
     }
@@ -259,7 +272,6 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   __syncwarp(mask);
 
   // ---------------------------------------------------------------- phase B
-  double dg0_sum = 0;
   const double wt = (t == 1) ? W[1] : W[0];  // Gauss weight of qy = t
   // the line loop stays rolled: a third of the code (instruction cache) and the linearisation
   // data of a whole line is requested before the shared-memory reads and the z contraction
@@ -466,10 +478,13 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const uint32_t nd = node[j];
+      if (kDiagCapable && A.diag && !(c == dg_c && j == dg_j && t == dg_t)) continue;
       if (!((nd >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u))
         red_add(A.dst_u + 3 * (size_t)(nd & ADAFLO_B200_NODE_MASK) + c, o[j]);
     }
   }
+  if (kDiagCapable && A.diag) __syncwarp(mask);
+  }  // pass
   if (WITH_P && !A.skip_p_test) {
     double o[4] = {0, 0, 0, 0};
     if (t < 2) {
@@ -539,7 +554,7 @@ int launch_vmult_r1_hn(const NSArgs &a, cudaStream_t s)
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE>
 int launch_vmult_r1_inst(const NSArgs &a, cudaStream_t s)
 {
-  if (a.hn_u) return launch_vmult_r1_hn<WITH_P, MODE, GEOM, VAR, TRANSPOSE, true>(a, s);
+  if (a.hn_u || a.diag) return launch_vmult_r1_hn<WITH_P, MODE, GEOM, VAR, TRANSPOSE, true>(a, s);
   return launch_vmult_r1_hn<WITH_P, MODE, GEOM, VAR, TRANSPOSE, false>(a, s);
 }
 

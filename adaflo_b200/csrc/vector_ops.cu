@@ -122,6 +122,18 @@ int vec_copy_indexed(cudaStream_t s, double *dst, const double *src, const uint3
   AB_CUDA(cudaGetLastError());
   return 0;
 }
+__global__ void k_set_indexed(double *__restrict__ dst, const uint32_t *__restrict__ idx, uint32_t n, double value)
+{
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[idx[i]] = value;
+}
+int vec_set_indexed(cudaStream_t s, double *dst, const uint32_t *idx, uint32_t n, double value)
+{
+  if (n == 0) return 0;
+  k_set_indexed<<<grid_for(n, sm_count_cached(), 1), kVecThreads, 0, s>>>(dst, idx, n, value);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
 int vec_pack(cudaStream_t s, double *buf, const double *vec, const uint32_t *idx, uint32_t n_nodes, int n_comp)
 {
   if (n_nodes == 0) return 0;

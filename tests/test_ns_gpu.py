@@ -275,3 +275,41 @@ def test_hanging_nodes(ctx, refine, var):
         assert rel_err(g.cpu().numpy(), getattr(O, name)(sp)) < TOL, name
     A.clear()
     mf.close()
+
+
+@pytest.mark.parametrize("hanging", [False, True])
+def test_compute_diagonal(ctx, hanging):
+    """diag(vmult) on the velocity block equals e_i^T A e_i of the oracle (sampled dofs); pressure diagonal is 0 / -1"""
+    from adaflo_b200.mesh import RefinedBoxMesh
+    import ctypes as C
+    mesh = RefinedBoxMesh((3, 3, 2), ((1, 3), (0, 2), (0, 1))) if hanging else BoxMesh((4, 3, 3))
+    dprm, oprm = flow_params(damping=-0.2, tau_grad_div=0.3)
+    dtw, otw = time_weights()
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, old, old_old)
+    A.initialize(mf, dtw, True)
+    lists = (mesh.u_lists, mesh.p_lists) if hanging else (None, None)
+    O = orc.OracleNavierStokesMatrix(mesh, oprm, otw, None, True, *lists)
+    m = mesh
+    u = beltrami_velocity(m.u.coords, 0.1).reshape(-1)
+    p = seeded_uniform(m.p.global_ids, 1, 8)
+    O.old_u, O.old_old_u = u.copy(), u.copy()
+    old.block(0).copy_(dev(ctx, u))
+    old_old.block(0).copy_(dev(ctx, u))
+    z = np.zeros
+    O.residual(z(O.n_u), z(O.n_p), u, p, z(O.n_u), z(O.n_p))
+    A.residual(BlockVector.like(mf), BlockVector(dev(ctx, u), dev(ctx, p)), BlockVector.like(mf))
+    du, dp = mf.initialize_dof_vector(0), mf.initialize_dof_vector(1)
+    capi.check(ctx.lib.adaflo_b200_ns_compute_diagonal(A.h, C.c_void_p(du.data_ptr()), C.c_void_p(dp.data_ptr())))
+    du, dp = du.cpu().numpy(), dp.cpu().numpy()
+    assert np.all(dp == 0.0)          # no pressure Dirichlet dofs here
+    rng = np.random.default_rng(1)
+    sample = rng.choice(O.n_u, size=60, replace=False)
+    for i in sample:
+        e = np.zeros(O.n_u)
+        e[i] = 1.0
+        col_u, _ = O.vmult(e, z(O.n_p))
+        assert abs(du[i] - col_u[i]) <= 1e-12 * max(1.0, abs(col_u[i])), (i, du[i], col_u[i])
+    A.clear()
+    mf.close()
