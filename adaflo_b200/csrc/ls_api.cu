@@ -34,6 +34,7 @@ LSArgs base_args(adaflo_b200_ls_t ls)
   a.n_sub = ls->prm.concentration_subdivisions;
   a.cell_ls = sp.cell_nodes;
   a.cell_u = ls->dof_vel >= 0 ? mf->spaces[ls->dof_vel].cell_nodes : nullptr;
+  a.hn = sp.hanging_masks;
   a.geom_row = q.cell_row;
   a.geom_table = q.table;
   a.geom = q.geometry_type;
@@ -82,7 +83,6 @@ int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: needs a 3-D FE_Q_iso_Q1(n_sub <= 4) space and the QIterated(QGauss(2), n_sub) quadrature");
   if (mf->quads[quad_ls].geometry_type == ADAFLO_B200_GEOM_GENERAL)
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: general (per-point) geometry is not implemented for the level-set operators");
-  if (sp.hanging_masks) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: hanging nodes are not implemented for the level-set operators");
   if (prm->convection_stabilization) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: convection_stabilization is not implemented");
   if (dof_vel >= 0 && (mf->spaces[dof_vel].nodes_per_cell != 27 || mf->spaces[dof_vel].n_comp != 3))
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: the velocity space must be Q2^3");
@@ -181,6 +181,8 @@ int adaflo_b200_ls_advance_concentration_rhs(adaflo_b200_ls_t ls, double *rhs, c
 {
   if (!ls || !rhs || !vel || !c || !c_old || !c_old_old) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   if (ls->dof_vel < 0) return fail(ADAFLO_B200_ERR_STATE, "advance_concentration_rhs: no velocity space given at create");
+  if (ls->mf->spaces[ls->dof_vel].hanging_masks)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "advance_concentration_rhs: velocity spaces with hanging nodes are not implemented");
   LSArgs a = base_args(ls);
   a.src[0] = c;
   a.aux[0] = c_old;
@@ -286,6 +288,8 @@ int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, doubl
 {
   if (!ls || !ns || !dst_u || !heaviside || !curvature) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   if (ns->mf != ls->mf) return fail(ADAFLO_B200_ERR_ARG, "compute_force: operator and level set must share the MatrixFree data");
+  if (ls->mf->spaces[ls->dof_ls].hanging_masks)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "compute_force: level-set spaces with hanging nodes are not implemented");
   adaflo_b200_mf_t mf = ls->mf;
   const Space &sp = mf->spaces[ls->dof_ls], &su = mf->spaces[ns->dof_u];
   const Quad &q = mf->quads[ns->quad_u];

@@ -18,6 +18,39 @@ namespace ab200 {
 
 __device__ __forceinline__ double g2(int p) { return p ? 0.7886751345948129 : 0.2113248654051871; }
 
+// Hanging nodes of FE_Q_iso_Q1(S): a child node m in direction d sits at the parent coordinate (sub S + m) / 2;
+// if that is an integer it coincides with a parent node, otherwise it is the mean of its two neighbours (hats).
+struct LsStencil {
+  int n;
+  uint32_t slot[8];
+  double w[8];
+};
+__device__ __forceinline__ void ls_stencil(const HnInfo hn, const uint32_t *cl, int S, int ix, int iy, int iz, LsStencil &st)
+{
+  const int n1 = S + 1;
+  const int idx[3] = {ix, iy, iz};
+  int i0[3], cnt[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const int e = (d + 1) % 3, f = (d + 2) % 3;
+    i0[d] = idx[d];
+    cnt[d] = 1;
+    if (hn.line(d, idx[e], idx[f], n1)) {
+      const int c2 = hn.sub(d) * S + idx[d];
+      i0[d] = c2 >> 1;
+      cnt[d] = (c2 & 1) ? 2 : 1;
+    }
+  }
+  st.n = 0;
+  for (int c = 0; c < cnt[2]; ++c)
+    for (int b = 0; b < cnt[1]; ++b)
+      for (int a = 0; a < cnt[0]; ++a) {
+        st.slot[st.n] = cl[(i0[0] + a) + n1 * ((i0[1] + b) + n1 * (i0[2] + c))];
+        st.w[st.n] = 1.0 / (cnt[0] * cnt[1] * cnt[2]);
+        ++st.n;
+      }
+}
+
 template <int OP>
 __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
 {
@@ -50,6 +83,31 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
   for (int n = 0; n < 8; ++n)
     node[n] = __ldg(A.cell_ls + (size_t)cell * N + (sx + (n & 1)) + n1 * ((sy + ((n >> 1) & 1)) + n1 * (sz + (n >> 2))));
 
+  const HnInfo hn(A.hn ? __ldg(A.hn + cell) : 0u);
+  const uint32_t *cl = A.cell_ls + (size_t)cell * N;
+  // nodal read / scatter-add of this thread's node n (resolves hanging-node constraints on the fly)
+  auto rd = [&](const double *vec, int n, bool res) -> double {
+    if (!hn.any()) {
+      const double v = vec[node[n] & ADAFLO_B200_NODE_MASK];
+      return (res && (node[n] >> ADAFLO_B200_FLAG_SHIFT)) ? 0.0 : v;
+    }
+    LsStencil st;
+    ls_stencil(hn, cl, S, sx + (n & 1), sy + ((n >> 1) & 1), sz + (n >> 2), st);
+    double v = 0;
+    for (int i = 0; i < st.n; ++i)
+      if (!(res && (st.slot[i] >> ADAFLO_B200_FLAG_SHIFT))) v = fma(st.w[i], vec[st.slot[i] & ADAFLO_B200_NODE_MASK], v);
+    return v;
+  };
+  auto add = [&](double *vec, int n, double v, bool skip_flagged) {
+    if (!hn.any()) {
+      if (!(skip_flagged && (node[n] >> ADAFLO_B200_FLAG_SHIFT))) red_add(vec + (node[n] & ADAFLO_B200_NODE_MASK), v);
+      return;
+    }
+    LsStencil st;
+    ls_stencil(hn, cl, S, sx + (n & 1), sy + ((n >> 1) & 1), sz + (n >> 2), st);
+    for (int i = 0; i < st.n; ++i)
+      if (!(skip_flagged && (st.slot[i] >> ADAFLO_B200_FLAG_SHIFT))) red_add(vec + (st.slot[i] & ADAFLO_B200_NODE_MASK), st.w[i] * v);
+  };
   const bool resolve = (OP == LS_ADVECT || OP == LS_DAMPED || OP == LS_REINIT || OP == LS_REINIT_DIFFUSE);
   const int n_fields = (OP == LS_DAMPED) ? A.n_comp : 1;
   double *pd = A.pointdata ? A.pointdata + ((size_t)cell * S3 + sub) * 24 : nullptr;
@@ -63,10 +121,9 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
   if (OP == LS_CURV_RHS || OP == LS_REINIT_RHS || OP == LS_ADVECT_RHS) {
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const size_t d = node[n] & ADAFLO_B200_NODE_MASK;
-      aux0[n] = A.aux[0] ? A.aux[0][d] : 0.0;
-      aux1[n] = A.aux[1] ? A.aux[1][d] : 0.0;
-      aux2[n] = A.aux[2] ? A.aux[2][d] : 0.0;
+      aux0[n] = A.aux[0] ? rd(A.aux[0], n, false) : 0.0;
+      aux1[n] = A.aux[1] ? rd(A.aux[1], n, false) : 0.0;
+      aux2[n] = A.aux[2] ? rd(A.aux[2], n, false) : 0.0;
     }
   }
   if (OP == LS_CURV_RHS) {  // dof-level normalisation, compute_curvature.cc:231-240
@@ -115,10 +172,7 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
     for (int n = 0; n < 8; ++n) out0[n] = out1[n] = out2[n] = 0;
     if (OP != LS_MASS_DIAG && OP != LS_CURV_RHS) {
 #pragma unroll
-      for (int n = 0; n < 8; ++n) {
-        const double v = A.src[f][node[n] & ADAFLO_B200_NODE_MASK];
-        c0[n] = (resolve && (node[n] >> ADAFLO_B200_FLAG_SHIFT)) ? 0.0 : v;
-      }
+      for (int n = 0; n < 8; ++n) c0[n] = rd(A.src[f], n, resolve);
     }
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
@@ -222,14 +276,13 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
     }
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      if (OP != LS_MASS_DIAG && (node[n] >> ADAFLO_B200_FLAG_SHIFT)) continue;
-      const size_t d = node[n] & ADAFLO_B200_NODE_MASK;
+      const bool skip = OP != LS_MASS_DIAG;
       if (OP == LS_NORMAL_RHS) {
-        red_add(A.dst[0] + d, out0[n]);
-        red_add(A.dst[1] + d, out1[n]);
-        red_add(A.dst[2] + d, out2[n]);
+        add(A.dst[0], n, out0[n], skip);
+        add(A.dst[1], n, out1[n], skip);
+        add(A.dst[2], n, out2[n], skip);
       } else
-        red_add(A.dst[f] + d, out0[n]);
+        add(A.dst[f], n, out0[n], skip);
     }
   }
 }

@@ -465,7 +465,7 @@ class RefinedBoxMesh:
             return None  # outside
         return bool(self.refined[i, j, k])
 
-    def _build_space(self, name, deg, n_comp, dirichlet_faces):
+    def _build_space(self, name, deg, n_comp, dirichlet_faces, iso_q1=False):
         nx, ny, nz = self.n
         L = 2 * deg                      # lattice steps per coarse cell (fine nodes)
         NX, NY, NZ = L * nx + 1, L * ny + 1, L * nz + 1
@@ -572,7 +572,7 @@ class RefinedBoxMesh:
         sp.hanging_mask = masks
 
         # ---- independent plain expansion: hanging value = coarse neighbour's interpolant at the point
-        gl = gauss_lobatto_01(n1)
+        gl = gauss_lobatto_01(n1) if not iso_q1 else None
         ptr = [0]
         idx, wts = [], []
         pts = lid(px, py, pz)
@@ -594,7 +594,10 @@ class RefinedBoxMesh:
                                         owner = (ci, cj, ck)
                         assert owner is not None
                         ref = [(x - L * owner[0]) / L, (y - L * owner[1]) / L, (z - L * owner[2]) / L]
-                        V = [lagrange_values(gl, np.array([r]))[0][0] for r in ref]
+                        if iso_q1:   # FE_Q_iso_Q1: piecewise linear hats on deg sub-intervals
+                            V = [np.maximum(0.0, 1.0 - np.abs(r * deg - np.arange(n1))) for r in ref]
+                        else:
+                            V = [lagrange_values(gl, np.array([r]))[0][0] for r in ref]
                         for kz in range(n1):
                             for ky in range(n1):
                                 for kx in range(n1):
@@ -607,6 +610,15 @@ class RefinedBoxMesh:
                     ptr.append(len(idx))
         lists = (np.array(ptr, dtype=np.int64), np.array(idx, dtype=np.int64), np.array(wts, dtype=np.float64))
         return sp, lists
+
+    def build_ls_space(self, n_sub=3, dirichlet_faces=()):
+        """level-set space FE_Q_iso_Q1(n_sub) with its hanging-node masks and plain expansion lists"""
+        self.ls, self.ls_lists = self._build_space("ls", n_sub, 1, dirichlet_faces, iso_q1=True)
+        self.ls.n_sub = n_sub
+        return self.ls
+
+    def cell_diameters(self):
+        return self.h_cell.max(axis=1)
 
     # ------------------------------------------------------------ geometry
     def cartesian_geometry(self):

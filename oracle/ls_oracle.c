@@ -28,6 +28,9 @@ typedef struct {
   const double *inv_jac;        /* [n_cells][NQ][3][3]  K[f][e] = d xi_f / d x_e */
   const double *jxw;            /* [n_cells][NQ] */
   const double *cell_diameters; /* [n_cells] */
+  /* optional plain constraint expansion (hanging nodes): local value = sum_k w[k] vec[idx[k]], rows = cell * N + n */
+  const int64_t *ptr, *idx;
+  const double *w;
 } ls_mesh;
 
 typedef struct {
@@ -65,6 +68,13 @@ static inline void gphi(const ls_table *t, int q, int n, real g[3]) { const int 
 static void gather(const ls_mesh *m, const ls_table *t, int cell, const double *vec, int resolve, real *loc)
 {
   for (int n = 0; n < t->N; ++n) {
+    if (m->ptr) {
+      real s = 0;
+      for (int64_t k = m->ptr[(int64_t)cell * t->N + n]; k < m->ptr[(int64_t)cell * t->N + n + 1]; ++k)
+        if (!(resolve && m->constrained && m->constrained[m->idx[k]])) s += (real)m->w[k] * (real)vec[m->idx[k]];
+      loc[n] = s;
+      continue;
+    }
     const int64_t d = m->cell_nodes[(int64_t)cell * t->N + n];
     loc[n] = (resolve && m->constrained && m->constrained[d]) ? 0 : (real)vec[d];
   }
@@ -72,6 +82,11 @@ static void gather(const ls_mesh *m, const ls_table *t, int cell, const double *
 static void scatter(const ls_mesh *m, const ls_table *t, int cell, const real *out, double *vec)
 {
   for (int n = 0; n < t->N; ++n) {
+    if (m->ptr) {
+      for (int64_t k = m->ptr[(int64_t)cell * t->N + n]; k < m->ptr[(int64_t)cell * t->N + n + 1]; ++k)
+        if (!(m->constrained && m->constrained[m->idx[k]])) vec[m->idx[k]] += (double)((real)m->w[k] * out[n]);
+      continue;
+    }
     const int64_t d = m->cell_nodes[(int64_t)cell * t->N + n];
     if (m->constrained && m->constrained[d]) continue;
     vec[d] += (double)out[n];
@@ -294,7 +309,11 @@ int ls_oracle_mass_diagonal(const ls_mesh *m, double *dst)
     for (int n = 0; n < t.N; ++n) out[n] = 0;
     for (int q = 0; q < t.NQ; ++q)
       for (int n = 0; n < t.N; ++n) out[n] += phi(&t, q, n) * phi(&t, q, n) * (real)m->jxw[(int64_t)c * t.NQ + q];
-    for (int n = 0; n < t.N; ++n) dst[m->cell_nodes[(int64_t)c * t.N + n]] += (double)out[n];  /* hanging-node constraints only */
+    {  /* hanging-node constraints only (no Dirichlet skipping) */
+      ls_mesh m2 = *m;
+      m2.constrained = 0;
+      scatter(&m2, &t, c, out, dst);
+    }
   }
   free(out);
   return 0;

@@ -284,7 +284,8 @@ class OracleNavierStokesMatrix:
 # --------------------------------------------------------------------------
 class _LSMesh(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("n_sub", C.c_int32), ("cell_nodes", C.c_void_p), ("constrained", C.c_void_p),
-                ("inv_jac", C.c_void_p), ("jxw", C.c_void_p), ("cell_diameters", C.c_void_p)]
+                ("inv_jac", C.c_void_p), ("jxw", C.c_void_p), ("cell_diameters", C.c_void_p),
+                ("ptr", C.c_void_p), ("idx", C.c_void_p), ("w", C.c_void_p)]
 
 
 class LSParams(C.Structure):
@@ -330,7 +331,9 @@ class OracleLevelSet:
         self.con = np.ascontiguousarray(ls.dirichlet.reshape(-1).astype(np.uint8))
         self.K, self.jxw = iterated_gauss_geometry(mesh, ls.n_sub, deform)
         self.cd = np.ascontiguousarray(mesh.cell_diameters())
-        self.c = _LSMesh(mesh.n_cells, ls.n_sub, _p(self.cell_nodes), _p(self.con), _p(self.K), _p(self.jxw), _p(self.cd))
+        self.lists = getattr(mesh, "ls_lists", None)   # plain constraint expansion on meshes with hanging nodes
+        lp = [_p(a) for a in self.lists] if self.lists is not None else [None, None, None]
+        self.c = _LSMesh(mesh.n_cells, ls.n_sub, _p(self.cell_nodes), _p(self.con), _p(self.K), _p(self.jxw), _p(self.cd), *lp)
         self.conv = np.zeros((mesh.n_cells, self.NQ, 3))
         self.normal_q = np.zeros((mesh.n_cells, self.NQ, 3))
         self.diag = None

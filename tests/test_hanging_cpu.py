@@ -7,13 +7,16 @@ import pytest
 from adaflo_b200.mesh import (HN_EDGE_X, HN_FACE_X, HN_SUBCELL_X, RefinedBoxMesh, gauss_lobatto_01, lagrange_values)
 
 
-def interpolation_matrix(n1, sub):
-    """values of the parent's 1-D Lagrange basis at the child's nodes (child 0: [0,1/2], child 1: [1/2,1])"""
+def interpolation_matrix(n1, sub, iso_q1=False):
+    """values of the parent's 1-D basis at the child's nodes (child 0: [0,1/2], child 1: [1/2,1])"""
+    if iso_q1:   # hats on n1 - 1 sub-intervals, equidistant nodes
+        x = 0.5 * np.arange(n1) / (n1 - 1) + 0.5 * sub
+        return np.maximum(0.0, 1.0 - np.abs(x[:, None] * (n1 - 1) - np.arange(n1)[None, :]))
     gl = gauss_lobatto_01(n1)
     return lagrange_values(gl, 0.5 * gl + 0.5 * sub)[0]
 
 
-def resolve_compressed(mask, vals, n1):
+def resolve_compressed(mask, vals, n1, iso_q1=False):
     """vals: [n1,n1,n1] indexed [z][y][x] holding the slot values; returns the cell-local nodal values.
     This is the algorithm the CUDA kernels implement (direction by direction, each line at most once)."""
     v = vals.copy()
@@ -25,7 +28,7 @@ def resolve_compressed(mask, vals, n1):
     outer = [0 if sub[d] == 0 else n1 - 1 for d in range(3)]
     for d in range(3):                      # interpolate along direction d
         e, f = (d + 1) % 3, (d + 2) % 3
-        M = interpolation_matrix(n1, sub[d])
+        M = interpolation_matrix(n1, sub[d], iso_q1)
         for ie in range(n1):
             for jf in range(n1):
                 need = (face[e] and ie == outer[e]) or (face[f] and jf == outer[f]) or \
@@ -76,3 +79,17 @@ def test_dof_counts():
     # Q2: 5^3 coarse nodes + fine nodes of the refined cell that are not hanging: the refined cell's 5^3 lattice
     # minus its 3^3 coarse nodes minus the hanging ones on the 3 interior-facing faces
     assert m.u.n_owned == 125 + (125 - 27) - 3 * (25 - 9) + 3 * (5 - 3) - 0
+
+
+def test_level_set_space_with_hanging_nodes():
+    m = RefinedBoxMesh((3, 3, 2), ((1, 3), (0, 2), (0, 1)))
+    sp = m.build_ls_space(3)
+    ptr, idx, w = m.ls_lists
+    rng = np.random.default_rng(5)
+    vec = rng.uniform(-1, 1, sp.n_owned)
+    plain = np.add.reduceat(w * vec[idx], ptr[:-1]).reshape(m.n_cells, 4, 4, 4)
+    for c in range(m.n_cells):
+        slots = vec[sp.cell_nodes[c].astype(np.int64)].reshape(4, 4, 4)
+        got = resolve_compressed(int(sp.hanging_mask[c]), slots, 4, iso_q1=True)
+        assert np.abs(got - plain[c]).max() < 1e-14
+    assert (sp.hanging_mask != 0).sum() > 0

@@ -188,3 +188,61 @@ def test_heaviside_and_force(ctx, geometry, interpolate):
     L.close()
     A.clear()
     mf.close()
+
+
+@pytest.mark.parametrize("refine", [((1, 3), (0, 2), (0, 1)), ((0, 1), (0, 1), (0, 1))])
+def test_level_set_operators_with_hanging_nodes(ctx, refine):
+    """FE_Q_iso_Q1(3) on a 2:1 refined mesh: on-the-fly constraint resolution in the sub-cell kernels vs the
+    oracle's plain expansion lists"""
+    from adaflo_b200.mesh import RefinedBoxMesh
+    n_sub = 3
+    mesh = RefinedBoxMesh((3, 3, 2), refine)
+    mesh.build_ls_space(n_sub, dirichlet_faces=(0,))
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    h_min = float(mesh.h_cell.min())
+    eps, eps_used = 1.5, 1.5 * h_min / n_sub
+    A = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, eps, eps_used, 4.0, h_min), mesh.cell_diameters(), dof_index_vel=-1)
+    A.set_time(75.0, -100.0, 25.0, 0.02)
+    O = orc.OracleLevelSet(mesh, orc.LSParams(eps, eps_used, 4.0, h_min, 0.02, 3, 0))
+    n = mesh.ls.n_owned
+    diag = O.mass_diagonal()
+    O.diag = diag
+    A.set_diagonal(dev(ctx, diag))
+    assert rel_err(A.initialize_mass_matrix_diagonal().cpu().numpy(), diag) < TOL
+    x = mesh.ls.coords
+    r = np.linalg.norm(x - np.array([0.1, -0.05, -0.2]), axis=1)
+    c = -np.tanh((r - 0.45) / 0.3)
+    src = seeded_uniform(mesh.ls.global_ids, 1, 10)
+    g = mf.initialize_dof_vector(2)
+    A.advance_concentration_vmult(g, dev(ctx, src))
+    assert rel_err(g.cpu().numpy(), O.advance_concentration_vmult(src, 75.0)) < TOL
+    rhs_o = [np.zeros(n) for _ in range(3)]
+    O.compute_normal_rhs(rhs_o, c)
+    rhs_g = [mf.initialize_dof_vector(2) for _ in range(3)]
+    A.compute_normal_rhs(rhs_g, dev(ctx, c))
+    for d in range(3):
+        assert rel_err(rhs_g[d].cpu().numpy(), rhs_o[d]) < TOL
+    normal = [x[:, d] - [0.1, -0.05, -0.2][d] + 0.02 * seeded_uniform(mesh.ls.global_ids, 1, 20 + d) for d in range(3)]
+    ndst = [mf.initialize_dof_vector(2) for _ in range(3)]
+    A.compute_normal_vmult(ndst, [dev(ctx, v) for v in normal])
+    for d, ref in enumerate(O.compute_normal_vmult(normal)):
+        assert rel_err(ndst[d].cpu().numpy(), ref) < TOL
+    o = np.zeros(n)
+    O.compute_curvature_rhs(o, normal)
+    g = mf.initialize_dof_vector(2)
+    A.compute_curvature_rhs(g, [dev(ctx, v) for v in normal])
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    g = mf.initialize_dof_vector(2)
+    A.compute_curvature_vmult(g, dev(ctx, src), True)
+    assert rel_err(g.cpu().numpy(), O.compute_curvature_vmult(src, True)) < TOL
+    o = np.zeros(n)
+    O.reinitialization_rhs(o, c, normal, False, True)
+    g = mf.initialize_dof_vector(2)
+    A.reinitialization_rhs(g, dev(ctx, c), [dev(ctx, v) for v in normal], False, True)
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    for diffuse_only in (False, True):
+        g = mf.initialize_dof_vector(2)
+        A.reinitialization_vmult(g, dev(ctx, src), diffuse_only)
+        assert rel_err(g.cpu().numpy(), O.reinitialization_vmult(src, diffuse_only)) < TOL
+    A.close()
+    mf.close()
