@@ -1,0 +1,148 @@
+"""Krylov loops on the device (callers of the operators): iteration counts and solutions
+match the same algorithms run in numpy on the CPU oracle's operators."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from adaflo_b200 import capi
+from adaflo_b200.mesh import BoxMesh, seeded_uniform
+from adaflo_b200.operators import BlockVector, DiagonalPreconditioner, LevelSetOperators, MatrixFree, NavierStokesMatrix
+from adaflo_b200.solvers import SolverBicgstab, SolverCG, SolverControl, SolverGMRES
+from oracle import oracle as orc
+
+from helpers import flow_params, rel_err, time_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(ctx, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+
+
+def numpy_pcg(A, b, inv_diag, rel_tol, max_iter=2000):
+    x = np.zeros_like(b)
+    r = b - A(x)
+    res0 = np.linalg.norm(r)
+    tol = rel_tol * res0
+    z = inv_diag * r
+    p = z.copy()
+    rz = r @ z
+    it = 0
+    while np.linalg.norm(r) > tol and it < max_iter:
+        it += 1
+        Ap = A(p)
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        if np.linalg.norm(r) <= tol:
+            break
+        z = inv_diag * r
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, it
+
+
+def test_reinitialization_cg_with_jacobi(ctx):
+    """the reinitialisation solve of level_set_okz_reinitialization.cc:334-336: CG, rel. tol 1e-6, Jacobi"""
+    n_sub = 3
+    mesh = BoxMesh((4, 4, 4))
+    mesh.build_ls_space(n_sub)
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    h_min = float(mesh.h.min())
+    eps, eps_used = 1.5, 1.5 * h_min / n_sub
+    A = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, eps, eps_used, 4.0, h_min), mesh.cell_diameters())
+    A.set_time(75.0, -100.0, 25.0, 0.02)
+    O = orc.OracleLevelSet(mesh, orc.LSParams(eps, eps_used, 4.0, h_min, 0.02, 3, 0))
+    x = mesh.ls.coords
+    r = np.linalg.norm(x, axis=1)
+    c = -np.tanh((r - 0.5) / (2 * eps_used)) * (1 + 0.05 * seeded_uniform(mesh.ls.global_ids, 1, 2))
+    normal = [-x[:, d] / np.maximum(r, 1e-3) for d in range(3)]
+    n = mesh.ls.n_owned
+    diag = O.mass_diagonal()
+    inv_diag = np.where(np.abs(diag) > 1e-10 * np.abs(diag).max(), 1.0 / diag, 1.0)   # diagonal_preconditioner.cc:46-51
+    rhs_o = np.zeros(n)
+    O.reinitialization_rhs(rhs_o, c, normal, False, True)
+    x_ref, it_ref = numpy_pcg(lambda v: O.reinitialization_vmult(v, False), rhs_o, inv_diag, 1e-6)
+    # device
+    d_diag = A.initialize_mass_matrix_diagonal()
+    P = DiagonalPreconditioner(ctx, d_diag)
+    rhs_g = mf.initialize_dof_vector(2)
+    A.reinitialization_rhs(rhs_g, dev(ctx, c), [dev(ctx, v) for v in normal], False, True)
+    ctl = SolverControl(2000, 1e-30, 1e-6)
+    xg = mf.initialize_dof_vector(2)
+    its = SolverCG(ctx, ctl).solve(lambda d, s: A.reinitialization_vmult(d, s, False), xg, rhs_g, P.vmult)
+    assert abs(its - it_ref) <= 1 and its > 3
+    assert rel_err(xg.cpu().numpy(), x_ref) < 1e-6
+    A.close()
+    mf.close()
+
+
+def test_advection_bicgstab(ctx):
+    """advance_concentration solve (advance_concentration.cc:626-636): BiCGStab + Jacobi on the nonsymmetric operator"""
+    n_sub = 3
+    mesh = BoxMesh((4, 4, 3))
+    mesh.build_ls_space(n_sub)
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    h_min = float(mesh.h.min())
+    A = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, 1.5, 1.5 * h_min / n_sub, 4.0, h_min), mesh.cell_diameters())
+    gamma = 75.0
+    A.set_time(gamma, -100.0, 25.0, 0.02)
+    from adaflo_b200.mesh import beltrami_velocity
+    vel = beltrami_velocity(mesh.u.coords, 0.0).reshape(-1)
+    c = np.tanh(mesh.ls.coords[:, 0] * 3)
+    rhs = mf.initialize_dof_vector(2)
+    A.advance_concentration_rhs(rhs, dev(ctx, vel), dev(ctx, c), dev(ctx, c), dev(ctx, c))
+    P = DiagonalPreconditioner(ctx, A.initialize_mass_matrix_diagonal())
+    xg = mf.initialize_dof_vector(2)
+    ctl = SolverControl(200, 1e-30, 1e-8)
+    its = SolverBicgstab(ctx, ctl).solve(A.advance_concentration_vmult, xg, rhs, P.vmult)
+    # true residual of the computed solution
+    Ax = mf.initialize_dof_vector(2)
+    A.advance_concentration_vmult(Ax, xg)
+    true_res = float((rhs - Ax).norm() / rhs.norm())
+    assert 1 <= its < 60 and true_res < 1e-7
+    A.close()
+    mf.close()
+
+
+def test_navier_stokes_gmres_matches_oracle_gmres(ctx):
+    """unpreconditioned GMRES(30) on NavierStokesMatrix::vmult vs scipy GMRES on the oracle's vmult: same
+    residual reduction after the same number of matrix-vector products"""
+    import scipy.sparse.linalg as spla
+    mesh = BoxMesh((3, 3, 2))
+    dprm, oprm = flow_params()
+    dtw, otw = time_weights()
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, old, old_old)
+    A.initialize(mf, dtw, True)
+    O = orc.OracleNavierStokesMatrix(mesh, oprm, otw)
+    nu, np_ = O.n_u, O.n_p
+    bu, bp = seeded_uniform(mesh.u.global_ids, 3, 1), seeded_uniform(mesh.p.global_ids, 1, 2)
+    O.apply_pressure_average_projection(bp)       # consistent right-hand side
+    n_iter = 25
+    x = [mf.initialize_dof_vector(0), mf.initialize_dof_vector(1)]
+    ctl = SolverControl(n_iter, 1e-30, 1e-14)
+    try:
+        SolverGMRES(ctx, ctl, 30).solve(lambda d, s: A.vmult(BlockVector(*d), BlockVector(*s)), x, [dev(ctx, bu), dev(ctx, bp)])
+    except Exception:
+        pass
+    hist = ctl.history
+
+    def mv(v):
+        ou, op = O.vmult(v[:nu].copy(), v[nu:].copy())
+        return np.concatenate([ou, op])
+    b = np.concatenate([bu, bp])
+    res = []
+    spla.gmres(spla.LinearOperator((nu + np_, nu + np_), matvec=mv), b, rtol=1e-14, restart=30, maxiter=1,
+               callback=lambda r: res.append(r), callback_type="pr_norm")
+    k = min(len(res), len(hist) - 1, n_iter)
+    assert k >= 20
+    # scipy reports the preconditioned relative residual per inner iteration
+    for j in range(k):
+        assert abs(hist[j + 1] / hist[0] - res[j]) < 1e-8 * max(1.0, res[j]) + 1e-10
+    A.clear()
+    mf.close()
