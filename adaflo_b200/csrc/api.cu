@@ -3,6 +3,7 @@
 // (source/navier_stokes_matrix.cc:85-483) around the cell kernels.
 #include <chrono>
 #include <cstdlib>
+#include <cstdint>
 #include <cstring>
 #include <new>
 
@@ -162,6 +163,7 @@ int adaflo_b200_ctx_destroy(adaflo_b200_ctx_t ctx)
   if (ctx->red_host) cudaFreeHost(ctx->red_host);
   cudaEventDestroy(ctx->ev_a);
   cudaEventDestroy(ctx->ev_b);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   delete ctx;
   return 0;
 }
@@ -190,7 +192,9 @@ int adaflo_b200_ctx_init_comm(adaflo_b200_ctx_t ctx, const unsigned char id[128]
     ctx->nranks = 1;
     return 0;
   }
-  return comm_init(ctx, id, rank, nranks);
+  AB_CHECK(comm_init(ctx, id, rank, nranks));
+  if (!ctx->comm_stream) AB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  return 0;
 }
 
 // ------------------------------------------------------------- matrix-free
@@ -285,6 +289,29 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
       AB_CHECK(upload(&q.cell_row, qd.cell_row, (size_t)d->n_cells, s));
     }
     mf->quads.push_back(q);
+  }
+  {  // decades whose cells touch a ghost node (they must wait for the halo import)
+    size_t lo = SIZE_MAX, hi = 0, count = 0;
+    for (int i = 0; i < d->n_spaces; ++i) {
+      const adaflo_b200_space_desc &sd = d->spaces[i];
+      if (!sd.n_ghost_nodes) continue;
+      for (uint32_t c = 0; c < d->n_cells; ++c)
+        for (uint32_t k = 0; k < sd.nodes_per_cell; ++k)
+          if ((sd.cell_nodes[(size_t)c * sd.nodes_per_cell + k] & ADAFLO_B200_NODE_MASK) >= sd.n_owned_nodes) {
+            const size_t g = c / kGroup;
+            if (g < lo) lo = g;
+            if (g + 1 > hi) hi = g + 1;
+            ++count;
+            break;
+          }
+    }
+    if (count) {
+      mf->ghost_decade_begin = lo;
+      mf->ghost_decade_end = hi;
+      // worthwhile only if the range is a small part of the mesh
+      mf->ghost_range_valid = (hi - lo) * 4 < n_groups(d->n_cells);
+    } else
+      mf->ghost_range_valid = true;  // no ghosts (lowest rank): empty range, the exports still overlap
   }
   AB_CUDA(cudaStreamSynchronize(s));  // host arrays may be freed by the caller now
   *out = mf;
@@ -514,10 +541,30 @@ static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const d
                              sp.n_local_entries()));
     in_p = ns->tmp_p;
   }
-  // cell_loop: ghost import of src, cells, compress(add) of dst (:236-242)
+  // cell_loop: ghost import of src, cells, compress(add) of dst (:236-242).  Like deal.II, the import is
+  // overlapped with the cells that touch no ghost dof: it runs on the communication stream while the
+  // interior decades run on the compute stream.
+  // Measured on 2 x B200, 128^3 cells per GPU: 2.21 ms overlapped vs 2.12 ms serial -- the 1.6 MB import costs
+  // less than the tail of a second kernel launch, so the overlap is opt-in (ADAFLO_B200_HALO_OVERLAP=1).
+  static const bool overlap_enabled = [] {
+    const char *k = std::getenv("ADAFLO_B200_VMULT_KERNEL"), *o = std::getenv("ADAFLO_B200_HALO_OVERLAP");
+    return !(k && !std::strcmp(k, "v1")) && (o && !std::strcmp(o, "1"));  // the legacy v1 kernel has no decade range
+  }();
+  const bool overlap = overlap_enabled && ctx->nranks > 1 && mf->ghost_range_valid && ctx->comm_stream;
   if (ctx->nranks > 1) {
-    AB_CHECK(comm_update_ghosts(mf, ns->dof_u, const_cast<double *>(src_u)));
-    AB_CHECK(comm_update_ghosts(mf, ns->dof_p, const_cast<double *>(in_p)));
+    const int spaces[2] = {ns->dof_u, ns->dof_p};
+    double *vecs[2] = {const_cast<double *>(src_u), const_cast<double *>(in_p)};
+    if (overlap) {
+      AB_CUDA(cudaEventRecord(ctx->ev_a, s));
+      AB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
+      cudaStream_t keep = ctx->stream;
+      ctx->stream = ctx->comm_stream;
+      const int rc = comm_update_ghosts_n(mf, 2, spaces, vecs);
+      ctx->stream = keep;
+      AB_CHECK(rc);
+      AB_CUDA(cudaEventRecord(ctx->ev_b, ctx->comm_stream));
+    } else
+      AB_CHECK(comm_update_ghosts_n(mf, 2, spaces, vecs));  // one NCCL group for both blocks
   }
   AB_CUDA(cudaMemsetAsync(dst_u, 0, su.n_local_entries() * sizeof(double), s));  // dst = 0, :229
   AB_CUDA(cudaMemsetAsync(dst_p, 0, sp.n_local_entries() * sizeof(double), s));
@@ -536,11 +583,30 @@ static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const d
     }
     AB_CUDA(cudaEventRecord((*ns->kernel_events)[ns->kernel_events_used].first, s));
   }
-  AB_CHECK(launch_cells(ns, a, true));
+  if (overlap) {  // interior decades first, then wait for the import and run the decades touching ghosts
+    const size_t n_dec = n_groups(mf->n_cells);
+    NSArgs b = a;
+    if (mf->ghost_decade_begin > 0) {
+      b.decade_begin = 0;
+      b.decade_end = mf->ghost_decade_begin;
+      AB_CHECK(launch_cells(ns, b, true));
+    }
+    if (mf->ghost_decade_end < n_dec) {
+      b.decade_begin = mf->ghost_decade_end;
+      b.decade_end = n_dec;
+      AB_CHECK(launch_cells(ns, b, true));
+    }
+    AB_CUDA(cudaStreamWaitEvent(s, ctx->ev_b, 0));
+    a.decade_begin = mf->ghost_decade_begin;
+    a.decade_end = mf->ghost_decade_end;
+  }
+  const bool cells_left = !overlap || a.decade_end > a.decade_begin;
+  if (cells_left) AB_CHECK(launch_cells(ns, a, true));
   if (ns->time_kernel) AB_CUDA(cudaEventRecord((*ns->kernel_events)[ns->kernel_events_used++].second, s));
   if (ctx->nranks > 1) {
-    AB_CHECK(comm_compress_add(mf, ns->dof_u, dst_u));
-    AB_CHECK(comm_compress_add(mf, ns->dof_p, dst_p));
+    const int spaces[2] = {ns->dof_u, ns->dof_p};
+    double *vecs[2] = {dst_u, dst_p};
+    AB_CHECK(comm_compress_add_n(mf, 2, spaces, vecs));
   }
   // constrained rows, :247-256
   AB_CHECK(vec_copy_indexed(s, dst_u, src_u, su.constrained, su.n_constrained, 1.0));

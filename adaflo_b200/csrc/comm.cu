@@ -103,48 +103,69 @@ int comm_allreduce(adaflo_b200_ctx_t ctx, double *dev, int k, int op_max)
   return 0;
 }
 
-// owner -> ghost import (LinearAlgebra::distributed::Vector::update_ghost_values)
-int comm_update_ghosts(adaflo_b200_mf_t mf, int space, double *vec)
+// owner -> ghost import (LinearAlgebra::distributed::Vector::update_ghost_values) of several vectors in ONE
+// NCCL group (one launch for the velocity and the pressure block of a vmult)
+int comm_update_ghosts_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *const *vecs)
 {
   adaflo_b200_ctx_t ctx = mf->ctx;
-  Space &sp = mf->spaces[space];
-  if (sp.exchange.empty() || ctx->nranks <= 1) return 0;
+  if (ctx->nranks <= 1) return 0;
   if (!ctx->nccl_comm) return fail(ADAFLO_B200_ERR_STATE, "communicator not initialised");
-  for (Exchange &e : sp.exchange)
-    if (e.n_send) AB_CHECK(vec_pack(ctx->stream, e.send_buf, vec, e.send_dev, e.n_send, sp.n_comp));
+  bool any = false;
+  for (int i = 0; i < n; ++i) {
+    Space &sp = mf->spaces[spaces[i]];
+    for (Exchange &e : sp.exchange) {
+      any = true;
+      if (e.n_send) AB_CHECK(vec_pack(ctx->stream, e.send_buf, vecs[i], e.send_dev, e.n_send, sp.n_comp));
+    }
+  }
+  if (!any) return 0;
   AB_NCCL(g_nccl.GroupStart());
-  for (Exchange &e : sp.exchange) {
-    if (e.n_send)
-      AB_NCCL(g_nccl.Send(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
-    if (e.n_recv)
-      AB_NCCL(g_nccl.Recv(vec + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
-                          (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    Space &sp = mf->spaces[spaces[i]];
+    for (Exchange &e : sp.exchange) {
+      if (e.n_send)
+        AB_NCCL(g_nccl.Send(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+      if (e.n_recv)
+        AB_NCCL(g_nccl.Recv(vecs[i] + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
+                            (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    }
   }
   AB_NCCL(g_nccl.GroupEnd());
   return 0;
 }
 
 // ghost -> owner accumulation (Vector::compress(VectorOperation::add)); ghost entries are zeroed afterwards
-int comm_compress_add(adaflo_b200_mf_t mf, int space, double *vec)
+int comm_compress_add_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *const *vecs)
 {
   adaflo_b200_ctx_t ctx = mf->ctx;
-  Space &sp = mf->spaces[space];
-  if (sp.exchange.empty() || ctx->nranks <= 1) return 0;
+  if (ctx->nranks <= 1) return 0;
   if (!ctx->nccl_comm) return fail(ADAFLO_B200_ERR_STATE, "communicator not initialised");
+  bool any = false;
+  for (int i = 0; i < n; ++i) any |= !mf->spaces[spaces[i]].exchange.empty();
+  if (!any) return 0;
   AB_NCCL(g_nccl.GroupStart());
-  for (Exchange &e : sp.exchange) {
-    if (e.n_recv)
-      AB_NCCL(g_nccl.Send(vec + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
-                          (ncclComm_t)ctx->nccl_comm, ctx->stream));
-    if (e.n_send)
-      AB_NCCL(g_nccl.Recv(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    Space &sp = mf->spaces[spaces[i]];
+    for (Exchange &e : sp.exchange) {
+      if (e.n_recv)
+        AB_NCCL(g_nccl.Send(vecs[i] + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
+                            (ncclComm_t)ctx->nccl_comm, ctx->stream));
+      if (e.n_send)
+        AB_NCCL(g_nccl.Recv(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    }
   }
   AB_NCCL(g_nccl.GroupEnd());
-  for (Exchange &e : sp.exchange)
-    if (e.n_send) AB_CHECK(vec_unpack_add(ctx->stream, vec, e.send_buf, e.send_dev, e.n_send, sp.n_comp));
-  if (sp.n_ghost_nodes)
-    AB_CUDA(cudaMemsetAsync(vec + sp.n_owned_entries(), 0, sizeof(double) * (size_t)sp.n_ghost_nodes * sp.n_comp, ctx->stream));
+  for (int i = 0; i < n; ++i) {
+    Space &sp = mf->spaces[spaces[i]];
+    for (Exchange &e : sp.exchange)
+      if (e.n_send) AB_CHECK(vec_unpack_add(ctx->stream, vecs[i], e.send_buf, e.send_dev, e.n_send, sp.n_comp));
+    if (sp.n_ghost_nodes)
+      AB_CUDA(cudaMemsetAsync(vecs[i] + sp.n_owned_entries(), 0, sizeof(double) * (size_t)sp.n_ghost_nodes * sp.n_comp, ctx->stream));
+  }
   return 0;
 }
+
+int comm_update_ghosts(adaflo_b200_mf_t mf, int space, double *vec) { return comm_update_ghosts_n(mf, 1, &space, &vec); }
+int comm_compress_add(adaflo_b200_mf_t mf, int space, double *vec) { return comm_compress_add_n(mf, 1, &space, &vec); }
 
 }  // namespace ab200

@@ -101,6 +101,10 @@ struct adaflo_b200_mf_s {
   uint32_t n_cells;
   std::vector<ab200::Space> spaces;
   std::vector<ab200::Quad> quads;
+  // cells touching ghost nodes of any space, if they form one contiguous decade range [begin, end)
+  // (true for contiguous partitions with lower-rank ownership); used to overlap the halo import
+  size_t ghost_decade_begin = 0, ghost_decade_end = 0;
+  bool ghost_range_valid = false;
 };
 
 struct adaflo_b200_ns_s {
@@ -163,6 +167,7 @@ struct NSArgs {
   int linearization;  // runtime copy (residual kernel)
   int physical_type;
   int transpose;      // Tvmult
+  size_t decade_begin, decade_end;  // range of cell decades of this launch (end == 0: all); halo overlap
   int diag;           // compute_diagonal: unit sources per cell-local slot (velocity block)
   int skip_p_test;    // linearization == projection: pressure block not integrated (:902-907)
 };
@@ -221,6 +226,8 @@ int allreduce_sum_host(adaflo_b200_ctx_t ctx, double *vals, int k);  // via devi
 // communication (comm.cu)
 int comm_update_ghosts(adaflo_b200_mf_t mf, int space, double *vec);
 int comm_compress_add(adaflo_b200_mf_t mf, int space, double *vec);
+int comm_update_ghosts_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *const *vecs);
+int comm_compress_add_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *const *vecs);
 int comm_allreduce(adaflo_b200_ctx_t ctx, double *dev, int k, int op_max);
 int comm_unique_id(unsigned char id[128]);
 int comm_init(adaflo_b200_ctx_t ctx, const unsigned char id[128], int rank, int nranks);

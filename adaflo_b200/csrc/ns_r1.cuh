@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cw = lane / 3;
   const int t = lane - 3 * cw;
-  const size_t g = (size_t)blockIdx.x * kR1Warps + warp;  // decade
+  const size_t g = (size_t)blockIdx.x * kR1Warps + warp + A.decade_begin;  // decade
   const size_t cell_l = g * kGroup + cw;
-  const bool active = (lane < 3 * kGroup) && (cell_l < A.n_cells);
+  const bool active = (lane < 3 * kGroup) && (cell_l < A.n_cells) && (g < A.decade_end);
   const unsigned mask = __ballot_sync(0xffffffffu, active);
   if (!active) return;
   const uint32_t cell = (uint32_t)cell_l;
@@ -542,10 +542,12 @@ int launch_vmult_r1_hn(const NSArgs &a, cudaStream_t s)
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
-  const size_t cells_per_block = (size_t)kR1Warps * kGroup;
-  const unsigned grid = (unsigned)((a.n_cells + cells_per_block - 1) / cells_per_block);
-  if (grid == 0) return 0;
-  kern<<<grid, kR1Warps * 32, smem, s>>>(a);
+  NSArgs b = a;
+  const size_t n_dec = n_groups(a.n_cells);
+  if (b.decade_end == 0 || b.decade_end > n_dec) b.decade_end = n_dec;  // default: all decades
+  if (b.decade_begin >= b.decade_end) return 0;
+  const unsigned grid = (unsigned)((b.decade_end - b.decade_begin + kR1Warps - 1) / kR1Warps);
+  kern<<<grid, kR1Warps * 32, smem, s>>>(b);
   AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;

@@ -35,7 +35,7 @@ def main():
         return obj[0]
     ctx.init_comm(rank, world, bcast)
 
-    n = (6, 5, 3 * world + 1)
+    n = (6, 5, 6 * world + 1)  # >= 18 decades per rank: the halo import overlaps the interior decades
     mesh = BoxMesh(n, rank=rank, nranks=world)
     gmesh = BoxMesh(n)
     dprm, oprm = flow_params(damping=-0.2, tau_grad_div=0.3)
