@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libadaflo_b200.so")
+LIB_PATH = os.environ.get("ADAFLO_B200_LIB") or os.path.join(_HERE, "lib", "libadaflo_b200.so")  # override: kernel A/B experiments
 
 
 class AdafloB200Error(RuntimeError):

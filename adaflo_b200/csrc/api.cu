@@ -67,6 +67,7 @@ static NSArgs make_args(adaflo_b200_ns_t ns, bool use_prec)
   adaflo_b200_mf_t mf = ns->mf;
   NSArgs a{};
   a.n_cells = mf->n_cells;
+  a.work_counter = ns->ctx->work_counter;
   a.np_cell = (int)mf->spaces[ns->dof_p].nodes_per_cell;
   a.cell_u = mf->spaces[ns->dof_u].cell_nodes;
   a.cell_p = mf->spaces[ns->dof_p].cell_nodes;
@@ -148,6 +149,9 @@ int adaflo_b200_ctx_create(adaflo_b200_ctx_t *out, int device, void *stream)
   c->red_capacity = 64 + (size_t)8 * c->sm_count * 8 + 64;
   AB_CUDA(cudaMalloc((void **)&c->red_dev, c->red_capacity * sizeof(double)));
   AB_CUDA(cudaMallocHost((void **)&c->red_host, 64 * sizeof(double)));
+  c->work_counter = nullptr;
+  AB_CUDA(cudaMalloc(&c->work_counter, 2 * sizeof(unsigned)));
+  AB_CUDA(cudaMemset(c->work_counter, 0, 2 * sizeof(unsigned)));
   AB_CUDA(cudaEventCreate(&c->ev_a));
   AB_CUDA(cudaEventCreate(&c->ev_b));
   *out = c;
@@ -161,6 +165,7 @@ int adaflo_b200_ctx_destroy(adaflo_b200_ctx_t ctx)
   comm_destroy(ctx);
   free_dev(ctx->red_dev);
   if (ctx->red_host) cudaFreeHost(ctx->red_host);
+  cudaFree(ctx->work_counter);
   cudaEventDestroy(ctx->ev_a);
   cudaEventDestroy(ctx->ev_b);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);

@@ -85,6 +85,7 @@ struct adaflo_b200_ctx_s {
   cudaStream_t stream;
   cudaStream_t comm_stream;
   cudaEvent_t ev_a, ev_b;
+  unsigned *work_counter;
   int sm_count;
   // reductions
   double *red_dev;     // scratch for block partials / results
@@ -167,6 +168,7 @@ struct NSArgs {
   int linearization;  // runtime copy (residual kernel)
   int physical_type;
   int transpose;      // Tvmult
+  unsigned *work_counter;  // ticket counter of the persistent cell kernel (per context)
   size_t decade_begin, decade_end;  // range of cell decades of this launch (end == 0: all); halo overlap
   int diag;           // compute_diagonal: unit sources per cell-local slot (velocity block)
   int skip_p_test;    // linearization == projection: pressure block not integrated (:902-907)

@@ -28,12 +28,22 @@
 
 namespace ab200 {
 
-constexpr int kR1Warps = 3;                 // warps per block (3 blocks of 3 warps fit the 227 KB shared memory of an SM)
-constexpr int kR1CompSmem = 93;             // three interleaved tiles of one component
-constexpr int kR1CellSmem = 3 * kR1CompSmem + 18 + 10;  // + pressure tile, padded to 307 = 3 (mod 16)
+// Shared-memory layout of one cell: entry (arr, c, qx, qy, k) of the velocity tiles at
+//   9 arr + 27 c + k + 3 qx + 81 qy            (arr: value / d/dx / d/dy part, c: component, k: z index)
+// and 12 slots for the pressure behind them.  81 = 1 and 259 = 3 (mod 16): the lanes (cell, t) of a warp hit the
+// 8-byte bank 3 cell + t both when t is the y index (phase B) and when it is k (phases A, C) -> no bank conflicts.
+#ifndef AB_R1_WARPS
+#define AB_R1_WARPS 11
+#endif
+constexpr int kR1Warps = AB_R1_WARPS;                // warps per block: one persistent block per SM, 11 x 20.7 KB of shared memory
+constexpr int kR1CompSmem = 27;
+constexpr int kR1QyStride = 81;
+constexpr int kR1PSmem = 243;               // offset of the pressure slots
+constexpr int kR1CellSmem = 259;
 constexpr int kR1WarpSmem = kGroup * kR1CellSmem;
+constexpr int kR1MaxReg = 168;              // 3 warps per SM sub-partition (16384 registers each)
 
-__device__ __forceinline__ int r1_idx(int qx, int qy, int k) { return k + 3 * qx + 33 * qy; }
+__device__ __forceinline__ int r1_idx(int qx, int qy, int k) { return k + 3 * qx + kR1QyStride * qy; }
 
 // bulk L2 prefetch of a contiguous block (TMA engine, no registers, no LSU wavefronts)
 __device__ __forceinline__ void l2_prefetch(const void *ptr, unsigned bytes)
@@ -98,22 +108,20 @@ __device__ __forceinline__ void load_lin(double (&L)[12], const double *lin_lane
   for (int r = 0; r < rows; ++r) L[r] = ld_pinned(lin_lane + (size_t)r * 270 + n * 30);
 }
 
+// One decade (10 cells) of the cell loop, executed by one warp: 3 lanes per cell.
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
-__global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSArgs A)
+__device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, double *warp_smem, const int lane)
 {
   AB_TABLES_Q2G3
-  extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cw = lane / 3;
   const int t = lane - 3 * cw;
-  const size_t g = (size_t)blockIdx.x * kR1Warps + warp + A.decade_begin;  // decade
   const size_t cell_l = g * kGroup + cw;
-  const bool active = (lane < 3 * kGroup) && (cell_l < A.n_cells) && (g < A.decade_end);
+  const bool active = (lane < 3 * kGroup) && (cell_l < A.n_cells);
   const unsigned mask = __ballot_sync(0xffffffffu, active);
   if (!active) return;
   const uint32_t cell = (uint32_t)cell_l;
-  double *s = smem + warp * kR1WarpSmem + cw * kR1CellSmem;
-  double *sp = s + 3 * kR1CompSmem;
+  double *s = warp_smem + cw * kR1CellSmem;
+  double *sp = s + kR1PSmem;
 
   // The per-point streams of this decade are consumed in phase B; ask the L2 for them now so
   // that their HBM latency overlaps the gather and the in-plane contractions of phase A.
@@ -258,18 +266,24 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
           if (hnp.any() && hnp.line(2, j % 2, j / 2, 2) && t < 2) pl[j] = t == 0 ? v0 : v1;
         }
       }
-      if (t < 2) {
+      if (t < 2) {  // the 8 vertex values of the cell (vertex j = 2 iy + ix of plane iz = t)
 #pragma unroll
-        for (int qy = 0; qy < 3; ++qy) {
-          const double y0 = NP[qy][0] * pl[0] + NP[qy][1] * pl[2];  // ix = 0
-          const double y1 = NP[qy][0] * pl[1] + NP[qy][1] * pl[3];  // ix = 1
-#pragma unroll
-          for (int qx = 0; qx < 3; ++qx) sp[t + 2 * (qx + 3 * qy)] = NP[qx][0] * y0 + NP[qx][1] * y1;
-        }
+        for (int j = 0; j < 4; ++j) sp[t + 2 * j] = pl[j];
       }
     }
   }
   __syncwarp(mask);
+  // pressure: all three lanes read the 8 vertex values and interpolate in y to their qy = t
+  double py[2][2] = {{0, 0}, {0, 0}}, pacc[2][2] = {{0, 0}, {0, 0}};  // [ix][iz]; pacc: transposed accumulators
+  const double npt0 = t == 0 ? NP[0][0] : (t == 1 ? 0.5 : NP[2][0]), npt1 = 1.0 - npt0;  // NP[t][.]
+  if (WITH_P) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      py[0][k] = npt0 * sp[k] + npt1 * sp[k + 4];
+      py[1][k] = npt0 * sp[k + 2] + npt1 * sp[k + 6];
+    }
+    __syncwarp(mask);  // the slots are reused for the transposed direction
+  }
 
   // ---------------------------------------------------------------- phase B
   const double wt = (t == 1) ? W[1] : W[0];  // Gauss weight of qy = t
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
     double val[3][3], dx[3][3], dy[3][3], dz[3][3];  // [c][qz]
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      const double *sc = s + c * kR1CompSmem + 3 * j + 33 * t;
+      const double *sc = s + c * kR1CompSmem + 3 * j + kR1QyStride * t;
       double T[3], Tx[3], Ty[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
@@ -299,7 +313,8 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
     }
     double pv[3] = {0, 0, 0};
     if (WITH_P) {
-      const double p0 = sp[0 + 2 * (j + 3 * t)], p1 = sp[1 + 2 * (j + 3 * t)];
+      const double npj0 = j == 0 ? NP[0][0] : (j == 1 ? 0.5 : NP[2][0]), npj1 = 1.0 - npj0;  // NP[j][.]
+      const double p0 = npj0 * py[0][0] + npj1 * py[1][0], p1 = npj0 * py[0][1] + npj1 * py[1][1];
 #pragma unroll
       for (int q = 0; q < 3; ++q) pv[q] = NP[q][0] * p0 + NP[q][1] * p1 + p_dg0;
     }
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
     // z contraction back, overwriting this lane's own tile entries
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      double *sc = s + c * kR1CompSmem + 3 * j + 33 * t;
+      double *sc = s + c * kR1CompSmem + 3 * j + kR1QyStride * t;
       double r[3] = {0, 0, 0}, rx[3], ry[3];
       if (MODE != MODE_STOKES) q2::val_t(val[c][0], val[c][1], val[c][2], r[0], r[1], r[2]);
       q2::der_t_add(dz[c][0], dz[c][1], dz[c][2], r[0], r[1], r[2]);
@@ -426,9 +441,20 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
     }
     if (WITH_P) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) sp[k + 2 * (j + 3 * t)] = NP[0][k] * tp[0] + NP[1][k] * tp[1] + NP[2][k] * tp[2];
+      for (int k = 0; k < 2; ++k) {
+        const double pz = NP[0][k] * tp[0] + NP[1][k] * tp[1] + NP[2][k] * tp[2];  // z^T, then x^T accumulated over the lines
+        const double npj0 = j == 0 ? NP[0][0] : (j == 1 ? 0.5 : NP[2][0]);
+        pacc[0][k] = fma(npj0, pz, pacc[0][k]);
+        pacc[1][k] = fma(1.0 - npj0, pz, pacc[1][k]);
+      }
       dg0_sum += tp[0] + tp[1] + tp[2];
     }
+  }
+  if (WITH_P) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int ix = 0; ix < 2; ++ix) sp[t + 3 * (ix + 2 * k)] = pacc[ix][k];
   }
   __syncwarp(mask);
 
@@ -487,18 +513,13 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   }  // pass
   if (WITH_P && !A.skip_p_test) {
     double o[4] = {0, 0, 0, 0};
-    if (t < 2) {
-      double y0[3], y1[3];
+    if (t < 2) {  // y^T over the three lanes' accumulators of plane iz = t
 #pragma unroll
-      for (int qy = 0; qy < 3; ++qy) {
-        const double a0 = sp[t + 2 * (0 + 3 * qy)], a1 = sp[t + 2 * (1 + 3 * qy)], a2 = sp[t + 2 * (2 + 3 * qy)];
-        y0[qy] = NP[0][0] * a0 + NP[1][0] * a1 + NP[2][0] * a2;
-        y1[qy] = NP[0][1] * a0 + NP[1][1] * a1 + NP[2][1] * a2;
+      for (int ix = 0; ix < 2; ++ix) {
+        const double a0 = sp[0 + 3 * (ix + 2 * t)], a1 = sp[1 + 3 * (ix + 2 * t)], a2 = sp[2 + 3 * (ix + 2 * t)];
+        o[ix] = NP[0][0] * a0 + NP[1][0] * a1 + NP[2][0] * a2;
+        o[2 + ix] = NP[0][1] * a0 + NP[1][1] * a1 + NP[2][1] * a2;
       }
-      o[0] = NP[0][0] * y0[0] + NP[1][0] * y0[1] + NP[2][0] * y0[2];
-      o[1] = NP[0][0] * y1[0] + NP[1][0] * y1[1] + NP[2][0] * y1[2];
-      o[2] = NP[0][1] * y0[0] + NP[1][1] * y0[1] + NP[2][1] * y0[2];
-      o[3] = NP[0][1] * y1[0] + NP[1][1] * y1[1] + NP[2][1] * y1[2];
     }
     if (HANGING) {
       if (hnp_z_warp) {
@@ -531,22 +552,60 @@ __global__ void __launch_bounds__(kR1Warps * 32, 3) ns_vmult_r1_kernel(const NSA
   }
 }
 
+// Persistent kernel: one block of kR1Warps independent warps per SM; every warp draws decades from a global
+// counter (A.work_counter, zeroed by the launcher) until the range [decade_begin, decade_end) is exhausted.  The
+// next ticket is drawn before the current decade is processed, so the atomic's latency is never exposed, and a
+// warp that is delayed (hanging-node cells, a slow SM) simply draws fewer decades.
+template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
+__global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
+{
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *warp_smem = smem + warp * kR1WarpSmem;
+  const unsigned n_dec = (unsigned)(A.decade_end - A.decade_begin);
+  // two tickets are held (current and next decade), the third is drawn while the current decade is processed
+  unsigned i = 0, i_n1 = 0;
+  if (lane == 0) {
+    i = atomicAdd(A.work_counter, 1u);
+    i_n1 = atomicAdd(A.work_counter, 1u);
+  }
+  i = __shfl_sync(0xffffffffu, i, 0);
+  i_n1 = __shfl_sync(0xffffffffu, i_n1, 0);
+  while (i < n_dec) {
+    unsigned i_n2 = 0;
+    if (lane == 0) {
+      i_n2 = atomicAdd(A.work_counter, 1u);
+    }
+    r1_decade<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>(A, A.decade_begin + i, warp_smem, lane);
+    __syncwarp();  // the tiles of this decade have been read before the next decade overwrites them
+    i = i_n1;
+    i_n1 = __shfl_sync(0xffffffffu, i_n2, 0);
+  }
+}
+
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
 int launch_vmult_r1_hn(const NSArgs &a, cudaStream_t s)
 {
   auto kern = ns_vmult_r1_kernel<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>;
   const size_t smem = sizeof(double) * kR1Warps * kR1WarpSmem;
   static bool configured = false;
+  static int n_sm = 0;
   if (!configured) {
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int dev = 0;
+    AB_CUDA(cudaGetDevice(&dev));
+    AB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     configured = true;
   }
+  if (!a.work_counter) return fail(ADAFLO_B200_ERR_STATE, "ns_vmult_r1: no work counter");
   NSArgs b = a;
   const size_t n_dec = n_groups(a.n_cells);
   if (b.decade_end == 0 || b.decade_end > n_dec) b.decade_end = n_dec;  // default: all decades
   if (b.decade_begin >= b.decade_end) return 0;
-  const unsigned grid = (unsigned)((b.decade_end - b.decade_begin + kR1Warps - 1) / kR1Warps);
+  const size_t blocks_needed = (b.decade_end - b.decade_begin + kR1Warps - 1) / kR1Warps;
+  const unsigned grid = (unsigned)(blocks_needed < (size_t)n_sm ? blocks_needed : (size_t)n_sm);
+  AB_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(unsigned), s));
   kern<<<grid, kR1Warps * 32, smem, s>>>(b);
   AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());

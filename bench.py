@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--preroll", type=float, default=0.7, help="seconds of untimed load before the timed steps (clock sampling)")
     ap.add_argument("--no-nonlinear-step", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="developer A/B mode: kernel timings + checksum only (not a bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -260,6 +261,12 @@ def main():
     ms_per_step = ms_total / args.steps
     value = n_dofs / (ms_per_step * 1e-3)
 
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"lib": os.environ.get("ADAFLO_B200_LIB", "default"), "burst_kernel_ms": b_k * 1e3, "burst_ms_per_step": b_ms / args.steps,
+                              "kernel_ms": k_avg * 1e3, "ms_per_step": ms_per_step, "clocks": clocks,
+                              "checksum": [float(dst.block(0).norm()), float(dst.block(1).norm())]}))
+        return
     # ---- e2e: HOST (pinned) vectors through adaflo_b200_ns_vmult_host
     nu_own, np_own = mf.n_owned(0), mf.n_owned(1)
     hu = src.block(0)[:nu_own].cpu().pin_memory()      # host vectors hold the locally owned range
