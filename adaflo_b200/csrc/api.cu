@@ -3,6 +3,7 @@
 // (source/navier_stokes_matrix.cc:85-483) around the cell kernels.
 #include <chrono>
 #include <cstdlib>
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <new>
@@ -318,6 +319,46 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
     } else
       mf->ghost_range_valid = true;  // no ghosts (lowest rank): empty range, the exports still overlap
   }
+  {  // host-vector pipeline metadata (adaflo_b200_ns_vmult_host): monotone node prefixes per cell chunk
+    const size_t n_dec = n_groups(d->n_cells);
+    // 16 ... 64 chunks of at least 2048 decades (a chunk is one launch of the persistent cell kernel)
+    const size_t n_chunks = n_dec < 16 ? (n_dec ? 1 : 0) : std::min<size_t>(64, std::max<size_t>(16, n_dec / 2048));
+    mf->pipeline_ok = n_chunks > 0;
+    for (size_t k = 0; k < n_chunks; ++k) mf->chunk_decade_end.push_back(k + 1 == n_chunks ? n_dec : (k + 1) * (n_dec / n_chunks));
+    for (int i = 0; i < d->n_spaces && mf->pipeline_ok; ++i) {
+      const adaflo_b200_space_desc &sd = d->spaces[i];
+      Space &sp = mf->spaces[i];
+      std::vector<uint32_t> cmax(n_chunks, 0), cmin(n_chunks, UINT32_MAX);
+      size_t k = 0;
+      for (uint32_t c = 0; c < d->n_cells; ++c) {
+        while (c / kGroup >= mf->chunk_decade_end[k]) ++k;
+        for (uint32_t j = 0; j < sd.nodes_per_cell; ++j) {
+          const uint32_t n = sd.cell_nodes[(size_t)c * sd.nodes_per_cell + j] & ADAFLO_B200_NODE_MASK;
+          cmax[k] = std::max(cmax[k], n + 1);
+          cmin[k] = std::min(cmin[k], n);
+        }
+      }
+      const uint32_t n_nodes = sd.n_owned_nodes + sd.n_ghost_nodes;
+      sp.chunk_need_hi.assign(n_chunks, 0);
+      sp.chunk_final_lo.assign(n_chunks, n_nodes);
+      uint32_t run = 0;
+      for (size_t q = 0; q < n_chunks; ++q) sp.chunk_need_hi[q] = run = std::max(run, cmax[q]);
+      run = n_nodes;
+      for (size_t q = n_chunks; q-- > 0;) {
+        sp.chunk_final_lo[q] = run;  // nodes below the minimum of all later chunks are final after chunk q
+        run = std::min(run, cmin[q]);
+      }
+      // constrained entries must be sorted to be applied prefix by prefix
+      sp.chunk_constrained_end.assign(n_chunks, sd.n_constrained);
+      for (uint32_t q = 1; q < sd.n_constrained; ++q)
+        if (sd.constrained_dofs[q] < sd.constrained_dofs[q - 1]) mf->pipeline_ok = false;
+      if (mf->pipeline_ok)
+        for (size_t q = 0; q < n_chunks; ++q)
+          sp.chunk_constrained_end[q] = (uint32_t)(std::lower_bound(sd.constrained_dofs, sd.constrained_dofs + sd.n_constrained,
+                                                                    (uint32_t)std::min<uint64_t>((uint64_t)sp.chunk_final_lo[q] * sd.n_components, UINT32_MAX)) -
+                                                   sd.constrained_dofs);
+    }
+  }
   AB_CUDA(cudaStreamSynchronize(s));  // host arrays may be freed by the caller now
   *out = mf;
   return 0;
@@ -472,6 +513,12 @@ int adaflo_b200_ns_destroy(adaflo_b200_ns_t ns)
                   ns->modes[1], ns->mode_weights[0], ns->mode_weights[1], ns->stage_u[0], ns->stage_u[1], ns->stage_p[0],
                   ns->stage_p[1], ns->tmp_p};
   for (void *p : ptrs) free_dev(p);
+  if (ns->pipe_events) {
+    for (cudaEvent_t e : *ns->pipe_events) cudaEventDestroy(e);
+    delete ns->pipe_events;
+  }
+  if (ns->up_stream) cudaStreamDestroy(ns->up_stream);
+  if (ns->down_stream) cudaStreamDestroy(ns->down_stream);
   if (ns->kernel_events) {
     for (auto &e : *ns->kernel_events) {
       cudaEventDestroy(e.first);
@@ -955,11 +1002,92 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
     if (!ns->stage_u[i]) AB_CUDA(cudaMalloc((void **)&ns->stage_u[i], nu * sizeof(double)));
     if (!ns->stage_p[i]) AB_CUDA(cudaMalloc((void **)&ns->stage_p[i], np * sizeof(double)));
   }
-  AB_CUDA(cudaMemcpyAsync(ns->stage_u[0], src_u_host, su.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
-  AB_CUDA(cudaMemcpyAsync(ns->stage_p[0], src_p_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
-  AB_CHECK(vmult_impl(ns, ns->stage_u[1], ns->stage_p[1], ns->stage_u[0], ns->stage_p[0], false));
-  AB_CUDA(cudaMemcpyAsync(dst_u_host, ns->stage_u[1], su.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
-  AB_CUDA(cudaMemcpyAsync(dst_p_host, ns->stage_p[1], sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  adaflo_b200_mf_t mf = ns->mf;
+  static const bool pipe_enabled = [] { const char *e = std::getenv("ADAFLO_B200_HOST_PIPELINE"); return !(e && !std::strcmp(e, "0")); }();
+  static const bool legacy_kernel = [] { const char *k = std::getenv("ADAFLO_B200_VMULT_KERNEL"); return k && !std::strcmp(k, "v1"); }();
+  const int mode = mode_of(ns->prm);
+  if (!pipe_enabled || legacy_kernel || !mf->pipeline_ok || ns->ctx->nranks > 1 || ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin)) {
+    // plain path: upload, vmult, download
+    AB_CUDA(cudaMemcpyAsync(ns->stage_u[0], src_u_host, su.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+    AB_CUDA(cudaMemcpyAsync(ns->stage_p[0], src_p_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+    AB_CHECK(vmult_impl(ns, ns->stage_u[1], ns->stage_p[1], ns->stage_u[0], ns->stage_p[0], false));
+    AB_CUDA(cudaMemcpyAsync(dst_u_host, ns->stage_u[1], su.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(cudaMemcpyAsync(dst_p_host, ns->stage_p[1], sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    AB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
+  // Pipelined path (one GPU): PCIe is full duplex, so the upload of the source prefix needed by cell chunk k+1, the
+  // cell kernel on chunk k and the download of the result prefix that chunk k-1 completed run concurrently on
+  // three streams.  The prefixes are monotone by construction (mf_create), so any cell numbering is handled; a
+  // numbering without locality merely degenerates to upload - compute - download.
+  const size_t n_chunks = mf->chunk_decade_end.size();
+  if (!ns->up_stream) AB_CUDA(cudaStreamCreateWithFlags(&ns->up_stream, cudaStreamNonBlocking));
+  if (!ns->down_stream) AB_CUDA(cudaStreamCreateWithFlags(&ns->down_stream, cudaStreamNonBlocking));
+  if (!ns->pipe_events) ns->pipe_events = new std::vector<cudaEvent_t>();
+  while (ns->pipe_events->size() < 2 * n_chunks + 1) {
+    cudaEvent_t e;
+    AB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ns->pipe_events->push_back(e);
+  }
+  std::chrono::steady_clock::time_point t0;
+  stats_begin(ns, t0);
+  double *du = ns->stage_u[1], *dp = ns->stage_p[1];
+  const double *xu = ns->stage_u[0], *xp = ns->stage_p[0];
+  cudaEvent_t ev_start = (*ns->pipe_events)[2 * n_chunks];
+  AB_CUDA(cudaEventRecord(ev_start, s));  // earlier work on the compute stream may still use the staging vectors
+  AB_CUDA(cudaStreamWaitEvent(ns->up_stream, ev_start, 0));
+  AB_CUDA(cudaStreamWaitEvent(ns->down_stream, ev_start, 0));
+  AB_CUDA(cudaMemsetAsync(du, 0, su.n_local_entries() * sizeof(double), s));
+  AB_CUDA(cudaMemsetAsync(dp, 0, sp.n_local_entries() * sizeof(double), s));
+  NSArgs a = make_args(ns, false);
+  a.src_u = xu;
+  a.src_p = xp;
+  a.dst_u = du;
+  a.dst_p = dp;
+  size_t up_u = 0, up_p = 0, down_u = 0, n_con = 0;
+  for (size_t k = 0; k < n_chunks; ++k) {
+    cudaEvent_t ev_up = (*ns->pipe_events)[2 * k], ev_done = (*ns->pipe_events)[2 * k + 1];
+    const size_t need_u = std::min<size_t>((size_t)su.chunk_need_hi[k] * su.n_comp, su.n_owned_entries());
+    const size_t need_p = std::min<size_t>((size_t)sp.chunk_need_hi[k] * sp.n_comp, sp.n_owned_entries());
+    if (need_u > up_u)
+      AB_CUDA(cudaMemcpyAsync(ns->stage_u[0] + up_u, src_u_host + up_u, (need_u - up_u) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+    if (need_p > up_p)
+      AB_CUDA(cudaMemcpyAsync(ns->stage_p[0] + up_p, src_p_host + up_p, (need_p - up_p) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+    up_u = std::max(up_u, need_u);
+    up_p = std::max(up_p, need_p);
+    if (k + 1 == n_chunks) {  // whatever no cell references (none on conforming meshes)
+      if (su.n_owned_entries() > up_u)
+        AB_CUDA(cudaMemcpyAsync(ns->stage_u[0] + up_u, src_u_host + up_u, (su.n_owned_entries() - up_u) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+      if (sp.n_owned_entries() > up_p)
+        AB_CUDA(cudaMemcpyAsync(ns->stage_p[0] + up_p, src_p_host + up_p, (sp.n_owned_entries() - up_p) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+    }
+    AB_CUDA(cudaEventRecord(ev_up, ns->up_stream));
+    AB_CUDA(cudaStreamWaitEvent(s, ev_up, 0));
+    a.decade_begin = k ? mf->chunk_decade_end[k - 1] : 0;
+    a.decade_end = mf->chunk_decade_end[k];
+    AB_CHECK(launch_cells(ns, a, true));
+    // constrained rows of the velocity prefix that is final now (:247-256), then its download
+    const size_t fin_u = k + 1 == n_chunks ? su.n_owned_entries() : std::min<size_t>((size_t)su.chunk_final_lo[k] * su.n_comp, up_u);
+    size_t con_end = k + 1 == n_chunks ? su.n_constrained : su.chunk_constrained_end[k];
+    if (k + 1 < n_chunks && (size_t)su.chunk_final_lo[k] * su.n_comp > up_u) con_end = n_con;  // (orphan nodes: wait for the last chunk)
+    if (con_end > n_con) AB_CHECK(vec_copy_indexed(s, du, xu, su.constrained + n_con, (uint32_t)(con_end - n_con), 1.0));
+    n_con = std::max(n_con, con_end);
+    AB_CUDA(cudaEventRecord(ev_done, s));
+    if (fin_u > down_u) {
+      AB_CUDA(cudaStreamWaitEvent(ns->down_stream, ev_done, 0));
+      AB_CUDA(cudaMemcpyAsync(dst_u_host + down_u, du + down_u, (fin_u - down_u) * sizeof(double), cudaMemcpyDeviceToHost, ns->down_stream));
+      down_u = fin_u;
+    }
+  }
+  // pressure block: constrained rows and the global null-space projection need the whole vector
+  AB_CHECK(vec_copy_indexed(s, dp, xp, sp.constrained, sp.n_constrained, -1.0));
+  if (projection_active(ns))
+    for (int m = 0; m < 2; ++m)
+      if (ns->has_mode[m])
+        AB_CHECK(vec_project(ns->ctx, dp, ns->mode_weights[m], ns->modes[m], ns->inv_weights[m], sp.n_owned_entries(), sp.n_local_entries()));
+  AB_CUDA(cudaMemcpyAsync(dst_p_host, dp, sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  stats_end(ns, t0);
+  AB_CUDA(cudaStreamSynchronize(ns->down_stream));
   AB_CUDA(cudaStreamSynchronize(s));
   return 0;
 }

@@ -65,6 +65,9 @@ struct Space {
   uint32_t *constrained;     // device
   std::vector<Exchange> exchange;
   std::vector<uint32_t> dg0_dofs;  // host: element-constant dofs (FE_Q_DG0)
+  // host-vector pipeline (vmult_host): per cell chunk, the node prefix the chunk needs as source, the node
+  // prefix that is final after the chunk, and the number of constrained entries inside the final prefix
+  std::vector<uint32_t> chunk_need_hi, chunk_final_lo, chunk_constrained_end;
   uint64_t n_owned_entries() const { return (uint64_t)n_owned_nodes * n_comp; }
   uint64_t n_local_entries() const { return (uint64_t)(n_owned_nodes + n_ghost_nodes) * n_comp; }
 };
@@ -106,6 +109,9 @@ struct adaflo_b200_mf_s {
   // (true for contiguous partitions with lower-rank ownership); used to overlap the halo import
   size_t ghost_decade_begin = 0, ghost_decade_end = 0;
   bool ghost_range_valid = false;
+  // host-vector pipeline: chunk k covers the decades [chunk_decade_end[k-1], chunk_decade_end[k])
+  std::vector<size_t> chunk_decade_end;
+  bool pipeline_ok = false;
 };
 
 struct adaflo_b200_ns_s {
@@ -125,6 +131,8 @@ struct adaflo_b200_ns_s {
   bool has_mode[2];
   // host staging for the *_host entry points
   double *stage_u[2], *stage_p[2];
+  cudaStream_t up_stream, down_stream;      // host-vector pipeline (created on first use)
+  std::vector<cudaEvent_t> *pipe_events;    // 2 per chunk: uploaded, computed
   double *tmp_p;  // scratch pressure vector (Tvmult)
   bool var;       // variable coefficients in use
   // statistics

@@ -212,6 +212,46 @@ def test_host_entry_point_matches_device(ctx):
     P.close()
 
 
+def test_host_entry_point_pipelined_chunks(ctx):
+    """>= 16 decades: vmult_host overlaps upload / cell chunks / download on three streams (16 cell chunks)."""
+    P = Pair(ctx, n=(6, 6, 7))
+    P.residual_both()
+    m = P.mesh
+    for seed in (91, 92):   # second call reuses the staging vectors and events
+        su, sp = seeded_uniform(m.u.global_ids, 3, seed), seeded_uniform(m.p.global_ids, 1, seed + 10)
+        ou, op = P.O.vmult(su, sp)
+        hu, hp = torch.from_numpy(su).pin_memory(), torch.from_numpy(sp).pin_memory()
+        du, dp = torch.full_like(hu, 7.0).pin_memory(), torch.full_like(hp, 7.0).pin_memory()
+        P.A.vmult_host(du, dp, hu, hp)
+        assert rel_err(du.numpy(), ou) < TOL and rel_err(dp.numpy(), op) < TOL
+        # and the device path afterwards (shared work counter, staging untouched)
+        (_, _), (gu, gp) = P.vmult_both(seed=seed)
+    P.close()
+
+
+def test_host_entry_point_pipelined_hanging_nodes(ctx):
+    from adaflo_b200.mesh import RefinedBoxMesh
+    mesh = RefinedBoxMesh((3, 3, 3), ((1, 3), (0, 2), (1, 2)))
+    dprm, oprm = flow_params(damping=-0.2, tau_grad_div=0.3)
+    dtw, otw = time_weights()
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, old, old_old)
+    A.initialize(mf, dtw, True)
+    O = orc.OracleNavierStokesMatrix(mesh, oprm, otw, None, True, mesh.u_lists, mesh.p_lists)
+    u0 = beltrami_velocity(mesh.u.coords, 0.1).reshape(-1) + 0.1 * seeded_uniform(mesh.u.global_ids, 3, 5)
+    p0 = seeded_uniform(mesh.p.global_ids, 1, 6)
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, u0, p0, np.zeros(O.n_u), np.zeros(O.n_p))
+    A.residual(BlockVector.like(mf), BlockVector(dev(ctx, u0), dev(ctx, p0)), BlockVector.like(mf))
+    su, sp = seeded_uniform(mesh.u.global_ids, 3, 93), seeded_uniform(mesh.p.global_ids, 1, 94)
+    ou, op = O.vmult(su, sp)
+    hu, hp = torch.from_numpy(su).pin_memory(), torch.from_numpy(sp).pin_memory()
+    du, dp = torch.empty_like(hu).pin_memory(), torch.empty_like(hp).pin_memory()
+    A.vmult_host(du, dp, hu, hp)
+    assert rel_err(du.numpy(), ou) < TOL and rel_err(dp.numpy(), op) < TOL
+
+
 @pytest.mark.parametrize("refine", [((1, 3), (0, 2), (1, 2)), ((0, 1), (0, 1), (0, 1)), ((1, 2), (1, 2), (0, 3))])
 @pytest.mark.parametrize("var", [False, True])
 def test_hanging_nodes(ctx, refine, var):
