@@ -36,6 +36,23 @@ METRIC = "ns_vmult_dofs_per_s"
 UNIT = "DoF/s"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the cell kernel at the bench workload, from the committed
+    summary of the latest `ncu --set full` capture (profiles/); None if the summary is missing."""
+    path = os.path.join(ROOT, "profiles", "r1_e_ns_vmult_r1_key_metrics.txt")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[2]) * scale[f[1]]
+                seen += 1
+    except OSError:
+        return None
+    return total if seen == 2 else None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -261,6 +278,18 @@ def main():
     ms_per_step = ms_total / args.steps
     value = n_dofs / (ms_per_step * 1e-3)
 
+    if args.kernel_only and os.environ.get("ADAFLO_B200_HOST_CHUNKS"):
+        nu_own, np_own = mf.n_owned(0), mf.n_owned(1)
+        hu = src.block(0)[:nu_own].cpu().pin_memory()
+        hp = src.block(1)[:np_own].cpu().pin_memory()
+        ou, op = torch.empty_like(hu).pin_memory(), torch.empty_like(hp).pin_memory()
+        A.vmult_host(ou, op, hu, hp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            A.vmult_host(ou, op, hu, hp)
+        torch.cuda.synchronize()
+        print("host chunks", os.environ["ADAFLO_B200_HOST_CHUNKS"], "e2e ms", (time.perf_counter() - t0) / 5 * 1e3)
     if args.kernel_only:
         if rank == 0:
             print(json.dumps({"lib": os.environ.get("ADAFLO_B200_LIB", "default"), "burst_kernel_ms": b_k * 1e3, "burst_ms_per_step": b_ms / args.steps,
@@ -329,8 +358,9 @@ def main():
                        "l2": "inputs larger than L2 (vectors 0.42 GB, linearisation data 5.4 GB per GPU)",
                        "partition": f"z-slabs x{world}", "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
-                         "kernel": "ns_vmult_r1_kernel<with_p, newton, cartesian>", "kernel_ms": k_avg * 1e3,
+                         "traffic": ncu_traffic() if n == 128 and world == 1 else None,
+                         "traffic_source": "profiles/r1_e_ns_vmult_r1_key_metrics.txt (ncu --set full, same workload, 1 GPU)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                         "kernel": "ns_vmult_r1_kernel<with_p, newton, cartesian> (persistent, 148 blocks x 11 warps)", "kernel_ms": k_avg * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_dof": B_PER_DOF_N},
             "e2e": {"value": n_dofs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (nu_own + np_own), "d2h_bytes_per_step": 8 * (nu_own + np_own),
                     "ms_per_step": e2e_t * 1e3, "rel_diff_vs_device_path": err},
