@@ -93,7 +93,7 @@ SYMBOLS = [
     "adaflo_b200_ls_compute_force",
     "adaflo_b200_vec_alloc", "adaflo_b200_vec_free", "adaflo_b200_vec_upload", "adaflo_b200_vec_download",
     "adaflo_b200_vec_set", "adaflo_b200_vec_axpy", "adaflo_b200_vec_sadd", "adaflo_b200_vec_scale",
-    "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_add_and_dot",
+    "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_multi_axpy", "adaflo_b200_vec_add_and_dot",
     "adaflo_b200_jacobi_reinit", "adaflo_b200_jacobi_vmult",
 ]
 
@@ -175,6 +175,7 @@ def load():
         "adaflo_b200_vec_scale": [vp, vp, vp, u64],
         "adaflo_b200_vec_dot": [vp, vp, vp, u64, C.POINTER(dbl)],
         "adaflo_b200_vec_multi_dot": [vp, vp, C.POINTER(vp), i32, u64, C.POINTER(dbl)],
+        "adaflo_b200_vec_multi_axpy": [vp, vp, C.POINTER(dbl), C.POINTER(vp), i32, u64],
         "adaflo_b200_vec_add_and_dot": [vp, vp, dbl, vp, vp, u64, C.POINTER(dbl)],
         "adaflo_b200_jacobi_reinit": [vp, vp, vp, u64],
         "adaflo_b200_jacobi_vmult": [vp, vp, vp, vp, u64, i32],

@@ -1145,6 +1145,11 @@ int adaflo_b200_vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const doub
 {
   return vec_multi_dot(ctx, x, ys, k, n, results_host, true);
 }
+int adaflo_b200_vec_multi_axpy(adaflo_b200_ctx_t ctx, double *y, const double *a_host, const double *const *xs, int k, uint64_t n)
+{
+  if (!ctx || (k > 0 && n && (!y || !a_host || !xs))) return fail(ADAFLO_B200_ERR_ARG, "vec_multi_axpy: null argument");
+  return vec_multi_axpy(ctx, y, a_host, xs, k, n);
+}
 int adaflo_b200_vec_add_and_dot(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, const double *z, uint64_t n, double *result_host)
 {
   return vec_add_and_dot(ctx, y, a, x, z, n, result_host);

@@ -222,6 +222,7 @@ int vec_sadd(cudaStream_t s, double *y, double sc, double a, const double *x, ui
 int vec_scale(cudaStream_t s, double *y, const double *sc, uint64_t n);
 int vec_copy_indexed(cudaStream_t s, double *dst, const double *src, const uint32_t *idx, uint32_t n, double sign);
 int vec_set_indexed(cudaStream_t s, double *dst, const uint32_t *idx, uint32_t n, double value);
+int vec_multi_axpy(adaflo_b200_ctx_t ctx, double *y, const double *a_host, const double *const *xs, int k, uint64_t n);
 int vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *ys, int k, uint64_t n, double *results_host,
                   bool to_host);
 int vec_project(adaflo_b200_ctx_t ctx, double *p, const double *w, const double *mode, double inv_weight, uint64_t n_owned,

@@ -194,6 +194,22 @@ __global__ void __launch_bounds__(kVecThreads) k_multi_dot(const double *__restr
   }
 }
 
+// y += sum_j a[j] x_j: one read-modify-write of y for up to kMaxDots vectors
+struct AxpyArgs {
+  const double *x[kMaxDots];
+  double a[kMaxDots];
+};
+template <int K>
+__global__ void __launch_bounds__(kVecThreads) k_multi_axpy(double *__restrict__ y, AxpyArgs p, uint64_t n)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    double v = y[i];
+#pragma unroll
+    for (int j = 0; j < K; ++j) v = fma(p.a[j], p.x[j][i], v);
+    y[i] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kVecThreads) k_add_and_dot(double *__restrict__ y, double a, const double *__restrict__ x,
                                                             const double *__restrict__ z, uint64_t n, double *__restrict__ partial)
 {
@@ -301,6 +317,33 @@ int vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *y
     AB_CUDA(cudaMemcpyAsync(ctx->red_host, ctx->red_dev, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
     AB_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int j = 0; j < k; ++j) results_host[j] = ctx->red_host[j];
+  }
+  return 0;
+}
+
+int vec_multi_axpy(adaflo_b200_ctx_t ctx, double *y, const double *a_host, const double *const *xs, int k, uint64_t n)
+{
+  if (n == 0) return 0;
+  const unsigned grid = grid_for(n, ctx->sm_count, 8);
+  for (int j0 = 0; j0 < k; j0 += kMaxDots) {
+    const int kk = k - j0 < kMaxDots ? k - j0 : kMaxDots;
+    AxpyArgs p;
+    for (int j = 0; j < kMaxDots; ++j) {
+      p.x[j] = xs[j0 + (j < kk ? j : 0)];
+      p.a[j] = j < kk ? a_host[j0 + j] : 0.0;
+    }
+    switch (kk) {
+      case 1: k_multi_axpy<1><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+      case 2: k_multi_axpy<2><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+      case 3: k_multi_axpy<3><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+      case 4: k_multi_axpy<4><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+      case 5: k_multi_axpy<5><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+      case 6: k_multi_axpy<6><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+      case 7: k_multi_axpy<7><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+      default: k_multi_axpy<8><<<grid, kVecThreads, 0, ctx->stream>>>(y, p, n); break;
+    }
+    AB_COUNT_LAUNCH();
+    AB_CUDA(cudaGetLastError());
   }
   return 0;
 }

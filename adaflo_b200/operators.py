@@ -104,6 +104,15 @@ class Context:
         check(self.lib.adaflo_b200_vec_multi_dot(self.h, _ptr(x), arr, k, n if n is not None else x.numel(), res))
         return [res[i] for i in range(k)]
 
+    def multi_axpy(self, y, coeffs, xs, n=None):
+        """y += sum_i coeffs[i] * xs[i] in one pass over y."""
+        k = len(xs)
+        if k == 0:
+            return
+        arr = (C.c_void_p * k)(*[x.data_ptr() for x in xs])
+        a = (C.c_double * k)(*[float(c) for c in coeffs])
+        check(self.lib.adaflo_b200_vec_multi_axpy(self.h, _ptr(y), a, arr, k, n if n is not None else y.numel()))
+
     def add_and_dot(self, y, a, x, z, n=None):
         r = C.c_double()
         check(self.lib.adaflo_b200_vec_add_and_dot(self.h, _ptr(y), a, _ptr(x), _ptr(z), n if n is not None else y.numel(), C.byref(r)))

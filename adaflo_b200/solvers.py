@@ -134,6 +134,11 @@ class SolverGMRES:
             out = [a + b for a, b in zip(out, part)]
         return out
 
+    def _maxpy(self, y, coeffs, X):
+        """y += sum_i coeffs[i] X[i], block by block, one pass over y per 8 vectors"""
+        for blk in range(len(y)):
+            self.ctx.multi_axpy(y[blk], coeffs, [v[blk] for v in X])
+
     def solve(self, A, x, b, P=None, ns=None):
         ctx, ctl, m = self.ctx, self.control, self.m
         ns = ns if ns is not None else [v.numel() for v in x]
@@ -169,16 +174,19 @@ class SolverGMRES:
                     A(w, z)
                 else:
                     A(w, V[j])
-                h = self._dots(w, V, ns)
-                for i, vi in enumerate(V):
-                    for k in range(nb):
-                        ctx.axpy(w[k], -h[i], vi[k])
-                h2 = self._dots(w, V, ns)            # re-orthogonalisation pass
-                for i, vi in enumerate(V):
-                    for k in range(nb):
-                        ctx.axpy(w[k], -h2[i], vi[k])
-                h = [a + c for a, c in zip(h, h2)]
-                hn = math.sqrt(self._dots(w, [w], ns)[0])
+                # classical Gram-Schmidt in two vector passes: V^T w and |w|^2 fused into one multi-dot, w -= V h
+                # fused into one multi-axpy.  The second (re-orthogonalisation) pass is taken only on severe
+                # cancellation |w_new| < |w_old| / 10, which bounds the loss of orthogonality by ~10 eps per step.
+                hw = self._dots(w, V + [w], ns)
+                h, ww = hw[:-1], hw[-1]
+                self._maxpy(w, [-a for a in h], V)
+                hn2 = self._dots(w, [w], ns)[0]
+                if hn2 < 1e-2 * ww:
+                    h2 = self._dots(w, V, ns)
+                    self._maxpy(w, [-a for a in h2], V)
+                    h = [a + c for a, c in zip(h, h2)]
+                    hn2 = self._dots(w, [w], ns)[0]
+                hn = math.sqrt(max(hn2, 0.0))
                 col = h + [hn]
                 for i in range(j):                   # apply previous Givens rotations
                     t0 = cs[i] * col[i] + sn[i] * col[i + 1]
@@ -195,7 +203,7 @@ class SolverGMRES:
                 res = abs(g[j + 1])
                 ctl.history.append(res)
                 if hn > 0:
-                    V.append([t.clone() * (1.0 / hn) for t in w])
+                    V.append([t * (1.0 / hn) for t in w])
                 if res <= tol or it_total >= ctl.max_iter or hn == 0:
                     break
             k_dim = len(H)
@@ -203,10 +211,7 @@ class SolverGMRES:
             for i in range(k_dim - 1, -1, -1):
                 s = g[i] - sum(H[c][i] * y[c] for c in range(i + 1, k_dim))
                 y[i] = s / H[i][i]
-            for i in range(k_dim):
-                src = Z[i] if P else V[i]
-                for k in range(nb):
-                    ctx.axpy(x[k], y[i], src[k])
+            self._maxpy(x, y, Z if P else V[:k_dim])
             if res <= tol:
                 break
             if it_total >= ctl.max_iter:

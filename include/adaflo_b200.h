@@ -329,6 +329,9 @@ int adaflo_b200_vec_scale(adaflo_b200_ctx_t ctx, double *y, const double *scalin
 int adaflo_b200_vec_dot(adaflo_b200_ctx_t ctx, const double *x, const double *y, uint64_t n, double *result_host);
 /* k dots of one vector against k others in one pass (GMRES Gram-Schmidt) */
 int adaflo_b200_vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *ys, int k, uint64_t n, double *results_host);
+/* y += sum_i a[i] xs[i] in one pass over y (GMRES: Gram-Schmidt update and solution update; deal.II does k axpys,
+ * lac/solver_gmres.h) */
+int adaflo_b200_vec_multi_axpy(adaflo_b200_ctx_t ctx, double *y, const double *a_host, const double *const *xs, int k, uint64_t n);
 /* add_and_dot: y += a x ; returns y . z   (deal.II Vector::add_and_dot, used by SolverCG) */
 int adaflo_b200_vec_add_and_dot(adaflo_b200_ctx_t ctx, double *y, double a, const double *x, const double *z, uint64_t n, double *result_host);
 /* DiagonalPreconditioner::reinit (guarded inverse, :38-60) and ::vmult (:99-124) */

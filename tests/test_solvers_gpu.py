@@ -146,3 +146,18 @@ def test_navier_stokes_gmres_matches_oracle_gmres(ctx):
         assert abs(hist[j + 1] / hist[0] - res[j]) < 1e-8 * max(1.0, res[j]) + 1e-10
     A.clear()
     mf.close()
+
+
+def test_multi_axpy_matches_torch(ctx):
+    """y += sum_i a_i x_i in one pass (k = 1, 8, 11: one and two kernel passes)"""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n = 10007
+    for k in (1, 8, 11):
+        y = torch.rand(n, generator=g, dtype=torch.float64).to(ctx.device)
+        xs = [torch.rand(n, generator=g, dtype=torch.float64).to(ctx.device) for _ in range(k)]
+        a = [0.25 * (i + 1) * (-1) ** i for i in range(k)]
+        ref = y.clone()
+        for ai, xi in zip(a, xs):
+            ref += ai * xi
+        ctx.multi_axpy(y, a, xs)
+        assert float((y - ref).abs().max()) < 1e-12
