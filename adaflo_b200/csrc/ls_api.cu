@@ -34,6 +34,7 @@ LSArgs base_args(adaflo_b200_ls_t ls)
   a.n_sub = ls->prm.concentration_subdivisions;
   a.cell_ls = sp.cell_nodes;
   a.cell_u = ls->dof_vel >= 0 ? mf->spaces[ls->dof_vel].cell_nodes : nullptr;
+  a.hn_u = ls->dof_vel >= 0 ? mf->spaces[ls->dof_vel].hanging_masks : nullptr;
   a.hn = sp.hanging_masks;
   a.geom_row = q.cell_row;
   a.geom_table = q.table;
@@ -181,8 +182,6 @@ int adaflo_b200_ls_advance_concentration_rhs(adaflo_b200_ls_t ls, double *rhs, c
 {
   if (!ls || !rhs || !vel || !c || !c_old || !c_old_old) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   if (ls->dof_vel < 0) return fail(ADAFLO_B200_ERR_STATE, "advance_concentration_rhs: no velocity space given at create");
-  if (ls->mf->spaces[ls->dof_vel].hanging_masks)
-    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "advance_concentration_rhs: velocity spaces with hanging nodes are not implemented");
   LSArgs a = base_args(ls);
   a.src[0] = c;
   a.aux[0] = c_old;

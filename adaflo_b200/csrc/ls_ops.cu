@@ -152,9 +152,35 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
       }
 #pragma unroll
     for (int p = 0; p < 8; ++p) uq[p][0] = uq[p][1] = uq[p][2] = 0;
+    // velocity space with hanging nodes (read_dof_values_plain of a distributed vector = the interpolated
+    // values): the cell list holds the parent's nodes on hanging faces / edges, interpolate line by line, all
+    // lines of one direction before the next (same order as the Navier-Stokes cell kernels)
+    const HnInfo hnu(A.hn_u ? __ldg(A.hn_u + cell) : 0u);
+    double U[3][27];
+    if (hnu.any()) {
+      for (int n = 0; n < 27; ++n) {
+        const size_t un = __ldg(A.cell_u + (size_t)cell * 27 + n) & ADAFLO_B200_NODE_MASK;
+        for (int c = 0; c < 3; ++c) U[c][n] = A.vel[3 * un + c];
+      }
+      const int stride[3] = {1, 3, 9};
+      for (int d = 0; d < 3; ++d) {
+        const int e = (d + 1) % 3, f = (d + 2) % 3;
+        for (int ie = 0; ie < 3; ++ie)
+          for (int jf = 0; jf < 3; ++jf)
+            if (hnu.line(d, ie, jf, 3)) {
+              const int n0 = ie * stride[e] + jf * stride[f];
+              for (int c = 0; c < 3; ++c) hn_q2(hnu.sub(d), U[c][n0], U[c][n0 + stride[d]], U[c][n0 + 2 * stride[d]]);
+            }
+      }
+    }
     for (int n = 0; n < 27; ++n) {
-      const size_t un = __ldg(A.cell_u + (size_t)cell * 27 + n) & ADAFLO_B200_NODE_MASK;
-      const double u0 = A.vel[3 * un], u1 = A.vel[3 * un + 1], u2 = A.vel[3 * un + 2];
+      double u0, u1, u2;
+      if (hnu.any()) {
+        u0 = U[0][n]; u1 = U[1][n]; u2 = U[2][n];
+      } else {
+        const size_t un = __ldg(A.cell_u + (size_t)cell * 27 + n) & ADAFLO_B200_NODE_MASK;
+        u0 = A.vel[3 * un]; u1 = A.vel[3 * un + 1]; u2 = A.vel[3 * un + 2];
+      }
       const int i = n % 3, j = (n / 3) % 3, k = n / 9;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {

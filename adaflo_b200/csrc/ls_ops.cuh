@@ -13,6 +13,7 @@ struct LSArgs {
   int n_sub;
   const uint32_t *cell_ls;   // [n_cells][(n_sub+1)^3], flag bit 29 = constrained
   const uint32_t *cell_u;    // [n_cells][27] (advect rhs)
+  const uint32_t *hn_u;      // [n_cells] hanging-node masks of the velocity space or null
   const uint32_t *hn;        // per-cell refinement masks of the level-set space or null
   const uint32_t *geom_row;
   const double *geom_table;

@@ -201,10 +201,27 @@ def test_level_set_operators_with_hanging_nodes(ctx, refine):
     mf = MatrixFree(ctx, mesh, "cartesian")
     h_min = float(mesh.h_cell.min())
     eps, eps_used = 1.5, 1.5 * h_min / n_sub
-    A = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, eps, eps_used, 4.0, h_min), mesh.cell_diameters(), dof_index_vel=-1)
+    A = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, eps, eps_used, 4.0, h_min), mesh.cell_diameters(), dof_index_vel=0)
     A.set_time(75.0, -100.0, 25.0, 0.02)
     O = orc.OracleLevelSet(mesh, orc.LSParams(eps, eps_used, 4.0, h_min, 0.02, 3, 0))
     n = mesh.ls.n_owned
+    # advection rhs with a velocity space that has hanging nodes (read_dof_values_plain of a distributed vector):
+    # the oracle gets the plainly expanded nodal values, one private entry per (cell, node)
+    vel = beltrami_velocity(mesh.u.coords, 0.0).reshape(-1) + 0.1 * seeded_uniform(mesh.u.global_ids, 3, 6)
+    ptr, idx, wts = mesh.u_lists
+    expanded = np.add.reduceat(wts * vel[idx], ptr[:-1]).reshape(mesh.n_cells, 3, 27)   # [cell][comp][node]
+    O.cell_u = np.arange(mesh.n_cells * 27, dtype=np.int64).reshape(mesh.n_cells, 27)
+    vel_ext = np.ascontiguousarray(expanded.transpose(0, 2, 1).reshape(-1))              # [(cell, node)][comp]
+    x = mesh.ls.coords
+    c_adv = -np.tanh((np.linalg.norm(x - np.array([0.1, -0.05, -0.2]), axis=1) - 0.45) / 0.3)
+    c_old, c_oo = c_adv + 0.05 * seeded_uniform(mesh.ls.global_ids, 1, 7), c_adv + 0.05 * seeded_uniform(mesh.ls.global_ids, 1, 8)
+    pre = seeded_uniform(mesh.ls.global_ids, 1, 9)
+    o = pre.copy()
+    O.advance_concentration_rhs(o, vel_ext, c_adv, c_old, c_oo, 75.0, -100.0, 25.0)
+    g = dev(ctx, pre)
+    A.advance_concentration_rhs(g, dev(ctx, vel), dev(ctx, c_adv), dev(ctx, c_old), dev(ctx, c_oo))
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    assert rel_err(A.pointdata_canonical(0).cpu().numpy(), O.conv) < TOL
     diag = O.mass_diagonal()
     O.diag = diag
     A.set_diagonal(dev(ctx, diag))
