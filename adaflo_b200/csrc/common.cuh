@@ -24,6 +24,16 @@ __host__ __device__ inline size_t coef_index(uint32_t cell, int row, int n_rows,
   const int cw = (int)(cell % kGroup);
   return ((g * n_rows + row) * 9 + (size_t)(3 * qx + qz)) * 30 + 3 * cw + qy;
 }
+// The 12-row linearisation array (u, grad u at every point) interleaves its rows in pairs, so that a lane of the
+// vmult kernel fetches two rows with one 16-byte load (480 contiguous bytes per warp): row r of the point lives at
+//   (((g * 6 + r / 2) * 9 + 3 qx + qz) * 30 + 3 cw + qy) * 2 + (r & 1)  =  lin_index(cell, qx, qy, qz) + lin_row(r)
+__host__ __device__ inline size_t lin_index(uint32_t cell, int qx, int qy, int qz)
+{
+  const size_t g = cell / kGroup;
+  const int cw = (int)(cell % kGroup);
+  return ((g * 6 * 9 + (size_t)(3 * qx + qz)) * 30 + 3 * cw + qy) * 2;
+}
+__host__ __device__ constexpr int lin_row(int r) { return (r >> 1) * 540 + (r & 1); }
 inline size_t n_groups(uint32_t n_cells) { return ((size_t)n_cells + kGroup - 1) / kGroup; }
 
 void set_error(const std::string &msg);

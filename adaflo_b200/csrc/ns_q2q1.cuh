@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) ns_vmult_kernel(const 
   double tp[3];
 #pragma unroll
   for (int qy = 0; qy < 3; ++qy) {
-    const double *lin = A.lin + coef_index(cell, 0, 12, a, qy, b);  // row stride 270
+    const double *lin = A.lin + lin_index(cell, a, qy, b);  // row r at lin_row(r)
     const double jxw = G.at(a, qy, b, W[a] * W[qy] * W[b]);
     const size_t q1 = coef_index(cell, 0, 1, a, qy, b);  // rho / mu / damping
     double g[3][3];  // g[d][e] = d u_d / d x_e
@@ -450,11 +450,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) ns_vmult_kernel(const 
       if (MODE == MODE_NEWTON) {
         double lu[3], lg[3][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
+        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + lin_row(d));
 #pragma unroll
         for (int d = 0; d < 3; ++d)
 #pragma unroll
-          for (int e = 0; e < 3; ++e) lg[d][e] = __ldg(lin + (3 + 3 * d + e) * 270);
+          for (int e = 0; e < 3; ++e) lg[d][e] = __ldg(lin + lin_row(3 + 3 * d + e));
         const double ltr = lg[0][0] + lg[1][1] + lg[2][2];
         if (!TRANSPOSE) {
           const double f1 = A.beta * div, f2 = A.beta * ltr;
@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) ns_vmult_kernel(const 
       } else if (MODE == MODE_PICARD) {
         double lu[3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + d * 270);
-        const double ldiv = __ldg(lin + 3 * 270);
+        for (int d = 0; d < 3; ++d) lu[d] = __ldg(lin + lin_row(d));
+        const double ldiv = __ldg(lin + lin_row(3));
 #pragma unroll
         for (int d = 0; d < 3; ++d) {
           double res = A.beta * ldiv * u[d];

@@ -99,13 +99,19 @@ __device__ __forceinline__ double ld_pinned(const double *p)
   return v;
 }
 
-// rows of the linearisation point of quadrature point n = 3 qx + qz of this lane
+// pinned 16-byte load of a row pair of the linearisation array
+__device__ __forceinline__ void ld_pinned2(const double *p, double &a, double &b)
+{
+  asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+
+// rows of the linearisation point of quadrature point n = 3 qx + qz of this lane (row pairs, see lin_index)
 template <int MODE>
 __device__ __forceinline__ void load_lin(double (&L)[12], const double *lin_lane, int n)
 {
-  constexpr int rows = MODE == MODE_NEWTON ? 12 : (MODE == MODE_PICARD ? 4 : 0);
+  constexpr int pairs = MODE == MODE_NEWTON ? 6 : (MODE == MODE_PICARD ? 2 : 0);
 #pragma unroll
-  for (int r = 0; r < rows; ++r) L[r] = ld_pinned(lin_lane + (size_t)r * 270 + n * 30);
+  for (int r = 0; r < pairs; ++r) ld_pinned2(lin_lane + (size_t)r * 540 + n * 60, L[2 * r], L[2 * r + 1]);
 }
 
 // One decade (10 cells) of the cell loop, executed by one warp: 3 lanes per cell.
@@ -138,7 +144,7 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
     }
   }
 
-  const double *lin_lane = A.lin + g * (12 * 270) + lane;
+  const double *lin_lane = A.lin + g * (12 * 270) + 2 * lane;
   Geometry<GEOM> G;  // table row of the cell (two dependent loads): issue before the gather
   G.init_blk(A, cell);
   const HnInfo hn((HANGING && A.hn_u) ? __ldg(A.hn_u + cell) : 0u);

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
   double tp[3];
 #pragma unroll
   for (int qy = 0; qy < 3; ++qy) {
-    double *lin = A.lin ? A.lin + coef_index(cell, 0, 12, a, qy, b) : nullptr;  // row stride 270
+    double *lin = A.lin ? A.lin + lin_index(cell, a, qy, b) : nullptr;  // row r at lin_row(r)
     const size_t q1 = coef_index(cell, 0, 1, a, qy, b);
     const double jxw = G.at(a, qy, b, W[a] * W[qy] * W[b]);
     double g[3][3];
@@ -164,9 +164,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
 #pragma unroll
             for (int e = 0; e < 3; ++e) res += eu[e] * g[d][e];
             conv[d] += A.tau1 * res;
-            lin[d * 270] = eu[d];
+            lin[lin_row(d)] = eu[d];
           }
-          lin[3 * 270] = ediv;
+          lin[lin_row(3)] = ediv;
         }
       } else {
 #pragma unroll
@@ -175,15 +175,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
 #pragma unroll
           for (int e = 0; e < 3; ++e) res += u[e] * g[d][e];
           conv[d] += A.tau1 * res;
-          lin[d * 270] = u[d];
+          lin[lin_row(d)] = u[d];
         }
         if (lz == ADAFLO_B200_COUPLED_IMPLICIT_NEWTON) {
 #pragma unroll
           for (int d = 0; d < 3; ++d)
 #pragma unroll
-            for (int e = 0; e < 3; ++e) lin[(3 + 3 * d + e) * 270] = g[d][e];
+            for (int e = 0; e < 3; ++e) lin[lin_row(3 + 3 * d + e)] = g[d][e];
         } else
-          lin[3 * 270] = div;
+          lin[lin_row(3)] = div;
       }
       const double rho = VAR ? __ldg(A.rho + q1) : A.rho0;
       const double damping = VAR ? __ldg(A.damp + q1) : A.damp0;

@@ -359,9 +359,14 @@ class NavierStokesMatrix:
         return self._coef(capi.COEF_LINEARIZED_VELOCITY)
 
     def to_canonical(self, blocked, n_rows):
+        """decade-blocked device order -> [cell][row][27 points, x fastest] (coef_index / lin_index in csrc/common.cuh)"""
         n_cells = self.matrix_free.mesh.n_cells
-        b = blocked.view(-1, n_rows, 3, 3, 10, 3)             # g, row, qx, qz, cw, qy
-        c = b.permute(0, 4, 1, 3, 5, 2).reshape(-1, n_rows, 27)  # g, cw, row, qz, qy, qx
+        if n_rows == 12:   # rows interleaved in pairs
+            b = blocked.view(-1, 6, 3, 3, 10, 3, 2)                      # g, row pair, qx, qz, cw, qy, row & 1
+            c = b.permute(0, 4, 1, 6, 3, 5, 2).reshape(-1, 12, 27)        # g, cw, pair, row & 1, qz, qy, qx
+        else:
+            b = blocked.view(-1, n_rows, 3, 3, 10, 3)                     # g, row, qx, qz, cw, qy
+            c = b.permute(0, 4, 1, 3, 5, 2).reshape(-1, n_rows, 27)       # g, cw, row, qz, qy, qx
         return c[:n_cells]
 
     def from_canonical(self, canonical, n_rows):
@@ -369,7 +374,10 @@ class NavierStokesMatrix:
         g = (n_cells + 9) // 10
         c = torch.zeros(g * 10, n_rows, 27, dtype=torch.float64, device=canonical.device)
         c[:n_cells] = canonical.reshape(n_cells, n_rows, 27)
-        b = c.view(g, 10, n_rows, 3, 3, 3).permute(0, 2, 5, 3, 1, 4)  # g, row, qx, qz, cw, qy
+        if n_rows == 12:
+            b = c.view(g, 10, 6, 2, 3, 3, 3).permute(0, 2, 6, 4, 1, 5, 3)  # g, pair, qx, qz, cw, qy, row & 1
+        else:
+            b = c.view(g, 10, n_rows, 3, 3, 3).permute(0, 2, 5, 3, 1, 4)   # g, row, qx, qz, cw, qy
         return b.reshape(-1)
 
     def set_coefficient(self, which, canonical):
