@@ -237,6 +237,8 @@ enum adaflo_b200_coefficient {
   ADAFLO_B200_COEF_DAMPING = 2,
   ADAFLO_B200_COEF_LINEARIZED_VELOCITY = 3
 };
+/* raw device storage in the decade-blocked order of csrc/common.cuh (coef_index; lin_index for the 12-row
+ * linearisation array, whose rows are interleaved in pairs) */
 int adaflo_b200_ns_coefficient_ptr(adaflo_b200_ns_t ns, int which, double **dev_ptr, uint64_t *n_doubles);
 /* pressure null-space data built by initialize (:110-168): device pointers */
 int adaflo_b200_ns_nullspace(adaflo_b200_ns_t ns, int mode, const double **modes, const double **weights, double *inverse_weight);
