@@ -39,7 +39,7 @@ UNIT = "DoF/s"
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the cell kernel at the bench workload, from the committed
     summary of the latest `ncu --set full` capture (profiles/); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_e_ns_vmult_r1_key_metrics.txt")
+    path = os.path.join(ROOT, "profiles", "r1_g_ns_vmult_r1_key_metrics.txt")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     total, seen = 0.0, 0
     try:
@@ -359,7 +359,7 @@ def main():
                        "partition": f"z-slabs x{world}", "setup_s": round(t_setup, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic() if n == 128 and world == 1 else None,
-                         "traffic_source": "profiles/r1_e_ns_vmult_r1_key_metrics.txt (ncu --set full, same workload, 1 GPU)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                         "traffic_source": "profiles/r1_g_ns_vmult_r1_key_metrics.txt (ncu --set full, same workload, 1 GPU)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
                          "kernel": "ns_vmult_r1_kernel<with_p, newton, cartesian> (persistent, 148 blocks x 11 warps)", "kernel_ms": k_avg * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_dof": B_PER_DOF_N},
             "e2e": {"value": n_dofs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (nu_own + np_own), "d2h_bytes_per_step": 8 * (nu_own + np_own),
