@@ -351,6 +351,15 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
         sp.chunk_final_lo[q] = run;  // nodes below the minimum of all later chunks are final after chunk q
         run = std::min(run, cmin[q]);
       }
+      // nodes exported to neighbours (multi-GPU): uploaded first so that the ghost import can start at once
+      sp.send_lo = n_nodes;
+      sp.send_hi = 0;
+      for (int e = 0; e < sd.n_exchange; ++e)
+        for (uint32_t q = 0; q < sd.exchange[e].n_send; ++q) {
+          sp.send_lo = std::min(sp.send_lo, sd.exchange[e].send[q]);
+          sp.send_hi = std::max(sp.send_hi, sd.exchange[e].send[q] + 1);
+        }
+      if (sp.send_hi <= sp.send_lo) sp.send_lo = sp.send_hi = n_nodes;
       // constrained entries must be sorted to be applied prefix by prefix
       sp.chunk_constrained_end.assign(n_chunks, sd.n_constrained);
       for (uint32_t q = 1; q < sd.n_constrained; ++q)
@@ -1009,7 +1018,8 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
   static const bool pipe_enabled = [] { const char *e = std::getenv("ADAFLO_B200_HOST_PIPELINE"); return !(e && !std::strcmp(e, "0")); }();
   static const bool legacy_kernel = [] { const char *k = std::getenv("ADAFLO_B200_VMULT_KERNEL"); return k && !std::strcmp(k, "v1"); }();
   const int mode = mode_of(ns->prm);
-  if (!pipe_enabled || legacy_kernel || !mf->pipeline_ok || ns->ctx->nranks > 1 || ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin)) {
+  const bool multi = ns->ctx->nranks > 1;
+  if (!pipe_enabled || legacy_kernel || !mf->pipeline_ok || ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin)) {
     // plain path: upload, vmult, download
     AB_CUDA(cudaMemcpyAsync(ns->stage_u[0], src_u_host, su.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
     AB_CUDA(cudaMemcpyAsync(ns->stage_p[0], src_p_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -1019,10 +1029,13 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
     AB_CUDA(cudaStreamSynchronize(s));
     return 0;
   }
-  // Pipelined path (one GPU): PCIe is full duplex, so the upload of the source prefix needed by cell chunk k+1, the
-  // cell kernel on chunk k and the download of the result prefix that chunk k-1 completed run concurrently on
-  // three streams.  The prefixes are monotone by construction (mf_create), so any cell numbering is handled; a
+  // Pipelined path: PCIe is full duplex, so the upload of the source prefix needed by cell chunk k+1, the cell
+  // kernel on chunk k and the download of the result prefix that chunk k-1 completed run concurrently on three
+  // streams.  The prefixes are monotone by construction (mf_create), so any cell numbering is handled; a
   // numbering without locality merely degenerates to upload - compute - download.
+  // Several GPUs: the entries this rank exports are uploaded FIRST and the ghost import runs at once; the
+  // compress(add) of the result follows the chunk that finishes the cells touching ghosts (the first one for
+  // contiguous partitions), and the exported range is held back from the download until it has been added.
   const size_t n_chunks = mf->chunk_decade_end.size();
   if (!ns->up_stream) AB_CUDA(cudaStreamCreateWithFlags(&ns->up_stream, cudaStreamNonBlocking));
   if (!ns->down_stream) AB_CUDA(cudaStreamCreateWithFlags(&ns->down_stream, cudaStreamNonBlocking));
@@ -1048,29 +1061,57 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
   a.dst_u = du;
   a.dst_p = dp;
   size_t up_u = 0, up_p = 0, down_u = 0, n_con = 0;
+  bool compressed = !multi;
+  // in-order upload of [from, to) that leaves out the export range [skip0, skip1) uploaded up front (multi-GPU)
+  cudaStream_t up = ns->up_stream;
+  auto upload = [up](double *dev, const double *host, size_t from, size_t to, size_t skip0, size_t skip1) -> int {
+    const size_t a1 = std::min(to, std::max(from, skip0)), b0 = std::max(from, std::min(to, skip1));
+    if (a1 > from) AB_CUDA(cudaMemcpyAsync(dev + from, host + from, (a1 - from) * sizeof(double), cudaMemcpyHostToDevice, up));
+    if (to > b0) AB_CUDA(cudaMemcpyAsync(dev + b0, host + b0, (to - b0) * sizeof(double), cudaMemcpyHostToDevice, up));
+    return 0;
+  };
+  const size_t skip_u0 = multi ? (size_t)su.send_lo * su.n_comp : 0, skip_u1 = multi ? (size_t)su.send_hi * su.n_comp : 0;
+  const size_t skip_p0 = multi ? (size_t)sp.send_lo * sp.n_comp : 0, skip_p1 = multi ? (size_t)sp.send_hi * sp.n_comp : 0;
+  if (multi) {
+    cudaEvent_t ev_s = (*ns->pipe_events)[0];  // (re-recorded as ev_up of chunk 0 below)
+    if (su.send_hi > su.send_lo)
+      AB_CUDA(cudaMemcpyAsync(ns->stage_u[0] + (size_t)su.send_lo * su.n_comp, src_u_host + (size_t)su.send_lo * su.n_comp,
+                              (size_t)(su.send_hi - su.send_lo) * su.n_comp * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+    if (sp.send_hi > sp.send_lo)
+      AB_CUDA(cudaMemcpyAsync(ns->stage_p[0] + (size_t)sp.send_lo * sp.n_comp, src_p_host + (size_t)sp.send_lo * sp.n_comp,
+                              (size_t)(sp.send_hi - sp.send_lo) * sp.n_comp * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+    AB_CUDA(cudaEventRecord(ev_s, ns->up_stream));
+    AB_CUDA(cudaStreamWaitEvent(s, ev_s, 0));
+    const int spaces[2] = {ns->dof_u, ns->dof_p};
+    double *vecs[2] = {ns->stage_u[0], ns->stage_p[0]};
+    AB_CHECK(comm_update_ghosts_n(mf, 2, spaces, vecs));
+  }
   for (size_t k = 0; k < n_chunks; ++k) {
     cudaEvent_t ev_up = (*ns->pipe_events)[2 * k], ev_done = (*ns->pipe_events)[2 * k + 1];
     const size_t need_u = std::min<size_t>((size_t)su.chunk_need_hi[k] * su.n_comp, su.n_owned_entries());
     const size_t need_p = std::min<size_t>((size_t)sp.chunk_need_hi[k] * sp.n_comp, sp.n_owned_entries());
-    if (need_u > up_u)
-      AB_CUDA(cudaMemcpyAsync(ns->stage_u[0] + up_u, src_u_host + up_u, (need_u - up_u) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
-    if (need_p > up_p)
-      AB_CUDA(cudaMemcpyAsync(ns->stage_p[0] + up_p, src_p_host + up_p, (need_p - up_p) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+    if (need_u > up_u) AB_CHECK(upload(ns->stage_u[0], src_u_host, up_u, need_u, skip_u0, skip_u1));
+    if (need_p > up_p) AB_CHECK(upload(ns->stage_p[0], src_p_host, up_p, need_p, skip_p0, skip_p1));
     up_u = std::max(up_u, need_u);
     up_p = std::max(up_p, need_p);
     if (k + 1 == n_chunks) {  // whatever no cell references (none on conforming meshes)
-      if (su.n_owned_entries() > up_u)
-        AB_CUDA(cudaMemcpyAsync(ns->stage_u[0] + up_u, src_u_host + up_u, (su.n_owned_entries() - up_u) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
-      if (sp.n_owned_entries() > up_p)
-        AB_CUDA(cudaMemcpyAsync(ns->stage_p[0] + up_p, src_p_host + up_p, (sp.n_owned_entries() - up_p) * sizeof(double), cudaMemcpyHostToDevice, ns->up_stream));
+      if (su.n_owned_entries() > up_u) AB_CHECK(upload(ns->stage_u[0], src_u_host, up_u, su.n_owned_entries(), skip_u0, skip_u1));
+      if (sp.n_owned_entries() > up_p) AB_CHECK(upload(ns->stage_p[0], src_p_host, up_p, sp.n_owned_entries(), skip_p0, skip_p1));
     }
     AB_CUDA(cudaEventRecord(ev_up, ns->up_stream));
     AB_CUDA(cudaStreamWaitEvent(s, ev_up, 0));
     a.decade_begin = k ? mf->chunk_decade_end[k - 1] : 0;
     a.decade_end = mf->chunk_decade_end[k];
     AB_CHECK(launch_cells(ns, a, true));
+    if (!compressed && (mf->chunk_decade_end[k] >= mf->ghost_decade_end || k + 1 == n_chunks)) {
+      const int spaces[2] = {ns->dof_u, ns->dof_p};  // all cells touching ghosts are done: export their contributions
+      double *vecs[2] = {du, dp};
+      AB_CHECK(comm_compress_add_n(mf, 2, spaces, vecs));
+      compressed = true;
+    }
     // constrained rows of the velocity prefix that is final now (:247-256), then its download
-    const size_t fin_u = k + 1 == n_chunks ? su.n_owned_entries() : std::min<size_t>((size_t)su.chunk_final_lo[k] * su.n_comp, up_u);
+    size_t fin_u = k + 1 == n_chunks ? su.n_owned_entries() : std::min<size_t>((size_t)su.chunk_final_lo[k] * su.n_comp, up_u);
+    if (!compressed) fin_u = std::min<size_t>(fin_u, (size_t)su.send_lo * su.n_comp);  // entries neighbours still add to
     size_t con_end = k + 1 == n_chunks ? su.n_constrained : su.chunk_constrained_end[k];
     if (k + 1 < n_chunks && (size_t)su.chunk_final_lo[k] * su.n_comp > up_u) con_end = n_con;  // (orphan nodes: wait for the last chunk)
     if (con_end > n_con) AB_CHECK(vec_copy_indexed(s, du, xu, su.constrained + n_con, (uint32_t)(con_end - n_con), 1.0));

@@ -78,6 +78,7 @@ struct Space {
   // host-vector pipeline (vmult_host): per cell chunk, the node prefix the chunk needs as source, the node
   // prefix that is final after the chunk, and the number of constrained entries inside the final prefix
   std::vector<uint32_t> chunk_need_hi, chunk_final_lo, chunk_constrained_end;
+  uint32_t send_lo = 0, send_hi = 0;  // node range covering all nodes this rank exports to its neighbours
   uint64_t n_owned_entries() const { return (uint64_t)n_owned_nodes * n_comp; }
   uint64_t n_local_entries() const { return (uint64_t)(n_owned_nodes + n_ghost_nodes) * n_comp; }
 };

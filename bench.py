@@ -362,7 +362,7 @@ def main():
                          "traffic_source": "profiles/r1_g_ns_vmult_r1_key_metrics.txt (ncu --set full, same workload, 1 GPU)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
                          "kernel": "ns_vmult_r1_kernel<with_p, newton, cartesian> (persistent, 148 blocks x 11 warps)", "kernel_ms": k_avg * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_dof": B_PER_DOF_N},
-            "e2e": {"value": n_dofs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * (nu_own + np_own), "d2h_bytes_per_step": 8 * (nu_own + np_own),
+            "e2e": {"value": n_dofs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * n_dofs, "d2h_bytes_per_step": 8 * n_dofs,   # all ranks
                     "ms_per_step": e2e_t * 1e3, "rel_diff_vs_device_path": err},
             "gpu_launches": int(launches),
             "clocks": clocks,
