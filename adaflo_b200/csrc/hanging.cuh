@@ -16,15 +16,15 @@ namespace ab200 {
 
 struct HnInfo {
   uint32_t m;
-  __device__ __forceinline__ explicit HnInfo(uint32_t mask) : m(mask) {}
-  __device__ __forceinline__ bool any() const { return m != 0; }
-  __device__ __forceinline__ int sub(int d) const { return (m >> d) & 1; }
-  __device__ __forceinline__ bool face(int d) const { return (m >> (3 + d)) & 1; }
-  __device__ __forceinline__ bool edge(int d) const { return (m >> (6 + d)) & 1; }
+  __host__ __device__ __forceinline__ explicit HnInfo(uint32_t mask) : m(mask) {}
+  __host__ __device__ __forceinline__ bool any() const { return m != 0; }
+  __host__ __device__ __forceinline__ int sub(int d) const { return (m >> d) & 1; }
+  __host__ __device__ __forceinline__ bool face(int d) const { return (m >> (3 + d)) & 1; }
+  __host__ __device__ __forceinline__ bool edge(int d) const { return (m >> (6 + d)) & 1; }
   // local index of the outer (parent-boundary) face in direction d for n1 nodes per direction
-  __device__ __forceinline__ int outer(int d, int n1) const { return sub(d) ? n1 - 1 : 0; }
+  __host__ __device__ __forceinline__ int outer(int d, int n1) const { return sub(d) ? n1 - 1 : 0; }
   // does the line along direction d through (ie, jf) [indices along d+1, d+2 (cyclic)] need interpolation?
-  __device__ __forceinline__ bool line(int d, int ie, int jf, int n1) const
+  __host__ __device__ __forceinline__ bool line(int d, int ie, int jf, int n1) const
   {
     const int e = (d + 1) % 3, f = (d + 2) % 3;
     const bool on_e = ie == outer(e, n1), on_f = jf == outer(f, n1);

@@ -2,6 +2,7 @@
 // operator-level logic of LevelSetOKZSolver{AdvanceConcentration, ComputeNormal, ComputeCurvature,
 // Reinitialization}::*_vmult / local_*_rhs around the sub-cell kernels of ls_ops.cu.
 #include <algorithm>
+#include <map>
 #include <new>
 #include <vector>
 
@@ -18,6 +19,11 @@ struct adaflo_b200_ls_s {
   const double *diag;          // not owned
   uint32_t *last_cell;         // device [n_dofs]: last cell of the cell loop containing the dof (Heaviside)
   signed char *cell_state;     // device [n_cells]
+  // hanging-dof extension of the level-set space (see LsHanging), all device pointers
+  uint32_t n_hang;
+  uint32_t *cell_ext, *hang_idx, *hang_n;
+  double *c_hang, *heav_hang, *curv_hang;
+  bool heav_hang_valid;
   double *interp;              // device [8][N] level set -> pressure interpolation
 };
 
@@ -110,14 +116,71 @@ int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   AB_CUDA(cudaMemsetAsync(ls->normal_q, 0, npd * sizeof(double), ctx->stream));
   {  // Heaviside bookkeeping: the reference loops over cells and the last writer of a shared dof wins
     const size_t N = sp.nodes_per_cell, n_dofs = sp.n_local_entries();
-    std::vector<uint32_t> cells((size_t)mf->n_cells * N), last(std::max<size_t>(1, n_dofs), 0u);
+    std::vector<uint32_t> cells((size_t)mf->n_cells * N), masks;
     if (!cells.empty()) AB_CUDA(cudaMemcpy(cells.data(), sp.cell_nodes, cells.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> ext, hang_idx, hang_n;
+    ls->n_hang = 0;
+    if (sp.hanging_masks && mf->n_cells) {
+      // Hanging dofs are not stored in this library's vectors, but compute_heaviside / compute_force read them
+      // plainly in the reference.  Identify them: a slot on a hanging line either coincides with one real dof or
+      // is the mean of 2/4/8 parents; two slots are the same hanging dof iff they have the same parents.
+      masks.resize(mf->n_cells);
+      AB_CUDA(cudaMemcpy(masks.data(), sp.hanging_masks, masks.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      ext.resize(cells.size());
+      std::map<std::vector<uint32_t>, uint32_t> ids;
+      const int n1 = S + 1;
+      for (uint32_t c = 0; c < mf->n_cells; ++c) {
+        const HnInfo hn(masks[c]);
+        for (int k = 0; k < n1; ++k)
+          for (int j = 0; j < n1; ++j)
+            for (int i = 0; i < n1; ++i) {
+              const size_t slot = c * N + i + n1 * (j + n1 * k);
+              if (!hn.any()) {
+                ext[slot] = cells[slot] & ADAFLO_B200_NODE_MASK;
+                continue;
+              }
+              LsStencil st;
+              ls_stencil(hn, cells.data() + c * N, S, i, j, k, st);
+              if (st.n == 1) {
+                ext[slot] = st.slot[0] & ADAFLO_B200_NODE_MASK;
+                continue;
+              }
+              std::vector<uint32_t> key(st.n);
+              for (int q = 0; q < st.n; ++q) key[q] = st.slot[q] & ADAFLO_B200_NODE_MASK;
+              std::sort(key.begin(), key.end());
+              auto it = ids.find(key);
+              if (it == ids.end()) {
+                it = ids.emplace(key, (uint32_t)hang_n.size()).first;
+                hang_n.push_back((uint32_t)st.n);
+                for (int q = 0; q < 8; ++q) hang_idx.push_back(q < st.n ? key[q] : 0u);
+              }
+              ext[slot] = (uint32_t)n_dofs + it->second;
+            }
+      }
+      ls->n_hang = (uint32_t)hang_n.size();
+    }
+    const std::vector<uint32_t> &lists = ext.empty() ? cells : ext;
+    std::vector<uint32_t> last(std::max<size_t>(1, n_dofs + ls->n_hang), 0u);
     for (uint32_t c = 0; c < mf->n_cells; ++c)
-      for (size_t i = 0; i < N; ++i) last[cells[c * N + i] & ADAFLO_B200_NODE_MASK] = c;
+      for (size_t i = 0; i < N; ++i) last[ext.empty() ? (lists[c * N + i] & ADAFLO_B200_NODE_MASK) : lists[c * N + i]] = c;
     AB_CUDA(cudaMalloc((void **)&ls->last_cell, last.size() * sizeof(uint32_t)));
     AB_CUDA(cudaMemcpy(ls->last_cell, last.data(), last.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     AB_CUDA(cudaMalloc((void **)&ls->cell_state, std::max<size_t>(1, mf->n_cells)));
     AB_CUDA(cudaMalloc((void **)&ls->interp, 8 * N * sizeof(double)));
+    if (!ext.empty()) {
+      AB_CUDA(cudaMalloc((void **)&ls->cell_ext, ext.size() * sizeof(uint32_t)));
+      AB_CUDA(cudaMemcpy(ls->cell_ext, ext.data(), ext.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      const size_t nh = std::max<size_t>(1, ls->n_hang);
+      AB_CUDA(cudaMalloc((void **)&ls->hang_idx, nh * 8 * sizeof(uint32_t)));
+      AB_CUDA(cudaMalloc((void **)&ls->hang_n, nh * sizeof(uint32_t)));
+      if (ls->n_hang) {
+        AB_CUDA(cudaMemcpy(ls->hang_idx, hang_idx.data(), hang_idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        AB_CUDA(cudaMemcpy(ls->hang_n, hang_n.data(), hang_n.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      }
+      AB_CUDA(cudaMalloc((void **)&ls->c_hang, nh * sizeof(double)));
+      AB_CUDA(cudaMalloc((void **)&ls->heav_hang, nh * sizeof(double)));
+      AB_CUDA(cudaMalloc((void **)&ls->curv_hang, nh * sizeof(double)));
+    }
   }
   AB_CUDA(cudaStreamSynchronize(ctx->stream));
   *out = ls;
@@ -133,6 +196,12 @@ int adaflo_b200_ls_destroy(adaflo_b200_ls_t ls)
   cudaFree(ls->conv);
   cudaFree(ls->normal_q);
   cudaFree(ls->last_cell);
+  cudaFree(ls->cell_ext);
+  cudaFree(ls->hang_idx);
+  cudaFree(ls->hang_n);
+  cudaFree(ls->c_hang);
+  cudaFree(ls->heav_hang);
+  cudaFree(ls->curv_hang);
   cudaFree(ls->cell_state);
   cudaFree(ls->interp);
   delete ls;
@@ -272,14 +341,28 @@ int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const 
   return launch_ls(a, diffuse_only ? LS_REINIT_RHS_DIFFUSE : LS_REINIT_RHS, ls->ctx->stream);
 }
 
+static LsHanging hanging_of(const adaflo_b200_ls_t ls)
+{
+  LsHanging h{};
+  h.n_real = (uint32_t)ls->mf->spaces[ls->dof_ls].n_local_entries();
+  h.n_hang = ls->n_hang;
+  h.cell_ext = ls->cell_ext;
+  h.hang_idx = ls->hang_idx;
+  h.hang_n = ls->hang_n;
+  return h;
+}
+
 int adaflo_b200_ls_compute_heaviside(adaflo_b200_ls_t ls, double *heaviside, const double *level_set)
 {
   if (!ls || !heaviside || !level_set) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   const Space &sp = ls->mf->spaces[ls->dof_ls];
   // level_set_okz.cc:516-520: distance scaled by 2 epsilon / concentration_subdivisions
   const double scale = ls->prm.epsilon * 2. / ls->prm.concentration_subdivisions;
+  if (ls->cell_ext && ls->ctx->nranks > 1)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "compute_heaviside: hanging nodes on partitioned meshes are not implemented");
+  ls->heav_hang_valid = true;
   return launch_heaviside(sp.cell_nodes, ls->last_cell, ls->cell_state, level_set, heaviside, (int)sp.nodes_per_cell, ls->mf->n_cells,
-                          sp.n_owned_entries(), scale, ls->ctx->stream);
+                          sp.n_owned_entries(), scale, hanging_of(ls), ls->c_hang, ls->heav_hang, ls->ctx->stream);
 }
 
 int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, double *dst_u, const double *heaviside, const double *curvature,
@@ -287,8 +370,9 @@ int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, doubl
 {
   if (!ls || !ns || !dst_u || !heaviside || !curvature) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   if (ns->mf != ls->mf) return fail(ADAFLO_B200_ERR_ARG, "compute_force: operator and level set must share the MatrixFree data");
-  if (ls->mf->spaces[ls->dof_ls].hanging_masks)
-    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "compute_force: level-set spaces with hanging nodes are not implemented");
+  if (ls->cell_ext && !ls->heav_hang_valid)
+    return fail(ADAFLO_B200_ERR_STATE, "compute_force: on meshes with hanging nodes the Heaviside values of the hanging dofs come from "
+                                       "compute_heaviside, which has not been called");
   adaflo_b200_mf_t mf = ls->mf;
   const Space &sp = mf->spaces[ls->dof_ls], &su = mf->spaces[ns->dof_u];
   const Quad &q = mf->quads[ns->quad_u];
@@ -305,6 +389,10 @@ int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, doubl
   f.cell_ls = sp.cell_nodes;
   f.n_sub = S;
   f.heaviside = heaviside;
+  f.hang = hanging_of(ls);
+  f.heaviside_hang = ls->heav_hang;
+  f.curvature_hang = ls->curv_hang;
+  if (ls->cell_ext) AB_CHECK(launch_hanging_mean(f.hang, curvature, ls->curv_hang, ls->ctx->stream));  // distributed curvature
   f.curvature = curvature;
   f.rho_q = ns->var ? ns->rho : nullptr;  // use_variable_parameters, level_set_okz.cc:333-334
   f.mu_q = ns->var ? ns->mu : nullptr;

@@ -29,7 +29,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ls_force_kernel(const For
   const uint32_t cell = (uint32_t)cell_l;
   double *s = smem + warp * kWarpSmem + cw * kCellSmem;
   const int n1 = F.n_sub + 1, NLS = n1 * n1 * n1;
-  const uint32_t *cl = F.cell_ls + (size_t)cell * NLS;
+  const bool ext = F.hang.cell_ext != nullptr;  // extended slot indices: real dof or n_real + hanging id
+  const uint32_t *cl = (ext ? F.hang.cell_ext : F.cell_ls) + (size_t)cell * NLS;
+  const uint32_t n_real = F.hang.n_real;
+  auto heav = [&](uint32_t e) { return (ext && e >= n_real) ? F.heaviside_hang[e - n_real] : F.heaviside[e]; };
+  auto curv = [&](uint32_t e) { return (ext && e >= n_real) ? F.curvature_hang[e - n_real] : F.curvature[e]; };
   Geometry<GEOM> G;
   G.init(A, cell);
 
@@ -39,7 +43,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ls_force_kernel(const For
 #pragma unroll
     for (int i = 0; i < 8; ++i) hp[i] = 0;
     for (int j = 0; j < NLS; ++j) {
-      const double h = F.heaviside[cl[j] & ADAFLO_B200_NODE_MASK];
+      const double h = heav(ext ? cl[j] : (cl[j] & ADAFLO_B200_NODE_MASK));
 #pragma unroll
       for (int i = 0; i < 8; ++i) hp[i] = fma(F.interp[i * NLS + j], h, hp[i]);
     }
@@ -55,10 +59,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ls_force_kernel(const For
           const double vx = F.hat_v[a][i], vy = F.hat_v[qy][j], vz = F.hat_v[b][k];
           const double w = vx * vy * vz;
           if (w == 0.0 && F.hat_d[a][i] * vy * vz == 0.0 && vx * F.hat_d[qy][j] * vz == 0.0 && vx * vy * F.hat_d[b][k] == 0.0) continue;
-          const size_t d = cl[i + n1 * (j + n1 * k)] & ADAFLO_B200_NODE_MASK;
-          const double h = F.heaviside[d];
+          const uint32_t d = ext ? cl[i + n1 * (j + n1 * k)] : (cl[i + n1 * (j + n1 * k)] & ADAFLO_B200_NODE_MASK);
+          const double h = heav(d);
           H = fma(w, h, H);
-          kap = fma(w, F.curvature[d], kap);
+          kap = fma(w, curv(d), kap);
           gr[0] = fma(F.hat_d[a][i] * vy * vz, h, gr[0]);
           gr[1] = fma(vx * F.hat_d[qy][j] * vz, h, gr[1]);
           gr[2] = fma(vx * vy * F.hat_d[b][k], h, gr[2]);
@@ -141,42 +145,82 @@ __device__ double discrete_heaviside(double x)
   return pos ? 1. - r : r;
 }
 
+// value of the (extended) dof e: real dofs from the vector, hanging dofs from the interpolated side array
+__device__ __forceinline__ double ext_value(const double *c, const double *c_hang, uint32_t n_real, uint32_t e)
+{
+  return e < n_real ? c[e] : c_hang[e - n_real];
+}
+// hanging dof = mean of its parents' values (FE_Q_iso_Q1 hats): out[h] = sum vec[idx] / n
+__global__ void k_hanging_mean(const LsHanging hang, const double *__restrict__ vec, double *__restrict__ out)
+{
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= hang.n_hang) return;
+  const uint32_t n = hang.hang_n[h];
+  double v = 0;
+  for (uint32_t i = 0; i < n; ++i) v += vec[hang.hang_idx[(size_t)h * 8 + i]];
+  out[h] = v / (double)n;
+}
 // pass 1: per cell, "is any |c_i| below the cut-off" and the sign of the first dof (level_set_okz.cc:497-503,530-536)
-__global__ void k_heaviside_cells(const uint32_t *__restrict__ cell_ls, const double *__restrict__ c, int N, uint32_t n_cells, double cutoff,
-                                  signed char *__restrict__ cell_state)
+__global__ void k_heaviside_cells(const uint32_t *__restrict__ cell_ls, const double *__restrict__ c, const double *__restrict__ c_hang,
+                                  uint32_t n_real, bool ext, int N, uint32_t n_cells, double cutoff, signed char *__restrict__ cell_state)
 {
   const uint32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
   if (cell >= n_cells) return;
   bool consider = false;
-  for (int i = 0; i < N; ++i) consider |= fabs(c[cell_ls[(size_t)cell * N + i] & ADAFLO_B200_NODE_MASK]) < cutoff;
-  const double c0 = c[cell_ls[(size_t)cell * N] & ADAFLO_B200_NODE_MASK];
+  for (int i = 0; i < N; ++i) {
+    const uint32_t e = cell_ls[(size_t)cell * N + i];
+    consider |= fabs(ext ? ext_value(c, c_hang, n_real, e) : c[e & ADAFLO_B200_NODE_MASK]) < cutoff;
+  }
+  const uint32_t e0 = cell_ls[(size_t)cell * N];
+  const double c0 = ext ? ext_value(c, c_hang, n_real, e0) : c[e0 & ADAFLO_B200_NODE_MASK];
   cell_state[cell] = consider ? 2 : (c0 < 0 ? 0 : 1);
 }
-// pass 2: per dof, the value written by the LAST cell of the cell loop that contains the dof
+// pass 2: per dof (real, then hanging), the value written by the LAST cell of the cell loop that contains the dof
 __global__ void k_heaviside_dofs(const uint32_t *__restrict__ last_cell, const signed char *__restrict__ cell_state, const double *__restrict__ c,
-                                 double scale, double cutoff, double *__restrict__ heaviside, uint64_t n)
+                                 const double *__restrict__ c_hang, double scale, double cutoff, double *__restrict__ heaviside,
+                                 double *__restrict__ heaviside_hang, uint64_t n_real, uint64_t n)
 {
   const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const signed char st = cell_state[last_cell[i]];
+  double h;
   if (st == 2) {
-    const double cv = c[i];
+    const double cv = i < n_real ? c[i] : c_hang[i - n_real];
     double distance = cv < -cutoff ? -3. : (cv > cutoff ? 3. : log((1 + cv) / (1 - cv)));
-    heaviside[i] = discrete_heaviside(distance * scale);  // :516-521
+    h = discrete_heaviside(distance * scale);  // :516-521
   } else
-    heaviside[i] = st;
+    h = st;
+  if (i < n_real)
+    heaviside[i] = h;
+  else
+    heaviside_hang[i - n_real] = h;
+}
+
+int launch_hanging_mean(const LsHanging &hang, const double *vec, double *out, cudaStream_t s)
+{
+  if (!hang.n_hang) return 0;
+  k_hanging_mean<<<(hang.n_hang + 127) / 128, 128, 0, s>>>(hang, vec, out);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launch_heaviside(const uint32_t *cell_ls, const uint32_t *last_cell, signed char *cell_state, const double *c, double *heaviside, int N,
-                     uint32_t n_cells, uint64_t n_dofs, double scale, cudaStream_t s)
+                     uint32_t n_cells, uint64_t n_dofs, double scale, const LsHanging &hang, double *c_hang, double *heaviside_hang,
+                     cudaStream_t s)
 {
   const double cutoff = tanh(2.0);
+  const bool ext = hang.cell_ext != nullptr;
+  if (ext) AB_CHECK(launch_hanging_mean(hang, c, c_hang, s));  // constraints.distribute: hanging values of the level set
   if (n_cells) {
-    k_heaviside_cells<<<(n_cells + 127) / 128, 128, 0, s>>>(cell_ls, c, N, n_cells, cutoff, cell_state);
+    k_heaviside_cells<<<(n_cells + 127) / 128, 128, 0, s>>>(ext ? hang.cell_ext : cell_ls, c, c_hang, hang.n_real, ext, N, n_cells, cutoff,
+                                                           cell_state);
     AB_COUNT_LAUNCH();
   }
-  if (n_dofs) {
-    k_heaviside_dofs<<<(unsigned)((n_dofs + 255) / 256), 256, 0, s>>>(last_cell, cell_state, c, scale, cutoff, heaviside, n_dofs);
+  const uint64_t n = n_dofs + (ext ? hang.n_hang : 0);
+  if (n) {
+    k_heaviside_dofs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(last_cell, cell_state, c, c_hang, scale, cutoff, heaviside, heaviside_hang,
+                                                                  n_dofs, n);
     AB_COUNT_LAUNCH();
   }
   AB_CUDA(cudaGetLastError());

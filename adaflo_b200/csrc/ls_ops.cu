@@ -18,39 +18,6 @@ namespace ab200 {
 
 __device__ __forceinline__ double g2(int p) { return p ? 0.7886751345948129 : 0.2113248654051871; }
 
-// Hanging nodes of FE_Q_iso_Q1(S): a child node m in direction d sits at the parent coordinate (sub S + m) / 2;
-// if that is an integer it coincides with a parent node, otherwise it is the mean of its two neighbours (hats).
-struct LsStencil {
-  int n;
-  uint32_t slot[8];
-  double w[8];
-};
-__device__ __forceinline__ void ls_stencil(const HnInfo hn, const uint32_t *cl, int S, int ix, int iy, int iz, LsStencil &st)
-{
-  const int n1 = S + 1;
-  const int idx[3] = {ix, iy, iz};
-  int i0[3], cnt[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    const int e = (d + 1) % 3, f = (d + 2) % 3;
-    i0[d] = idx[d];
-    cnt[d] = 1;
-    if (hn.line(d, idx[e], idx[f], n1)) {
-      const int c2 = hn.sub(d) * S + idx[d];
-      i0[d] = c2 >> 1;
-      cnt[d] = (c2 & 1) ? 2 : 1;
-    }
-  }
-  st.n = 0;
-  for (int c = 0; c < cnt[2]; ++c)
-    for (int b = 0; b < cnt[1]; ++b)
-      for (int a = 0; a < cnt[0]; ++a) {
-        st.slot[st.n] = cl[(i0[0] + a) + n1 * ((i0[1] + b) + n1 * (i0[2] + c))];
-        st.w[st.n] = 1.0 / (cnt[0] * cnt[1] * cnt[2]);
-        ++st.n;
-      }
-}
-
 template <int OP>
 __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
 {

@@ -302,6 +302,9 @@ int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const 
                                         int diffuse_only, int first_reinit_step);
 /* LevelSetOKZSolver::compute_heaviside, level_set_okz.cc:479-540 (dof-wise; a dof shared by several cells takes
  * the value of the last cell in the cell order of the uploaded lists, as the reference's cell loop does) */
+/* On meshes with hanging nodes the reference stores a Heaviside value for every hanging dof as well (plain reads,
+ * level_set_okz.cc:341,497-536); compute_heaviside keeps those inside the handle and compute_force uses them, so
+ * compute_force must follow a compute_heaviside call there. */
 int adaflo_b200_ls_compute_heaviside(adaflo_b200_ls_t ls, double *heaviside, const double *level_set);
 /* LevelSetOKZSolver::local_compute_force, level_set_okz.cc:317-409: dst_u += (v, sigma kappa grad(H) - g rho e_z);
  * writes rho_q, mu_q of the operator when it uses variable coefficients.  interpolation_host: the

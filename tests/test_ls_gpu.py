@@ -263,3 +263,94 @@ def test_level_set_operators_with_hanging_nodes(ctx, refine):
         assert rel_err(g.cpu().numpy(), O.reinitialization_vmult(src, diffuse_only)) < TOL
     A.close()
     mf.close()
+
+
+@pytest.mark.parametrize("refine", [((1, 3), (0, 2), (0, 1)), ((0, 1), (0, 1), (0, 1))])
+@pytest.mark.parametrize("interpolate", [False, True])
+def test_heaviside_and_force_with_hanging_nodes(ctx, refine, interpolate):
+    """compute_heaviside / local_compute_force read the Heaviside function PLAINLY (level_set_okz.cc:341,497-536), so the
+    hanging dofs of the level-set space carry their own values H(interpolated c), last cell wins.  The oracle runs
+    on an extended dof space (real dofs + one dof per hanging lattice point) built from the mesh's plain expansion
+    lists; the velocity test functions are distributed with the plain velocity lists."""
+    from adaflo_b200.mesh import RefinedBoxMesh
+    from adaflo_b200.operators import BlockVector, NavierStokesMatrix
+    from helpers import flow_params, time_weights
+    n_sub = 3
+    mesh = RefinedBoxMesh((3, 3, 2), refine)
+    mesh.build_ls_space(n_sub)
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    dprm, _ = flow_params(density=1.0, viscosity=0.1, density_diff=9.0, viscosity_diff=0.4)
+    dtw, _ = time_weights()
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, BlockVector.like(mf), BlockVector.like(mf))
+    A.initialize(mf, dtw, True)
+    h_min = float(mesh.h_cell.min())
+    eps = 1.5
+    L = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, eps, eps * h_min / n_sub, 4.0, h_min), mesh.cell_diameters())
+    n, N = mesh.ls.n_owned, (n_sub + 1) ** 3
+    # ---- extended dof space from the plain expansion lists
+    ptr, idx, wts = mesh.ls_lists
+    ext = np.zeros((mesh.n_cells, N), dtype=np.int64)
+    hanging = {}
+    for c in range(mesh.n_cells):
+        for j in range(N):
+            k = c * N + j
+            a, b = ptr[k], ptr[k + 1]
+            if b - a == 1:
+                ext[c, j] = idx[a]
+            else:
+                key = tuple(sorted(idx[a:b].tolist()))
+                if key not in hanging:
+                    hanging[key] = (len(hanging), idx[a:b].copy(), wts[a:b].copy())
+                ext[c, j] = n + hanging[key][0]
+    assert len(hanging) > 0
+
+    def extend(v):
+        out = np.zeros(n + len(hanging))
+        out[:n] = v
+        for hid, ii, ww in hanging.values():
+            out[n + hid] = float(ww @ v[ii])
+        return out
+
+    x = mesh.ls.coords
+    r = np.linalg.norm(x - np.array([0.1, -0.05, -0.2]), axis=1)
+    c = -np.tanh((r - 0.5) / (2 * 0.08))
+    H_ext = orc.compute_heaviside(ext, extend(c), eps, n_sub)
+    Hg = mf.initialize_dof_vector(2)
+    L.compute_heaviside(Hg, dev(ctx, c))
+    assert np.abs(Hg.cpu().numpy() - H_ext[:n]).max() < 1e-14
+    assert ((H_ext > 0) & (H_ext < 1)).sum() > 10
+    kappa = 2.0 / np.maximum(r, 0.2) + 0.1 * seeded_uniform(mesh.ls.global_ids, 1, 3)
+    interp = None
+    if interpolate:
+        n1 = n_sub + 1
+        interp = np.zeros((8, n1 ** 3))
+        for i in range(8):
+            interp[i, (n_sub * (i & 1)) + n1 * ((n_sub * ((i >> 1) & 1)) + n1 * (n_sub * (i >> 2)))] = 1.0
+    # ---- oracle force: private velocity entries per (cell, node), then the plain distribution
+    K, jxw = mesh.general_geometry(3, None)
+    K, jxw = np.ascontiguousarray(K), np.ascontiguousarray(jxw)
+    cu = np.arange(mesh.n_cells * 27, dtype=np.int64).reshape(mesh.n_cells, 27)
+    local = np.zeros(mesh.n_cells * 27 * 3)
+    rho_q, mu_q = np.zeros((mesh.n_cells, 27)), np.zeros((mesh.n_cells, 27))
+    ip = None if interp is None else np.ascontiguousarray(interp)
+    import ctypes as C
+    orc.ls_lib().ls_oracle_force(mesh.n_cells, n_sub, orc._p(np.ascontiguousarray(ext)), orc._p(cu), None, orc._p(K), orc._p(jxw),
+                                 orc._p(H_ext), orc._p(extend(kappa)), C.c_double(0.07), C.c_double(0.98), C.c_double(1.0),
+                                 C.c_double(9.0), C.c_double(0.1), C.c_double(0.4), 1, orc._p(ip), orc._p(local), orc._p(rho_q),
+                                 orc._p(mu_q))
+    pre = seeded_uniform(mesh.u.global_ids, 3, 4)
+    o = pre.copy()
+    uptr, uidx, uw = mesh.u_lists                      # per (cell, comp, node): entries node * 3 + comp and weights
+    loc = local.reshape(mesh.n_cells, 27, 3).transpose(0, 2, 1).reshape(-1)   # -> (cell, comp, node)
+    con = mesh.u.dirichlet.reshape(-1)
+    contrib = np.repeat(loc, np.diff(uptr)) * uw
+    keep = ~con[uidx]
+    np.add.at(o, uidx[keep], contrib[keep])
+    g = dev(ctx, pre)
+    L.compute_force(A, g, Hg, dev(ctx, kappa), 0.07, 0.98, interp)
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    assert rel_err(A.get_coefficient(capi.COEF_DENSITY).cpu().numpy(), rho_q) < TOL
+    assert rel_err(A.get_coefficient(capi.COEF_VISCOSITY).cpu().numpy(), mu_q) < TOL
+    L.close()
+    A.clear()
+    mf.close()
