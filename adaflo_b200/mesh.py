@@ -414,6 +414,54 @@ HN_FACE_X, HN_FACE_Y, HN_FACE_Z = 8, 16, 32
 HN_EDGE_X, HN_EDGE_Y, HN_EDGE_Z = 64, 128, 256
 
 
+class BoxMesh2D:
+    """2-D box of n = (nx, ny) Q2/Q1 cells and its one-cell-thick 3-D extrusion.
+
+    The library has 3-D kernels only; a 2-D operator is applied exactly as A_2d = R A_3d E on the extruded mesh
+    (`mesh3d`, thickness 1): E copies a 2-D field to the 3 (velocity) / 2 (pressure) node planes with w = 0, R sums
+    the planes -- the z basis functions sum to 1, so every 3-D bilinear form reduces to the 2-D one for z-constant
+    fields ("2-D problems").  The third velocity component is constrained everywhere.
+    Vectors: velocity entry (node, c) = 2 node + c, nodes lexicographic (x fastest)."""
+
+    def __init__(self, n, lower=(-1.0, -1.0), upper=(1.0, 1.0), dirichlet_edges=(0, 1, 2, 3)):
+        self.dim = 2
+        self.n = (int(n[0]), int(n[1]))
+        self.lower = np.asarray(lower, dtype=np.float64)
+        self.upper = np.asarray(upper, dtype=np.float64)
+        self.h = (self.upper - self.lower) / np.asarray(self.n, dtype=np.float64)
+        nx, ny = self.n
+        self.n_cells = nx * ny
+        self.mesh3d = m3 = BoxMesh((nx, ny, 1), lower=(self.lower[0], self.lower[1], 0.0), upper=(self.upper[0], self.upper[1], 1.0),
+                                   dirichlet_faces=tuple(dirichlet_edges))
+        m3.u.dirichlet[:, 2] = True                         # w = 0: never read, never written
+        NXu, NYu, NXp, NYp = 2 * nx + 1, 2 * ny + 1, nx + 1, ny + 1
+        self.n_u_nodes, self.n_p_nodes = NXu * NYu, NXp * NYp
+        # 2-D cell lists = bottom plane of the extruded lists (node3d = plane * k + node2d)
+        self.cell_u = m3.u.cell_nodes[:, :9].astype(np.int64)
+        self.cell_p = m3.p.cell_nodes[:, :4].astype(np.int64)
+        assert self.cell_u.max() < self.n_u_nodes and self.cell_p.max() < self.n_p_nodes
+        self.u_dirichlet = m3.u.dirichlet[: self.n_u_nodes, :2].copy()
+        self.u_coords = m3.u.coords[: self.n_u_nodes, :2].copy()
+        self.p_coords = m3.p.coords[: self.n_p_nodes, :2].copy()
+        self.u_ids = np.arange(self.n_u_nodes, dtype=np.int64)
+        self.p_ids = np.arange(self.n_p_nodes, dtype=np.int64)
+        # extension maps: 3-D vector entries of a 2-D entry
+        nodes = np.arange(self.n_u_nodes)
+        self.ext_u = (3 * (nodes[:, None, None] + self.n_u_nodes * np.arange(3)[None, :, None]) + np.arange(2)[None, None, :])
+        self.ext_u = self.ext_u.transpose(0, 2, 1).reshape(self.n_u_nodes * 2, 3)       # [2 node + c][plane]
+        self.ext_p = np.arange(self.n_p_nodes)[:, None] + self.n_p_nodes * np.arange(2)[None, :]
+
+    def extend(self, u2d, p2d):
+        m3 = self.mesh3d
+        u3, p3 = np.zeros(m3.u.n_owned * 3), np.zeros(m3.p.n_owned)
+        u3[self.ext_u] = np.asarray(u2d)[:, None]
+        p3[self.ext_p] = np.asarray(p2d)[:, None]
+        return u3, p3
+
+    def restrict(self, u3d, p3d):
+        return np.asarray(u3d)[self.ext_u].sum(axis=1), np.asarray(p3d)[self.ext_p].sum(axis=1)
+
+
 class RefinedBoxMesh:
     """Box of n coarse cells where the coarse cells inside ``refine`` = ((i0,i1),(j0,j1),(k0,k1))
     are split into 8 children (one level, single rank).  Produces

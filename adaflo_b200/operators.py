@@ -419,6 +419,88 @@ class NavierStokesMatrix:
         check(self.lib.adaflo_b200_ns_vmult_host(self.h, hp(dst_u), hp(dst_p), hp(src_u), hp(src_p)))
 
 
+class NavierStokesMatrix2D:
+    """NavierStokesMatrix<2> for Q2/Q1 on Cartesian box meshes (adaflo_b200.mesh.BoxMesh2D).
+
+    The CUDA kernels are three-dimensional.  A 2-D operator is applied exactly as A_2d = R A_3d E on the
+    one-cell-thick extrusion of the mesh: E copies a 2-D field to the node planes (third velocity component
+    constrained to zero), R sums the planes; the z shape functions sum to one, so every bilinear form of
+    source/navier_stokes_matrix.cc reduces to its 2-D counterpart for z-constant fields (verified against an
+    independent dense 2-D oracle, tests/test_2d_cpu.py / tests/test_2d_gpu.py).  Vectors are 2-D: velocity entry
+    (node, c) = 2 node + c.  Meant for the small 2-D configurations; it costs 3-D work per 2-D cell."""
+
+    def __init__(self, parameters, ctx, mesh2d, time_stepping, pressure_average_fix=True):
+        self.mesh2d, self.ctx = mesh2d, ctx
+        self.mf = MatrixFree(ctx, mesh2d.mesh3d, "cartesian")
+        self.old, self.old_old = BlockVector.like(self.mf), BlockVector.like(self.mf)
+        self.A = NavierStokesMatrix(parameters, 0, 1, 0, 1, self.old, self.old_old)
+        self.A.initialize(self.mf, time_stepping, pressure_average_fix)
+        dev = ctx.device
+        self.ext_u = torch.from_numpy(mesh2d.ext_u).to(dev)
+        self.ext_p = torch.from_numpy(mesh2d.ext_p).to(dev)
+        self.constrained_u = torch.from_numpy(np.nonzero(mesh2d.u_dirichlet.reshape(-1))[0]).to(dev)
+        self._src, self._dst, self._aux = BlockVector.like(self.mf), BlockVector.like(self.mf), BlockVector.like(self.mf)
+
+    # ---- extension / restriction on the device
+    def _extend(self, dst3: BlockVector, u2, p2):
+        dst3.block(0).zero_()
+        dst3.block(0)[self.ext_u] = u2.unsqueeze(1)
+        if p2 is not None:
+            dst3.block(1).zero_()
+            dst3.block(1)[self.ext_p] = p2.unsqueeze(1)
+
+    def _restrict(self, src3: BlockVector, u2, p2):
+        torch.sum(src3.block(0)[self.ext_u], dim=1, out=u2)
+        if p2 is not None:
+            torch.sum(src3.block(1)[self.ext_p], dim=1, out=p2)
+
+    def initialize_dof_vectors(self):
+        dev = self.ctx.device
+        return (torch.zeros(self.mesh2d.n_u_nodes * 2, dtype=torch.float64, device=dev),
+                torch.zeros(self.mesh2d.n_p_nodes, dtype=torch.float64, device=dev))
+
+    def set_old_solutions(self, old_u2, old_old_u2):
+        self._extend(self._aux, old_u2, None)
+        self.old.block(0).copy_(self._aux.block(0))
+        self._extend(self._aux, old_old_u2, None)
+        self.old_old.block(0).copy_(self._aux.block(0))
+
+    def _apply(self, op, dst2, src2):
+        self._extend(self._src, src2[0], src2[1])
+        op(self._dst, self._src)
+        self._restrict(self._dst, dst2[0], dst2[1])
+        dst2[0][self.constrained_u] = src2[0][self.constrained_u]   # one copy of a constrained row, not one per plane
+
+    def vmult(self, dst2, src2):
+        self._apply(self.A.vmult, dst2, src2)
+
+    def Tvmult(self, dst2, src2):
+        self._apply(self.A.Tvmult, dst2, src2)
+
+    def velocity_vmult(self, dst_u2, src_u2):
+        self._extend(self._src, src_u2, None)
+        self.A.velocity_vmult(self._dst.block(0), self._src.block(0))
+        self._restrict(self._dst, dst_u2, None)
+        dst_u2[self.constrained_u] = src_u2[self.constrained_u]
+
+    def residual(self, rhs2, src2, user2):
+        """rhs = user - (cell integrals + rhs preload), navier_stokes_matrix.cc:266-293; also stores the linearisation"""
+        self._extend(self._src, src2[0], src2[1])
+        self._dst.block(0).zero_()
+        self._dst.block(1).zero_()
+        self._aux.block(0).zero_()
+        self._aux.block(1).zero_()
+        self.A.residual(self._dst, self._src, self._aux)           # = -(cell integrals) on the extrusion
+        pre_u, pre_p = rhs2[0].clone(), rhs2[1].clone()
+        self._restrict(self._dst, rhs2[0], rhs2[1])
+        rhs2[0].add_(user2[0] - pre_u)
+        rhs2[1].add_(user2[1] - pre_p)
+
+    def clear(self):
+        self.A.clear()
+        self.mf.close()
+
+
 class DiagonalPreconditioner:
     """adaflo::DiagonalPreconditioner<double> (source/diagonal_preconditioner.cc:38-124)."""
 
