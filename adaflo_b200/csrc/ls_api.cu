@@ -85,7 +85,9 @@ int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
     return fail(ADAFLO_B200_ERR_ARG, "ls_create: dof/quad index out of range");
   const Space &sp = mf->spaces[dof_ls];
   const int S = prm->concentration_subdivisions;
-  if (prm->dim != 3 || S < 1 || S > 4 || sp.fe_kind != ADAFLO_B200_FE_Q_ISO_Q1 || sp.degree != S || sp.n_comp != 1 ||
+  // dim == 2: a 2-D problem on its one-cell-thick extrusion (the spaces and kernels are three-dimensional either way;
+  // dim enters the pseudo time step of the reinitialisation and the curvature correction)
+  if ((prm->dim != 3 && prm->dim != 2) || S < 1 || S > 4 || sp.fe_kind != ADAFLO_B200_FE_Q_ISO_Q1 || sp.degree != S || sp.n_comp != 1 ||
       sp.nodes_per_cell != (uint32_t)((S + 1) * (S + 1) * (S + 1)) || mf->quads[quad_ls].n_q_1d != 2 * S)
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: needs a 3-D FE_Q_iso_Q1(n_sub <= 4) space and the QIterated(QGauss(2), n_sub) quadrature");
   if (mf->quads[quad_ls].geometry_type == ADAFLO_B200_GEOM_GENERAL)

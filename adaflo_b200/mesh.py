@@ -451,6 +451,32 @@ class BoxMesh2D:
         self.ext_u = self.ext_u.transpose(0, 2, 1).reshape(self.n_u_nodes * 2, 3)       # [2 node + c][plane]
         self.ext_p = np.arange(self.n_p_nodes)[:, None] + self.n_p_nodes * np.arange(2)[None, :]
 
+    def build_ls_space(self, n_sub=3, dirichlet_edges=()):
+        """FE_Q_iso_Q1(n_sub) level-set space: (n_sub nx + 1)(n_sub ny + 1) nodes, extruded to n_sub + 1 node planes"""
+        ls3 = self.mesh3d.build_ls_space(n_sub, dirichlet_faces=tuple(dirichlet_edges))
+        nx, ny = self.n
+        self.n_sub = n_sub
+        self.n_ls_nodes = (n_sub * nx + 1) * (n_sub * ny + 1)
+        n1 = n_sub + 1
+        self.cell_ls = ls3.cell_nodes[:, : n1 * n1].astype(np.int64)
+        assert self.cell_ls.max() < self.n_ls_nodes
+        self.ls_dirichlet = ls3.dirichlet[: self.n_ls_nodes, 0].copy()
+        self.ls_coords = ls3.coords[: self.n_ls_nodes, :2].copy()
+        self.ls_ids = np.arange(self.n_ls_nodes, dtype=np.int64)
+        self.ext_ls = np.arange(self.n_ls_nodes)[:, None] + self.n_ls_nodes * np.arange(n1)[None, :]
+        return ls3
+
+    def cell_diameters(self):
+        return np.full(self.n_cells, float(self.h.max()))
+
+    def extend_ls(self, v2d):
+        v3 = np.zeros(self.mesh3d.ls.n_owned)
+        v3[self.ext_ls] = np.asarray(v2d)[:, None]
+        return v3
+
+    def restrict_ls(self, v3d):
+        return np.asarray(v3d)[self.ext_ls].sum(axis=1)
+
     def extend(self, u2d, p2d):
         m3 = self.mesh3d
         u3, p3 = np.zeros(m3.u.n_owned * 3), np.zeros(m3.p.n_owned)

@@ -608,3 +608,111 @@ class LevelSetOperators:
         n = t.shape[0]
         t = t.view(n, s, s, s, 3, 2, 2, 2).permute(0, 1, 5, 2, 6, 3, 7, 4)   # cell, sz,pc, sy,pb, sx,pa, comp
         return t.reshape(n, (2 * s) ** 3, 3)
+
+
+class LevelSetOperators2D:
+    """The level-set operators of LevelSetOperators for dim = 2 (FE_Q_iso_Q1(n_sub) on BoxMesh2D), applied through the
+    3-D kernels on the one-cell-thick extrusion like NavierStokesMatrix2D: fields are copied to the n_sub + 1 node
+    planes (third normal / velocity component zero), results are summed over the planes.  The hat functions sum to
+    one in z, so all weak forms reduce exactly; two fix-ups: the mass diagonal is 3/2 of the plane sum (sum_a int
+    N_a^2 dz = 2/3), and constrained rows get diag * src once.  Point-wise operations (Heaviside, curvature
+    correction) are read from one plane.  Checked against an independent dense 2-D restatement (tests/test_2d_gpu.py)."""
+
+    def __init__(self, ctx, mesh2d, parameters: capi.LSParams, cell_diameters=None):
+        assert parameters.dim == 2, "LSParams.dim must be 2 (pseudo time step and curvature correction depend on it)"
+        self.ctx, self.mesh2d = ctx, mesh2d
+        self.mf = MatrixFree(ctx, mesh2d.mesh3d, "cartesian")
+        cd = mesh2d.cell_diameters() if cell_diameters is None else cell_diameters
+        self.L = LevelSetOperators(self.mf, parameters, cd)
+        dev = ctx.device
+        self.ext = torch.from_numpy(mesh2d.ext_ls).to(dev)
+        self.ext_u = torch.from_numpy(mesh2d.ext_u).to(dev)
+        self.con = torch.from_numpy(np.nonzero(mesh2d.ls_dirichlet)[0]).to(dev)
+        self.n, self.n3 = mesh2d.n_ls_nodes, self.mf.initialize_dof_vector(2).numel()
+        d3 = self.L.initialize_mass_matrix_diagonal()
+        self.L.set_diagonal(d3)
+        self.diag = 1.5 * self._R(d3)
+
+    def new_vector(self):
+        return torch.zeros(self.n, dtype=torch.float64, device=self.ctx.device)
+
+    def _E(self, v2):
+        v3 = torch.zeros(self.n3, dtype=torch.float64, device=self.ctx.device)
+        if v2 is not None:
+            v3[self.ext] = v2.unsqueeze(1)
+        return v3
+
+    def _R(self, v3):
+        return v3[self.ext].sum(dim=1)
+
+    def _rows(self, dst2, src2):
+        dst2[self.con] = self.diag[self.con] * src2[self.con]
+
+    def set_time(self, weight, weight_old, weight_old_old, step_size):
+        self.L.set_time(weight, weight_old, weight_old_old, step_size)
+
+    def initialize_mass_matrix_diagonal(self):
+        return self.diag.clone()
+
+    def advance_concentration_vmult(self, dst, src):
+        d3 = self._E(None)
+        self.L.advance_concentration_vmult(d3, self._E(src))
+        dst.copy_(self._R(d3))
+        self._rows(dst, src)
+
+    def advance_concentration_rhs(self, rhs, vel, c, c_old, c_old_old):
+        u3 = torch.zeros(self.mf.initialize_dof_vector(0).numel(), dtype=torch.float64, device=self.ctx.device)
+        u3[self.ext_u] = vel.unsqueeze(1)
+        r3 = self._E(None)
+        self.L.advance_concentration_rhs(r3, u3, self._E(c), self._E(c_old), self._E(c_old_old))
+        rhs.add_(self._R(r3))
+
+    def compute_normal_vmult(self, dst, src):
+        d3 = [self._E(None) for _ in range(3)]
+        self.L.compute_normal_vmult(d3, [self._E(src[0]), self._E(src[1]), self._E(None)])
+        for d in range(2):
+            dst[d].copy_(self._R(d3[d]))
+            self._rows(dst[d], src[d])
+
+    def compute_normal_rhs(self, rhs, level_set):
+        r3 = [self._E(None) for _ in range(3)]
+        self.L.compute_normal_rhs(r3, self._E(level_set))
+        for d in range(2):
+            rhs[d].add_(self._R(r3[d]))
+
+    def compute_curvature_vmult(self, dst, src, apply_diffusion=True):
+        d3 = self._E(None)
+        self.L.compute_curvature_vmult(d3, self._E(src), apply_diffusion)
+        dst.copy_(self._R(d3))
+        self._rows(dst, src)
+
+    def compute_curvature_rhs(self, rhs, normal):
+        r3 = self._E(None)
+        self.L.compute_curvature_rhs(r3, [self._E(normal[0]), self._E(normal[1]), self._E(None)])
+        rhs.add_(self._R(r3))
+
+    def curvature_correction(self, curvature, level_set):
+        k3 = self._E(curvature)
+        self.L.curvature_correction(k3, self._E(level_set))
+        curvature.copy_(k3[self.ext[:, 0]])
+
+    def reinitialization_vmult(self, dst, src, diffuse_only=False):
+        d3 = self._E(None)
+        self.L.reinitialization_vmult(d3, self._E(src), diffuse_only)
+        dst.copy_(self._R(d3))
+        self._rows(dst, src)
+
+    def reinitialization_rhs(self, rhs, solution, normal, diffuse_only=False, first_reinit_step=True):
+        r3 = self._E(None)
+        n3 = None if normal is None else [self._E(normal[0]), self._E(normal[1]), self._E(None)]
+        self.L.reinitialization_rhs(r3, self._E(solution), n3, diffuse_only, first_reinit_step)
+        rhs.add_(self._R(r3))
+
+    def compute_heaviside(self, heaviside, level_set):
+        h3 = self._E(None)
+        self.L.compute_heaviside(h3, self._E(level_set))
+        heaviside.copy_(h3[self.ext[:, 0]])
+
+    def close(self):
+        self.L.close()
+        self.mf.close()

@@ -72,3 +72,78 @@ def test_2d_stokes_is_symmetric():
     lhs = ax[0] @ yu + ax[1] @ yp
     rhs = xu @ ay[0] + xp @ ay[1]
     assert abs(lhs - rhs) < 1e-11 * max(abs(lhs), 1.0)
+
+
+# ---------------------------------------------------------------------------------------------- level set
+def ls_setup(n=(4, 3), n_sub=3, dirichlet_edges=()):
+    from oracle.ls_oracle_2d import OracleLevelSet2D
+    m = BoxMesh2D(n)
+    m.build_ls_space(n_sub, dirichlet_edges)
+    h_min = float(m.h.min())
+    eps, eps_used, step = 1.5, 1.5 * h_min / n_sub, 0.02
+    cd = m.cell_diameters()
+    O2 = OracleLevelSet2D(m, n_sub, eps, eps_used, h_min, step, cd)
+    O3 = orc.OracleLevelSet(m.mesh3d, orc.LSParams(eps, eps_used, 4.0, h_min, step, 2, 0))
+    O3.cd[:] = cd                                    # the 2-D cell diameters, not those of the extruded hexahedra
+    d3 = O3.mass_diagonal()
+    O3.diag = d3
+    O2.diag = O2.mass_diagonal()
+    return m, O2, O3, (eps, eps_used, h_min, step)
+
+
+def ls_fields(m):
+    x = m.ls_coords
+    r = np.linalg.norm(x - np.array([0.1, -0.05]), axis=1)
+    c = -np.tanh((r - 0.45) / 0.3)
+    vec = lambda s: seeded_uniform(m.ls_ids, 1, s)
+    return c, vec
+
+
+@pytest.mark.parametrize("dirichlet_edges", [(), (0,)])
+def test_2d_level_set_oracle_equals_extruded_3d_oracle(dirichlet_edges):
+    m, O2, O3, _ = ls_setup(dirichlet_edges=dirichlet_edges)
+    c, vec = ls_fields(m)
+    E, R = m.extend_ls, m.restrict_ls
+    con = m.ls_dirichlet
+    # mass diagonal: sum_a int N_a^2 dz = 2/3 for the hats with the composite Gauss rule
+    assert rel_err(1.5 * R(O3.diag), O2.diag) < 1e-13
+    # advection rhs (evaluates the Q2 velocity) and vmult
+    vel = taylor_velocity_2d(m.u_coords, 0.0).reshape(-1) + 0.1 * seeded_uniform(m.u_ids, 2, 6)
+    c_old, c_oo = c + 0.05 * vec(7), c + 0.05 * vec(8)
+    r2 = vec(9)
+    r3 = E(np.zeros_like(r2))
+    pre = r2.copy()
+    O2.advance_concentration_rhs(r2, vel, c, c_old, c_oo, 75.0, -100.0, 25.0)
+    O3.advance_concentration_rhs(r3, m.extend(vel, np.zeros(m.n_p_nodes))[0], E(c), E(c_old), E(c_oo), 75.0, -100.0, 25.0)
+    assert rel_err(R(r3) + pre, r2) < 1e-13
+    src = vec(10)
+
+    def fix(d, s):                                   # constrained rows: diag * src once, not per node plane
+        d = d.copy()
+        d[con] = O2.diag[con] * s[con]
+        return d
+    assert rel_err(fix(R(O3.advance_concentration_vmult(E(src), 75.0)), src), O2.advance_concentration_vmult(src, 75.0)) < 1e-13
+    # normal projection
+    n2 = [np.zeros(O2.n) for _ in range(2)]
+    n3 = [np.zeros(O3.n) for _ in range(3)]
+    O2.compute_normal_rhs(n2, c)
+    O3.compute_normal_rhs(n3, E(c))
+    assert rel_err(R(n3[0]), n2[0]) < 1e-13 and rel_err(R(n3[1]), n2[1]) < 1e-13 and np.abs(n3[2]).max() < 1e-13
+    normal = [m.ls_coords[:, d] - [0.1, -0.05][d] + 0.02 * vec(20 + d) for d in range(2)]
+    v3 = O3.compute_normal_vmult([E(normal[0]), E(normal[1]), np.zeros(O3.n)])
+    v2 = O2.compute_normal_vmult(normal, 4.0)
+    for d in range(2):
+        assert rel_err(fix(R(v3[d]), normal[d]), v2[d]) < 1e-13
+    # curvature
+    k2, k3 = np.zeros(O2.n), np.zeros(O3.n)
+    O2.compute_curvature_rhs(k2, normal)
+    O3.compute_curvature_rhs(k3, [E(normal[0]), E(normal[1]), np.zeros(O3.n)])
+    assert rel_err(R(k3), k2) < 1e-13
+    assert rel_err(fix(R(O3.compute_curvature_vmult(E(src), True)), src), O2.compute_curvature_vmult(src, True)) < 1e-13
+    # reinitialisation
+    q2, q3 = np.zeros(O2.n), np.zeros(O3.n)
+    O2.reinitialization_rhs(q2, c, normal, False, True)
+    O3.reinitialization_rhs(q3, E(c), [E(normal[0]), E(normal[1]), np.zeros(O3.n)], False, True)
+    assert rel_err(R(q3), q2) < 1e-13
+    for diffuse_only in (False, True):
+        assert rel_err(fix(R(O3.reinitialization_vmult(E(src), diffuse_only)), src), O2.reinitialization_vmult(src, diffuse_only)) < 1e-13

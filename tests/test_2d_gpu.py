@@ -62,3 +62,69 @@ def test_2d_operators_match_dense_2d_oracle(ctx, lin):
     rhs = float(su0 @ a0[0].cpu().numpy() + sp @ a0[1].cpu().numpy())
     assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs), 1.0)
     A.clear()
+
+
+@pytest.mark.parametrize("dirichlet_edges", [(), (0,)])
+def test_2d_level_set_operators_match_dense_2d_oracle(ctx, dirichlet_edges):
+    from adaflo_b200.operators import LevelSetOperators2D
+    from oracle import oracle as orc
+    from test_2d_cpu import ls_fields, ls_setup, taylor_velocity_2d
+    from adaflo_b200.mesh import seeded_uniform
+    n_sub = 3
+    m, O, _, (eps, eps_used, h_min, step) = ls_setup(n=(5, 4), n_sub=n_sub, dirichlet_edges=dirichlet_edges)
+    L = LevelSetOperators2D(ctx, m, capi.LSParams(2, n_sub, 0, 0, eps, eps_used, 4.0, h_min))
+    L.set_time(75.0, -100.0, 25.0, step)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    c, vec = ls_fields(m)
+    assert rel_err(L.initialize_mass_matrix_diagonal().cpu().numpy(), O.diag) < TOL
+    vel = taylor_velocity_2d(m.u_coords, 0.0).reshape(-1) + 0.1 * seeded_uniform(m.u_ids, 2, 6)
+    c_old, c_oo = c + 0.05 * vec(7), c + 0.05 * vec(8)
+    pre = vec(9)
+    o = pre.copy()
+    O.advance_concentration_rhs(o, vel, c, c_old, c_oo, 75.0, -100.0, 25.0)
+    g = dev(pre)
+    L.advance_concentration_rhs(g, dev(vel), dev(c), dev(c_old), dev(c_oo))
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    src = vec(10)
+    g = L.new_vector()
+    L.advance_concentration_vmult(g, dev(src))
+    assert rel_err(g.cpu().numpy(), O.advance_concentration_vmult(src, 75.0)) < TOL
+    ro = [np.zeros(O.n) for _ in range(2)]
+    O.compute_normal_rhs(ro, c)
+    rg = [L.new_vector() for _ in range(2)]
+    L.compute_normal_rhs(rg, dev(c))
+    normal = [m.ls_coords[:, d] - [0.1, -0.05][d] + 0.02 * vec(20 + d) for d in range(2)]
+    vg = [L.new_vector() for _ in range(2)]
+    L.compute_normal_vmult(vg, [dev(v) for v in normal])
+    vo = O.compute_normal_vmult(normal, 4.0)
+    for d in range(2):
+        assert rel_err(rg[d].cpu().numpy(), ro[d]) < TOL and rel_err(vg[d].cpu().numpy(), vo[d]) < TOL
+    o = np.zeros(O.n)
+    O.compute_curvature_rhs(o, normal)
+    g = L.new_vector()
+    L.compute_curvature_rhs(g, [dev(v) for v in normal])
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    g = L.new_vector()
+    L.compute_curvature_vmult(g, dev(src), True)
+    assert rel_err(g.cpu().numpy(), O.compute_curvature_vmult(src, True)) < TOL
+    o = np.zeros(O.n)
+    O.reinitialization_rhs(o, c, normal, False, True)
+    g = L.new_vector()
+    L.reinitialization_rhs(g, dev(c), [dev(v) for v in normal], False, True)
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    for diffuse_only in (False, True):
+        g = L.new_vector()
+        L.reinitialization_vmult(g, dev(src), diffuse_only)
+        assert rel_err(g.cpu().numpy(), O.reinitialization_vmult(src, diffuse_only)) < TOL
+    # point-wise operations
+    H = L.new_vector()
+    L.compute_heaviside(H, dev(c))
+    H_ref = orc.compute_heaviside(m.cell_ls, c, eps, n_sub)
+    assert np.abs(H.cpu().numpy() - H_ref).max() < 1e-14
+    kap = 2.0 / np.maximum(np.linalg.norm(m.ls_coords, axis=1), 0.2)
+    kg = dev(kap)
+    L.curvature_correction(kg, dev(c))
+    ko = kap.copy()
+    orc.ls_lib().ls_oracle_curvature_correction(__import__("ctypes").c_int64(O.n), __import__("ctypes").c_double(eps_used), 2, orc._p(c), orc._p(ko))
+    assert rel_err(kg.cpu().numpy(), ko) < TOL
+    L.close()
