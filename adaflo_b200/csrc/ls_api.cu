@@ -416,6 +416,7 @@ int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, doubl
   }
   f.surface_tension = surface_tension;
   f.gravity = gravity;
+  f.gravity_dir = ls->prm.dim - 1;
   f.density = ns->prm.density;
   f.density_diff = ns->prm.density_diff;
   f.viscosity = ns->prm.viscosity;

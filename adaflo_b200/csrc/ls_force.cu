@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ls_force_kernel(const For
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       double f = F.surface_tension * kap * g[d];
-      if (d == 2) f -= F.gravity * rho;  // :396-400
+      if (d == F.gravity_dir) f -= F.gravity * rho;  // force[dim - 1], :396-400
       tv[d][qy] = f * jxw;
       zero3[d][qy] = 0;
     }

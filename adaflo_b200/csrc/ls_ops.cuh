@@ -87,6 +87,7 @@ struct ForceArgs {
   const double *interp;      // [8][n1^3] level set -> pressure interpolation or null
   double hat_v[3][5], hat_d[3][5];  // FE_Q_iso_Q1 hats and derivatives at the 3 Gauss points
   double surface_tension, gravity, density, density_diff, viscosity, viscosity_diff;
+  int gravity_dir;           // dim - 1 (2-D problems on the extrusion: 1)
 };
 
 int launch_ls(const LSArgs &a, int op, cudaStream_t s);

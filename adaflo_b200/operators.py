@@ -618,10 +618,12 @@ class LevelSetOperators2D:
     N_a^2 dz = 2/3), and constrained rows get diag * src once.  Point-wise operations (Heaviside, curvature
     correction) are read from one plane.  Checked against an independent dense 2-D restatement (tests/test_2d_gpu.py)."""
 
-    def __init__(self, ctx, mesh2d, parameters: capi.LSParams, cell_diameters=None):
+    def __init__(self, ctx, mesh2d, parameters: capi.LSParams, cell_diameters=None, matrix_free=None):
+        """matrix_free: share the MatrixFree of a NavierStokesMatrix2D built after mesh2d.build_ls_space (compute_force)"""
         assert parameters.dim == 2, "LSParams.dim must be 2 (pseudo time step and curvature correction depend on it)"
         self.ctx, self.mesh2d = ctx, mesh2d
-        self.mf = MatrixFree(ctx, mesh2d.mesh3d, "cartesian")
+        self._own_mf = matrix_free is None
+        self.mf = MatrixFree(ctx, mesh2d.mesh3d, "cartesian") if matrix_free is None else matrix_free
         cd = mesh2d.cell_diameters() if cell_diameters is None else cell_diameters
         self.L = LevelSetOperators(self.mf, parameters, cd)
         dev = ctx.device
@@ -713,6 +715,14 @@ class LevelSetOperators2D:
         self.L.compute_heaviside(h3, self._E(level_set))
         heaviside.copy_(h3[self.ext[:, 0]])
 
+    def compute_force(self, ns2d, dst_u2, heaviside, curvature, surface_tension, gravity):
+        """local_compute_force for dim = 2 (gravity on the y component); ns2d: NavierStokesMatrix2D sharing self.mf.
+        rho / mu at the quadrature points are written into ns2d's (extruded) coefficient arrays."""
+        f3 = torch.zeros(self.mf.initialize_dof_vector(0).numel(), dtype=torch.float64, device=self.ctx.device)
+        self.L.compute_force(ns2d.A, f3, self._E(heaviside), self._E(curvature), surface_tension, gravity, None)
+        dst_u2.add_(f3[self.ext_u].sum(dim=1))
+
     def close(self):
         self.L.close()
-        self.mf.close()
+        if self._own_mf:
+            self.mf.close()

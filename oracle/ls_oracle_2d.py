@@ -141,3 +141,39 @@ class OracleLevelSet2D:
         else:
             tg = -D[:, :, None] * g
         self._scatter(self._integ(None, tg), rhs)
+
+
+def compute_force_2d(mesh2d, n_sub, heaviside, curvature, sigma, gravity, rho0, drho, mu0, dmu, variable, dst_u):
+    """dense LevelSetOKZSolver::local_compute_force (level_set_okz.cc:317-409) for dim = 2 on QGauss(3)^2, without the
+    level-set -> pressure interpolation; returns (rho_q, mu_q) [n_cells, 9]; gravity acts on component dim - 1 = y"""
+    m = mesh2d
+    n1 = n_sub + 1
+    s35 = np.sqrt(0.6)
+    gp = np.array([0.5 - 0.5 * s35, 0.5, 0.5 + 0.5 * s35])
+    gw = np.array([5.0, 8.0, 5.0]) / 18.0
+    hv, hd, L2 = np.zeros((3, n1)), np.zeros((3, n1)), np.zeros((3, 3))
+    for p in range(3):
+        s = min(int(gp[p] * n_sub), n_sub - 1)
+        xi = gp[p] * n_sub - s
+        hv[p, s], hv[p, s + 1] = 1 - xi, xi
+        hd[p, s], hd[p, s + 1] = -float(n_sub), float(n_sub)
+        x = gp[p]
+        L2[p] = [2 * (x - 0.5) * (x - 1), 4 * x * (1 - x), 2 * x * (x - 0.5)]
+    phi = np.einsum("bj,ai->baji", hv, hv).reshape(9, n1 * n1)
+    gx = np.einsum("bj,ai->baji", hv, hd).reshape(9, n1 * n1)
+    gy = np.einsum("bj,ai->baji", hd, hv).reshape(9, n1 * n1)
+    phiu = np.einsum("bj,ai->baji", L2, L2).reshape(9, 9)
+    jxw = np.einsum("b,a->ba", gw, gw).reshape(9) * np.prod(m.h)
+    Hl, kl = np.asarray(heaviside)[m.cell_ls], np.asarray(curvature)[m.cell_ls]
+    H = np.einsum("qn,cn->cq", phi, Hl)
+    kap = np.einsum("qn,cn->cq", phi, kl)
+    g = np.stack([np.einsum("qn,cn->cq", gx, Hl) / m.h[0], np.einsum("qn,cn->cq", gy, Hl) / m.h[1]], axis=-1)
+    rho = rho0 + drho * H if variable else np.full_like(H, rho0)
+    mu = mu0 + dmu * H
+    f = sigma * kap[:, :, None] * g
+    f[:, :, 1] -= gravity * rho
+    out = np.einsum("qn,cqd->cnd", phiu, f * jxw[None, :, None])
+    keep = ~m.u_dirichlet[m.cell_u]
+    idx = 2 * m.cell_u[:, :, None] + np.arange(2)[None, None, :]
+    np.add.at(dst_u, idx[keep], out[keep])
+    return rho, mu

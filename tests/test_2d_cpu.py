@@ -147,3 +147,21 @@ def test_2d_level_set_oracle_equals_extruded_3d_oracle(dirichlet_edges):
     assert rel_err(R(q3), q2) < 1e-13
     for diffuse_only in (False, True):
         assert rel_err(fix(R(O3.reinitialization_vmult(E(src), diffuse_only)), src), O2.reinitialization_vmult(src, diffuse_only)) < 1e-13
+
+
+def test_2d_force_oracle_equals_extruded_3d_oracle_without_gravity():
+    """surface-tension part of local_compute_force (the 3-D oracle applies gravity in z, so gravity = 0 here; the
+    gravity term of the 2-D path is checked on the device against the 2-D oracle)"""
+    from oracle.ls_oracle_2d import compute_force_2d
+    m, O2, O3, (eps, _, _, _) = ls_setup()
+    c, vec = ls_fields(m)
+    H = orc.compute_heaviside(m.cell_ls, c, eps, m.n_sub)
+    kap = 2.0 / np.maximum(np.linalg.norm(m.ls_coords, axis=1), 0.2) + 0.1 * vec(3)
+    f2 = np.zeros(m.n_u_nodes * 2)
+    rho2, mu2 = compute_force_2d(m, m.n_sub, H, kap, 0.07, 0.0, 1.0, 9.0, 0.1, 0.4, True, f2)
+    f3 = np.zeros(m.mesh3d.u.n_owned * 3)
+    rho3, mu3 = orc.compute_force(m.mesh3d, m.extend_ls(H), m.extend_ls(kap), 0.07, 0.0, 1.0, 9.0, 0.1, 0.4, True, None, f3)
+    fu, _ = m.restrict(f3, np.zeros(m.mesh3d.p.n_owned))
+    assert rel_err(fu, f2) < 1e-13
+    assert rel_err(rho3.reshape(-1, 3, 9), np.repeat(rho2[:, None, :], 3, axis=1)) < 1e-13
+    assert rel_err(mu3.reshape(-1, 3, 9), np.repeat(mu2[:, None, :], 3, axis=1)) < 1e-13

@@ -128,3 +128,33 @@ def test_2d_level_set_operators_match_dense_2d_oracle(ctx, dirichlet_edges):
     orc.ls_lib().ls_oracle_curvature_correction(__import__("ctypes").c_int64(O.n), __import__("ctypes").c_double(eps_used), 2, orc._p(c), orc._p(ko))
     assert rel_err(kg.cpu().numpy(), ko) < TOL
     L.close()
+
+
+def test_2d_force_matches_dense_2d_oracle(ctx):
+    """surface tension + gravity (on y = component dim - 1) and the rho / mu update of the 2-D operator"""
+    from adaflo_b200.operators import LevelSetOperators2D
+    from oracle import oracle as orc
+    from oracle.ls_oracle_2d import compute_force_2d
+    from test_2d_cpu import ls_fields, ls_setup
+    n_sub = 3
+    m, O, _, (eps, eps_used, h_min, step) = ls_setup(n=(5, 4), n_sub=n_sub)
+    dprm, _ = flow_params(density=1.0, viscosity=0.1, density_diff=9.0, viscosity_diff=0.4)
+    dtw, _ = time_weights()
+    A = NavierStokesMatrix2D(dprm, ctx, m, dtw, True)          # built after build_ls_space: its MatrixFree has the LS space
+    L = LevelSetOperators2D(ctx, m, capi.LSParams(2, n_sub, 0, 0, eps, eps_used, 4.0, h_min), matrix_free=A.mf)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    c, vec = ls_fields(m)
+    H = orc.compute_heaviside(m.cell_ls, c, eps, n_sub)
+    kap = 2.0 / np.maximum(np.linalg.norm(m.ls_coords, axis=1), 0.2) + 0.1 * vec(3)
+    from adaflo_b200.mesh import seeded_uniform
+    pre = seeded_uniform(m.u_ids, 2, 4)
+    o = pre.copy()
+    rho_q, mu_q = compute_force_2d(m, n_sub, H, kap, 0.07, 0.98, 1.0, 9.0, 0.1, 0.4, True, o)
+    g = dev(pre)
+    L.compute_force(A, g, dev(H), dev(kap), 0.07, 0.98)
+    assert rel_err(g.cpu().numpy(), o) < TOL
+    rho3 = A.A.get_coefficient(capi.COEF_DENSITY).cpu().numpy().reshape(-1, 3, 9)
+    mu3 = A.A.get_coefficient(capi.COEF_VISCOSITY).cpu().numpy().reshape(-1, 3, 9)
+    assert rel_err(rho3, np.repeat(rho_q[:, None, :], 3, axis=1)) < TOL and rel_err(mu3, np.repeat(mu_q[:, None, :], 3, axis=1)) < TOL
+    L.close()
+    A.clear()
