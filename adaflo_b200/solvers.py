@@ -130,8 +130,10 @@ class SolverGMRES:
     def _dots(self, w, V, ns):
         out = [0.0] * len(V)
         for blk, nb in enumerate(ns):
-            part = self.ctx.multi_dot(w[blk], [v[blk] for v in V], nb)
-            out = [a + b for a, b in zip(out, part)]
+            for j0 in range(0, len(V), 64):          # the library reduces at most 64 dots per call
+                part = self.ctx.multi_dot(w[blk], [v[blk] for v in V[j0:j0 + 64]], nb)
+                for j, val in enumerate(part):
+                    out[j0 + j] += val
         return out
 
     def _maxpy(self, y, coeffs, X):
