@@ -45,6 +45,8 @@ LSArgs base_args(adaflo_b200_ls_t ls)
   a.geom_row = q.cell_row;
   a.geom_table = q.table;
   a.geom = q.geometry_type;
+  a.inv_jac = q.inv_jac;
+  a.jxw_q = q.jxw;
   a.cell_diameters = ls->cell_diameters;
   a.gamma = ls->weight;
   a.w_old = ls->weight_old;
@@ -90,8 +92,6 @@ int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   if ((prm->dim != 3 && prm->dim != 2) || S < 1 || S > 4 || sp.fe_kind != ADAFLO_B200_FE_Q_ISO_Q1 || sp.degree != S || sp.n_comp != 1 ||
       sp.nodes_per_cell != (uint32_t)((S + 1) * (S + 1) * (S + 1)) || mf->quads[quad_ls].n_q_1d != 2 * S)
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: needs a 3-D FE_Q_iso_Q1(n_sub <= 4) space and the QIterated(QGauss(2), n_sub) quadrature");
-  if (mf->quads[quad_ls].geometry_type == ADAFLO_B200_GEOM_GENERAL)
-    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: general (per-point) geometry is not implemented for the level-set operators");
   if (prm->convection_stabilization) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: convection_stabilization is not implemented");
   if (dof_vel >= 0 && (mf->spaces[dof_vel].nodes_per_cell != 27 || mf->spaces[dof_vel].n_comp != 3))
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ls_create: the velocity space must be Q2^3");

@@ -31,7 +31,10 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
   // geometry of the cell (Cartesian or affine); the sub-cell is the cell scaled by 1 / n_sub
   double K[3][3] = {{0}};
   double det;
-  if (A.geom == ADAFLO_B200_GEOM_CARTESIAN) {
+  const bool general = A.geom == ADAFLO_B200_GEOM_GENERAL;  // K and JxW per point, loaded in the point loop
+  if (general) {
+    det = 0;
+  } else if (A.geom == ADAFLO_B200_GEOM_CARTESIAN) {
     const double *row = A.geom_table + 4 * (size_t)A.geom_row[cell];
     K[0][0] = row[0]; K[1][1] = row[1]; K[2][2] = row[2]; det = row[3];
   } else {
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
       for (int e = 0; e < 3; ++e) K[f][e] = row[3 * f + e];
     det = row[9];
   }
-  const double jxw = det / (8.0 * S3);  // Gauss(2) weights: 1/2 per direction on the sub-cell
+  double jxw = det / (8.0 * S3);  // Gauss(2) weights: 1/2 per direction on the sub-cell
   const double dS = (double)S;          // slope of the hat functions in cell reference coordinates
 
   uint32_t node[8];
@@ -170,6 +173,16 @@ __global__ void __launch_bounds__(128) ls_subcell_kernel(const LSArgs A)
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       const double vx[2] = {1 - g2(p & 1), g2(p & 1)}, vy[2] = {1 - g2((p >> 1) & 1), g2((p >> 1) & 1)}, vz[2] = {1 - g2(p >> 2), g2(p >> 2)};
+      if (general) {  // MappingQ cells: inverse Jacobian and JxW of this point
+        const int nq1 = 2 * S;
+        const size_t NQ = (size_t)nq1 * nq1 * nq1;
+        const size_t q = (2 * sx + (p & 1)) + (size_t)nq1 * ((2 * sy + ((p >> 1) & 1)) + (size_t)nq1 * (2 * sz + (p >> 2)));
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+#pragma unroll
+          for (int e = 0; e < 3; ++e) K[f][e] = __ldg(A.inv_jac + ((size_t)cell * 9 + 3 * f + e) * NQ + q);
+        jxw = __ldg(A.jxw_q + (size_t)cell * NQ + q);
+      }
       double psi[8], gp[8][3];  // shape values and real-space gradients
 #pragma unroll
       for (int n = 0; n < 8; ++n) {

@@ -18,7 +18,9 @@ struct LSArgs {
   const uint32_t *hn;        // per-cell refinement masks of the level-set space or null
   const uint32_t *geom_row;
   const double *geom_table;
-  int geom;                  // cartesian / affine
+  int geom;                  // cartesian / affine / general
+  const double *inv_jac;     // general: [n_cells][9][NQ], q = qx + nq1 (qy + nq1 qz) on QIterated(QGauss(2), n_sub)
+  const double *jxw_q;       // general: [n_cells][NQ]
   const double *cell_diameters;
   const double *src[3];
   double *dst[3];

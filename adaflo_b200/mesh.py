@@ -296,13 +296,14 @@ class BoxMesh:
         index = np.zeros(self.n_cells, dtype=np.uint32)
         return table, index
 
-    def general_geometry(self, n_q_1d=3, deform=None):
+    def general_geometry(self, n_q_1d=3, deform=None, rule=None):
         """Per-quadrature-point inverse Jacobian K[f][e]=d xi_f/d x_e and JxW.
 
         Returns invJ [n_cells, n_q, 3, 3] and JxW [n_cells, n_q]; ``deform`` is
         ``(X) -> (x, dx/dX)`` on physical box coordinates (identity if None).
         """
-        qp, qw = gauss_legendre_01(n_q_1d)
+        qp, qw = gauss_legendre_01(n_q_1d) if rule is None else rule   # rule: 1-D points / weights on [0, 1]
+        n_q_1d = len(qp)
         qz, qy, qx = np.meshgrid(np.arange(n_q_1d), np.arange(n_q_1d), np.arange(n_q_1d), indexing="ij")
         qx, qy, qz = qx.reshape(-1), qy.reshape(-1), qz.reshape(-1)
         w = qw[qx] * qw[qy] * qw[qz]
@@ -319,6 +320,13 @@ class BoxMesh:
         det = np.linalg.det(J)
         K = np.linalg.inv(J)                                                  # K[f][e] = dxi_f/dx_e
         return np.ascontiguousarray(K), det * w[None, :]
+
+    def iterated_geometry(self, n_sub, deform=None):
+        """geometry on QIterated(QGauss(2), n_sub), the level-set quadrature (source/two_phase_base.cc:265-268)"""
+        g, w = gauss_legendre_01(2)
+        pts = np.concatenate([(s + np.asarray(g, dtype=np.float64)) / n_sub for s in range(n_sub)])
+        wts = np.concatenate([np.asarray(w, dtype=np.float64) / n_sub for _ in range(n_sub)])
+        return self.general_geometry(2 * n_sub, deform, rule=(pts, wts))
 
     def quadrature_points(self, n_q_1d=3, deform=None):
         qp, _ = gauss_legendre_01(n_q_1d)

@@ -184,7 +184,10 @@ class MatrixFree:
                 row = np.arange(mesh.n_cells, dtype=np.uint32)
                 q.geometry_type = capi.GEOM_AFFINE
             elif geometry == "general":
-                K, jxw = mesh.general_geometry(nq1, deform)
+                if i == 2:   # level-set quadrature: QIterated(QGauss(2), n_sub)
+                    K, jxw = mesh.iterated_geometry(ls_space.n_sub, deform)
+                else:
+                    K, jxw = mesh.general_geometry(nq1, deform)
                 invj = np.ascontiguousarray(K.reshape(mesh.n_cells, nq1 ** 3, 9).transpose(0, 2, 1))
                 jxw = np.ascontiguousarray(jxw)
                 keep += [invj, jxw]

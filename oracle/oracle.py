@@ -307,8 +307,12 @@ def ls_lib():
     return _ls_lib
 
 
-def iterated_gauss_geometry(mesh, n_sub, deform=None):
-    """inverse Jacobians and JxW on QIterated(QGauss(2), n_sub) (q = qx + nq qy + nq^2 qz), affine cells"""
+def iterated_gauss_geometry(mesh, n_sub, deform=None, general=False):
+    """inverse Jacobians and JxW on QIterated(QGauss(2), n_sub) (q = qx + nq qy + nq^2 qz); affine cells unless
+    general (then per point, mesh.iterated_geometry)"""
+    if general:
+        K, jxw = mesh.iterated_geometry(n_sub, deform)
+        return np.ascontiguousarray(K), np.ascontiguousarray(jxw)
     K1, _ = mesh.general_geometry(1, deform)                   # cell-centre Jacobian (exact for affine cells)
     nq = (2 * n_sub) ** 3
     det = 1.0 / np.linalg.det(K1[:, 0])
@@ -320,7 +324,7 @@ def iterated_gauss_geometry(mesh, n_sub, deform=None):
 class OracleLevelSet:
     """Dense CPU restatement of the matrix-free level-set operators on one rank."""
 
-    def __init__(self, mesh, prm: LSParams, deform=None):
+    def __init__(self, mesh, prm: LSParams, deform=None, general=False):
         self.mesh = mesh
         self.prm = prm
         ls = mesh.ls
@@ -329,7 +333,7 @@ class OracleLevelSet:
         self.NQ = (2 * ls.n_sub) ** 3
         self.cell_nodes = np.ascontiguousarray(ls.cell_nodes.astype(np.int64))
         self.con = np.ascontiguousarray(ls.dirichlet.reshape(-1).astype(np.uint8))
-        self.K, self.jxw = iterated_gauss_geometry(mesh, ls.n_sub, deform)
+        self.K, self.jxw = iterated_gauss_geometry(mesh, ls.n_sub, deform, general)
         self.cd = np.ascontiguousarray(mesh.cell_diameters())
         self.lists = getattr(mesh, "ls_lists", None)   # plain constraint expansion on meshes with hanging nodes
         lp = [_p(a) for a in self.lists] if self.lists is not None else [None, None, None]

@@ -34,7 +34,7 @@ class LSPair:
         self.A = LevelSetOperators(self.mf, self.dprm, cd)
         self.gamma, self.w_old, self.w_oo, self.dt = 75.0, -100.0, 25.0, 0.02
         self.A.set_time(self.gamma, self.w_old, self.w_oo, self.dt)
-        self.O = orc.OracleLevelSet(mesh, self.oprm, deform)
+        self.O = orc.OracleLevelSet(mesh, self.oprm, deform, general=(geometry == "general"))
         x = mesh.ls.coords if deform is None else deform(mesh.ls.coords)[0]
         r = np.linalg.norm(x - np.array([0.1, -0.05, -0.2]), axis=1)
         self.c = -np.tanh((r - 0.45) / (2 * 0.12)) + 0.01 * seeded_uniform(mesh.ls.global_ids, 1, 5)
@@ -52,7 +52,7 @@ class LSPair:
         self.mf.close()
 
 
-@pytest.mark.parametrize("geometry", ["cartesian", "affine"])
+@pytest.mark.parametrize("geometry", ["cartesian", "affine", "general"])
 @pytest.mark.parametrize("n_sub", [3, 4])
 @pytest.mark.parametrize("dirichlet", [(), (0, 3)])
 def test_level_set_operators(ctx, geometry, n_sub, dirichlet):
@@ -151,11 +151,7 @@ def test_heaviside_and_force(ctx, geometry, interpolate):
     mesh = BoxMesh((4, 3, 3))
     mesh.build_ls_space(n_sub)
     deform = deformation(geometry)
-    ls_geometry = "cartesian" if geometry == "general" else geometry   # level-set kernels: compressed geometry only
-    mf = MatrixFree(ctx, mesh, geometry, deform) if geometry != "general" else None
-    if mf is None:
-        # general geometry for the NS quadrature is exercised with a mesh whose level-set quadrature stays Cartesian
-        pytest.skip("mixed geometry descriptions are not expressible through the Python MatrixFree helper")
+    mf = MatrixFree(ctx, mesh, geometry, deform)
     dprm, _ = flow_params(density=1.0, viscosity=0.1, density_diff=9.0, viscosity_diff=0.4)
     dtw, _ = time_weights()
     A = NavierStokesMatrix(dprm, 0, 1, 0, 1, BlockVector.like(mf), BlockVector.like(mf))
