@@ -327,6 +327,11 @@ class NavierStokesMatrix:
         self._require()
         check(self.lib.adaflo_b200_ns_fix_linearization_point(self.h))
 
+    def compute_diagonal(self, diagonal: BlockVector):
+        """exact diagonal of vmult (velocity block by unit-source passes, pressure block 0 / -1 on constrained rows)"""
+        self._require()
+        check(self.lib.adaflo_b200_ns_compute_diagonal(self.h, _ptr(diagonal.block(0)), _ptr(diagonal.block(1))))
+
     def apply_pressure_average_projection(self, vector):
         self._require()
         check(self.lib.adaflo_b200_ns_apply_pressure_average_projection(self.h, _ptr(vector)))

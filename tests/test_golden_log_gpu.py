@@ -1,6 +1,7 @@
 """The CUDA path against the reference's own golden log tests/beltrami_3d.output (3-D Beltrami flow, 16^3 cells,
 BDF-2, dt = 0.05): four time steps are advanced ON THE DEVICE (Newton with NavierStokesMatrix::residual / vmult,
-unpreconditioned GMRES from adaflo_b200.solvers, converged to the log's nonlinear tolerance 1e-9) and the quantities
+flexible GMRES with the device block preconditioner of adaflo_b200.preconditioner, converged to the log's nonlinear
+tolerance 1e-9) and the quantities
 of the log that do not depend on the reference's ILU preconditioner are compared digit by digit:
   * the first nonlinear residual (u, p) of time steps #1 - #4          (beltrami_3d.output:13,33,44,56)
   * the L2 errors of velocity and pressure at t = 0.2                  (beltrami_3d.output:63)
@@ -12,6 +13,7 @@ import torch
 from adaflo_b200 import capi
 from adaflo_b200.mesh import BoxMesh, beltrami_pressure, beltrami_velocity
 from adaflo_b200.operators import BlockVector, Context, MatrixFree, NavierStokesMatrix
+from adaflo_b200.preconditioner import NavierStokesPreconditioner
 from adaflo_b200.solvers import NoConvergence, SolverControl, SolverGMRES
 from oracle import oracle as orc
 
@@ -40,6 +42,7 @@ def test_device_time_stepping_reproduces_the_golden_log():
     dirichlet = torch.from_numpy(np.nonzero(mesh.u.dirichlet.reshape(-1))[0]).to(ctx.device)
     nu, npp = mf.n_owned(0), mf.n_owned(1)
     rhs, zero, upd = BlockVector.like(mf), BlockVector.like(mf), BlockVector.like(mf)
+    lin_iterations = []
     for step in range(1, 5):
         # init_time_advance (navier_stokes.cc:659-685): shift the history, extrapolate, new Dirichlet values
         for b in range(2):
@@ -61,12 +64,14 @@ def test_device_time_stepping_reproduces_the_golden_log():
                 break
             upd.block(0).zero_()
             upd.block(1).zero_()
-            ctl = SolverControl(4000, 1e-14, 1e-7)
+            ctl = SolverControl(100, 1e-14, 1e-7)
+            P = NavierStokesPreconditioner(ctx, A, mf)                      # (diagonal of the new linearisation)
             try:
-                SolverGMRES(ctx, ctl, 150).solve(lambda d, s: A.vmult(BlockVector(*d), BlockVector(*s)), [upd.block(0), upd.block(1)],
-                                                 [rhs.block(0), rhs.block(1)], None, [nu, npp])
+                SolverGMRES(ctx, ctl, 100).solve(lambda d, s: A.vmult(BlockVector(*d), BlockVector(*s)), [upd.block(0), upd.block(1)],
+                                                 [rhs.block(0), rhs.block(1)], P.vmult, [nu, npp])
             except NoConvergence:
                 pass                                                        # Newton continues with the inexact update
+            lin_iterations.append(ctl.last_step)
             sol.block(0).add_(upd.block(0))
             sol.block(1).add_(upd.block(1))
         else:
@@ -85,3 +90,5 @@ def test_device_time_stepping_reproduces_the_golden_log():
     e_p = O.l2_error(1, sol.block(1).cpu().numpy(), beltrami_pressure(xq, 0.2)[..., None], n_q_1d=4)
     assert f"{e_u:.4g}" == GOLDEN_ERRORS_T02[1], e_u
     assert f"{e_p:.4g}" == GOLDEN_ERRORS_T02[0], e_p
+    # the block preconditioner keeps the outer iteration counts in the range of the reference's (30 for 1e-5 with ILU)
+    assert max(lin_iterations) <= 40, lin_iterations
