@@ -322,10 +322,12 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
   {  // host-vector pipeline metadata (adaflo_b200_ns_vmult_host): monotone node prefixes per cell chunk
     const size_t n_dec = n_groups(d->n_cells);
     // 16 chunks: measured optimum at 128^3 cells (4: 11.6 ms, 8: 11.0, 16: 10.6, 32: 11.8, 64: 13.9 ms per vmult_host;
-    // each chunk costs about 70 us of stream hand-over, fill and drain shrink with the chunk size)
+    // a chunk costs about 70 us of stream hand-over).  Graded chunks (small first and last ones, to shorten the
+    // pipeline fill and drain) measured 11.0 vs 10.9 ms: the remainder over max(H2D, D2H) = 8.5 ms is the
+    // bidirectional PCIe rate, not fill/drain.
     size_t n_chunks = n_dec < 16 ? (n_dec ? 1 : 0) : 16;
-    if (const char *e = std::getenv("ADAFLO_B200_HOST_CHUNKS"))  // tuning knob
-      if (n_dec >= 16) n_chunks = std::min<size_t>(n_dec, std::max<long>(1, std::atol(e)));
+    const char *e_chunks = std::getenv("ADAFLO_B200_HOST_CHUNKS");  // tuning knob
+    if (e_chunks && *e_chunks && n_dec >= 16) n_chunks = std::min<size_t>(n_dec, std::max<long>(1, std::atol(e_chunks)));
     mf->pipeline_ok = n_chunks > 0;
     for (size_t k = 0; k < n_chunks; ++k) mf->chunk_decade_end.push_back(k + 1 == n_chunks ? n_dec : (k + 1) * (n_dec / n_chunks));
     for (int i = 0; i < d->n_spaces && mf->pipeline_ok; ++i) {

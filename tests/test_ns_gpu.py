@@ -219,7 +219,7 @@ def test_host_entry_point_matches_device(ctx):
 
 def test_host_entry_point_pipelined_chunks(ctx):
     """>= 16 decades: vmult_host overlaps upload / cell chunks / download on three streams (16 cell chunks)."""
-    P = Pair(ctx, n=(6, 6, 7))
+    P = Pair(ctx, n=(10, 8, 8))
     P.residual_both()
     m = P.mesh
     for seed in (91, 92):   # second call reuses the staging vectors and events
