@@ -15,12 +15,15 @@
 //    the physics and contracts back in z, overwriting the same tile entries.
 //  * phase C: lane t owns node plane t again, transposed in-plane contractions, scatter.
 //    => one shared-memory round trip per direction pair instead of two.
-//  * tile index = k + 3 qx + 33 qy (+9 per array) and a cell stride of 3 (mod 16) doubles
-//    make the bank pair of every access equal to the lane number: conflict free in both
-//    ownership patterns.
-//  * all per-quadrature-point data (linearisation point, rho/mu/damping, Jacobians) and
-//    the cell->node lists are stored decade-blocked, [decade][row][3 qx + qz][30 lanes], so
-//    each warp-level load reads 240 contiguous bytes (see coef_index in common.cuh).
+//  * tile entry (array, component, qx, qy, k) at 9 arr + 27 c + k + 3 qx + 81 qy, cell stride 259 doubles: 81 = 1 and
+//    259 = 3 (mod 16) make the 8-byte bank of every access 3 cell + t in both ownership patterns (conflict free,
+//    243 of 259 slots used); the pressure travels as its 8 vertex values / 12 transposed accumulators.
+//  * all per-quadrature-point data (linearisation point, rho/mu/damping, Jacobians) and the cell->node lists are
+//    stored decade-blocked, [decade][row][3 qx + qz][30 lanes], so each warp-level load is contiguous (coef_index in
+//    common.cuh); the 12 linearisation rows are interleaved in pairs and fetched with 16-byte loads (lin_index).
+//  * the kernel is persistent: one block of 10-11 independent warps per SM, every warp draws decades from a global
+//    ticket counter; a launch can be restricted to a decade range (host-vector pipeline, halo overlap).
+// Measured history, rejected variants and the ncu evidence: DESIGN.md section 3.
 #pragma once
 
 #include "hanging.cuh"
