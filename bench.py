@@ -53,6 +53,29 @@ def ncu_traffic():
     return total if seen == 2 else None
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host vectors of the
+    end-to-end path are allocated next to its PCIe root port (matters with several ranks per box).  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -185,6 +208,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = Context(local_rank)
@@ -356,7 +380,7 @@ def main():
             "config": {"workload": f"ns_vmult Q2/Q1 3D box {n}^3 cells/GPU ({n_dofs_rank} DoFs/GPU, {n_dofs} total), Newton stored linearisation, "
                                    "Cartesian, constant coefficients, Dirichlet u on all faces, pressure mean fixed",
                        "l2": "inputs larger than L2 (vectors 0.42 GB, linearisation data 5.4 GB per GPU)",
-                       "partition": f"z-slabs x{world}", "setup_s": round(t_setup, 1)},
+                       "partition": f"z-slabs x{world}", "setup_s": round(t_setup, 1), "numa_node_rank0": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic() if n == 128 and world == 1 else None,
                          "traffic_source": "profiles/r1_g_ns_vmult_r1_key_metrics.txt (ncu --set full, same workload, 1 GPU)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
