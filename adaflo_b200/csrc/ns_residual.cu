@@ -175,15 +175,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 2) ns_residual_kernel(con
 #pragma unroll
           for (int e = 0; e < 3; ++e) res += u[e] * g[d][e];
           conv[d] += A.tau1 * res;
-          lin[lin_row(d)] = u[d];
         }
         if (lz == ADAFLO_B200_COUPLED_IMPLICIT_NEWTON) {
+          // the 12 rows are interleaved in pairs (lin_index): six 16-byte stores
+          const double L[12] = {u[0], u[1], u[2], g[0][0], g[0][1], g[0][2], g[1][0], g[1][1], g[1][2], g[2][0], g[2][1], g[2][2]};
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-#pragma unroll
-            for (int e = 0; e < 3; ++e) lin[lin_row(3 + 3 * d + e)] = g[d][e];
-        } else
-          lin[lin_row(3)] = div;
+          for (int r = 0; r < 6; ++r) *reinterpret_cast<double2 *>(lin + lin_row(2 * r)) = make_double2(L[2 * r], L[2 * r + 1]);
+        } else {
+          *reinterpret_cast<double2 *>(lin + lin_row(0)) = make_double2(u[0], u[1]);
+          *reinterpret_cast<double2 *>(lin + lin_row(2)) = make_double2(u[2], div);
+        }
       }
       const double rho = VAR ? __ldg(A.rho + q1) : A.rho0;
       const double damping = VAR ? __ldg(A.damp + q1) : A.damp0;
