@@ -340,6 +340,14 @@ namespace adaflo_b200
     bool    use_variable_coefficients() const { return parameters.density_diff != 0 || parameters.viscosity_diff != 0; }
 
     /// (accumulated wall time, number of calls) since the last query; resets the counters.
+    /// the C-ABI handle (for the level-set force, which writes rho / mu into this operator)
+    adaflo_b200_ns_t handle() const
+    {
+      if (!h)
+        throw ExcNotInitialized();
+      return h;
+    }
+
     std::pair<double, unsigned int> get_matvec_statistics() const
     {
       require();

@@ -75,3 +75,43 @@ def test_cpp_navier_stokes_matrix_matches_oracle(tmp_path):
     assert rel_err(got["vmult_u"], ou) < 1e-12 and rel_err(got["vmult_p"], op) < 1e-12
     assert abs(got["scalars"][0] - (ou @ su + op @ sp)) < 1e-10 * abs(ou @ su + op @ sp)
     assert got["scalars"][1] == 1
+
+
+def test_cpp_level_set_classes_match_oracle(tmp_path):
+    """include/adaflo_b200/level_set_okz.h: LevelSetOKZSolver{AdvanceConcentration, ComputeNormal, ComputeCurvature,
+    Reinitialization} driven from C++ (tests/cpp/level_set_driver.cpp)"""
+    driver = os.path.join(ROOT, "tests", "cpp", "level_set_driver")
+    assert os.path.exists(driver), "build the driver with __graft_entry__.build()"
+    n_sub = 3
+    mesh = BoxMesh((4, 3, 3), lower=(-1, -1, -1), upper=(1.0, 0.7, 0.5))
+    mesh.build_ls_space(n_sub)
+    h_min = float(mesh.h.min())
+    eps, eps_used, dt = 1.5, 1.5 * h_min / n_sub, 0.02
+    O = orc.OracleLevelSet(mesh, orc.LSParams(eps, eps_used, 4.0, h_min, dt, 3, 0))
+    O.diag = O.mass_diagonal()
+    x = mesh.ls.coords
+    c = -np.tanh((np.linalg.norm(x - np.array([0.1, -0.05, -0.2]), axis=1) - 0.45) / 0.24)
+    vec = lambda s: seeded_uniform(mesh.ls.global_ids, 1, s)
+    c_old, c_oo, src = c + 0.05 * vec(7), c + 0.05 * vec(8), vec(10)
+    vel = beltrami_velocity(mesh.u.coords, 0.0).reshape(-1) + 0.1 * seeded_uniform(mesh.u.global_ids, 3, 6)
+    table, row = mesh.cartesian_geometry()
+    write_dump(tmp_path / "in.bin", {
+        "meta": np.array([mesh.n_cells, mesh.u.n_owned, mesh.p.n_owned, mesh.ls.n_owned, n_sub], dtype=np.uint32),
+        "params": np.array([eps, eps_used, 4.0, h_min, 75.0, -100.0, 25.0, dt]),
+        "cell_u": mesh.u.encoded_cell_nodes(), "cell_p": mesh.p.encoded_cell_nodes(), "cell_ls": mesh.ls.encoded_cell_nodes(),
+        "geom_table": table, "geom_row": row, "cell_diameters": mesh.cell_diameters(),
+        "c": c, "c_old": c_old, "c_old_old": c_oo, "src": src, "vel": vel})
+    r = subprocess.run([driver, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0
+    got = read_dump(tmp_path / "out.bin")
+    assert rel_err(got["mass_diagonal"], O.diag) < 1e-12
+    o = np.zeros(O.n)
+    O.advance_concentration_rhs(o, vel, c, c_old, c_oo, 75.0, -100.0, 25.0)
+    assert rel_err(got["advance_rhs"], o) < 1e-12
+    assert rel_err(got["advance_vmult"], O.advance_concentration_vmult(src, 75.0)) < 1e-12
+    nr = [np.zeros(O.n) for _ in range(3)]
+    O.compute_normal_rhs(nr, c)
+    assert rel_err(got["normal_rhs_0"], nr[0]) < 1e-12 and rel_err(got["normal_rhs_2"], nr[2]) < 1e-12
+    assert rel_err(got["curvature_vmult"], O.compute_curvature_vmult(src, True)) < 1e-12
+    assert rel_err(got["reinit_vmult_diffuse"], O.reinitialization_vmult(src, True)) < 1e-12
