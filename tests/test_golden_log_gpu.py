@@ -5,7 +5,7 @@ tolerance 1e-9) and the quantities
 of the log that do not depend on the reference's ILU preconditioner are compared digit by digit:
   * the first nonlinear residual (u, p) of time steps #1 - #4          (beltrami_3d.output:13,33,44,56)
   * the L2 errors of velocity and pressure at t = 0.2                  (beltrami_3d.output:63)
-The golden numbers below are copied from that file; the oracle is used only to integrate the error norms."""
+The golden numbers are the fixture tests/golden/beltrami_3d_output.json (copied from that file); the oracle is used only to integrate the error norms."""
 import numpy as np
 import pytest
 import torch
@@ -21,8 +21,13 @@ from helpers import flow_params
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN_FIRST_RESIDUALS = [("2.590e+00", "6.423e-02"), ("2.348e+00", "5.678e-02"), ("2.793e-01", "6.590e-03"), ("2.398e-01", "5.825e-03")]
-GOLDEN_ERRORS_T02 = ("0.02156", "0.0007541")   # ||e_p||_L2, ||e_u||_L2
+import json
+import os
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "beltrami_3d_output.json")) as _f:
+    _GOLDEN = json.load(_f)
+GOLDEN_FIRST_RESIDUALS = [(_GOLDEN["first_nonlinear_residual"][str(k)]["u"], _GOLDEN["first_nonlinear_residual"][str(k)]["p"]) for k in range(1, 5)]
+GOLDEN_ERRORS_T02 = (_GOLDEN["l2_errors_t0.2"]["e_p"], _GOLDEN["l2_errors_t0.2"]["e_u"])   # ||e_p||_L2, ||e_u||_L2
 
 
 def test_device_time_stepping_reproduces_the_golden_log():
