@@ -377,3 +377,29 @@ def test_compute_diagonal(ctx, hanging):
         assert abs(du[i] - col_u[i]) <= 1e-12 * max(1.0, abs(col_u[i])), (i, du[i], col_u[i])
     A.clear()
     mf.close()
+
+
+def test_device_poiseuille_is_a_discrete_stokes_solution(ctx):
+    """analytic pin of the CUDA path (no oracle involved): u = (0.5/nu)(1-y^2) e_x, p = 2 - x lie in Q2/Q1
+    (tests/poiseuille.cc:74-112), so the Stokes residual computed on the device vanishes on every row whose test
+    function does not touch the open in/outflow faces, and the flow is discretely divergence free"""
+    nu = 0.8
+    mesh = BoxMesh((4, 4, 2), dirichlet_faces=(2, 3, 4, 5))
+    dprm, _ = flow_params(physical_type=capi.STOKES, viscosity=nu)
+    dtw, _ = time_weights()
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, BlockVector.like(mf), BlockVector.like(mf))
+    A.initialize(mf, dtw, False)
+    x = mesh.u.coords
+    u = np.zeros((len(x), 3))
+    u[:, 0] = 0.5 / nu * (1 - x[:, 1] ** 2)
+    p = 2.0 - mesh.p.coords[:, 0]
+    rhs = BlockVector.like(mf)
+    A.residual(rhs, BlockVector(dev(ctx, u.reshape(-1)), dev(ctx, p)), BlockVector.like(mf))
+    ru = rhs.block(0).cpu().numpy().reshape(-1, 3)
+    rp = rhs.block(1).cpu().numpy()
+    interior = np.abs(np.abs(x[:, 0]) - 1) > 1e-12
+    assert np.abs(ru[interior]).max() < 1e-12 and np.abs(rp).max() < 1e-12
+    assert np.abs(ru[~interior]).max() > 1e-3      # the traction integral of the exact solution on the open faces
+    A.clear()
+    mf.close()
