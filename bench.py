@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="cells per direction per GPU")
-    ap.add_argument("--cpu-layers", type=int, default=8, help="z layers of the CPU baseline sample")
+    ap.add_argument("--cpu-layers", type=int, default=32, help="z layers of the CPU baseline sample (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--preroll", type=float, default=0.7, help="seconds of untimed load before the timed steps (clock sampling)")
@@ -396,7 +396,7 @@ def main():
                       "note": "same K steps right after warm-up, before the GPU reaches its power limit (rank 0 timing)"},
         }
         if not args.no_cpu_baseline and world >= 1:
-            cb, _ = cpu_port_sample(n, max(2, min(n, args.cpu_layers)), 3, 1)
+            cb, _ = cpu_port_sample(n, max(2, min(n, args.cpu_layers)), 10, 2)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     if world > 1:
