@@ -507,7 +507,8 @@ class RefinedBoxMesh:
 
     Cells: unrefined coarse cells first (lexicographic), then the children (parent-major)."""
 
-    def __init__(self, n, refine, lower=(-1.0, -1.0, -1.0), upper=(1.0, 1.0, 1.0), dirichlet_faces=(0, 1, 2, 3, 4, 5)):
+    def __init__(self, n, refine, lower=(-1.0, -1.0, -1.0), upper=(1.0, 1.0, 1.0), dirichlet_faces=(0, 1, 2, 3, 4, 5),
+                 augmented=False):
         self.dim = 3
         self.n = tuple(int(v) for v in n)
         self.lower = np.asarray(lower, dtype=np.float64)
@@ -540,6 +541,36 @@ class RefinedBoxMesh:
         self.origin = self.lower[None, :] + 0.5 * self.hc[None, :] * self.cells[:, 1:4]
         self.u, self.u_lists = self._build_space("u", 2, 3, dirichlet_faces)
         self.p, self.p_lists = self._build_space("p", 1, 1, ())
+        self.augmented = augmented
+        if augmented:
+            self._append_dg0()
+
+    def _append_dg0(self):
+        """FE_Q_DG0(1): one element-constant pressure dof per cell behind the Q1 nodes (source/navier_stokes.cc:98-106);
+        the hanging-node masks concern the 8 vertex slots only"""
+        sp = self.p
+        n_q1 = sp.n_owned
+        dg = n_q1 + np.arange(self.n_cells, dtype=np.int64)
+        sp.cell_nodes = np.concatenate([sp.cell_nodes.astype(np.int64), dg[:, None]], axis=1).astype(np.uint32)
+        sp.nodes_per_cell = 9
+        sp.n_dg0, sp.n_q1_owned = self.n_cells, n_q1
+        sp.global_ids = np.concatenate([sp.global_ids, sp.global_ids.max() + 1 + np.arange(self.n_cells)])
+        sp.coords = np.concatenate([sp.coords, self.origin + 0.5 * self.h_cell])
+        sp.dirichlet = np.concatenate([sp.dirichlet, np.zeros((self.n_cells, 1), bool)])
+        sp.n_owned = sp.n_owned_global = n_q1 + self.n_cells
+        # plain expansion lists: 9 rows per cell, the last one is the cell's own constant
+        ptr, idx, w = self.p_lists
+        nptr, nidx, nw = [0], [], []
+        for c in range(self.n_cells):
+            for node in range(8):
+                a, b = ptr[c * 8 + node], ptr[c * 8 + node + 1]
+                nidx.extend(idx[a:b].tolist())
+                nw.extend(w[a:b].tolist())
+                nptr.append(len(nidx))
+            nidx.append(int(dg[c]))
+            nw.append(1.0)
+            nptr.append(len(nidx))
+        self.p_lists = (np.array(nptr, dtype=np.int64), np.array(nidx, dtype=np.int64), np.array(nw, dtype=np.float64))
 
     def _is_refined(self, i, j, k):
         nx, ny, nz = self.n

@@ -124,6 +124,7 @@ class OracleNavierStokesMatrix:
         self.mesh = mesh
         self.prm = prm
         self.tw = tw
+        self._u_lists, self._p_lists = u_lists, p_lists
         self.mu = OracleMesh(mesh, 3, deform, u_lists, p_lists)   # quad_index_u: QGauss(3)
         self.mp = OracleMesh(mesh, 2, deform, u_lists, p_lists)   # quad_index_p: QGauss(2)
         nc, nq = mesh.n_cells, 27
@@ -274,7 +275,7 @@ class OracleNavierStokesMatrix:
         return dst
 
     def l2_error(self, n_comp, vec, exact_q, n_q_1d=3, deform=None):
-        om = self.mu if n_q_1d == 3 else OracleMesh(self.mesh, n_q_1d, deform)
+        om = self.mu if n_q_1d == 3 else OracleMesh(self.mesh, n_q_1d, deform, self._u_lists, self._p_lists)
         exact_q = np.ascontiguousarray(exact_q)
         return lib().oracle_l2_error(C.byref(om.c), n_comp, _p(vec), _p(exact_q))
 

@@ -140,3 +140,87 @@ def test_oracle_shape_tables_are_consistent():
     assert v[0, 0] == 0.6872983346207416 and d[0, 1] == 3.0983866769659336
     x, w = orc.gauss01(3)
     assert abs(w.sum() - 1) < 1e-15 and w[1] == 0.4444444444444444
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# tests/beltrami_3d_augp.output: the same flow on a locally refined mesh (2:1 hanging nodes) with augmented Taylor-Hood
+# elements Q2/(Q1+DG0) -- pins the hanging-node constraints, the element-constant pressure and the second null-space mode
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "beltrami_3d_augp_output.json")) as _f:
+    GOLDEN_AUGP = json.load(_f)
+
+
+def augp_mesh():
+    from adaflo_b200.mesh import RefinedBoxMesh
+    # tests/beltrami.cc:385-412, see the "_mesh" entry of the fixture
+    return RefinedBoxMesh((8, 8, 8), ((4, 8), (0, 2), (0, 2)), augmented=True)
+
+
+def count_hanging(lists):
+    ptr, idx, w = lists
+    keys = set()
+    for k in range(len(ptr) - 1):
+        if ptr[k + 1] - ptr[k] > 1:
+            keys.add((tuple(idx[ptr[k]:ptr[k + 1]].tolist()), tuple(np.round(w[ptr[k]:ptr[k + 1]], 12).tolist())))
+    return len(keys)
+
+
+def test_augp_mesh_and_dof_counts_match_golden_log():
+    mesh = augp_mesh()
+    assert mesh.n_cells == GOLDEN_AUGP["n_active_cells"]["value"]
+    # deal.II counts constrained dofs: vertices of fine cells on coarse edges / faces (= the hanging Q1 nodes) carry
+    # their own Q2 dofs as well, identified with the coarse edge / face dofs by constraints
+    hanging_p = count_hanging(mesh.p_lists)
+    hanging_u = count_hanging(mesh.u_lists) // 3
+    assert mesh.p.n_owned + hanging_p == GOLDEN_AUGP["n_dofs"]["pressure"]
+    assert 3 * (mesh.u.n_owned + hanging_u + hanging_p) == GOLDEN_AUGP["n_dofs"]["velocity"]
+
+
+def test_augp_interpolation_errors_match_golden_log():
+    """VectorTools::interpolate gives hanging nodes the exact values and the error is integrated before any
+    constraint is distributed: plain nodal interpolation on every cell, DG0 part zero (navier_stokes.cc:1414-1430)"""
+    import ctypes as C
+    mesh = augp_mesh()
+    nc = mesh.n_cells
+
+    def local_coords(k):
+        a = np.arange(k + 1) / k
+        lz, ly, lx = np.meshgrid(a, a, a, indexing="ij")
+        loc = np.stack([lx.reshape(-1), ly.reshape(-1), lz.reshape(-1)], axis=1)
+        return (mesh.origin[:, None, :] + mesh.h_cell[:, None, :] * loc[None, :, :]).reshape(-1, 3)
+    uvals = beltrami_velocity(local_coords(2), 0.0)
+    pvals = np.concatenate([beltrami_pressure(local_coords(1), 0.0).reshape(nc, 8), np.zeros((nc, 1))], axis=1).reshape(-1)
+    rows = np.arange(nc * 81)
+    u_idx = (3 * ((rows // 81) * 27 + rows % 27) + (rows % 81) // 27).astype(np.int64)
+    u_lists = (np.arange(nc * 81 + 1, dtype=np.int64), u_idx, np.ones(nc * 81))
+    p_lists = (np.arange(nc * 9 + 1, dtype=np.int64), np.arange(nc * 9, dtype=np.int64), np.ones(nc * 9))
+    om = orc.OracleMesh(mesh, 4, None, u_lists, p_lists)
+    xq = mesh.quadrature_points(4)
+    e_u = orc.lib().oracle_l2_error(C.byref(om.c), 3, orc._p(np.ascontiguousarray(uvals.reshape(-1))),
+                                    orc._p(np.ascontiguousarray(beltrami_velocity(xq, 0.0))))
+    e_p = orc.lib().oracle_l2_error(C.byref(om.c), 1, orc._p(pvals), orc._p(np.ascontiguousarray(beltrami_pressure(xq, 0.0)[..., None])))
+    assert f"{e_p:.4g}" == GOLDEN_AUGP["l2_errors_t0"]["e_p"] == "0.09298"
+    assert f"{e_u:.4g}" == GOLDEN_AUGP["l2_errors_t0"]["e_u"] == "0.001572"
+
+
+def augp_first_residual_inputs(mesh, dt=0.05):
+    u0 = beltrami_velocity(mesh.u.coords, 0.0).reshape(-1)
+    p0 = beltrami_pressure(mesh.p.coords, 0.0).reshape(-1)
+    p0[mesh.p.n_q1_owned:] = 0.0                                  # DG0 part of the interpolated pressure
+    u = u0.copy()
+    d = mesh.u.dirichlet.reshape(-1)
+    u[d] = beltrami_velocity(mesh.u.coords, dt).reshape(-1)[d]
+    return u0, p0, u
+
+
+def test_augp_first_nonlinear_residual_matches_golden_log():
+    mesh = augp_mesh()
+    _, oprm = flow_params(augmented=True)
+    dt = 0.05
+    ns = orc.OracleNavierStokesMatrix(mesh, oprm, orc.TimeWeights(1 / dt, -1 / dt, 0.0, 1.0, 1.0, 0.0), None, True, mesh.u_lists, mesh.p_lists)
+    u0, p0, u = augp_first_residual_inputs(mesh, dt)
+    ns.old_u, ns.old_old_u = u0.copy(), np.zeros_like(u0)
+    ru, rp = np.zeros(ns.n_u), np.zeros(ns.n_p)
+    ns.residual(ru, rp, u, p0, np.zeros(ns.n_u), np.zeros(ns.n_p))
+    ns.apply_pressure_average_projection(rp)                      # both null-space modes (Q1 constant, DG0 constant)
+    assert f"{np.linalg.norm(ru):.3e}" == GOLDEN_AUGP["first_nonlinear_residual"]["1"]["u"] == "2.953e+00"
+    assert f"{np.linalg.norm(rp):.3e}" == GOLDEN_AUGP["first_nonlinear_residual"]["1"]["p"] == "1.886e-01"
