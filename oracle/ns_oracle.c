@@ -509,6 +509,7 @@ double oracle_l2_error(const oracle_mesh *m, int n_comp, const double *vec, cons
       for (int d = 0; d < n_comp; ++d) {
         real v = 0;
         for (int n = 0; n < N; ++n) v += t.val[q * N + n] * loc[d * N + n];
+        if (n_comp == 1 && m->p_dg0) v += loc[N]; /* FE_Q_DG0: the element-constant part */
         real e = v - (real)exact_q[((int64_t)cell * NQ + q) * n_comp + d];
         sum += e * e * JxW;
       }

@@ -136,8 +136,4 @@ def test_device_time_stepping_on_the_refined_augmented_mesh_reproduces_the_golde
     e_u = O.l2_error(3, u_h, beltrami_velocity(xq, 0.2), n_q_1d=4)
     e_p = O.l2_error(1, p_h, beltrami_pressure(xq, 0.2)[..., None], n_q_1d=4)
     assert f"{e_u:.4g}" == gold["l2_errors_t0.2"]["e_u"], e_u
-    # OPEN POINT: the pressure error of the log (0.02287) is not reproduced (0.026 here; 0.0244 is the minimum over all
-    # constant shifts, so it is not the pressure constant).  Velocity, all first residuals (u and p rows) and the
-    # velocity error agree to all printed digits, so the difference sits in how the reference evaluates / gauges the
-    # Q1 + DG0 pressure for the error norm, not in the operators.  Kept as a bound until understood.
-    assert 0.02 < e_p < 0.03, e_p
+    assert f"{e_p:.4g}" == gold["l2_errors_t0.2"]["e_p"], e_p
