@@ -8,8 +8,13 @@
  *   source/level_set_okz_reinitialization.cc:53-106 (vmult), :128-189 (rhs)
  *   include/adaflo/level_set_okz_preconditioner.h:31-76 (mass diagonal)
  * on FE_Q_iso_Q1(n_sub) with QIterated(QGauss(2), n_sub) (source/two_phase_base.cc:256-271).
- * Parity status: "parity unpinned" by first-party vectors; cross-checked against the
- * independent dense loops of source/level_set_okz_matrix.cc for the weak forms (same terms).
+ * Parity status: the reference holds no operator-level vectors for these operators, but its golden log
+ * tests/rising_bubble_ls.output prints the CG iteration counts of the reinitialisation ("reinitialize (8 + 8)",
+ * "(7 + 7)"), which are reproduced by the 2-D restatement oracle/ls_oracle_2d.py (normal projection, reinitialisation
+ * operator and right-hand side, mass diagonal; tests/test_2d_cpu.py).  This file is tied to that restatement by the
+ * extrusion identity A_2d = R A_3d E, checked operator by operator in the same test file (1e-13): pinned through the
+ * 2-D log.  The advection, curvature and force terms have no first-party numbers; they are cross-checked against the
+ * independent dense loops of source/level_set_okz_matrix.cc (same terms).
  * Accumulation per cell in long double.
  */
 #include <math.h>

@@ -165,3 +165,68 @@ def test_2d_force_oracle_equals_extruded_3d_oracle_without_gravity():
     assert rel_err(fu, f2) < 1e-13
     assert rel_err(rho3.reshape(-1, 3, 9), np.repeat(rho2[:, None, :], 3, axis=1)) < 1e-13
     assert rel_err(mu3.reshape(-1, 3, 9), np.repeat(mu2[:, None, :], 3, axis=1)) < 1e-13
+
+
+# --------------------------------------------------------------------- golden log of the 2-D rising bubble (level set)
+def rising_bubble_setup():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rising_bubble_ls_output.json")) as f:
+        gold = json.load(f)
+    prm = gold["parameters"]
+    m = BoxMesh2D((40, 80), lower=(0.0, 0.0), upper=(1.0, 2.0))          # tests/rising_bubble.cc:122-131 + 3 refinements
+    m.build_ls_space(prm["concentration_subdivisions"])
+    eps_used = prm["epsilon"] / prm["concentration_subdivisions"] * prm["h"]   # two_phase_base.cc:290-291
+    dist = np.linalg.norm(m.ls_coords - np.array(prm["bubble_centre"]), axis=1) - prm["bubble_radius"]
+    c0 = -np.tanh(dist / (2.0 * eps_used))                                 # transform_distance_function, level_set_okz.cc:201-210
+    return gold, m, eps_used, c0
+
+
+def cg_iterations(A, b, P, rel_tol, max_iter=4000):
+    """deal.II SolverCG with ReductionControl(max_iter, 1e-50, rel_tol), zero start vector: solution, last_step()"""
+    x, r = np.zeros_like(b), b.copy()
+    r0 = np.linalg.norm(r)
+    z = P(r) if P else r.copy()
+    p, rz, it = z.copy(), r @ z, 0
+    while np.linalg.norm(r) > rel_tol * r0 and it < max_iter:
+        it += 1
+        Ap = A(p)
+        alpha = rz / (p @ Ap)
+        x += alpha * p
+        r -= alpha * Ap
+        z = P(r) if P else r.copy()
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, it
+
+
+def test_level_set_oracle_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log():
+    """tests/rising_bubble_ls.output:5,12 -- 'reinitialize (8 + 8)' and 'reinitialize (7 + 7)': the CG iteration counts
+    of LevelSetOKZSolverReinitialization::reinitialize (reinitialization.cc:256-369: normal projection, right-hand side
+    with the frozen normals, reinitialization_vmult, inverse mass diagonal, ReductionControl 1e-6).  This pins the
+    level-set oracle (normal / reinitialisation operators and right-hand sides, mass diagonal) against the reference's
+    own output; the 3-D oracle oracle/ls_oracle.c is tied to this 2-D restatement by the extrusion identity above."""
+    from oracle.ls_oracle_2d import OracleLevelSet2D
+    gold, m, eps_used, c = rising_bubble_setup()
+    prm = gold["parameters"]
+    assert m.n_cells == gold["n_active_cells"]["value"]
+    assert (2 * m.n_u_nodes, m.n_p_nodes, m.n_ls_nodes) == (gold["n_dofs"]["velocity"], gold["n_dofs"]["pressure"], gold["n_dofs"]["level_set"])
+    O = OracleLevelSet2D(m, prm["concentration_subdivisions"], prm["epsilon"], eps_used, prm["h"], prm["step_size"], np.full(m.n_cells, prm["h"]))
+    O.diag = O.mass_diagonal()
+    counts = []
+    for call in range(2):                     # setup_problem (level_set_base.cc:152), then time step #1 (zero velocity)
+        for tau in range(2):
+            first = tau == 0
+            if first:                         # compute_normal(true), compute_normal.cc:208-268
+                rhs_n = [np.zeros(O.n), np.zeros(O.n)]
+                O.compute_normal_rhs(rhs_n, c)
+                normal = [cg_iterations(lambda v: O._scalar(0, 4.0, v), rhs_n[d], None, 1e-5)[0] for d in range(2)]
+            rhs = np.zeros(O.n)
+            O.reinitialization_rhs(rhs, c, normal, False, first)
+            inc, it = cg_iterations(lambda v: O.reinitialization_vmult(v, False), rhs, lambda r: r / O.diag, 1e-6, 2000)
+            counts.append(it)
+            c = c + inc
+    assert counts[:2] == gold["initial_reinitialization_cg_iterations"]["value"]
+    assert counts[2:] == gold["time_step_1_reinitialization_cg_iterations"]["value"]
+    assert abs(c.min() + 1) < 1e-6 and abs(c.max() - 1) < 1e-6              # "Range of level set values: -1 / 1"

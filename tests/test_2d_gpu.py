@@ -158,3 +158,50 @@ def test_2d_force_matches_dense_2d_oracle(ctx):
     assert rel_err(rho3, np.repeat(rho_q[:, None, :], 3, axis=1)) < TOL and rel_err(mu3, np.repeat(mu_q[:, None, :], 3, axis=1)) < TOL
     L.close()
     A.clear()
+
+
+def test_device_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log(ctx):
+    """tests/rising_bubble_ls.output:5,12 on the device: 2-D level-set operators (extrusion path), device CG with the
+    inverse mass diagonal -- 'reinitialize (8 + 8)' at set-up and '(7 + 7)' in time step #1"""
+    from adaflo_b200.operators import LevelSetOperators2D
+    from adaflo_b200.solvers import SolverCG, SolverControl
+    from test_2d_cpu import rising_bubble_setup
+    gold, m, eps_used, c0 = rising_bubble_setup()
+    prm = gold["parameters"]
+    L = LevelSetOperators2D(ctx, m, capi.LSParams(2, prm["concentration_subdivisions"], 0, 0, prm["epsilon"], eps_used, 4.0, prm["h"]),
+                            cell_diameters=np.full(m.n_cells, prm["h"]))
+    L.set_time(1.0 / prm["step_size"], -1.0 / prm["step_size"], 0.0, prm["step_size"])
+    c = torch.from_numpy(c0).to(ctx.device)
+    inv_diag = 1.0 / L.diag
+    zero = L.new_vector()
+
+    def solve(A, b, P, rel_tol, max_iter):
+        x = L.new_vector()
+        ctl = SolverControl(max_iter, 1e-50, rel_tol)
+        SolverCG(ctx, ctl).solve(A, x, b, P)
+        return x, ctl.last_step
+
+    def normal_component(d, rhs_d):
+        def A(dst, src):
+            out = [L.new_vector(), L.new_vector()]
+            L.compute_normal_vmult(out, [src, zero] if d == 0 else [zero, src])
+            dst.copy_(out[d])
+        return solve(A, rhs_d, None, 1e-5, 4000)[0]
+
+    counts = []
+    for call in range(2):
+        for tau in range(2):
+            first = tau == 0
+            if first:
+                rhs_n = [L.new_vector(), L.new_vector()]
+                L.compute_normal_rhs(rhs_n, c)
+                normal = [normal_component(d, rhs_n[d]) for d in range(2)]
+            rhs = L.new_vector()
+            L.reinitialization_rhs(rhs, c, normal, False, first)
+            inc, it = solve(lambda dst, src: L.reinitialization_vmult(dst, src, False), rhs,
+                            lambda dst, src: torch.mul(src, inv_diag, out=dst), 1e-6, 2000)
+            counts.append(it)
+            c = c + inc
+    assert counts[:2] == gold["initial_reinitialization_cg_iterations"]["value"], counts
+    assert counts[2:] == gold["time_step_1_reinitialization_cg_iterations"]["value"], counts
+    L.close()
