@@ -6,7 +6,9 @@ dim = 2 as numpy contractions over all cells.  The library runs 2-D level-set pr
 one-cell-thick extrusion (adaflo_b200.operators.LevelSetOperators2D); this file is the independent check.
 Parity status: pinned against the reference's golden log tests/rising_bubble_ls.output:5,12 -- the CG iteration counts
 "reinitialize (8 + 8)" and "(7 + 7)" of LevelSetOKZSolverReinitialization::reinitialize are reproduced with these
-operators (normal projection, reinitialisation operator / right-hand side, mass diagonal; tests/test_2d_cpu.py).  The
+operators (normal projection, reinitialisation operator / right-hand side, mass diagonal), and line 13 -- the first
+Navier-Stokes residual 0.0198 = norm of the force vector (curvature, Heaviside, compute_force) -- as well
+(tests/test_2d_cpu.py).  The
 3-D oracle is tied to this file through the extrusion identity in the same test file.
 """
 import numpy as np
@@ -145,7 +147,8 @@ class OracleLevelSet2D:
         self._scatter(self._integ(None, tg), rhs)
 
 
-def compute_force_2d(mesh2d, n_sub, heaviside, curvature, sigma, gravity, rho0, drho, mu0, dmu, variable, dst_u):
+def compute_force_2d(mesh2d, n_sub, heaviside, curvature, sigma, gravity, rho0, drho, mu0, dmu, variable, dst_u, interpolate=False,
+                     u_dirichlet=None):
     """dense LevelSetOKZSolver::local_compute_force (level_set_okz.cc:317-409) for dim = 2 on QGauss(3)^2, without the
     level-set -> pressure interpolation; returns (rho_q, mu_q) [n_cells, 9]; gravity acts on component dim - 1 = y"""
     m = mesh2d
@@ -170,12 +173,25 @@ def compute_force_2d(mesh2d, n_sub, heaviside, curvature, sigma, gravity, rho0, 
     H = np.einsum("qn,cn->cq", phi, Hl)
     kap = np.einsum("qn,cn->cq", phi, kl)
     g = np.stack([np.einsum("qn,cn->cq", gx, Hl) / m.h[0], np.einsum("qn,cn->cq", gy, Hl) / m.h[1]], axis=-1)
+    if interpolate:   # gradient of the Q1 interpolant of H (interpolate_grad_onto_pressure, level_set_okz.cc:367-378)
+        corners = [0, n_sub, n1 * n_sub, n1 * n_sub + n_sub]
+        Hc = Hl[:, corners]                                                  # [c, (ix, iy)]
+        x = gp
+        g1x = np.stack([-(1 - x), (1 - x), -x, x], axis=-1)                   # d/dxi of the 4 bilinear shapes at eta = x[qy]
+        gxq = np.zeros((9, 4)); gyq = np.zeros((9, 4))
+        for qy in range(3):
+            for qx in range(3):
+                q = qx + 3 * qy
+                gxq[q] = [-(1 - x[qy]), (1 - x[qy]), -x[qy], x[qy]]
+                gyq[q] = [-(1 - x[qx]), -x[qx], (1 - x[qx]), x[qx]]
+        g = np.stack([np.einsum("qn,cn->cq", gxq, Hc) / m.h[0], np.einsum("qn,cn->cq", gyq, Hc) / m.h[1]], axis=-1)
     rho = rho0 + drho * H if variable else np.full_like(H, rho0)
     mu = mu0 + dmu * H
     f = sigma * kap[:, :, None] * g
     f[:, :, 1] -= gravity * rho
     out = np.einsum("qn,cqd->cnd", phiu, f * jxw[None, :, None])
-    keep = ~m.u_dirichlet[m.cell_u]
+    dirichlet = m.u_dirichlet if u_dirichlet is None else u_dirichlet
+    keep = ~dirichlet[m.cell_u]
     idx = 2 * m.cell_u[:, :, None] + np.arange(2)[None, None, :]
     np.add.at(dst_u, idx[keep], out[keep])
     return rho, mu

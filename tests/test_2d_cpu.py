@@ -230,3 +230,29 @@ def test_level_set_oracle_reproduces_the_reinitialisation_counts_of_the_rising_b
     assert counts[:2] == gold["initial_reinitialization_cg_iterations"]["value"]
     assert counts[2:] == gold["time_step_1_reinitialization_cg_iterations"]["value"]
     assert abs(c.min() + 1) < 1e-6 and abs(c.max() - 1) < 1e-6              # "Range of level set values: -1 / 1"
+
+    # ---- first Navier-Stokes residual of time step #1 (line 13: 0.0198).  The velocity and pressure are still zero, so
+    # the residual is the force vector: curvature (compute_curvature.cc:326-372: normal with 1e-7, right-hand side,
+    # projection with 1e-8, correction), Heaviside function, compute_force with the level-set -> pressure interpolation
+    # ("grad pressure compatible = 1"), variable density, gravity on y; no-slip on bottom / top, symmetry on the sides
+    from oracle.ls_oracle_2d import compute_force_2d
+    n_sub = prm["concentration_subdivisions"]
+    rhs_n = [np.zeros(O.n), np.zeros(O.n)]
+    O.compute_normal_rhs(rhs_n, c)
+    normal = [cg_iterations(lambda v: O._scalar(0, 4.0, v), rhs_n[d], None, 1e-7)[0] for d in range(2)]
+    rk = np.zeros(O.n)
+    O.compute_curvature_rhs(rk, normal)
+    kappa, _ = cg_iterations(lambda v: O.compute_curvature_vmult(v, True), rk, None, 1e-8)
+    big = kappa > 1e-4
+    with np.errstate(divide="ignore", invalid="ignore"):
+        distance = np.where((1 - c * c) > 1e-2, eps_used * np.log((1 + c) / (1 - c)), 0.0)
+    kappa[big] = 1.0 / (1.0 / kappa[big] + distance[big])                     # dim - 1 = 1
+    H = orc.compute_heaviside(m.cell_ls, c, prm["epsilon"], n_sub)
+    x = m.u_coords
+    dirichlet = np.zeros_like(m.u_dirichlet)
+    dirichlet[(np.abs(x[:, 1]) < 1e-12) | (np.abs(x[:, 1] - 2) < 1e-12), :] = True      # set_no_slip_boundary(0)
+    dirichlet[(np.abs(x[:, 0]) < 1e-12) | (np.abs(x[:, 0] - 1) < 1e-12), 0] = True      # set_symmetry_boundary(2)
+    f = np.zeros(m.n_u_nodes * 2)
+    compute_force_2d(m, n_sub, H, kappa, prm["surface_tension"], prm["gravity"], prm["density"], prm["density_difference"],
+                     prm["viscosity"], prm["viscosity_difference"], True, f, interpolate=True, u_dirichlet=dirichlet)
+    assert f"{np.linalg.norm(f):.3g}" == gold["time_step_1_first_navier_stokes_residual"]["value"]
