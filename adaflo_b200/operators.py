@@ -723,11 +723,21 @@ class LevelSetOperators2D:
         self.L.compute_heaviside(h3, self._E(level_set))
         heaviside.copy_(h3[self.ext[:, 0]])
 
-    def compute_force(self, ns2d, dst_u2, heaviside, curvature, surface_tension, gravity):
+    def compute_force(self, ns2d, dst_u2, heaviside, curvature, surface_tension, gravity, interpolate=False):
         """local_compute_force for dim = 2 (gravity on the y component); ns2d: NavierStokesMatrix2D sharing self.mf.
-        rho / mu at the quadrature points are written into ns2d's (extruded) coefficient arrays."""
+        rho / mu at the quadrature points are written into ns2d's (extruded) coefficient arrays.
+        interpolate: take the gradient of the Heaviside function from its nodal interpolant on the pressure space
+        (interpolate_grad_onto_pressure, level_set_okz.cc:367-378); the extruded field is constant in z, so the
+        corner-picking matrix of the 3-D element gives the 2-D interpolant on every node plane."""
         f3 = torch.zeros(self.mf.initialize_dof_vector(0).numel(), dtype=torch.float64, device=self.ctx.device)
-        self.L.compute_force(ns2d.A, f3, self._E(heaviside), self._E(curvature), surface_tension, gravity, None)
+        interp = None
+        if interpolate:
+            s = self.L.parameters.concentration_subdivisions
+            n1 = s + 1
+            interp = np.zeros((8, n1 ** 3))
+            for i in range(8):
+                interp[i, s * (i & 1) + n1 * (s * ((i >> 1) & 1) + n1 * s * (i >> 2))] = 1.0
+        self.L.compute_force(ns2d.A, f3, self._E(heaviside), self._E(curvature), surface_tension, gravity, interp)
         dst_u2.add_(f3[self.ext_u].sum(dim=1))
 
     def close(self):

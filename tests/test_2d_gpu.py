@@ -130,8 +130,10 @@ def test_2d_level_set_operators_match_dense_2d_oracle(ctx, dirichlet_edges):
     L.close()
 
 
-def test_2d_force_matches_dense_2d_oracle(ctx):
-    """surface tension + gravity (on y = component dim - 1) and the rho / mu update of the 2-D operator"""
+@pytest.mark.parametrize("interpolate", [False, True])
+def test_2d_force_matches_dense_2d_oracle(ctx, interpolate):
+    """surface tension + gravity (on y = component dim - 1) and the rho / mu update of the 2-D operator; with
+    'interpolate' the Heaviside gradient comes from the pressure-space interpolant as in tests/rising_bubble_ls.prm"""
     from adaflo_b200.operators import LevelSetOperators2D
     from oracle import oracle as orc
     from oracle.ls_oracle_2d import compute_force_2d
@@ -149,9 +151,9 @@ def test_2d_force_matches_dense_2d_oracle(ctx):
     from adaflo_b200.mesh import seeded_uniform
     pre = seeded_uniform(m.u_ids, 2, 4)
     o = pre.copy()
-    rho_q, mu_q = compute_force_2d(m, n_sub, H, kap, 0.07, 0.98, 1.0, 9.0, 0.1, 0.4, True, o)
+    rho_q, mu_q = compute_force_2d(m, n_sub, H, kap, 0.07, 0.98, 1.0, 9.0, 0.1, 0.4, True, o, interpolate=interpolate)
     g = dev(pre)
-    L.compute_force(A, g, dev(H), dev(kap), 0.07, 0.98)
+    L.compute_force(A, g, dev(H), dev(kap), 0.07, 0.98, interpolate)
     assert rel_err(g.cpu().numpy(), o) < TOL
     rho3 = A.A.get_coefficient(capi.COEF_DENSITY).cpu().numpy().reshape(-1, 3, 9)
     mu3 = A.A.get_coefficient(capi.COEF_VISCOSITY).cpu().numpy().reshape(-1, 3, 9)
