@@ -13,8 +13,10 @@
  * "(7 + 7)"), which are reproduced by the 2-D restatement oracle/ls_oracle_2d.py (normal projection, reinitialisation
  * operator and right-hand side, mass diagonal; tests/test_2d_cpu.py).  This file is tied to that restatement by the
  * extrusion identity A_2d = R A_3d E, checked operator by operator in the same test file (1e-13): pinned through the
- * 2-D log.  The advection, curvature and force terms have no first-party numbers; they are cross-checked against the
- * independent dense loops of source/level_set_okz_matrix.cc (same terms).
+ * 2-D logs.  The curvature, Heaviside and force terms are pinned the same way by the first Navier-Stokes residuals of
+ * tests/rising_bubble_ls.output:14 (0.0198) and tests/spurious_currents_ls.output:10 (0.365).  The advection terms
+ * have no first-party numbers; they are cross-checked against the independent dense loops of
+ * source/level_set_okz_matrix.cc (same terms).
  * Accumulation per cell in long double.
  */
 #include <math.h>

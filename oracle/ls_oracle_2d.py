@@ -4,12 +4,13 @@ QIterated(QGauss(2), n_sub), Cartesian cells).
 TEST INFRASTRUCTURE ONLY.  Same weak forms as oracle/ls_oracle.c (which cites the reference lines), written for
 dim = 2 as numpy contractions over all cells.  The library runs 2-D level-set problems through its 3-D kernels on a
 one-cell-thick extrusion (adaflo_b200.operators.LevelSetOperators2D); this file is the independent check.
-Parity status: pinned against the reference's golden log tests/rising_bubble_ls.output:5,12 -- the CG iteration counts
+Parity status: pinned against the reference's golden log tests/rising_bubble_ls.output:6,13 -- the CG iteration counts
 "reinitialize (8 + 8)" and "(7 + 7)" of LevelSetOKZSolverReinitialization::reinitialize are reproduced with these
-operators (normal projection, reinitialisation operator / right-hand side, mass diagonal), and line 13 -- the first
-Navier-Stokes residual 0.0198 = norm of the force vector (curvature, Heaviside, compute_force) -- as well
-(tests/test_2d_cpu.py).  The
-3-D oracle is tied to this file through the extrusion identity in the same test file.
+operators (normal projection, reinitialisation operator / right-hand side, mass diagonal), and line 14 -- the first
+Navier-Stokes residual 0.0198 = norm of the force vector (curvature, Heaviside, compute_force) -- as well; and against
+tests/spurious_currents_ls.output:9,10 -- "reinitialize (8 + 7)" and the first residual 0.365 of a surface-tension-only
+problem, which pins the curvature (normalised divergence, projection, distance correction) to three digits
+(tests/test_2d_cpu.py).  The 3-D oracle is tied to this file through the extrusion identity in the same test file.
 """
 import numpy as np
 

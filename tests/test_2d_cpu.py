@@ -201,8 +201,46 @@ def cg_iterations(A, b, P, rel_tol, max_iter=4000):
     return x, it
 
 
+def corrected_curvature(O, c, eps_used):
+    """LevelSetOKZSolverComputeCurvature::compute_curvature (level_set_okz_compute_curvature.cc:326-378) for dim = 2:
+    normal with tolerance 1e-7 (compute_normal(false)), right-hand side, projection with tolerance 1e-8, correction by the
+    distance.  Both projections are solved with the ASSEMBLED projection matrix of
+    level_set_okz_preconditioner.cc:61-180, mass + 4 delta^2 Laplace -- i.e. compute_normal_vmult's operator with
+    damping_scale_factor 4 -- not with compute_curvature_vmult (1 delta^2); the surface-tension dominated log of
+    spurious_currents_ls tells the two apart (0.365 vs 0.363)."""
+    rhs_n = [np.zeros(O.n), np.zeros(O.n)]
+    O.compute_normal_rhs(rhs_n, c)
+    normal = [cg_iterations(lambda v: O._scalar(0, 4.0, v), rhs_n[d], None, 1e-7)[0] for d in range(2)]
+    rk = np.zeros(O.n)
+    O.compute_curvature_rhs(rk, normal)
+    kappa, _ = cg_iterations(lambda v: O._scalar(0, 4.0, v), rk, None, 1e-8)
+    big = kappa > 1e-4
+    with np.errstate(divide="ignore", invalid="ignore"):
+        distance = np.where((1 - c * c) > 1e-2, eps_used * np.log((1 + c) / (1 - c)), 0.0)
+    kappa[big] = 1.0 / (1.0 / kappa[big] + distance[big])                     # distance / (dim - 1), dim = 2
+    return kappa
+
+
+def reinitialize(O, c, n_steps):
+    """LevelSetOKZSolverReinitialization::reinitialize (reinitialization.cc:256-369) with n_steps stabilised steps:
+    returns the new level set and the CG iteration count of every step"""
+    counts = []
+    for tau in range(n_steps):
+        first = tau == 0
+        if first:                         # compute_normal(true), compute_normal.cc:208-268
+            rhs_n = [np.zeros(O.n), np.zeros(O.n)]
+            O.compute_normal_rhs(rhs_n, c)
+            normal = [cg_iterations(lambda v: O._scalar(0, 4.0, v), rhs_n[d], None, 1e-5)[0] for d in range(2)]
+        rhs = np.zeros(O.n)
+        O.reinitialization_rhs(rhs, c, normal, False, first)
+        inc, it = cg_iterations(lambda v: O.reinitialization_vmult(v, False), rhs, lambda r: r / O.diag, 1e-6, 2000)
+        counts.append(it)
+        c = c + inc
+    return c, counts
+
+
 def test_level_set_oracle_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log():
-    """tests/rising_bubble_ls.output:5,12 -- 'reinitialize (8 + 8)' and 'reinitialize (7 + 7)': the CG iteration counts
+    """tests/rising_bubble_ls.output:6,13 -- 'reinitialize (8 + 8)' and 'reinitialize (7 + 7)': the CG iteration counts
     of LevelSetOKZSolverReinitialization::reinitialize (reinitialization.cc:256-369: normal projection, right-hand side
     with the frozen normals, reinitialization_vmult, inverse mass diagonal, ReductionControl 1e-6).  This pins the
     level-set oracle (normal / reinitialisation operators and right-hand sides, mass diagonal) against the reference's
@@ -216,37 +254,19 @@ def test_level_set_oracle_reproduces_the_reinitialisation_counts_of_the_rising_b
     O.diag = O.mass_diagonal()
     counts = []
     for call in range(2):                     # setup_problem (level_set_base.cc:152), then time step #1 (zero velocity)
-        for tau in range(2):
-            first = tau == 0
-            if first:                         # compute_normal(true), compute_normal.cc:208-268
-                rhs_n = [np.zeros(O.n), np.zeros(O.n)]
-                O.compute_normal_rhs(rhs_n, c)
-                normal = [cg_iterations(lambda v: O._scalar(0, 4.0, v), rhs_n[d], None, 1e-5)[0] for d in range(2)]
-            rhs = np.zeros(O.n)
-            O.reinitialization_rhs(rhs, c, normal, False, first)
-            inc, it = cg_iterations(lambda v: O.reinitialization_vmult(v, False), rhs, lambda r: r / O.diag, 1e-6, 2000)
-            counts.append(it)
-            c = c + inc
+        c, its = reinitialize(O, c, 2)
+        counts += its
     assert counts[:2] == gold["initial_reinitialization_cg_iterations"]["value"]
     assert counts[2:] == gold["time_step_1_reinitialization_cg_iterations"]["value"]
     assert abs(c.min() + 1) < 1e-6 and abs(c.max() - 1) < 1e-6              # "Range of level set values: -1 / 1"
 
-    # ---- first Navier-Stokes residual of time step #1 (line 13: 0.0198).  The velocity and pressure are still zero, so
-    # the residual is the force vector: curvature (compute_curvature.cc:326-372: normal with 1e-7, right-hand side,
-    # projection with 1e-8, correction), Heaviside function, compute_force with the level-set -> pressure interpolation
-    # ("grad pressure compatible = 1"), variable density, gravity on y; no-slip on bottom / top, symmetry on the sides
+    # ---- first Navier-Stokes residual of time step #1 (line 14: 0.0198).  The velocity and pressure are still zero, so
+    # the residual is the force vector: curvature, Heaviside function, compute_force with the level-set -> pressure
+    # interpolation ("grad pressure compatible = 1"), variable density, gravity on y; no-slip on bottom / top, symmetry
+    # on the sides
     from oracle.ls_oracle_2d import compute_force_2d
     n_sub = prm["concentration_subdivisions"]
-    rhs_n = [np.zeros(O.n), np.zeros(O.n)]
-    O.compute_normal_rhs(rhs_n, c)
-    normal = [cg_iterations(lambda v: O._scalar(0, 4.0, v), rhs_n[d], None, 1e-7)[0] for d in range(2)]
-    rk = np.zeros(O.n)
-    O.compute_curvature_rhs(rk, normal)
-    kappa, _ = cg_iterations(lambda v: O.compute_curvature_vmult(v, True), rk, None, 1e-8)
-    big = kappa > 1e-4
-    with np.errstate(divide="ignore", invalid="ignore"):
-        distance = np.where((1 - c * c) > 1e-2, eps_used * np.log((1 + c) / (1 - c)), 0.0)
-    kappa[big] = 1.0 / (1.0 / kappa[big] + distance[big])                     # dim - 1 = 1
+    kappa = corrected_curvature(O, c, eps_used)
     H = orc.compute_heaviside(m.cell_ls, c, prm["epsilon"], n_sub)
     x = m.u_coords
     dirichlet = np.zeros_like(m.u_dirichlet)
@@ -255,4 +275,39 @@ def test_level_set_oracle_reproduces_the_reinitialisation_counts_of_the_rising_b
     f = np.zeros(m.n_u_nodes * 2)
     compute_force_2d(m, n_sub, H, kappa, prm["surface_tension"], prm["gravity"], prm["density"], prm["density_difference"],
                      prm["viscosity"], prm["viscosity_difference"], True, f, interpolate=True, u_dirichlet=dirichlet)
+    assert f"{np.linalg.norm(f):.3g}" == gold["time_step_1_first_navier_stokes_residual"]["value"]
+
+
+def test_level_set_oracle_reproduces_the_first_step_of_the_spurious_currents_log():
+    """tests/spurious_currents_ls.output:9,10 -- 'advect [0/0] and reinitialize (8 + 7)' and the first Navier-Stokes
+    residual 0.365 of time step #1 (tests/spurious_currents.cc:263-270: 80 x 80 cells on [-2.5, 2.5]^2, no-slip everywhere,
+    FE_Q_iso_Q1(3), surface tension 1, no gravity, constant density).  Velocity and pressure are zero, so the residual is
+    the norm of sigma kappa grad H: unlike the gravity-dominated rising bubble this pins the curvature itself (normal
+    projection, normalised divergence, projection with the 4 delta^2 matrix, distance correction) to three digits."""
+    import json
+    import os
+    from oracle.ls_oracle_2d import OracleLevelSet2D, compute_force_2d
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spurious_currents_ls_output.json")) as f:
+        gold = json.load(f)
+    prm = gold["parameters"]
+    n_sub, h = prm["concentration_subdivisions"], prm["h"]
+    m = BoxMesh2D((80, 80), lower=(-2.5, -2.5), upper=(2.5, 2.5))
+    m.build_ls_space(n_sub)
+    assert m.n_cells == gold["n_active_cells"]["value"] and float(m.h[0]) == gold["mesh_size"]["value"]
+    assert (2 * m.n_u_nodes, m.n_p_nodes, m.n_ls_nodes) == (gold["n_dofs"]["velocity"], gold["n_dofs"]["pressure"], gold["n_dofs"]["level_set"])
+    eps_used = prm["epsilon"] / n_sub * h
+    dist = np.linalg.norm(m.ls_coords - np.array(prm["bubble_centre"]), axis=1) - prm["bubble_radius"]
+    c = -np.tanh(dist / (2.0 * eps_used))
+    O = OracleLevelSet2D(m, n_sub, prm["epsilon"], eps_used, h, prm["step_size"], np.full(m.n_cells, h))
+    O.diag = O.mass_diagonal()
+    c, counts = reinitialize(O, c, 2)          # 'number initial reinit steps = 0': the first reinitialisation is in step #1
+    assert counts == gold["time_step_1_reinitialization_cg_iterations"]["value"]
+    kappa = corrected_curvature(O, c, eps_used)
+    inside = dist < -0.2
+    assert abs(np.median(kappa[np.abs(dist) < 0.02]) - 2.0) < 0.05          # circle of radius 0.5: kappa = (dim - 1) / r
+    H = orc.compute_heaviside(m.cell_ls, c, prm["epsilon"], n_sub)
+    assert H[inside].min() == 1.0 and H[dist > 0.2].max() == 0.0
+    f = np.zeros(m.n_u_nodes * 2)
+    compute_force_2d(m, n_sub, H, kappa, prm["surface_tension"], prm["gravity"], prm["density"], prm["density_difference"],
+                     prm["viscosity"], prm["viscosity_difference"], True, f, interpolate=True)
     assert f"{np.linalg.norm(f):.3g}" == gold["time_step_1_first_navier_stokes_residual"]["value"]

@@ -163,7 +163,7 @@ def test_2d_force_matches_dense_2d_oracle(ctx, interpolate):
 
 
 def test_device_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log(ctx):
-    """tests/rising_bubble_ls.output:5,12 on the device: 2-D level-set operators (extrusion path), device CG with the
+    """tests/rising_bubble_ls.output:6,13 on the device: 2-D level-set operators (extrusion path), device CG with the
     inverse mass diagonal -- 'reinitialize (8 + 8)' at set-up and '(7 + 7)' in time step #1"""
     from adaflo_b200.operators import LevelSetOperators2D
     from adaflo_b200.solvers import SolverCG, SolverControl
