@@ -224,3 +224,19 @@ def test_augp_first_nonlinear_residual_matches_golden_log():
     ns.apply_pressure_average_projection(rp)                      # both null-space modes (Q1 constant, DG0 constant)
     assert f"{np.linalg.norm(ru):.3e}" == GOLDEN_AUGP["first_nonlinear_residual"]["1"]["u"] == "2.953e+00"
     assert f"{np.linalg.norm(rp):.3e}" == GOLDEN_AUGP["first_nonlinear_residual"]["1"]["p"] == "1.886e-01"
+
+
+def test_golden_fixtures_match_the_reference_logs():
+    """every number of tests/golden/*.json stands on the cited line of the reference's log (tests/golden/check_golden.py);
+    runs only where the reference tree exists (the development container) -- the fixtures are what travels"""
+    import importlib.util
+    import os
+    root = os.environ.get("ADAFLO_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(root, "tests")):
+        pytest.skip("reference tree not present")
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("check_golden", os.path.join(here, "golden", "check_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    report, bad = mod.check_all(root)
+    assert len(report) == 4 and not bad, "\n".join(bad)
