@@ -168,10 +168,10 @@ def test_2d_force_oracle_equals_extruded_3d_oracle_without_gravity():
 
 
 # --------------------------------------------------------------------- golden log of the 2-D rising bubble (level set)
-def rising_bubble_setup():
+def rising_bubble_setup(fixture="rising_bubble_ls_output.json"):
     import json
     import os
-    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rising_bubble_ls_output.json")) as f:
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", fixture)) as f:
         gold = json.load(f)
     prm = gold["parameters"]
     m = BoxMesh2D((40, 80), lower=(0.0, 0.0), upper=(1.0, 2.0))          # tests/rising_bubble.cc:122-131 + 3 refinements
@@ -239,14 +239,16 @@ def reinitialize(O, c, n_steps):
     return c, counts
 
 
-def test_level_set_oracle_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log():
-    """tests/rising_bubble_ls.output:6,13 -- 'reinitialize (8 + 8)' and 'reinitialize (7 + 7)': the CG iteration counts
+@pytest.mark.parametrize("fixture", ["rising_bubble_ls_output.json", "rising_bubble_ls_picard_output.json"])
+def test_level_set_oracle_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log(fixture):
+    """tests/rising_bubble_ls.output:6,13 -- 'reinitialize (8 + 8)' and 'reinitialize (7 + 7)' with FE_Q_iso_Q1(4) -- and
+    tests/rising_bubble_ls_picard.output:6,13 -- '(8 + 7)' and '(7 + 7)' with FE_Q_iso_Q1(3): the CG iteration counts
     of LevelSetOKZSolverReinitialization::reinitialize (reinitialization.cc:256-369: normal projection, right-hand side
     with the frozen normals, reinitialization_vmult, inverse mass diagonal, ReductionControl 1e-6).  This pins the
     level-set oracle (normal / reinitialisation operators and right-hand sides, mass diagonal) against the reference's
     own output; the 3-D oracle oracle/ls_oracle.c is tied to this 2-D restatement by the extrusion identity above."""
     from oracle.ls_oracle_2d import OracleLevelSet2D
-    gold, m, eps_used, c = rising_bubble_setup()
+    gold, m, eps_used, c = rising_bubble_setup(fixture)
     prm = gold["parameters"]
     assert m.n_cells == gold["n_active_cells"]["value"]
     assert (2 * m.n_u_nodes, m.n_p_nodes, m.n_ls_nodes) == (gold["n_dofs"]["velocity"], gold["n_dofs"]["pressure"], gold["n_dofs"]["level_set"])
