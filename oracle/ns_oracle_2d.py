@@ -8,9 +8,11 @@ projection :191-205), as dense numpy contractions over all cells -- no sum facto
 runs 2-D problems through its 3-D kernels on a one-cell-thick extrusion (adaflo_b200.operators.NavierStokesMatrix2D);
 this file is the independent check of that construction.
 
-Parity status: no 2-D golden log of the reference is reachable (tests/beltrami_2d is Q4/Q3 on an adaptive mesh,
-SURVEY F4); the 2-D oracle is cross-validated against the pinned 3-D oracle through the extrusion identity
-A_2d = R A_3d E (tests/test_2d_cpu.py), i.e. "pinned through the 3-D oracle", not against a 2-D reference log.
+Parity status: pinned against the reference's golden log tests/couette.output:10 -- the first nonlinear residual
+1.601e+01 of the 2-D lid-driven channel (Q2/Q1, 64 x 16 cells, BDF-2 start-up weights, Dirichlet lid, constrained
+tangential velocity on the open boundaries) is reproduced to all printed digits -- and cross-validated against the pinned
+3-D oracle through the extrusion identity A_2d = R A_3d E (both in tests/test_2d_cpu.py).  tests/beltrami_2d is Q4/Q3
+on an adaptive mesh and stays out of reach.
 """
 import numpy as np
 

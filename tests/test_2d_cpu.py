@@ -74,6 +74,38 @@ def test_2d_stokes_is_symmetric():
     assert abs(lhs - rhs) < 1e-11 * max(abs(lhs), 1.0)
 
 
+def test_2d_oracle_reproduces_the_first_residual_of_the_couette_log():
+    """tests/couette.output:10 -- first nonlinear residual 1.601e+01 of time step #1 (tests/couette.cc:113-145: 64 x 16
+    cells on [-2,2] x [-1,0], no-slip at the bottom, lid velocity (2, 0) at the top, open boundaries with zero external
+    pressure left and right: there the tangential velocity is constrained and no face term arises).  The solution is zero
+    (ZeroFunction start) except for the lid values of apply_boundary_conditions; step #1 of BDF-2 uses implicit Euler
+    weights (time_stepping.cc:158-198).  A direct pin of the dense 2-D restatement against a 2-D log of the reference."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "couette_output.json")) as f:
+        gold = json.load(f)
+    prm = gold["parameters"]
+    m = BoxMesh2D((64, 16), lower=(-2.0, -1.0), upper=(2.0, 0.0))
+    assert m.n_cells == gold["n_active_cells"]["value"] and float(m.h[0]) == gold["mesh_size"]["value"]
+    assert (2 * m.n_u_nodes, m.n_p_nodes) == (gold["n_dofs"]["velocity"], gold["n_dofs"]["pressure"])
+    x = m.u_coords
+    bottom, top = np.abs(x[:, 1] + 1) < 1e-12, np.abs(x[:, 1]) < 1e-12
+    sides = (np.abs(x[:, 0] - 2) < 1e-12) | (np.abs(x[:, 0] + 2) < 1e-12)
+    dirichlet = np.zeros_like(m.u_dirichlet)
+    dirichlet[bottom | top, :] = True
+    dirichlet[sides, 1] = True                    # set_open_boundary_with_normal_flux: tangential component constrained
+    m.u_dirichlet = dirichlet
+    dt = prm["dt"]
+    O = OracleNavierStokes2D(m, capi.INCOMPRESSIBLE, capi.NEWTON, prm["density"], prm["viscosity"], 0.0, 0.0, 0.5,
+                             (1 / dt, -1 / dt, 0.0, 1.0), pressure_average_fix=False)
+    u = np.zeros(O.n_u)
+    u.reshape(-1, 2)[top] = prm["lid_velocity"]
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, u, np.zeros(O.n_p), np.zeros(O.n_u), np.zeros(O.n_p))
+    assert f"{np.sqrt(ru @ ru + rp @ rp):.3e}" == gold["first_nonlinear_residual"]["value"]
+    assert np.linalg.norm(rp) < 1e-14               # the lid field is divergence free
+
+
 # ---------------------------------------------------------------------------------------------- level set
 def ls_setup(n=(4, 3), n_sub=3, dirichlet_edges=()):
     from oracle.ls_oracle_2d import OracleLevelSet2D
