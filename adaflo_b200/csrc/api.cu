@@ -121,6 +121,34 @@ static bool projection_active(const adaflo_b200_ns_t ns)
 
 }  // namespace ab200
 
+// canonical <-> decade-blocked copies of a coefficient array.  Canonical is the reference's own storage order,
+// AlignedVector<VectorizedArray<double>> indexed [cell batch][q] (navier_stokes_matrix.h:293-395; the linearisation point
+// is a pair<Tensor<1,dim,VA>, Tensor<2,dim,VA>> per point, i.e. 12 consecutive VectorizedArrays):
+//   canonical[((batch * 27 + q) * n_rows + row) * lanes + lane],  q = qx + 3 qy + 9 qz,
+// slot batch * lanes + lane holds cell slot_cell[...] (identity if null; 0xffffffff marks an empty lane).
+namespace ab200 {
+template <bool TO_CANONICAL>
+__global__ void k_coef_canonical(double *blocked, double *canonical, const uint32_t *slot_cell, uint32_t n_slots, uint32_t lanes,
+                                 uint32_t n_cells, int n_rows)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (slot, q)
+  if (i >= (size_t)n_slots * 27) return;
+  const uint32_t slot = (uint32_t)(i / 27);
+  const int q = (int)(i % 27), qx = q % 3, qy = (q / 3) % 3, qz = q / 9;
+  const uint32_t cell = slot_cell ? slot_cell[slot] : slot;
+  if (cell >= n_cells) return;
+  const uint32_t batch = slot / lanes, lane = slot % lanes;
+  double *can = canonical + (((size_t)batch * 27 + q) * n_rows) * lanes + lane;
+  for (int r = 0; r < n_rows; ++r) {
+    double *b = blocked + (n_rows == 12 ? lin_index(cell, qx, qy, qz) + lin_row(r) : coef_index(cell, r, n_rows, qx, qy, qz));
+    if (TO_CANONICAL)
+      can[(size_t)r * lanes] = *b;
+    else
+      *b = can[(size_t)r * lanes];
+  }
+}
+}  // namespace ab200
+
 using namespace ab200;
 
 extern "C" {
@@ -237,7 +265,8 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
       for (uint32_t c = 0; c < d->n_cells; ++c)
         for (int iz = 0; iz < n1; ++iz)
           for (int j = 0; j < nj; ++j)
-            blk[((size_t)(c / kGroup) * nj + j) * 30 + 3 * (c % kGroup) + iz] = sd.cell_nodes[(size_t)c * sd.nodes_per_cell + iz * nj + j];
+            blk[((size_t)(c / kGroup) * nj + j) * 30 + 3 * (c % kGroup) + iz] =
+              sd.cell_nodes[(size_t)c * sd.nodes_per_cell + kernel_node(j % n1, j / n1, iz, n1)];
       AB_CHECK(upload(&sp.cell_nodes_blk, blk.data(), blk.size(), s));
       AB_CUDA(cudaStreamSynchronize(s));
     }
@@ -256,7 +285,10 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
       x.recv_first = xd.recv_first;
       x.n_recv = xd.n_recv;
       AB_CHECK(upload(&x.send_dev, xd.send, (size_t)xd.n_send, s));
-      if (xd.n_send) AB_CUDA(cudaMalloc((void **)&x.send_buf, sizeof(double) * (size_t)xd.n_send * sd.n_components));
+      if (xd.n_send) {
+        AB_CUDA(cudaMalloc((void **)&x.send_buf, sizeof(double) * (size_t)xd.n_send * sd.n_components));
+        x.send_slots = 1;
+      }
       sp.exchange.push_back(x);
     }
     mf->spaces.push_back(sp);
@@ -952,6 +984,62 @@ int adaflo_b200_ns_coefficient_ptr(adaflo_b200_ns_t ns, int which, double **dev_
   *dev_ptr = p;
   if (n) *n = p ? cnt : 0;
   return 0;
+}
+
+
+static int coef_canonical(adaflo_b200_ns_t ns, int which, double *canonical, int on_host, uint32_t n_batches, uint32_t lanes,
+                          const uint32_t *slot_cell_host, bool to_canonical)
+{
+  if (!ns || !canonical || lanes == 0) return fail(ADAFLO_B200_ERR_ARG, "coefficient_canonical: bad argument");
+  double *blocked = nullptr;
+  uint64_t cnt = 0;
+  AB_CHECK(adaflo_b200_ns_coefficient_ptr(ns, which, &blocked, &cnt));
+  if (!blocked) return fail(ADAFLO_B200_ERR_STATE, "coefficient_canonical: array not allocated (constant coefficients)");
+  const int n_rows = which == ADAFLO_B200_COEF_LINEARIZED_VELOCITY ? 12 : 1;
+  const uint64_t n_slots64 = (uint64_t)n_batches * lanes;
+  if (n_slots64 == 0) return 0;
+  if (n_slots64 > 0xffffffffull) return fail(ADAFLO_B200_ERR_ARG, "coefficient_canonical: too many slots");
+  const uint32_t n_slots = (uint32_t)n_slots64;
+  if (!slot_cell_host && n_slots < ns->mf->n_cells) return fail(ADAFLO_B200_ERR_ARG, "coefficient_canonical: fewer slots than cells");
+  cudaStream_t s = ns->ctx->stream;
+  const size_t n = (size_t)n_slots * 27 * n_rows;
+  double *dev = canonical;
+  uint32_t *map = nullptr;
+  if (on_host) {
+    AB_CUDA(cudaMalloc((void **)&dev, n * sizeof(double)));
+    if (!to_canonical) AB_CUDA(cudaMemcpyAsync(dev, canonical, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    else AB_CUDA(cudaMemsetAsync(dev, 0, n * sizeof(double), s));
+  }
+  if (slot_cell_host) {
+    AB_CUDA(cudaMalloc((void **)&map, (size_t)n_slots * sizeof(uint32_t)));
+    AB_CUDA(cudaMemcpyAsync(map, slot_cell_host, (size_t)n_slots * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  }
+  const unsigned grid = (unsigned)(((size_t)n_slots * 27 + 255) / 256);
+  if (to_canonical)
+    ab200::k_coef_canonical<true><<<grid, 256, 0, s>>>(blocked, dev, map, n_slots, lanes, ns->mf->n_cells, n_rows);
+  else
+    ab200::k_coef_canonical<false><<<grid, 256, 0, s>>>(blocked, dev, map, n_slots, lanes, ns->mf->n_cells, n_rows);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  if (on_host && to_canonical) AB_CUDA(cudaMemcpyAsync(canonical, dev, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (on_host || map) {
+    AB_CUDA(cudaStreamSynchronize(s));
+    if (on_host) cudaFree(dev);
+    if (map) cudaFree(map);
+  }
+  return 0;
+}
+
+int adaflo_b200_ns_set_coefficient_canonical(adaflo_b200_ns_t ns, int which, const double *canonical, int on_host, uint32_t n_batches,
+                                             uint32_t lanes, const uint32_t *slot_cell_host)
+{
+  return coef_canonical(ns, which, const_cast<double *>(canonical), on_host, n_batches, lanes, slot_cell_host, false);
+}
+
+int adaflo_b200_ns_get_coefficient_canonical(adaflo_b200_ns_t ns, int which, double *canonical, int on_host, uint32_t n_batches,
+                                             uint32_t lanes, const uint32_t *slot_cell_host)
+{
+  return coef_canonical(ns, which, canonical, on_host, n_batches, lanes, slot_cell_host, true);
 }
 
 int adaflo_b200_ns_nullspace(adaflo_b200_ns_t ns, int mode, const double **modes, const double **weights, double *inv)

@@ -9,6 +9,7 @@
 #include <nccl.h>
 
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 
@@ -103,6 +104,28 @@ int comm_allreduce(adaflo_b200_ctx_t ctx, double *dev, int k, int op_max)
   return 0;
 }
 
+// Several vectors of the SAME space may travel in one group (the three components of a normal field): vector i of the
+// call uses slot "number of earlier vectors of its space" of every exchange's staging buffer, which grows on demand.
+static int reserve_slots(adaflo_b200_mf_t mf, int n, const int *spaces, std::vector<int> &slot_of)
+{
+  slot_of.assign(n, 0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j)
+      if (spaces[j] == spaces[i]) ++slot_of[i];
+  for (int i = 0; i < n; ++i) {
+    Space &sp = mf->spaces[spaces[i]];
+    for (Exchange &e : sp.exchange) {
+      if (!e.n_send || slot_of[i] < e.send_slots) continue;
+      // all earlier work on the stream may still use the old buffer
+      AB_CUDA(cudaStreamSynchronize(mf->ctx->stream));
+      if (e.send_buf) cudaFree(e.send_buf);
+      e.send_slots = slot_of[i] + 1;
+      AB_CUDA(cudaMalloc((void **)&e.send_buf, sizeof(double) * (size_t)e.n_send * sp.n_comp * e.send_slots));
+    }
+  }
+  return 0;
+}
+
 // owner -> ghost import (LinearAlgebra::distributed::Vector::update_ghost_values) of several vectors in ONE
 // NCCL group (one launch for the velocity and the pressure block of a vmult)
 int comm_update_ghosts_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *const *vecs)
@@ -110,12 +133,15 @@ int comm_update_ghosts_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *
   adaflo_b200_ctx_t ctx = mf->ctx;
   if (ctx->nranks <= 1) return 0;
   if (!ctx->nccl_comm) return fail(ADAFLO_B200_ERR_STATE, "communicator not initialised");
+  std::vector<int> slot_of;
+  AB_CHECK(reserve_slots(mf, n, spaces, slot_of));
   bool any = false;
   for (int i = 0; i < n; ++i) {
     Space &sp = mf->spaces[spaces[i]];
     for (Exchange &e : sp.exchange) {
       any = true;
-      if (e.n_send) AB_CHECK(vec_pack(ctx->stream, e.send_buf, vecs[i], e.send_dev, e.n_send, sp.n_comp));
+      if (e.n_send)
+        AB_CHECK(vec_pack(ctx->stream, e.send_buf + (size_t)slot_of[i] * e.n_send * sp.n_comp, vecs[i], e.send_dev, e.n_send, sp.n_comp));
     }
   }
   if (!any) return 0;
@@ -124,7 +150,8 @@ int comm_update_ghosts_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *
     Space &sp = mf->spaces[spaces[i]];
     for (Exchange &e : sp.exchange) {
       if (e.n_send)
-        AB_NCCL(g_nccl.Send(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+        AB_NCCL(g_nccl.Send(e.send_buf + (size_t)slot_of[i] * e.n_send * sp.n_comp, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer,
+                            (ncclComm_t)ctx->nccl_comm, ctx->stream));
       if (e.n_recv)
         AB_NCCL(g_nccl.Recv(vecs[i] + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
                             (ncclComm_t)ctx->nccl_comm, ctx->stream));
@@ -143,6 +170,8 @@ int comm_compress_add_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *c
   bool any = false;
   for (int i = 0; i < n; ++i) any |= !mf->spaces[spaces[i]].exchange.empty();
   if (!any) return 0;
+  std::vector<int> slot_of;
+  AB_CHECK(reserve_slots(mf, n, spaces, slot_of));
   AB_NCCL(g_nccl.GroupStart());
   for (int i = 0; i < n; ++i) {
     Space &sp = mf->spaces[spaces[i]];
@@ -151,14 +180,16 @@ int comm_compress_add_n(adaflo_b200_mf_t mf, int n, const int *spaces, double *c
         AB_NCCL(g_nccl.Send(vecs[i] + (size_t)e.recv_first * sp.n_comp, (size_t)e.n_recv * sp.n_comp, ncclDouble, e.peer,
                             (ncclComm_t)ctx->nccl_comm, ctx->stream));
       if (e.n_send)
-        AB_NCCL(g_nccl.Recv(e.send_buf, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+        AB_NCCL(g_nccl.Recv(e.send_buf + (size_t)slot_of[i] * e.n_send * sp.n_comp, (size_t)e.n_send * sp.n_comp, ncclDouble, e.peer,
+                            (ncclComm_t)ctx->nccl_comm, ctx->stream));
     }
   }
   AB_NCCL(g_nccl.GroupEnd());
   for (int i = 0; i < n; ++i) {
     Space &sp = mf->spaces[spaces[i]];
     for (Exchange &e : sp.exchange)
-      if (e.n_send) AB_CHECK(vec_unpack_add(ctx->stream, vecs[i], e.send_buf, e.send_dev, e.n_send, sp.n_comp));
+      if (e.n_send)
+        AB_CHECK(vec_unpack_add(ctx->stream, vecs[i], e.send_buf + (size_t)slot_of[i] * e.n_send * sp.n_comp, e.send_dev, e.n_send, sp.n_comp));
     if (sp.n_ghost_nodes)
       AB_CUDA(cudaMemsetAsync(vecs[i] + sp.n_owned_entries(), 0, sizeof(double) * (size_t)sp.n_ghost_nodes * sp.n_comp, ctx->stream));
   }

@@ -12,28 +12,54 @@
 
 namespace ab200 {
 
+// Axis roles of the vmult cell kernel (ns_r1.cuh).  Three lanes own one cell: in phases A/C lane t owns the node plane
+// t of kernel axis Z, in phase B it owns the lines (X = j, Y = t) and contracts along Z.  The kernel axes are a cyclic
+// rotation of the mesh axes, kernel (X, Y, Z) = mesh (y, z, x): the 30 lanes of a decade of x-neighbours then gather
+// (and scatter) 21 consecutive nodes of one mesh line per instruction -- 16 instead of 30 sectors, 4.5 instead of 13
+// L1 tag look-ups (profiles/r1_g: the gather and the scatter were two thirds of the global LSU wavefronts).  Any cell
+// numbering is valid; only the coalescing depends on it.  AB_R1_ROT=0 restores kernel axes = mesh axes (A/B builds).
+#ifndef AB_R1_ROT
+#define AB_R1_ROT 0
+#endif
+constexpr int kAxX = AB_R1_ROT ? 1 : 0, kAxY = AB_R1_ROT ? 2 : 1, kAxZ = AB_R1_ROT ? 0 : 2;  // mesh direction of a kernel axis
+
 // Per-quadrature-point arrays on QGauss(3) and the cell->node lists used by the vmult kernel
 // are stored "decade blocked": cells are grouped in tens (one warp of the vmult kernel owns a
-// decade, 3 lanes per cell) and the point (qx,qy,qz) of cell 10 g + cw, row r of n_rows, lives at
-//   ((g * n_rows + r) * 9 + 3 qx + qz) * 30 + 3 cw + qy
-// so that the 30 lanes of a warp read 240 contiguous bytes per (row, qx, qz).
+// decade, 3 lanes per cell) and the point with kernel indices (kx,ky,kz) of cell 10 g + cw, row r of n_rows, lives at
+//   ((g * n_rows + r) * 9 + 3 kx + kz) * 30 + 3 cw + ky
+// so that the 30 lanes of a warp read 240 contiguous bytes per (row, kx, kz).  All code outside ns_r1.cuh addresses
+// these arrays through coef_index / lin_index with MESH point indices (qx,qy,qz).
 constexpr int kGroup = 10;
+__host__ __device__ inline size_t coef_slot(int qx, int qy, int qz, int cw)
+{
+  const int q[3] = {qx, qy, qz};
+  return (size_t)(3 * q[kAxX] + q[kAxZ]) * 30 + 3 * cw + q[kAxY];
+}
 __host__ __device__ inline size_t coef_index(uint32_t cell, int row, int n_rows, int qx, int qy, int qz)
 {
   const size_t g = cell / kGroup;
   const int cw = (int)(cell % kGroup);
-  return ((g * n_rows + row) * 9 + (size_t)(3 * qx + qz)) * 30 + 3 * cw + qy;
+  return (g * n_rows + row) * 270 + coef_slot(qx, qy, qz, cw);
 }
 // The 12-row linearisation array (u, grad u at every point) interleaves its rows in pairs, so that a lane of the
 // vmult kernel fetches two rows with one 16-byte load (480 contiguous bytes per warp): row r of the point lives at
-//   (((g * 6 + r / 2) * 9 + 3 qx + qz) * 30 + 3 cw + qy) * 2 + (r & 1)  =  lin_index(cell, qx, qy, qz) + lin_row(r)
+//   (((g * 6 + r / 2) * 9 + 3 kx + kz) * 30 + 3 cw + ky) * 2 + (r & 1)  =  lin_index(cell, qx, qy, qz) + lin_row(r)
 __host__ __device__ inline size_t lin_index(uint32_t cell, int qx, int qy, int qz)
 {
   const size_t g = cell / kGroup;
   const int cw = (int)(cell % kGroup);
-  return ((g * 6 * 9 + (size_t)(3 * qx + qz)) * 30 + 3 * cw + qy) * 2;
+  return (g * 6 * 270 + coef_slot(qx, qy, qz, cw)) * 2;
 }
 __host__ __device__ constexpr int lin_row(int r) { return (r >> 1) * 540 + (r & 1); }
+// cell-local (lexicographic, x fastest) index of the node with kernel indices (ix, iy, iz), n1 nodes per direction
+__host__ __device__ inline int kernel_node(int ix, int iy, int iz, int n1)
+{
+  int m[3];
+  m[kAxX] = ix;
+  m[kAxY] = iy;
+  m[kAxZ] = iz;
+  return m[0] + n1 * (m[1] + n1 * m[2]);
+}
 inline size_t n_groups(uint32_t n_cells) { return ((size_t)n_cells + kGroup - 1) / kGroup; }
 
 void set_error(const std::string &msg);
@@ -61,7 +87,8 @@ struct Exchange {
   uint32_t *send_dev;  // local node indices
   uint32_t recv_first;
   uint32_t n_recv;
-  double *send_buf;    // n_send * n_comp
+  double *send_buf;    // send_slots * n_send * n_comp (one slot per vector of this space in one exchange group)
+  int send_slots;
   double *recv_buf;    // n_recv * n_comp (compress direction)
 };
 
@@ -69,7 +96,7 @@ struct Space {
   int fe_kind, degree, n_comp;
   uint32_t n_owned_nodes, n_ghost_nodes, nodes_per_cell;
   uint32_t *cell_nodes;      // device [n_cells][nodes_per_cell]
-  uint32_t *cell_nodes_blk;  // device, decade blocked: u: [g][9 (ix+3iy)][10 cw][3 iz]; p: [g][4 (ix+2iy)][10 cw][3 iz (2 used)]
+  uint32_t *cell_nodes_blk;  // device, decade blocked, KERNEL node indices (kernel_node): u: [g][9 (ix+3iy)][10 cw][3 iz]; p: [g][4 (ix+2iy)][10 cw][3 iz (2 used)]
   uint32_t *hanging_masks;   // device [n_cells] or null
   uint32_t n_constrained;
   uint32_t *constrained;     // device
@@ -203,6 +230,7 @@ int launch_ns_vmult_cartesian(const NSArgs &a, bool with_p, int mode, bool var, 
 int launch_ns_vmult_affine(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
 int launch_ns_vmult_general(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
 int launch_ns_residual(const NSArgs &a, int geom, bool var, cudaStream_t s);
+int launch_ns_residual_r1(const NSArgs &a, int geom, bool var, cudaStream_t s);  // Newton / Picard / Stokes, vmult mapping
 
 struct PArgs {
   uint32_t n_cells;

@@ -70,6 +70,41 @@ int finish_vmult(adaflo_b200_ls_t ls, double *dst, const double *src)
   return 0;
 }
 
+// MatrixFree::cell_loop semantics on a partitioned mesh (level_set_okz_*.cc call cell_loop for every operator): import the
+// ghost values of the sources before the cells, add the ghost contributions of the destinations to their owners after.
+int import_ghosts(adaflo_b200_ls_t ls, int space, int n, const double *const *vecs)
+{
+  if (ls->ctx->nranks <= 1) return 0;
+  int spaces[4];
+  double *v[4];
+  int m = 0;
+  for (int i = 0; i < n && m < 4; ++i)
+    if (vecs[i]) {
+      spaces[m] = space;
+      v[m++] = const_cast<double *>(vecs[i]);  // the ghost section of a source is scratch (as in deal.II)
+    }
+  return m ? comm_update_ghosts_n(ls->mf, m, spaces, v) : 0;
+}
+int import_ghosts(adaflo_b200_ls_t ls, int space, const double *v)
+{
+  return import_ghosts(ls, space, 1, &v);
+}
+int compress(adaflo_b200_ls_t ls, int space, int n, double *const *vecs)
+{
+  if (ls->ctx->nranks <= 1) return 0;
+  int spaces[4] = {space, space, space, space};
+  return comm_compress_add_n(ls->mf, n, spaces, vecs);
+}
+int compress(adaflo_b200_ls_t ls, int space, double *v) { return compress(ls, space, 1, &v); }
+// right-hand sides are ADDED into the caller's vector; its ghost section must not carry stale data into compress(add)
+int zero_ghosts(adaflo_b200_ls_t ls, int space, double *v)
+{
+  const Space &sp = ls->mf->spaces[space];
+  if (ls->ctx->nranks > 1 && sp.n_ghost_nodes)
+    AB_CUDA(cudaMemsetAsync(v + sp.n_owned_entries(), 0, sizeof(double) * (size_t)sp.n_ghost_nodes * sp.n_comp, ls->ctx->stream));
+  return 0;
+}
+
 int zero(adaflo_b200_ls_t ls, double *v)
 {
   AB_CUDA(cudaMemsetAsync(v, 0, ls->mf->spaces[ls->dof_ls].n_local_entries() * sizeof(double), ls->ctx->stream));
@@ -233,18 +268,21 @@ int adaflo_b200_ls_mass_diagonal(adaflo_b200_ls_t ls, double *diag)
   AB_CHECK(zero(ls, diag));
   LSArgs a = base_args(ls);
   a.dst[0] = diag;
-  return launch_ls(a, LS_MASS_DIAG, ls->ctx->stream);
+  AB_CHECK(launch_ls(a, LS_MASS_DIAG, ls->ctx->stream));
+  return compress(ls, ls->dof_ls, diag);
 }
 
 int adaflo_b200_ls_advance_concentration_vmult(adaflo_b200_ls_t ls, double *dst, const double *src)
 {
   if (!ls || !dst || !src) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   AB_CHECK(zero(ls, dst));
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, src));
   LSArgs a = base_args(ls);
   a.src[0] = src;
   a.dst[0] = dst;
   a.pointdata = ls->conv;
   AB_CHECK(launch_ls(a, LS_ADVECT, ls->ctx->stream));
+  AB_CHECK(compress(ls, ls->dof_ls, dst));
   return finish_vmult(ls, dst, src);
 }
 
@@ -260,7 +298,14 @@ int adaflo_b200_ls_advance_concentration_rhs(adaflo_b200_ls_t ls, double *rhs, c
   a.vel = vel;
   a.dst[0] = rhs;
   a.pointdata = ls->conv;
-  return launch_ls(a, LS_ADVECT_RHS, ls->ctx->stream);
+  {
+    const double *in[3] = {c, c_old, c_old_old};
+    AB_CHECK(import_ghosts(ls, ls->dof_ls, 3, in));
+    AB_CHECK(import_ghosts(ls, ls->dof_vel, vel));
+    AB_CHECK(zero_ghosts(ls, ls->dof_ls, rhs));
+  }
+  AB_CHECK(launch_ls(a, LS_ADVECT_RHS, ls->ctx->stream));
+  return compress(ls, ls->dof_ls, rhs);
 }
 
 int adaflo_b200_ls_compute_normal_vmult(adaflo_b200_ls_t ls, double *const dst[3], const double *const src[3])
@@ -274,7 +319,9 @@ int adaflo_b200_ls_compute_normal_vmult(adaflo_b200_ls_t ls, double *const dst[3
   }
   a.n_comp = 3;
   a.delta_scale = ls->prm.damping_scale_factor;
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, 3, src));
   AB_CHECK(launch_ls(a, LS_DAMPED, ls->ctx->stream));
+  AB_CHECK(compress(ls, ls->dof_ls, 3, dst));
   for (int d = 0; d < 3; ++d) AB_CHECK(finish_vmult(ls, dst[d], src[d]));
   return 0;
 }
@@ -285,7 +332,10 @@ int adaflo_b200_ls_compute_normal_rhs(adaflo_b200_ls_t ls, double *const rhs[3],
   LSArgs a = base_args(ls);
   a.src[0] = level_set;
   for (int d = 0; d < 3; ++d) a.dst[d] = rhs[d];
-  return launch_ls(a, LS_NORMAL_RHS, ls->ctx->stream);
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, level_set));
+  for (int d = 0; d < 3; ++d) AB_CHECK(zero_ghosts(ls, ls->dof_ls, rhs[d]));
+  AB_CHECK(launch_ls(a, LS_NORMAL_RHS, ls->ctx->stream));
+  return compress(ls, ls->dof_ls, 3, rhs);
 }
 
 int adaflo_b200_ls_compute_curvature_vmult(adaflo_b200_ls_t ls, double *dst, const double *src, int apply_diffusion)
@@ -296,7 +346,9 @@ int adaflo_b200_ls_compute_curvature_vmult(adaflo_b200_ls_t ls, double *dst, con
   a.src[0] = src;
   a.dst[0] = dst;
   a.delta_scale = apply_diffusion ? 1.0 : 0.0;
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, src));
   AB_CHECK(launch_ls(a, LS_DAMPED, ls->ctx->stream));
+  AB_CHECK(compress(ls, ls->dof_ls, dst));
   return finish_vmult(ls, dst, src);
 }
 
@@ -306,7 +358,10 @@ int adaflo_b200_ls_compute_curvature_rhs(adaflo_b200_ls_t ls, double *rhs, const
   LSArgs a = base_args(ls);
   for (int d = 0; d < 3; ++d) a.aux[d] = normal[d];
   a.dst[0] = rhs;
-  return launch_ls(a, LS_CURV_RHS, ls->ctx->stream);
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, 3, normal));
+  AB_CHECK(zero_ghosts(ls, ls->dof_ls, rhs));
+  AB_CHECK(launch_ls(a, LS_CURV_RHS, ls->ctx->stream));
+  return compress(ls, ls->dof_ls, rhs);
 }
 
 int adaflo_b200_ls_curvature_correction(adaflo_b200_ls_t ls, double *curvature, const double *level_set)
@@ -324,7 +379,9 @@ int adaflo_b200_ls_reinitialization_vmult(adaflo_b200_ls_t ls, double *dst, cons
   a.src[0] = src;
   a.dst[0] = dst;
   a.pointdata = ls->normal_q;
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, src));
   AB_CHECK(launch_ls(a, diffuse_only ? LS_REINIT_DIFFUSE : LS_REINIT, ls->ctx->stream));
+  AB_CHECK(compress(ls, ls->dof_ls, dst));
   return finish_vmult(ls, dst, src);
 }
 
@@ -340,7 +397,11 @@ int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const 
   a.dst[0] = rhs;
   a.pointdata = ls->normal_q;
   a.first_step = first_reinit_step;
-  return launch_ls(a, diffuse_only ? LS_REINIT_RHS_DIFFUSE : LS_REINIT_RHS, ls->ctx->stream);
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, solution));
+  if (normal) AB_CHECK(import_ghosts(ls, ls->dof_ls, 3, normal));
+  AB_CHECK(zero_ghosts(ls, ls->dof_ls, rhs));
+  AB_CHECK(launch_ls(a, diffuse_only ? LS_REINIT_RHS_DIFFUSE : LS_REINIT_RHS, ls->ctx->stream));
+  return compress(ls, ls->dof_ls, rhs);
 }
 
 static LsHanging hanging_of(const adaflo_b200_ls_t ls)
@@ -363,6 +424,7 @@ int adaflo_b200_ls_compute_heaviside(adaflo_b200_ls_t ls, double *heaviside, con
   if (ls->cell_ext && ls->ctx->nranks > 1)
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "compute_heaviside: hanging nodes on partitioned meshes are not implemented");
   ls->heav_hang_valid = true;
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, level_set));
   return launch_heaviside(sp.cell_nodes, ls->last_cell, ls->cell_state, level_set, heaviside, (int)sp.nodes_per_cell, ls->mf->n_cells,
                           sp.n_owned_entries(), scale, hanging_of(ls), ls->c_hang, ls->heav_hang, ls->ctx->stream);
 }
@@ -417,11 +479,19 @@ int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, doubl
   f.surface_tension = surface_tension;
   f.gravity = gravity;
   f.gravity_dir = ls->prm.dim - 1;
+  if (ls->cell_ext && ls->ctx->nranks > 1)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "compute_force: hanging nodes on partitioned meshes are not implemented");
+  {
+    const double *in[2] = {heaviside, curvature};
+    AB_CHECK(import_ghosts(ls, ls->dof_ls, 2, in));
+    AB_CHECK(zero_ghosts(ls, ns->dof_u, dst_u));
+  }
   f.density = ns->prm.density;
   f.density_diff = ns->prm.density_diff;
   f.viscosity = ns->prm.viscosity;
   f.viscosity_diff = ns->prm.viscosity_diff;
-  return launch_ls_force(f, q.geometry_type, ls->ctx->stream);
+  AB_CHECK(launch_ls_force(f, q.geometry_type, ls->ctx->stream));
+  return compress(ls, ns->dof_u, dst_u);
 }
 
 int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_ptr, uint64_t *n)

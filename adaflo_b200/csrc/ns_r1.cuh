@@ -35,6 +35,30 @@ namespace ab200 {
 //   9 arr + 27 c + k + 3 qx + 81 qy            (arr: value / d/dx / d/dy part, c: component, k: z index)
 // and 12 slots for the pressure behind them.  81 = 1 and 259 = 3 (mod 16): the lanes (cell, t) of a warp hit the
 // 8-byte bank 3 cell + t both when t is the y index (phase B) and when it is k (phases A, C) -> no bank conflicts.
+#ifndef AB_R1_MERGE
+#define AB_R1_MERGE 0
+#endif
+#ifndef AB_R1_EVF   // linearisation rows are read once: mark their L2 lines evict-first when they are consumed (A/B: no gain)
+#define AB_R1_EVF 0
+#endif
+#ifndef AB_R1_PFLANE  // L2 prefetch by per-lane prefetch instructions instead of one bulk request of the TMA engine
+#define AB_R1_PFLANE 0
+#endif
+#ifndef AB_R1_IDXEV  // cell->node lists: read once, same policy
+#define AB_R1_IDXEV 0
+#endif
+#ifndef AB_R1_PFEV   // the L2 prefetch itself carries the evict-first policy
+#define AB_R1_PFEV 0
+#endif
+#ifndef AB_R1_RING   // register ring for the linearisation rows (see phase B)
+#define AB_R1_RING 0
+#endif
+#ifndef AB_R1_UNROLLJ  // line loop of phase B unrolled: no loop-carried register constraints (no spills at 168 registers)
+#define AB_R1_UNROLLJ 0
+#endif
+#ifndef AB_R1_SCHED  // 1: tickets handed out by a scheduler warp (see the kernel); 0: every worker draws its own
+#define AB_R1_SCHED 0
+#endif
 #ifndef AB_R1_WARPS
 #define AB_R1_WARPS 11
 #endif
@@ -51,7 +75,13 @@ __device__ __forceinline__ int r1_idx(int qx, int qy, int k) { return k + 3 * qx
 // bulk L2 prefetch of a contiguous block (TMA engine, no registers, no LSU wavefronts)
 __device__ __forceinline__ void l2_prefetch(const void *ptr, unsigned bytes)
 {
+#if AB_R1_PFEV
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(ptr), "r"(bytes), "l"(pol) : "memory");
+#else
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -102,22 +132,78 @@ __device__ __forceinline__ double ld_pinned(const double *p)
   return v;
 }
 
-// pinned 16-byte load of a row pair of the linearisation array
-__device__ __forceinline__ void ld_pinned2(const double *p, double &a, double &b)
+// L2 eviction policy "evict first" for data that is read exactly once per launch (the per-point streams, the cell->node
+// lists): once consumed, their lines are the first to go, so the lines the TMA prefetch has brought in for the decades
+// in flight and the node planes of the vectors (reused by the next cell layer) survive.  Measured: -12 % kernel time.
+__device__ __forceinline__ uint64_t policy_evict_first()
 {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// pinned 16-byte load of a row pair of the linearisation array
+__device__ __forceinline__ void ld_pinned2(const double *p, double &a, double &b, const uint64_t pol)
+{
+#if AB_R1_EVF
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(a), "=d"(b) : "l"(p), "l"(pol));
+#else
   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+#endif
+}
+
+// read-once 4-byte load (cell->node lists)
+__device__ __forceinline__ uint32_t ld_once(const uint32_t *p, const uint64_t pol)
+{
+#if AB_R1_IDXEV
+  uint32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+#else
+  return __ldg(p);
+#endif
 }
 
 // rows of the linearisation point of quadrature point n = 3 qx + qz of this lane (row pairs, see lin_index)
 template <int MODE>
-__device__ __forceinline__ void load_lin(double (&L)[12], const double *lin_lane, int n)
+__device__ __forceinline__ void load_lin(double (&L)[12], const double *lin_lane, int n, const uint64_t pol)
 {
   constexpr int pairs = MODE == MODE_NEWTON ? 6 : (MODE == MODE_PICARD ? 2 : 0);
 #pragma unroll
-  for (int r = 0; r < pairs; ++r) ld_pinned2(lin_lane + (size_t)r * 540 + n * 60, L[2 * r], L[2 * r + 1]);
+  for (int r = 0; r < pairs; ++r) ld_pinned2(lin_lane + (size_t)r * 540 + n * 60, L[2 * r], L[2 * r + 1], pol);
 }
 
-// One decade (10 cells) of the cell loop, executed by one warp: 3 lanes per cell.
+// refinement mask (hanging.cuh: three 3-bit groups indexed by mesh direction) re-indexed by kernel axis; the rotation
+// of the axes is cyclic, so HnInfo::line (which uses the cyclic successors of a direction) stays valid
+__device__ __forceinline__ uint32_t hn_to_kernel_axes(uint32_t m)
+{
+  if (kAxX == 0) return m;
+  uint32_t r = 0;
+#pragma unroll
+  for (int g = 0; g < 9; g += 3) {
+    const uint32_t grp = (m >> g) & 7u;
+    r |= (((grp >> kAxX) & 1u) | (((grp >> kAxY) & 1u) << 1) | (((grp >> kAxZ) & 1u) << 2)) << g;
+  }
+  return r;
+}
+
+template <int MODE, int GEOM, bool VAR>
+__device__ __forceinline__ void r1_prefetch(const NSArgs &A, const size_t g)
+{
+  if (MODE == MODE_NEWTON || MODE == MODE_PICARD) l2_prefetch(A.lin + g * (12 * 270), (MODE == MODE_NEWTON ? 12 : 4) * 270 * 8);
+  if (VAR) {
+    if (MODE != MODE_STOKES) l2_prefetch(A.rho + g * 270, 270 * 8);
+    if (MODE != MODE_STOKES) l2_prefetch(A.damp + g * 270, 270 * 8);
+    l2_prefetch(A.mu + g * 270, 270 * 8);
+  }
+  if (GEOM == ADAFLO_B200_GEOM_GENERAL) {
+    l2_prefetch(A.inv_jac + g * (9 * 270), 9 * 270 * 8);
+    l2_prefetch(A.jxw + g * 270, 270 * 8);
+  }
+}
+
+// One decade (10 cells) of the cell loop, executed by one warp: 3 lanes per cell.  x, y, z, ix, qx ... below are
+// KERNEL axes (common.cuh: kernel (X, Y, Z) = mesh (y, z, x)); only the geometry sees mesh axes.
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
 __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, double *warp_smem, const int lane)
 {
@@ -132,40 +218,54 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   double *s = warp_smem + cw * kR1CellSmem;
   double *sp = s + kR1PSmem;
 
-  // The per-point streams of this decade are consumed in phase B; ask the L2 for them now so
-  // that their HBM latency overlaps the gather and the in-plane contractions of phase A.
-  if (lane == 0) {
-    if (MODE == MODE_NEWTON || MODE == MODE_PICARD) l2_prefetch(A.lin + g * (12 * 270), (MODE == MODE_NEWTON ? 12 : 4) * 270 * 8);
-    if (VAR) {
-      if (MODE != MODE_STOKES) l2_prefetch(A.rho + g * 270, 270 * 8);
-      if (MODE != MODE_STOKES) l2_prefetch(A.damp + g * 270, 270 * 8);
-      l2_prefetch(A.mu + g * 270, 270 * 8);
-    }
-    if (GEOM == ADAFLO_B200_GEOM_GENERAL) {
-      l2_prefetch(A.inv_jac + g * (9 * 270), 9 * 270 * 8);
-      l2_prefetch(A.jxw + g * 270, 270 * 8);
-    }
-  }
+  // The per-point streams of this decade are consumed in phase B; ask the L2 for them now (TMA engine) so that their
+  // HBM latency overlaps the gather and the in-plane contractions of phase A.  (Asking for the warp's next decade
+  // instead -- at the start of phase A, B or C -- was measured 5-30 % slower: the data is evicted before use.)
+#if AB_R1_PFLANE
+  if (MODE == MODE_NEWTON) {
+    const char *blk = reinterpret_cast<const char *>(A.lin + g * (12 * 270));
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+      if (lane + 30 * i < 203) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + (size_t)(lane + 30 * i) * 128));  // 30 active lanes
+  } else if (lane == 0)
+    r1_prefetch<MODE, GEOM, VAR>(A, g);
+#else
+  if (lane == 0) r1_prefetch<MODE, GEOM, VAR>(A, g);
+#endif
 
   const double *lin_lane = A.lin + g * (12 * 270) + 2 * lane;
   Geometry<GEOM> G;  // table row of the cell (two dependent loads): issue before the gather
   G.init_blk(A, cell);
-  const HnInfo hn((HANGING && A.hn_u) ? __ldg(A.hn_u + cell) : 0u);
-  const HnInfo hnp((HANGING && WITH_P && A.hn_p) ? __ldg(A.hn_p + cell) : 0u);
+  const HnInfo hn(hn_to_kernel_axes((HANGING && A.hn_u) ? __ldg(A.hn_u + cell) : 0u));
+  const HnInfo hnp(hn_to_kernel_axes((HANGING && WITH_P && A.hn_p) ? __ldg(A.hn_p + cell) : 0u));
   const bool hn_z_warp = HANGING && __any_sync(mask, hn.any() && (hn.face(0) || hn.face(1) || hn.edge(2)));
   const bool hnp_z_warp = HANGING && WITH_P && __any_sync(mask, hnp.any() && (hnp.face(0) || hnp.face(1) || hnp.edge(2)));
 
   // ---------------------------------------------------------------- phase A
   uint32_t node[9];
+  uint64_t pol = policy_evict_first();  // re-created where it is needed: it must not occupy registers across the phases
 #pragma unroll
-  for (int j = 0; j < 9; ++j) node[j] = __ldg(A.cell_u_blk + (g * 9 + j) * 30 + lane);
+  for (int j = 0; j < 9; ++j) node[j] = ld_once(A.cell_u_blk + (g * 9 + j) * 30 + lane, pol);
+#if AB_R1_MERGE
+  // x-neighbours of a decade share a node plane: lane (cw + 1, t = 0) and lane (cw, t = 2) then scatter to the same
+  // nodes.  The upper lane hands its contribution to the lower one (one shuffle), which issues a single atomic.
+  unsigned merge_recv = 0, merge_send = 0;  // bit j: this lane receives from lane + 1 / gives to lane - 1
+  if (!HANGING) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const uint32_t up = __shfl_down_sync(mask, node[j], 1), dn = __shfl_up_sync(mask, node[j], 1);
+      if (t == 2 && lane + 1 < 3 * kGroup && ((mask >> (lane + 1)) & 1u) && up == node[j]) merge_recv |= 1u << j;
+      if (t == 0 && lane > 0 && dn == node[j]) merge_send |= 1u << j;
+    }
+  }
+#endif
   uint32_t pnode[4] = {0, 0, 0, 0};
   double p_dg0 = 0;
   uint32_t dg0_node = 0;
   if (WITH_P) {
     if (t < 2) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) pnode[j] = __ldg(A.cell_p_blk + (g * 4 + j) * 30 + lane);
+      for (int j = 0; j < 4; ++j) pnode[j] = ld_once(A.cell_p_blk + (g * 4 + j) * 30 + lane, pol);
     }
     if (A.np_cell == 9) {
       dg0_node = __ldg(A.cell_p + (size_t)cell * 9 + 8);
@@ -296,14 +396,27 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
 
   // ---------------------------------------------------------------- phase B
   const double wt = (t == 1) ? W[1] : W[0];  // Gauss weight of qy = t
-  // the line loop stays rolled: a third of the code (instruction cache) and the linearisation
-  // data of a whole line is requested before the shared-memory reads and the z contraction
+  // The line loop stays rolled (a third of the code: instruction cache).  The linearisation rows of line j + 1 are
+  // requested as soon as the physics of line j has consumed its rows -- before the z contraction back and the tile
+  // writes of line j, the tile reads and the z contraction of line j + 1 -- at no cost in registers (the rows of line
+  // j are dead by then); the rows of line 0 are requested before the pressure interpolation.
+  double LQ[3][12];
+  pol = policy_evict_first();
+#if AB_R1_RING
+#pragma unroll
+  for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, qz, pol);
+#endif
+#if AB_R1_UNROLLJ
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
   for (int j = 0; j < 3; ++j) {
     const double wj = (j == 1) ? W[1] : W[0];
-    double LQ[3][12];
+#if !AB_R1_RING
 #pragma unroll
-    for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, 3 * j + qz);
+    for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, 3 * j + qz, pol);
+#endif
     double val[3][3], dx[3][3], dy[3][3], dz[3][3];  // [c][qz]
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -338,7 +451,10 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
       double gr[3][3];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        const double r[3] = {dx[d][qz], dy[d][qz], dz[d][qz]};
+        double r[3];  // reference derivatives in mesh order (kernel axes -> mesh axes, common.cuh)
+        r[kAxX] = dx[d][qz];
+        r[kAxY] = dy[d][qz];
+        r[kAxZ] = dz[d][qz];
         G.to_real(r, gr[d]);
       }
       const double div = gr[0][0] + gr[1][1] + gr[2][2];
@@ -427,11 +543,17 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
         double tr[3];
         G.to_ref(S[d], jxw, tr);
         val[d][qz] = conv[d];
-        dx[d][qz] = tr[0];
-        dy[d][qz] = tr[1];
-        dz[d][qz] = tr[2];
+        dx[d][qz] = tr[kAxX];
+        dy[d][qz] = tr[kAxY];
+        dz[d][qz] = tr[kAxZ];
       }
     }
+#if AB_R1_RING
+    if (j < 2) {  // all rows of this line are consumed: request the next line's now
+#pragma unroll
+      for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, 3 * (j + 1) + qz, pol);
+    }
+#endif
     // z contraction back, overwriting this lane's own tile entries
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -514,6 +636,13 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
     for (int j = 0; j < 9; ++j) {
       const uint32_t nd = node[j];
       if (kDiagCapable && A.diag && !(c == dg_c && j == dg_j && t == dg_t)) continue;
+#if AB_R1_MERGE
+      if (!HANGING) {
+        const double from_up = __shfl_down_sync(mask, o[j], 1);
+        if ((merge_recv >> j) & 1u) o[j] += from_up;
+        if ((merge_send >> j) & 1u) continue;
+      }
+#endif
       if (!((nd >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u))
         red_add(A.dst_u + 3 * (size_t)(nd & ADAFLO_B200_NODE_MASK) + c, o[j]);
     }
@@ -561,17 +690,72 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   }
 }
 
-// Persistent kernel: one block of kR1Warps independent warps per SM; every warp draws decades from a global
-// counter (A.work_counter, zeroed by the launcher) until the range [decade_begin, decade_end) is exhausted.  The
-// next ticket is drawn before the current decade is processed, so the atomic's latency is never exposed, and a
-// warp that is delayed (hanging-node cells, a slow SM) simply draws fewer decades.
+// Persistent kernel: one block per SM with kR1Warps independent worker warps and one scheduler warp.  Decades of the
+// launch's range [decade_begin, decade_end) are handed out dynamically from a global ticket counter (A.work_counter,
+// zeroed by the launcher): tickets go out in time order, so the decades in flight are neighbours in memory, and a warp
+// that is delayed (hanging-node cells, a slow SM) simply draws fewer.  (A static assignment with a dynamic tail was
+// measured 8 % slower.)  The workers do not draw tickets themselves: ptxas turns an atomic on a warp-uniform address
+// into a warp-aggregated one whose result is shuffled -- or spilled -- at once, which exposed the atomic's latency once
+// per decade (11 % of the stall samples in profiles/r2_a).  The scheduler warp keeps two shared-memory slots per worker
+// filled with that worker's next tickets instead; the worker takes one with a shared-memory load at the end of a decade.
+constexpr unsigned kNoTicket = 0xffffffffu;
+
+__device__ __forceinline__ unsigned ld_slot(const unsigned *p)
+{
+  unsigned v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_slot(unsigned *p, unsigned v)
+{
+  asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
 __global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
 {
   extern __shared__ double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *warp_smem = smem + warp * kR1WarpSmem;
   const unsigned n_dec = (unsigned)(A.decade_end - A.decade_begin);
+#if AB_R1_SCHED
+  __shared__ unsigned slot[2 * kR1Warps];  // two ticket slots per worker: a refill (one atomic round trip) is never waited for
+  if (threadIdx.x < 2 * kR1Warps) slot[threadIdx.x] = kNoTicket;
+  __syncthreads();
+  if (warp == kR1Warps) {  // scheduler warp: lane l keeps slot l filled until it has handed out a ticket beyond the range
+    if (lane < 2 * kR1Warps) {
+      for (;;) {
+        if (ld_slot(slot + lane) == kNoTicket) {
+          const unsigned t = atomicAdd(A.work_counter, 1u);
+          st_slot(slot + lane, t);
+          if (t >= n_dec) break;
+        } else
+          __nanosleep(100);
+      }
+    }
+    return;
+  }
+  double *warp_smem = smem + warp * kR1WarpSmem;
+  unsigned k = 0, finished = 0;  // slot in turn; bit k set: slot k has delivered its final ticket
+  while (finished != 3u) {
+    if ((finished >> k) & 1u) k ^= 1u;
+    unsigned i = 0;
+    if (lane == 0) {
+      unsigned *const my = slot + 2 * warp + k;
+      while ((i = ld_slot(my)) == kNoTicket) {
+      }
+      st_slot(my, kNoTicket);
+    }
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n_dec) {
+      finished |= 1u << k;
+      continue;
+    }
+    r1_decade<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>(A, A.decade_begin + i, warp_smem, lane);
+    __syncwarp();  // the tiles of this decade have been read before the next decade overwrites them
+    k ^= 1u;
+  }
+#else
+  double *warp_smem = smem + warp * kR1WarpSmem;
   // two tickets are held (current and next decade), the third is drawn while the current decade is processed
   unsigned i = 0, i_n1 = 0;
   if (lane == 0) {
@@ -582,14 +766,13 @@ __global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
   i_n1 = __shfl_sync(0xffffffffu, i_n1, 0);
   while (i < n_dec) {
     unsigned i_n2 = 0;
-    if (lane == 0) {
-      i_n2 = atomicAdd(A.work_counter, 1u);
-    }
+    if (lane == 0) i_n2 = atomicAdd(A.work_counter, 1u);
     r1_decade<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>(A, A.decade_begin + i, warp_smem, lane);
-    __syncwarp();  // the tiles of this decade have been read before the next decade overwrites them
+    __syncwarp();
     i = i_n1;
     i_n1 = __shfl_sync(0xffffffffu, i_n2, 0);
   }
+#endif
 }
 
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
@@ -615,7 +798,7 @@ int launch_vmult_r1_hn(const NSArgs &a, cudaStream_t s)
   const size_t blocks_needed = (b.decade_end - b.decade_begin + kR1Warps - 1) / kR1Warps;
   const unsigned grid = (unsigned)(blocks_needed < (size_t)n_sm ? blocks_needed : (size_t)n_sm);
   AB_CUDA(cudaMemsetAsync(b.work_counter, 0, sizeof(unsigned), s));
-  kern<<<grid, kR1Warps * 32, smem, s>>>(b);
+  kern<<<grid, (kR1Warps + AB_R1_SCHED) * 32, smem, s>>>(b);
   AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;

@@ -7,6 +7,8 @@
 // linearly, so w_old*u_old + w_oldold*u_oldold (and, for the extrapolating
 // linearisations, the extrapolated velocity) are combined at dof level and
 // evaluated once instead of evaluating every old vector separately.
+#include <cstdlib>
+
 #include "ns_q2q1.cuh"
 
 namespace ab200 {
@@ -258,6 +260,13 @@ int launch_ns_residual(const NSArgs &a, int geom, bool var, cudaStream_t s)
                       a.physical_type != ADAFLO_B200_STOKES;
   if (extrap && a.physical_type != ADAFLO_B200_INCOMPRESSIBLE)
     return fail(ADAFLO_B200_ERR_UNSUPPORTED, "extrapolating linearization requires physical_type == incompressible");
+  // Newton / Picard / Stokes: the kernel on the vmult mapping (ns_residual_r1.cu); the extrapolating linearisations need a
+  // third evaluated field and stay on this file's 9-lane kernel.  ADAFLO_B200_RESIDUAL_KERNEL=v1 forces the latter (A/B).
+  static const bool force_v1 = [] {
+    const char *e = std::getenv("ADAFLO_B200_RESIDUAL_KERNEL");
+    return e && std::string(e) == "v1";
+  }();
+  if (!extrap && !force_v1 && a.cell_u_blk && a.cell_p_blk) return launch_ns_residual_r1(a, geom, var, s);
 #define AB_CASE(G, V, E) \
   if (geom == G && var == V && extrap == E) return launch_res_inst<G, V, E>(a, s);
   AB_CASE(0, false, false) AB_CASE(0, false, true) AB_CASE(0, true, false) AB_CASE(0, true, true)

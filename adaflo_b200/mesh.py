@@ -275,11 +275,10 @@ class BoxMesh:
         sp.n_owned = n_q1_owned + self.n_cells
         sp.recv = [(peer, first + shift, cnt) for (peer, first, cnt) in sp.recv]
 
-    def build_ls_space(self, n_sub=3, dirichlet_faces=()):
+    def build_ls_space(self, n_sub=3, dirichlet_faces=(), build_coords=True):
         """Level-set space FE_Q_iso_Q1(n_sub) (source/level_set_base.cc:54-60): (n_sub+1)^3 nodes per
         cell on the uniform (n_sub n + 1)^3 lattice, lexicographic in the cell."""
-        assert self.nranks == 1, "level-set spaces are built for single-rank meshes"
-        self.ls = self._build_space("ls", n_sub, 1, dirichlet_faces, True, equidistant=True)
+        self.ls = self._build_space("ls", n_sub, 1, dirichlet_faces, build_coords, equidistant=True)
         self.ls.n_sub = n_sub
         return self.ls
 

@@ -348,11 +348,10 @@ class NavierStokesMatrix:
             return None
         return device_view(p.value, n.value, self.ctx.device)
 
-    # Per-quadrature-point coefficient arrays (navier_stokes_matrix.h:162-178,293-395).  On the
-    # device they are decade blocked (adaflo_b200/csrc/common.cuh, coef_index):
-    #   [decade g][row][3 qx + qz][cell in decade][qy]        (n_rows = 1, or 12 for the linearisation)
-    # begin_*() return the raw device views; *_canonical helpers convert to/from the reference
-    # order [cell][row][q], q = qx + 3 qy + 9 qz.
+    # Per-quadrature-point coefficient arrays (navier_stokes_matrix.h:162-178,293-395).  On the device they are
+    # decade blocked (csrc/common.cuh, coef_index / lin_index) -- a layout private to the library.  begin_*() return the
+    # raw device views; set_coefficient / get_coefficient go through the C ABI's canonical copies
+    # (adaflo_b200_ns_{set,get}_coefficient_canonical: the reference's [cell batch][q][row][lane] order).
     def begin_densities(self):
         return self._coef(capi.COEF_DENSITY)
 
@@ -366,37 +365,23 @@ class NavierStokesMatrix:
         """rows 0..2 velocity, 3+3d+e = d u_d / d x_e"""
         return self._coef(capi.COEF_LINEARIZED_VELOCITY)
 
-    def to_canonical(self, blocked, n_rows):
-        """decade-blocked device order -> [cell][row][27 points, x fastest] (coef_index / lin_index in csrc/common.cuh)"""
-        n_cells = self.matrix_free.mesh.n_cells
-        if n_rows == 12:   # rows interleaved in pairs
-            b = blocked.view(-1, 6, 3, 3, 10, 3, 2)                      # g, row pair, qx, qz, cw, qy, row & 1
-            c = b.permute(0, 4, 1, 6, 3, 5, 2).reshape(-1, 12, 27)        # g, cw, pair, row & 1, qz, qy, qx
-        else:
-            b = blocked.view(-1, n_rows, 3, 3, 10, 3)                     # g, row, qx, qz, cw, qy
-            c = b.permute(0, 4, 1, 3, 5, 2).reshape(-1, n_rows, 27)       # g, cw, row, qz, qy, qx
-        return c[:n_cells]
-
-    def from_canonical(self, canonical, n_rows):
-        n_cells = canonical.shape[0]
-        g = (n_cells + 9) // 10
-        c = torch.zeros(g * 10, n_rows, 27, dtype=torch.float64, device=canonical.device)
-        c[:n_cells] = canonical.reshape(n_cells, n_rows, 27)
-        if n_rows == 12:
-            b = c.view(g, 10, 6, 2, 3, 3, 3).permute(0, 2, 6, 4, 1, 5, 3)  # g, pair, qx, qz, cw, qy, row & 1
-        else:
-            b = c.view(g, 10, n_rows, 3, 3, 3).permute(0, 2, 5, 3, 1, 4)   # g, row, qx, qz, cw, qy
-        return b.reshape(-1)
-
     def set_coefficient(self, which, canonical):
-        """which: capi.COEF_*; canonical: [n_cells, 27] (or [n_cells, 12, 27]) device tensor"""
-        n_rows = 12 if which == capi.COEF_LINEARIZED_VELOCITY else 1
-        self._coef(which).copy_(self.from_canonical(canonical, n_rows))
+        """which: capi.COEF_*; canonical: [n_cells, 27] (or [n_cells, 12, 27]) device tensor, q = qx + 3 qy + 9 qz"""
+        self._require()
+        n_cells = self.matrix_free.mesh.n_cells
+        if which == capi.COEF_LINEARIZED_VELOCITY:
+            c = canonical.reshape(n_cells, 12, 27).permute(0, 2, 1).contiguous()   # ABI order: [cell][q][row]
+        else:
+            c = canonical.reshape(n_cells, 27).contiguous()
+        check(self.lib.adaflo_b200_ns_set_coefficient_canonical(self.h, which, _ptr(c), 0, n_cells, 1, None))
 
     def get_coefficient(self, which):
+        self._require()
+        n_cells = self.matrix_free.mesh.n_cells
         n_rows = 12 if which == capi.COEF_LINEARIZED_VELOCITY else 1
-        t = self.to_canonical(self._coef(which), n_rows)
-        return t if n_rows == 12 else t.reshape(-1, 27)
+        c = torch.zeros(n_cells, 27, n_rows, dtype=torch.float64, device=self.ctx.device)
+        check(self.lib.adaflo_b200_ns_get_coefficient_canonical(self.h, which, _ptr(c), 0, n_cells, 1, None))
+        return c.permute(0, 2, 1).contiguous() if n_rows == 12 else c.reshape(n_cells, 27)
 
     def use_variable_coefficients(self):
         return self.parameters.density_diff != 0 or self.parameters.viscosity_diff != 0

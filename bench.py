@@ -141,6 +141,7 @@ def cpu_port_sample(n_xy, layers, steps, warmup):
     rng = np.random.default_rng(999)
     lin = rng.uniform(-1, 1, size=(mesh.n_cells, 12, 27))
     port = cpu_port.CpuPortVmult(mesh, 1, 30.0, 1.0, 0.5, 1.0, 1.0, 0.0, 0.0, lin)
+    cpu_port.use_all_cores()   # explicit: torchrun exports OMP_NUM_THREADS=1 to its workers
     su = seeded_uniform(mesh.u.global_ids, 3, 12345)
     sp = seeded_uniform(mesh.p.global_ids, 1, 12345)
     du, dp = np.zeros_like(su), np.zeros_like(sp)
@@ -159,6 +160,124 @@ def cpu_port_sample(n_xy, layers, steps, warmup):
     return {"value": n_dofs / t, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{n_xy}x{n_xy}x{layers} cells slab of the 128^3 workload ({n_dofs} DoFs), Newton/Cartesian/constant coefficients, "
                       f"{steps} vmult cell loops, mean {t * 1e3:.1f} ms each; oracle/ns_cpu_port.c (restatement, not adaflo+deal.II)"}, t
+
+
+def parity_vs_single_gpu(ctx, rank, world, local_rank):
+    """Cross-N parity inside the bench (the driver's GPU-test box has one GPU): residual + vmult of one small box on the
+    N-rank partition against the SAME global problem applied by a single-rank operator on rank 0's GPU; inputs are seeded
+    by global DoF id.  Returns the largest relative l2 difference over the blocks (all ranks)."""
+    import torch
+    import torch.distributed as dist
+    from adaflo_b200 import capi
+    from adaflo_b200.mesh import BoxMesh, beltrami_velocity, seeded_uniform
+    from adaflo_b200.operators import BlockVector, Context, MatrixFree, NavierStokesMatrix
+    n = (12, 10, 6 * world + 1)
+    prm = capi.FlowParams(capi.INCOMPRESSIBLE, capi.NEWTON, 0, 0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.5)
+    tw = capi.TimeWeights(30.0, -40.0, 10.0, 1.0, 2.0, -1.0)
+
+    def dev(a, c):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(c.device)
+
+    def apply(c, mesh):
+        mf = MatrixFree(c, mesh, "cartesian")
+        sol, old, old_old = BlockVector.like(mf), BlockVector.like(mf), BlockVector.like(mf)
+        A = NavierStokesMatrix(prm, 0, 1, 0, 1, old, old_old)
+        A.initialize(mf, tw, True)
+        u0 = beltrami_velocity(mesh.u.coords, 0.0).reshape(-1)
+        for v in (sol, old, old_old):
+            v.block(0).copy_(dev(u0, c))
+        rhs, zero, dst = BlockVector.like(mf), BlockVector.like(mf), BlockVector.like(mf)
+        A.residual(rhs, sol, zero)
+        src = BlockVector(dev(seeded_uniform(mesh.u.global_ids, 3, 12345), c), dev(seeded_uniform(mesh.p.global_ids, 1, 12345), c))
+        A.vmult(dst, src)
+        out = [rhs.block(0).clone(), rhs.block(1).clone(), dst.block(0).clone(), dst.block(1).clone()]
+        c.synchronize()
+        A.clear()
+        mf.close()
+        return out
+
+    mesh = BoxMesh(n, rank=rank, nranks=world)
+    mine = apply(ctx, mesh)
+    gmesh = BoxMesh(n)
+    sizes = [gmesh.u.n_local * 3, gmesh.p.n_local, gmesh.u.n_local * 3, gmesh.p.n_local]
+    if rank == 0:
+        serial = Context(local_rank)
+        ref = apply(serial, gmesh)
+        serial.close()
+    else:
+        ref = [torch.empty(k, dtype=torch.float64, device=ctx.device) for k in sizes]
+    worst = 0.0
+    for k, (got, full) in enumerate(zip(mine, ref)):
+        full = full.contiguous()
+        dist.broadcast(full, src=0)
+        sp, nc = (mesh.u, 3) if k % 2 == 0 else (mesh.p, 1)
+        ids = torch.from_numpy(np.asarray(sp.global_ids[: sp.n_owned]).astype(np.int64)).to(ctx.device)
+        want = full.reshape(-1, nc)[ids]
+        have = got.reshape(-1, nc)[: sp.n_owned]
+        num = torch.stack([((have - want) ** 2).sum(), (want ** 2).sum()])
+        dist.all_reduce(num)
+        worst = max(worst, float(torch.sqrt(num[0] / num[1])))
+    return {"max_rel_l2_diff": worst, "mesh": "x".join(map(str, n)) + " cells", "checked": ["residual_u", "residual_p", "vmult_u", "vmult_p"],
+            "note": "N-rank partition vs single-rank operator on the same global problem (global-id seeded inputs)"}
+
+
+def run_level_set(args):
+    """--workload ls: the level-set operator applications at n^3 cells, FE_Q_iso_Q1(3), one GPU,
+    each with its algorithmic-bytes model.  Extra measurement; the headline line stays the Navier-Stokes vmult."""
+    import torch
+    from adaflo_b200 import capi
+    from adaflo_b200.mesh import BoxMesh, seeded_uniform
+    from adaflo_b200.operators import Context, LevelSetOperators, MatrixFree
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    ctx = Context(0)
+    n, n_sub = args.n, 3
+    mesh = BoxMesh((n, n, n), build_coords=False)
+    mesh.build_ls_space(n_sub, build_coords=False)
+    mf = MatrixFree(ctx, mesh, "cartesian")
+    h_min = float(mesh.h.min())
+    eps = 1.5
+    A = LevelSetOperators(mf, capi.LSParams(3, n_sub, 0, 0, eps, eps * h_min / n_sub, 4.0, h_min), mesh.cell_diameters())
+    A.set_time(75.0, -100.0, 25.0, 0.02)
+    n_dofs = mesh.ls.n_owned
+    pts_per_dof, idx_per_dof = (2 * n_sub) ** 3 / n_sub ** 3, 4.0 * (n_sub + 1) ** 3 / n_sub ** 3
+    for which in (0, 1):   # per-point streams: a smooth unit field (values do not matter for the timing)
+        A.pointdata(which).fill_(0.57735)
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    src = [dev(seeded_uniform(mesh.ls.global_ids, 1, 100 + k)) for k in range(3)]
+    dst = [mf.initialize_dof_vector(2) for _ in range(3)]
+    peak, which_peak = measured_peak()
+    ops = {
+        "advance_concentration_vmult": (lambda: A.advance_concentration_vmult(dst[0], src[0]), 16 + idx_per_dof + 24 * pts_per_dof),
+        "reinitialization_vmult": (lambda: A.reinitialization_vmult(dst[0], src[0], False), 16 + idx_per_dof + 24 * pts_per_dof),
+        "compute_normal_vmult": (lambda: A.compute_normal_vmult(dst, src), 3 * 16 + idx_per_dof),
+        "compute_curvature_vmult": (lambda: A.compute_curvature_vmult(dst[0], src[0], True), 16 + idx_per_dof),
+    }
+    out = {}
+    l0 = ctx.lib.adaflo_b200_kernel_launch_count()
+    for name, (fn, bpd) in ops.items():
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        gbs = bpd * n_dofs / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "dofs_per_s": n_dofs / (ms * 1e-3), "bytes_per_dof": bpd, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+    line = {"metric": "ls_operator_dofs_per_s", "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "dtype": "f64",
+            "data": "synthetic", "higher_is_better": True,
+            "config": {"workload": f"level-set operators on {n}^3 cells, FE_Q_iso_Q1({n_sub}), {n_dofs} DoFs, QIterated(QGauss(2),{n_sub}), Cartesian",
+                       "byte_model": "per level-set DoF: 8 src + 8 dst per component, 4 B x (n_sub+1)^3 indices per cell, 24 B per quadrature "
+                                     "point for the stored convection velocity / frozen normal (advection, reinitialisation)"},
+            "peak_gbs": peak, "peak_source": which_peak, "operators": out,
+            "gpu_launches": int(ctx.lib.adaflo_b200_kernel_launch_count() - l0)}
+    print(json.dumps(line))
 
 
 def run_reference(args):
@@ -189,12 +308,15 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--preroll", type=float, default=0.7, help="seconds of untimed load before the timed steps (clock sampling)")
     ap.add_argument("--no-nonlinear-step", action="store_true")
+    ap.add_argument("--workload", default="ns", choices=["ns", "ls"], help="ns: the headline Navier-Stokes vmult line; ls: level-set operator timings (extra)")
     ap.add_argument("--kernel-only", action="store_true", help="developer A/B mode: kernel timings + checksum only (not a bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "ls":
+        return run_level_set(args)
 
     import torch
     import torch.distributed as dist
@@ -218,6 +340,10 @@ def main():
             dist.broadcast_object_list(obj, src=0)
             return obj[0]
         ctx.init_comm(rank, world, bcast)
+
+    cross_n = parity_vs_single_gpu(ctx, rank, world, local_rank) if world > 1 else None
+    if cross_n is not None and cross_n["max_rel_l2_diff"] > 1e-12:
+        raise SystemExit(f"bench.py: {world}-rank result differs from the single-rank operator: {cross_n}")
 
     n = args.n
     t_setup = time.perf_counter()
@@ -286,12 +412,17 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    torch.cuda.synchronize()
-    t_pre = time.perf_counter()
-    while time.perf_counter() - t_pre < args.preroll:
-        for _ in range(10):
-            A.vmult(dst, src)
-        torch.cuda.synchronize()
+    # The pre-roll count is fixed BEFORE the loop and agreed between the ranks (every vmult carries NCCL send/recv and an
+    # all-reduce, so all ranks must issue the same number of them; a wall-clock bound per rank deadlocked round 1's N=2 run).
+    pre = torch.tensor([max(10, int(args.preroll * 1e3 / max(b_ms / args.steps, 1e-3)))], dtype=torch.int64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(pre, op=dist.ReduceOp.MAX)
+    n_preroll = int(pre.item())
+    barrier()
+    for i in range(n_preroll):
+        A.vmult(dst, src)
+        if i % 10 == 9:
+            torch.cuda.synchronize()
     ms_total, k_avg_local, launches = timed_steps()
     clocks = sampler.stop() if rank == 0 else None
     k_launches, k_seconds = 1, k_avg_local
@@ -338,6 +469,23 @@ def main():
     e2e_t = float(te[0])
     # parity of the two paths (cheap sanity, not timed)
     err = float((ou.to(ctx.device) - dst.block(0)[:nu_own]).norm() / dst.block(0)[:nu_own].norm())
+
+    # ---- the residual kernel (producer of the linearisation point; once per Newton iteration)
+    res_vecs = (BlockVector.like(mf), BlockVector.like(mf))
+    for _ in range(2):
+        A.residual(res_vecs[0], sol, res_vecs[1])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(5):
+        A.residual(res_vecs[0], sol, res_vecs[1])
+    e1.record()
+    barrier()
+    residual_ms = e0.elapsed_time(e1) / 5
+    del res_vecs
+    # algorithmic bytes per DoF of residual: 3 velocity vectors + pressure read (3 x 8 + ...), rhs read-modify-write 16,
+    # indices 5.6, linearisation point written 103.68
+    res_bytes = (24.0 + 16.0 + 5.6 + 103.68) * n_dofs_rank
 
     # ---- time per nonlinear step (north_star / SURVEY 8(d)): residual + k GMRES iterations per Newton step with
     # the golden iteration counts of tests/beltrami_3d.output:13-16, no preconditioner (the reference's Trilinos
@@ -394,12 +542,16 @@ def main():
                     "ms_per_step": e2e_t * 1e3, "rel_diff_vs_device_path": err},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "residual": {"ms": residual_ms, "bytes_per_dof": 149.28, "achieved_gbs": res_bytes / (residual_ms * 1e-3) / 1e9,
+                         "frac_of_hbm_peak": res_bytes / (residual_ms * 1e-3) / 1e9 / peak,
+                         "note": "NavierStokesMatrix::residual incl. ghost import, sadd and the store of the linearisation point (rank 0 timing)"},
             "nonlinear_step": nl,
+            "parity_vs_1gpu": cross_n,
             "burst": {"ms_per_step": b_ms / args.steps, "kernel_ms": b_k * 1e3, "value": n_dofs / (b_ms / args.steps * 1e-3),
                       "roofline_frac": B_PER_DOF_N * n_dofs_rank / b_k / 1e9 / peak,
                       "note": "same K steps right after warm-up, before the GPU reaches its power limit (rank 0 timing)"},
         }
-        if not args.no_cpu_baseline and world >= 1:
+        if not args.no_cpu_baseline and world == 1:   # cpu_baseline: rank 0 at N = 1 only
             cb, _ = cpu_port_sample(n, max(2, min(n, args.cpu_layers)), 10, 2)
             line["cpu_baseline"] = cb
         print(json.dumps(line))

@@ -240,6 +240,17 @@ enum adaflo_b200_coefficient {
 /* raw device storage in the decade-blocked order of csrc/common.cuh (coef_index; lin_index for the 12-row
  * linearisation array, whose rows are interleaved in pairs) */
 int adaflo_b200_ns_coefficient_ptr(adaflo_b200_ns_t ns, int which, double **dev_ptr, uint64_t *n_doubles);
+/* The same arrays in the reference's own storage order (navier_stokes_matrix.h:293-395: AlignedVector<
+ * VectorizedArray<double>> indexed [cell batch][q], the linearisation point 12 consecutive VectorizedArrays per point):
+ *   canonical[((batch * 27 + q) * n_rows + row) * lanes + lane],  q = qx + 3 qy + 9 qz,  n_rows = 1 or 12,
+ * where slot batch * lanes + lane holds device cell slot_cell_host[slot] (identity if NULL; 0xffffffff = empty lane of a
+ * partially filled batch).  `canonical` is a device pointer, or a host pointer if on_host != 0 (synchronous copy).  This is
+ * what the external writers of the reference (level_set_okz.cc:351-364, navier_stokes.cc:1178-1196) and the C++ mirror's
+ * begin_densities(macro_cell) & co. go through; the decade-blocked device order stays private to the library. */
+int adaflo_b200_ns_set_coefficient_canonical(adaflo_b200_ns_t ns, int which, const double *canonical, int on_host, uint32_t n_batches,
+                                             uint32_t lanes, const uint32_t *slot_cell_host);
+int adaflo_b200_ns_get_coefficient_canonical(adaflo_b200_ns_t ns, int which, double *canonical, int on_host, uint32_t n_batches,
+                                             uint32_t lanes, const uint32_t *slot_cell_host);
 /* pressure null-space data built by initialize (:110-168): device pointers */
 int adaflo_b200_ns_nullspace(adaflo_b200_ns_t ns, int mode, const double **modes, const double **weights, double *inverse_weight);
 /* get_matvec_statistics: :1194-1206 (count, accumulated seconds; resets) */

@@ -62,3 +62,10 @@ class CpuPortVmult:
 
 def max_threads():
     return lib().port_max_threads()
+
+
+def use_all_cores():
+    """Run the port on every core of this process's affinity mask, whatever OMP_NUM_THREADS says (torchrun exports
+    OMP_NUM_THREADS=1 to its workers); returns the thread count now in effect."""
+    lib().port_set_threads(len(os.sched_getaffinity(0)))
+    return max_threads()

@@ -173,6 +173,16 @@ int port_ns_vmult_cells(const port_args *A, const double *src_u, const double *s
   return threads;
 }
 
+/* explicit thread count: launchers such as torchrun export OMP_NUM_THREADS=1 to their workers */
+void port_set_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int port_max_threads(void)
 {
 #ifdef _OPENMP
