@@ -15,7 +15,7 @@ struct adaflo_b200_ls_s {
   int dof_ls, dof_vel, quad_ls;
   double weight, weight_old, weight_old_old, step_size;
   double *cell_diameters;      // device
-  double *conv, *normal_q;     // device [cell][sub][3][8]
+  double *conv, *normal_q;     // device [cell][3][8 points][sub-cell]
   const double *diag;          // not owned
   uint32_t *last_cell;         // device [n_dofs]: last cell of the cell loop containing the dof (Heaviside)
   signed char *cell_state;     // device [n_cells]

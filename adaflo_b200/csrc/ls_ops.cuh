@@ -26,7 +26,7 @@ struct LSArgs {
   double *dst[3];
   const double *aux[3];      // additional input vectors (old level sets / normal field)
   const double *vel;         // velocity vector (advect rhs)
-  double *pointdata;         // conv or frozen normals [cell][sub][3][8]
+  double *pointdata;         // conv or frozen normals [cell][3][8 points][sub-cell]
   double gamma, w_old, w_oo; // time weights
   double delta_scale, eps_ratio, epsilon_used, dtau_inv;
   int first_step;

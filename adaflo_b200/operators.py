@@ -588,18 +588,19 @@ class LevelSetOperators:
                                                     float(surface_tension), float(gravity), _np(ip)))
 
     def pointdata(self, which):
-        """0: evaluated_convection, 1: evaluated_normal; device view [n_cells, n_sub^3, 3, 8]"""
+        """0: evaluated_convection, 1: evaluated_normal; device view [n_cells, 3, 8, n_sub^3] (component, point of the
+        sub-cell, sub-cell: the layout of the cell kernel in csrc/ls_ops.cu)"""
         p, n = C.c_void_p(), C.c_uint64()
         check(self.lib.adaflo_b200_ls_pointdata_ptr(self.h, which, C.byref(p), C.byref(n)))
         s = self.parameters.concentration_subdivisions
-        return device_view(p.value, n.value, self.ctx.device).view(-1, s ** 3, 3, 8)
+        return device_view(p.value, n.value, self.ctx.device).view(-1, 3, 8, s ** 3)
 
     def pointdata_canonical(self, which):
         """[n_cells, NQ, 3] with q = qx + nq qy + nq^2 qz, the order the oracle uses"""
         s = self.parameters.concentration_subdivisions
-        t = self.pointdata(which)                               # cell, (sz,sy,sx), comp, (pc,pb,pa)
+        t = self.pointdata(which)                               # cell, comp, (pc,pb,pa), (sz,sy,sx)
         n = t.shape[0]
-        t = t.view(n, s, s, s, 3, 2, 2, 2).permute(0, 1, 5, 2, 6, 3, 7, 4)   # cell, sz,pc, sy,pb, sx,pa, comp
+        t = t.view(n, 3, 2, 2, 2, s, s, s).permute(0, 5, 2, 6, 3, 7, 4, 1)   # cell, sz,pc, sy,pb, sx,pa, comp
         return t.reshape(n, (2 * s) ** 3, 3)
 
 

@@ -323,7 +323,7 @@ int adaflo_b200_ls_compute_heaviside(adaflo_b200_ls_t ls, double *heaviside, con
  * interpolate_grad_onto_pressure, else NULL */
 int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, double *dst_u, const double *heaviside, const double *curvature,
                                  double surface_tension, double gravity, const double *interpolation_host);
-/* evaluated_convection (which = 0) / evaluated_normal (which = 1): device arrays [cell][sub-cell][3][8 points] */
+/* evaluated_convection (which = 0) / evaluated_normal (which = 1): device arrays [cell][3 components][8 points of a sub-cell][n_sub^3 sub-cells] */
 int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_ptr, uint64_t *n_doubles);
 
 /* ------------------------------------------------- Krylov-step vector kernels
