@@ -42,15 +42,19 @@ __host__ __device__ inline size_t coef_index(uint32_t cell, int row, int n_rows,
   return (g * n_rows + row) * 270 + coef_slot(qx, qy, qz, cw);
 }
 // The 12-row linearisation array (u, grad u at every point) interleaves its rows in pairs, so that a lane of the
-// vmult kernel fetches two rows with one 16-byte load (480 contiguous bytes per warp): row r of the point lives at
-//   (((g * 6 + r / 2) * 9 + 3 kx + kz) * 30 + 3 cw + ky) * 2 + (r & 1)  =  lin_index(cell, qx, qy, qz) + lin_row(r)
+// vmult kernel fetches two rows with one 16-byte load (480 contiguous bytes per warp), and is POINT-major inside a
+// decade: [g][point n = 3 kx + kz][row pair][30 lanes][2].  The six row pairs of one point are 2880 contiguous bytes:
+// one bulk copy of the TMA engine stages the rows of one point of all 10 cells (ns_r2.cuh).  Row r of the point lives at
+//   g * 3240 + n * 360 + (r / 2) * 60 + (3 cw + ky) * 2 + (r & 1)  =  lin_index(cell, qx, qy, qz) + lin_row(r)
+constexpr int kLinPairStride = 60, kLinPointStride = 360, kLinDecade = 3240;  // doubles
 __host__ __device__ inline size_t lin_index(uint32_t cell, int qx, int qy, int qz)
 {
   const size_t g = cell / kGroup;
   const int cw = (int)(cell % kGroup);
-  return (g * 6 * 270 + coef_slot(qx, qy, qz, cw)) * 2;
+  const size_t slot = coef_slot(qx, qy, qz, cw);  // n * 30 + lane
+  return g * kLinDecade + (slot / 30) * kLinPointStride + (slot % 30) * 2;
 }
-__host__ __device__ constexpr int lin_row(int r) { return (r >> 1) * 540 + (r & 1); }
+__host__ __device__ constexpr int lin_row(int r) { return (r >> 1) * kLinPairStride + (r & 1); }
 // cell-local (lexicographic, x fastest) index of the node with kernel indices (ix, iy, iz), n1 nodes per direction
 __host__ __device__ inline int kernel_node(int ix, int iy, int iz, int n1)
 {

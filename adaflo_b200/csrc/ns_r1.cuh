@@ -59,6 +59,9 @@ namespace ab200 {
 #ifndef AB_R1_SCHED  // 1: tickets handed out by a scheduler warp (see the kernel); 0: every worker draws its own
 #define AB_R1_SCHED 0
 #endif
+#ifndef AB_R1_PLAIN_TICKET  // ticket atomic that ptxas cannot aggregate (see the kernel)
+#define AB_R1_PLAIN_TICKET 1
+#endif
 #ifndef AB_R1_WARPS
 #define AB_R1_WARPS 11
 #endif
@@ -170,7 +173,7 @@ __device__ __forceinline__ void load_lin(double (&L)[12], const double *lin_lane
 {
   constexpr int pairs = MODE == MODE_NEWTON ? 6 : (MODE == MODE_PICARD ? 2 : 0);
 #pragma unroll
-  for (int r = 0; r < pairs; ++r) ld_pinned2(lin_lane + (size_t)r * 540 + n * 60, L[2 * r], L[2 * r + 1], pol);
+  for (int r = 0; r < pairs; ++r) ld_pinned2(lin_lane + r * kLinPairStride + n * kLinPointStride, L[2 * r], L[2 * r + 1], pol);
 }
 
 // refinement mask (hanging.cuh: three 3-bit groups indexed by mesh direction) re-indexed by kernel axis; the rotation
@@ -190,7 +193,11 @@ __device__ __forceinline__ uint32_t hn_to_kernel_axes(uint32_t m)
 template <int MODE, int GEOM, bool VAR>
 __device__ __forceinline__ void r1_prefetch(const NSArgs &A, const size_t g)
 {
-  if (MODE == MODE_NEWTON || MODE == MODE_PICARD) l2_prefetch(A.lin + g * (12 * 270), (MODE == MODE_NEWTON ? 12 : 4) * 270 * 8);
+  if (MODE == MODE_NEWTON) l2_prefetch(A.lin + g * kLinDecade, kLinDecade * 8);
+  if (MODE == MODE_PICARD) {  // rows 0-3 = the first two row pairs of every point
+#pragma unroll
+    for (int n = 0; n < 9; ++n) l2_prefetch(A.lin + g * kLinDecade + n * kLinPointStride, 2 * kLinPairStride * 8);
+  }
   if (VAR) {
     if (MODE != MODE_STOKES) l2_prefetch(A.rho + g * 270, 270 * 8);
     if (MODE != MODE_STOKES) l2_prefetch(A.damp + g * 270, 270 * 8);
@@ -223,7 +230,7 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   // instead -- at the start of phase A, B or C -- was measured 5-30 % slower: the data is evicted before use.)
 #if AB_R1_PFLANE
   if (MODE == MODE_NEWTON) {
-    const char *blk = reinterpret_cast<const char *>(A.lin + g * (12 * 270));
+    const char *blk = reinterpret_cast<const char *>(A.lin + g * kLinDecade);
 #pragma unroll
     for (int i = 0; i < 7; ++i)
       if (lane + 30 * i < 203) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + (size_t)(lane + 30 * i) * 128));  // 30 active lanes
@@ -233,7 +240,7 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   if (lane == 0) r1_prefetch<MODE, GEOM, VAR>(A, g);
 #endif
 
-  const double *lin_lane = A.lin + g * (12 * 270) + 2 * lane;
+  const double *lin_lane = A.lin + g * kLinDecade + 2 * lane;
   Geometry<GEOM> G;  // table row of the cell (two dependent loads): issue before the gather
   G.init_blk(A, cell);
   const HnInfo hn(hn_to_kernel_axes((HANGING && A.hn_u) ? __ldg(A.hn_u + cell) : 0u));
@@ -756,7 +763,13 @@ __global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
   }
 #else
   double *warp_smem = smem + warp * kR1WarpSmem;
-  // two tickets are held (current and next decade), the third is drawn while the current decade is processed
+  // two tickets are held (current and next decade), the third is drawn while the current decade is processed.
+  // ptxas turns an atomic on a provably warp-uniform address into a warp-aggregated one and shuffles -- i.e. waits for --
+  // its result at once (5 % of the stall samples of profiles/r1_g sat on that shuffle): the address is therefore offset by
+  // a zero read from shared memory, which the compiler cannot see through, and the result is consumed after the decade.
+  __shared__ unsigned opaque_zero[32];  // indexed by warp: a block-uniform address would make the loaded value provably uniform
+  if (threadIdx.x < 32) opaque_zero[threadIdx.x] = 0;
+  __syncthreads();
   unsigned i = 0, i_n1 = 0;
   if (lane == 0) {
     i = atomicAdd(A.work_counter, 1u);
@@ -766,7 +779,15 @@ __global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
   i_n1 = __shfl_sync(0xffffffffu, i_n1, 0);
   while (i < n_dec) {
     unsigned i_n2 = 0;
+#if AB_R1_PLAIN_TICKET
+    if (lane == 0) {
+      unsigned z;
+      asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(z) : "r"((unsigned)__cvta_generic_to_shared(opaque_zero + warp)) : "memory");
+      asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(i_n2) : "l"(A.work_counter + z) : "memory");
+    }
+#else
     if (lane == 0) i_n2 = atomicAdd(A.work_counter, 1u);
+#endif
     r1_decade<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>(A, A.decade_begin + i, warp_smem, lane);
     __syncwarp();
     i = i_n1;

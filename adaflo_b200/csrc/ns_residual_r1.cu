@@ -195,7 +195,7 @@ __device__ __forceinline__ void r1_residual_decade(const NSArgs &A, const size_t
   // ---------------------------------------------------------------- phase B
   const double wt = (t == 1) ? W[1] : W[0];
   double dg0_sum = 0;
-  double *lin_lane = A.lin ? A.lin + g * (12 * 270) + 2 * lane : nullptr;
+  double *lin_lane = A.lin ? A.lin + g * kLinDecade + 2 * lane : nullptr;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {  // unrolled: no loop-carried register constraints (ns_r1.cuh)
     const double wj = (j == 1) ? W[1] : W[0];
@@ -254,17 +254,17 @@ __device__ __forceinline__ void r1_residual_decade(const NSArgs &A, const size_t
           conv[d] = A.gamma * u[d] + hist[d][qz] + A.tau1 * res;  // :727-732, :783-790
         }
         if (lin_lane) {  // linearized_velocities (:791-798): rows u_d, then d u_d / d x_e (Newton) or the divergence (Picard)
-          double *l = lin_lane + (3 * j + qz) * 60;
+          double *l = lin_lane + (3 * j + qz) * kLinPointStride;
           if (newton) {
             st_pair(l, u[0], u[1]);
-            st_pair(l + 540, u[2], gr[0][0]);
-            st_pair(l + 2 * 540, gr[0][1], gr[0][2]);
-            st_pair(l + 3 * 540, gr[1][0], gr[1][1]);
-            st_pair(l + 4 * 540, gr[1][2], gr[2][0]);
-            st_pair(l + 5 * 540, gr[2][1], gr[2][2]);
+            st_pair(l + kLinPairStride, u[2], gr[0][0]);
+            st_pair(l + 2 * kLinPairStride, gr[0][1], gr[0][2]);
+            st_pair(l + 3 * kLinPairStride, gr[1][0], gr[1][1]);
+            st_pair(l + 4 * kLinPairStride, gr[1][2], gr[2][0]);
+            st_pair(l + 5 * kLinPairStride, gr[2][1], gr[2][2]);
           } else {
             st_pair(l, u[0], u[1]);
-            st_pair(l + 540, u[2], div);
+            st_pair(l + kLinPairStride, u[2], div);
           }
         }
         const double rho = VAR ? __ldg(A.rho + g * 270 + slot) : A.rho0;
