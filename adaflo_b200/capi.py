@@ -62,6 +62,25 @@ class TimeWeights(C.Structure):
                 ("tau1", C.c_double), ("extrapolate_old", C.c_double), ("extrapolate_old_old", C.c_double)]
 
 
+class SolverControlABI(C.Structure):
+    """adaflo_b200_solver_control"""
+    _fields_ = [("max_iter", C.c_int), ("abs_tol", C.c_double), ("rel_tol", C.c_double), ("last_step", C.c_int),
+                ("initial_value", C.c_double), ("last_value", C.c_double), ("history", C.POINTER(C.c_double)), ("history_capacity", C.c_int),
+                ("history_size", C.c_int)]
+
+
+class OperatorRef(C.Structure):
+    """adaflo_b200_operator_ref: a library operator as the user data of adaflo_b200_apply_operator"""
+    _fields_ = [("kind", C.c_int), ("handle", C.c_void_p), ("flag", C.c_int), ("inv_diag", C.c_void_p), ("n", C.c_uint64),
+                ("n_blocks", C.c_int)]
+
+
+# int (*adaflo_b200_apply_fn)(void *user, double *const *dst, const double *const *src)
+APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p))
+OP_NS_VMULT, OP_NS_VELOCITY, OP_NS_PRESSURE_POISSON, OP_NS_PRESSURE_MASS, OP_LS_ADVECT, OP_LS_NORMAL, OP_LS_CURVATURE, OP_LS_REINIT, OP_JACOBI, \
+    OP_LS_NORMAL_SCALAR = range(10)
+ERR_NO_CONVERGENCE = 6
+
 INCOMPRESSIBLE, INCOMPRESSIBLE_STATIONARY, STOKES = 0, 1, 2
 NEWTON, PICARD, SEMI_IMPLICIT, EXPLICIT, PROJECTION = 0, 1, 2, 3, 4
 FE_Q, FE_Q_DG0, FE_Q_ISO_Q1 = 0, 1, 2
@@ -73,7 +92,7 @@ SYMBOLS = [
     "adaflo_b200_last_error", "adaflo_b200_version",
     "adaflo_b200_ctx_create", "adaflo_b200_ctx_destroy", "adaflo_b200_ctx_set_stream", "adaflo_b200_ctx_synchronize",
     "adaflo_b200_comm_unique_id", "adaflo_b200_ctx_init_comm",
-    "adaflo_b200_mf_create", "adaflo_b200_mf_destroy", "adaflo_b200_mf_vector_size",
+    "adaflo_b200_mf_create", "adaflo_b200_mf_destroy", "adaflo_b200_mf_vector_size", "adaflo_b200_mf_space_info",
     "adaflo_b200_mf_update_ghost_values", "adaflo_b200_mf_compress_add",
     "adaflo_b200_ns_create", "adaflo_b200_ns_destroy", "adaflo_b200_ns_set_flow_params",
     "adaflo_b200_ns_set_time_weights", "adaflo_b200_ns_set_old_solutions",
@@ -84,7 +103,9 @@ SYMBOLS = [
     "adaflo_b200_ns_apply_pressure_average_projection", "adaflo_b200_ns_apply_pressure_shift",
     "adaflo_b200_ns_coefficient_ptr", "adaflo_b200_ns_set_coefficient_canonical", "adaflo_b200_ns_get_coefficient_canonical",
     "adaflo_b200_ns_nullspace", "adaflo_b200_ns_get_matvec_statistics",
-    "adaflo_b200_ns_vmult_host", "adaflo_b200_ns_set_kernel_timing", "adaflo_b200_ns_get_kernel_timing",
+    "adaflo_b200_ns_vmult_host", "adaflo_b200_ns_velocity_vmult_host", "adaflo_b200_ns_pressure_poisson_vmult_host",
+    "adaflo_b200_ns_pressure_mass_vmult_host", "adaflo_b200_ns_pressure_convdiff_vmult_host", "adaflo_b200_ns_divergence_vmult_add_host",
+    "adaflo_b200_ns_set_kernel_timing", "adaflo_b200_ns_get_kernel_timing",
     "adaflo_b200_kernel_launch_count",
     "adaflo_b200_ls_create", "adaflo_b200_ls_destroy", "adaflo_b200_ls_set_time", "adaflo_b200_ls_set_diagonal",
     "adaflo_b200_ls_mass_diagonal", "adaflo_b200_ls_advance_concentration_vmult", "adaflo_b200_ls_advance_concentration_rhs",
@@ -96,6 +117,9 @@ SYMBOLS = [
     "adaflo_b200_vec_set", "adaflo_b200_vec_axpy", "adaflo_b200_vec_sadd", "adaflo_b200_vec_scale",
     "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_multi_axpy", "adaflo_b200_vec_add_and_dot",
     "adaflo_b200_jacobi_reinit", "adaflo_b200_jacobi_vmult",
+    "adaflo_b200_solve_cg", "adaflo_b200_solve_bicgstab", "adaflo_b200_solve_gmres", "adaflo_b200_apply_operator",
+    "adaflo_b200_ls_projection_vmult", "adaflo_b200_ls_compute_normal", "adaflo_b200_ls_compute_curvature", "adaflo_b200_ls_reinitialize",
+    "adaflo_b200_ls_advance_concentration",
 ]
 
 _lib = None
@@ -124,6 +148,7 @@ def load():
         "adaflo_b200_mf_create": [vp, C.POINTER(MFDesc), C.POINTER(vp)],
         "adaflo_b200_mf_destroy": [vp],
         "adaflo_b200_mf_vector_size": [vp, i32, C.POINTER(u64), C.POINTER(u64)],
+        "adaflo_b200_mf_space_info": [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         "adaflo_b200_mf_update_ghost_values": [vp, i32, vp],
         "adaflo_b200_mf_compress_add": [vp, i32, vp],
         "adaflo_b200_ns_create": [vp, vp, C.POINTER(FlowParams), i32, i32, i32, i32, i32, C.POINTER(vp)],
@@ -149,6 +174,11 @@ def load():
         "adaflo_b200_ns_nullspace": [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(dbl)],
         "adaflo_b200_ns_get_matvec_statistics": [vp, C.POINTER(u64), C.POINTER(dbl)],
         "adaflo_b200_ns_vmult_host": [vp, vp, vp, vp, vp],
+        "adaflo_b200_ns_velocity_vmult_host": [vp, vp, vp],
+        "adaflo_b200_ns_pressure_poisson_vmult_host": [vp, vp, vp],
+        "adaflo_b200_ns_pressure_mass_vmult_host": [vp, vp, vp],
+        "adaflo_b200_ns_pressure_convdiff_vmult_host": [vp, vp, vp],
+        "adaflo_b200_ns_divergence_vmult_add_host": [vp, vp, vp, i32],
         "adaflo_b200_ns_set_kernel_timing": [vp, i32],
         "adaflo_b200_ns_get_kernel_timing": [vp, C.POINTER(u64), C.POINTER(dbl)],
         "adaflo_b200_ls_create": [vp, vp, C.POINTER(LSParams), i32, i32, i32, vp, C.POINTER(vp)],
@@ -182,6 +212,18 @@ def load():
         "adaflo_b200_vec_add_and_dot": [vp, vp, dbl, vp, vp, u64, C.POINTER(dbl)],
         "adaflo_b200_jacobi_reinit": [vp, vp, vp, u64],
         "adaflo_b200_jacobi_vmult": [vp, vp, vp, vp, u64, i32],
+        "adaflo_b200_solve_cg": [vp, i32, C.POINTER(u64), C.POINTER(u64), APPLY_FN, vp, APPLY_FN, vp, C.POINTER(vp), C.POINTER(vp),
+                                 C.POINTER(SolverControlABI)],
+        "adaflo_b200_solve_bicgstab": [vp, i32, C.POINTER(u64), C.POINTER(u64), APPLY_FN, vp, APPLY_FN, vp, C.POINTER(vp), C.POINTER(vp),
+                                       C.POINTER(SolverControlABI)],
+        "adaflo_b200_solve_gmres": [vp, i32, C.POINTER(u64), C.POINTER(u64), APPLY_FN, vp, APPLY_FN, vp, C.POINTER(vp), C.POINTER(vp), i32,
+                                    C.POINTER(SolverControlABI)],
+        "adaflo_b200_apply_operator": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "adaflo_b200_ls_projection_vmult": [vp, vp, vp],
+        "adaflo_b200_ls_compute_normal": [vp, C.POINTER(vp), vp, i32, C.POINTER(i32)],
+        "adaflo_b200_ls_compute_curvature": [vp, vp, vp, C.POINTER(vp), i32, i32, C.POINTER(i32)],
+        "adaflo_b200_ls_reinitialize": [vp, vp, C.POINTER(vp), dbl, C.c_uint, C.c_uint, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)],
+        "adaflo_b200_ls_advance_concentration": [vp, vp, vp, vp, vp, dbl, C.POINTER(dbl), C.POINTER(i32)],
     }
     for name, args in sig.items():
         if os.environ.get("ADAFLO_B200_LIB") and not hasattr(lib, name):

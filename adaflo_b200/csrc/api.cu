@@ -191,6 +191,7 @@ int adaflo_b200_ctx_destroy(adaflo_b200_ctx_t ctx)
 {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
+  solver_pool_release(ctx);
   comm_destroy(ctx);
   free_dev(ctx->red_dev);
   if (ctx->red_host) cudaFreeHost(ctx->red_host);
@@ -439,6 +440,15 @@ int adaflo_b200_mf_vector_size(adaflo_b200_mf_t mf, int space, uint64_t *n_owned
   if (!mf || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "mf_vector_size: bad argument");
   if (n_owned) *n_owned = mf->spaces[space].n_owned_entries();
   if (n_local) *n_local = mf->spaces[space].n_local_entries();
+  return 0;
+}
+
+int adaflo_b200_mf_space_info(adaflo_b200_mf_t mf, int space, int *fe_kind, int *degree, int *n_components)
+{
+  if (!mf || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "mf_space_info: bad argument");
+  if (fe_kind) *fe_kind = mf->spaces[space].fe_kind;
+  if (degree) *degree = mf->spaces[space].degree;
+  if (n_components) *n_components = mf->spaces[space].n_comp;
   return 0;
 }
 
@@ -1091,6 +1101,73 @@ int adaflo_b200_ns_get_kernel_timing(adaflo_b200_ns_t ns, uint64_t *launches, do
 }
 
 uint64_t adaflo_b200_kernel_launch_count(void) { return (uint64_t)g_launches; }
+
+// Host-pointer entries of the sub-block operators: what the reference's Trilinos wrappers do around them
+// (VelocityMatrix::Multiply navier_stokes_preconditioner.cc:332-343, PressurePoissonMatrix::Multiply :421-433: memcpy the
+// Epetra vector into a distributed vector, vmult, memcpy back).  Owned entries only; staging vectors are reused.
+namespace {
+enum { HOST_VELOCITY = 0, HOST_POISSON = 1, HOST_MASS = 2, HOST_CONVDIFF = 3 };
+int ensure_stage(adaflo_b200_ns_t ns)
+{
+  const Space &su = ns->mf->spaces[ns->dof_u], &sp = ns->mf->spaces[ns->dof_p];
+  for (int i = 0; i < 2; ++i) {
+    if (!ns->stage_u[i]) AB_CUDA(cudaMalloc((void **)&ns->stage_u[i], su.n_local_entries() * sizeof(double)));
+    if (!ns->stage_p[i]) AB_CUDA(cudaMalloc((void **)&ns->stage_p[i], sp.n_local_entries() * sizeof(double)));
+  }
+  return 0;
+}
+int sub_operator_host(adaflo_b200_ns_t ns, int which, double *dst_host, const double *src_host)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "host sub-operator: operator not initialised");
+  if (!dst_host || !src_host) return fail(ADAFLO_B200_ERR_ARG, "host sub-operator: null vector");
+  AB_CHECK(ensure_stage(ns));
+  cudaStream_t s = ns->ctx->stream;
+  const Space &sp = ns->mf->spaces[which == HOST_VELOCITY ? ns->dof_u : ns->dof_p];
+  double *src = which == HOST_VELOCITY ? ns->stage_u[0] : ns->stage_p[0], *dst = which == HOST_VELOCITY ? ns->stage_u[1] : ns->stage_p[1];
+  AB_CUDA(cudaMemcpyAsync(src, src_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+  switch (which) {
+    case HOST_VELOCITY: AB_CHECK(adaflo_b200_ns_velocity_vmult(ns, dst, src)); break;
+    case HOST_POISSON: AB_CHECK(adaflo_b200_ns_pressure_poisson_vmult(ns, dst, src)); break;
+    case HOST_MASS: AB_CHECK(adaflo_b200_ns_pressure_mass_vmult(ns, dst, src)); break;
+    default: AB_CHECK(adaflo_b200_ns_pressure_convdiff_vmult(ns, dst, src)); break;
+  }
+  AB_CUDA(cudaMemcpyAsync(dst_host, dst, sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  AB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+}  // namespace
+
+int adaflo_b200_ns_velocity_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, const double *src_u_host)
+{
+  return sub_operator_host(ns, HOST_VELOCITY, dst_u_host, src_u_host);
+}
+int adaflo_b200_ns_pressure_poisson_vmult_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_p_host)
+{
+  return sub_operator_host(ns, HOST_POISSON, dst_p_host, src_p_host);
+}
+int adaflo_b200_ns_pressure_mass_vmult_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_p_host)
+{
+  return sub_operator_host(ns, HOST_MASS, dst_p_host, src_p_host);
+}
+int adaflo_b200_ns_pressure_convdiff_vmult_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_p_host)
+{
+  return sub_operator_host(ns, HOST_CONVDIFF, dst_p_host, src_p_host);
+}
+int adaflo_b200_ns_divergence_vmult_add_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_u_host, int weight_by_viscosity)
+{
+  if (!ns) return fail(ADAFLO_B200_ERR_STATE, "divergence_vmult_add_host: operator not initialised");
+  if (!dst_p_host || !src_u_host) return fail(ADAFLO_B200_ERR_ARG, "divergence_vmult_add_host: null vector");
+  AB_CHECK(ensure_stage(ns));
+  cudaStream_t s = ns->ctx->stream;
+  const Space &su = ns->mf->spaces[ns->dof_u], &sp = ns->mf->spaces[ns->dof_p];
+  AB_CUDA(cudaMemcpyAsync(ns->stage_u[0], src_u_host, su.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+  AB_CUDA(cudaMemsetAsync(ns->stage_p[1], 0, sp.n_local_entries() * sizeof(double), s));
+  AB_CUDA(cudaMemcpyAsync(ns->stage_p[1], dst_p_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));  // "add": dst is an input
+  AB_CHECK(adaflo_b200_ns_divergence_vmult_add(ns, ns->stage_p[1], ns->stage_u[0], weight_by_viscosity));
+  AB_CUDA(cudaMemcpyAsync(dst_p_host, ns->stage_p[1], sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  AB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
 
 int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *dst_p_host, const double *src_u_host,
                               const double *src_p_host)

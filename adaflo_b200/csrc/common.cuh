@@ -228,6 +228,9 @@ struct NSArgs {
 enum { MODE_STOKES = 0, MODE_NEWTON = 1, MODE_PICARD = 2, MODE_NOCONV = 3 };
 
 int upload_shape_tables(cudaStream_t s);
+void solver_pool_release(adaflo_b200_ctx_t ctx);  // solvers.cu: work vectors of the Krylov drivers
+double *pool_get(adaflo_b200_ctx_t ctx, size_t doubles);  // per-context pool of device work vectors (null: out of memory)
+void pool_put(adaflo_b200_ctx_t ctx, double *p);
 
 // launchers (one translation unit per geometry type keeps compile times down)
 int launch_ns_vmult_cartesian(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);

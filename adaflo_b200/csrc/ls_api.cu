@@ -2,6 +2,7 @@
 // operator-level logic of LevelSetOKZSolver{AdvanceConcentration, ComputeNormal, ComputeCurvature,
 // Reinitialization}::*_vmult / local_*_rhs around the sub-cell kernels of ls_ops.cu.
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <new>
 #include <vector>
@@ -17,6 +18,7 @@ struct adaflo_b200_ls_s {
   double *cell_diameters;      // device
   double *conv, *normal_q;     // device [cell][3][8 points][sub-cell]
   const double *diag;          // not owned
+  double *inv_diag;            // owned: DiagonalPreconditioner::inverse_diagonal_vector of diag (CG / BiCGStab preconditioner)
   uint32_t *last_cell;         // device [n_dofs]: last cell of the cell loop containing the dof (Heaviside)
   signed char *cell_state;     // device [n_cells]
   // hanging-dof extension of the level-set space (see LsHanging), all device pointers
@@ -58,6 +60,16 @@ LSArgs base_args(adaflo_b200_ls_t ls)
   a.dtau_inv = std::max(0.95 / (1. / (dim * dim) * ls->prm.minimal_edge_length / ls->prm.concentration_subdivisions), 1. / (5. * ls->step_size));
   a.n_comp = 1;
   return a;
+}
+
+int ensure_pointdata(adaflo_b200_ls_t ls, double **which)
+{
+  if (*which) return 0;
+  const int S = ls->prm.concentration_subdivisions;
+  const size_t npd = (size_t)ls->mf->n_cells * S * S * S * 24;
+  AB_CUDA(cudaMalloc((void **)which, std::max<size_t>(1, npd) * sizeof(double)));
+  AB_CUDA(cudaMemsetAsync(*which, 0, npd * sizeof(double), ls->ctx->stream));
+  return 0;
 }
 
 int finish_vmult(adaflo_b200_ls_t ls, double *dst, const double *src)
@@ -144,13 +156,14 @@ int adaflo_b200_ls_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   ls->weight_old_old = 0;
   ls->step_size = 1;
   ls->diag = nullptr;
+  ls->inv_diag = nullptr;
   const size_t npd = (size_t)mf->n_cells * S * S * S * 24;
   AB_CUDA(cudaMalloc((void **)&ls->cell_diameters, std::max<size_t>(1, mf->n_cells) * sizeof(double)));
   AB_CUDA(cudaMemcpyAsync(ls->cell_diameters, cell_diameters_host, mf->n_cells * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  AB_CUDA(cudaMalloc((void **)&ls->conv, std::max<size_t>(1, npd) * sizeof(double)));
-  AB_CUDA(cudaMalloc((void **)&ls->normal_q, std::max<size_t>(1, npd) * sizeof(double)));
-  AB_CUDA(cudaMemsetAsync(ls->conv, 0, npd * sizeof(double), ctx->stream));
-  AB_CUDA(cudaMemsetAsync(ls->normal_q, 0, npd * sizeof(double), ctx->stream));
+  (void)npd;  // the per-point streams (24 B per point each) are allocated on first use: the four level-set classes of the
+              // reference each own a handle (include/adaflo_b200/level_set_okz.h) and most never touch them
+  ls->conv = nullptr;
+  ls->normal_q = nullptr;
   {  // Heaviside bookkeeping: the reference loops over cells and the last writer of a shared dof wins
     const size_t N = sp.nodes_per_cell, n_dofs = sp.n_local_entries();
     std::vector<uint32_t> cells((size_t)mf->n_cells * N), masks;
@@ -230,6 +243,7 @@ int adaflo_b200_ls_destroy(adaflo_b200_ls_t ls)
   cudaSetDevice(ls->ctx->device);
   cudaStreamSynchronize(ls->ctx->stream);
   cudaFree(ls->cell_diameters);
+  cudaFree(ls->inv_diag);
   cudaFree(ls->conv);
   cudaFree(ls->normal_q);
   cudaFree(ls->last_cell);
@@ -259,7 +273,10 @@ int adaflo_b200_ls_set_diagonal(adaflo_b200_ls_t ls, const double *diag)
 {
   if (!ls) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   ls->diag = diag;
-  return 0;
+  if (!diag) return 0;
+  const uint64_t n = ls->mf->spaces[ls->dof_ls].n_owned_entries();
+  if (!ls->inv_diag) AB_CUDA(cudaMalloc((void **)&ls->inv_diag, std::max<uint64_t>(1, n) * sizeof(double)));
+  return adaflo_b200_jacobi_reinit(ls->ctx, ls->inv_diag, diag, n);  // diagonal_preconditioner.cc:38-60
 }
 
 int adaflo_b200_ls_mass_diagonal(adaflo_b200_ls_t ls, double *diag)
@@ -280,6 +297,7 @@ int adaflo_b200_ls_advance_concentration_vmult(adaflo_b200_ls_t ls, double *dst,
   LSArgs a = base_args(ls);
   a.src[0] = src;
   a.dst[0] = dst;
+  AB_CHECK(ensure_pointdata(ls, &ls->conv));
   a.pointdata = ls->conv;
   AB_CHECK(launch_ls(a, LS_ADVECT, ls->ctx->stream));
   AB_CHECK(compress(ls, ls->dof_ls, dst));
@@ -297,6 +315,7 @@ int adaflo_b200_ls_advance_concentration_rhs(adaflo_b200_ls_t ls, double *rhs, c
   a.aux[1] = c_old_old;
   a.vel = vel;
   a.dst[0] = rhs;
+  AB_CHECK(ensure_pointdata(ls, &ls->conv));
   a.pointdata = ls->conv;
   {
     const double *in[3] = {c, c_old, c_old_old};
@@ -324,6 +343,21 @@ int adaflo_b200_ls_compute_normal_vmult(adaflo_b200_ls_t ls, double *const dst[3
   AB_CHECK(compress(ls, ls->dof_ls, 3, dst));
   for (int d = 0; d < 3; ++d) AB_CHECK(finish_vmult(ls, dst[d], src[d]));
   return 0;
+}
+
+int adaflo_b200_ls_projection_vmult(adaflo_b200_ls_t ls, double *dst, const double *src)
+{
+  if (!ls || !dst || !src) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(zero(ls, dst));
+  LSArgs a = base_args(ls);
+  a.src[0] = src;
+  a.dst[0] = dst;
+  a.n_comp = 1;
+  a.delta_scale = ls->prm.damping_scale_factor;
+  AB_CHECK(import_ghosts(ls, ls->dof_ls, src));
+  AB_CHECK(launch_ls(a, LS_DAMPED, ls->ctx->stream));
+  AB_CHECK(compress(ls, ls->dof_ls, dst));
+  return finish_vmult(ls, dst, src);
 }
 
 int adaflo_b200_ls_compute_normal_rhs(adaflo_b200_ls_t ls, double *const rhs[3], const double *level_set)
@@ -378,6 +412,7 @@ int adaflo_b200_ls_reinitialization_vmult(adaflo_b200_ls_t ls, double *dst, cons
   LSArgs a = base_args(ls);
   a.src[0] = src;
   a.dst[0] = dst;
+  AB_CHECK(ensure_pointdata(ls, &ls->normal_q));
   a.pointdata = ls->normal_q;
   AB_CHECK(import_ghosts(ls, ls->dof_ls, src));
   AB_CHECK(launch_ls(a, diffuse_only ? LS_REINIT_DIFFUSE : LS_REINIT, ls->ctx->stream));
@@ -395,6 +430,7 @@ int adaflo_b200_ls_reinitialization_rhs(adaflo_b200_ls_t ls, double *rhs, const 
   if (normal)
     for (int d = 0; d < 3; ++d) a.aux[d] = normal[d];
   a.dst[0] = rhs;
+  AB_CHECK(ensure_pointdata(ls, &ls->normal_q));
   a.pointdata = ls->normal_q;
   a.first_step = first_reinit_step;
   AB_CHECK(import_ghosts(ls, ls->dof_ls, solution));
@@ -498,9 +534,157 @@ int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_pt
 {
   if (!ls || !dev_ptr) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   const int S = ls->prm.concentration_subdivisions;
+  AB_CHECK(ensure_pointdata(ls, which == 0 ? &ls->conv : &ls->normal_q));
   *dev_ptr = which == 0 ? ls->conv : ls->normal_q;
   if (n) *n = (uint64_t)ls->mf->n_cells * S * S * S * 24;
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Solver-level routines of the level-set classes: right-hand side, Krylov solve with the diagonal
+// preconditioner, update -- the bodies of compute_normal / compute_curvature / reinitialize / advance_concentration with
+// the matrix-free operators in place of the assembled projection matrix + ILU (the matrix-free CG calls are still in
+// the reference as comments: compute_normal.cc:258-260, compute_curvature.cc:331).
+namespace {
+struct Work {  // pool vector, released on scope exit
+  adaflo_b200_ctx_t ctx;
+  double *p;
+  Work(adaflo_b200_ctx_t c, uint64_t n) : ctx(c), p(pool_get(c, n)) {}
+  ~Work() { if (p) pool_put(ctx, p); }
+  Work(const Work &) = delete;
+  Work &operator=(const Work &) = delete;
+};
+int ls_zero(adaflo_b200_ls_t ls, double *v) { return zero(ls, v); }
+int need_diag(adaflo_b200_ls_t ls, const char *who)
+{
+  if (!ls->diag || !ls->inv_diag) return fail(ADAFLO_B200_ERR_STATE, std::string(who) + ": the preconditioner diagonal has not been set (ls_set_diagonal)");
+  return 0;
+}
+}  // namespace
+
+int adaflo_b200_ls_compute_normal(adaflo_b200_ls_t ls, double *const normal[3], const double *level_set, int fast_computation, int *iterations)
+{
+  if (!ls || !normal || !level_set) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(need_diag(ls, "compute_normal"));
+  const Space &sp = ls->mf->spaces[ls->dof_ls];
+  const uint64_t n_owned = sp.n_owned_entries(), n_local = sp.n_local_entries();
+  Work r0(ls->ctx, n_local), r1(ls->ctx, n_local), r2(ls->ctx, n_local);
+  if (!r0.p || !r1.p || !r2.p) return fail(ADAFLO_B200_ERR_CUDA, "compute_normal: out of device memory");
+  double *rhs[3] = {r0.p, r1.p, r2.p};
+  for (int d = 0; d < 3; ++d) AB_CHECK(ls_zero(ls, rhs[d]));
+  AB_CHECK(adaflo_b200_ls_compute_normal_rhs(ls, rhs, level_set));
+  // compute_normal.cc:252-261: ReductionControl(4000, 1e-50, fast ? 1e-5 : 1e-7), SolverCG on the block vector
+  adaflo_b200_operator_ref A = {ADAFLO_B200_OP_LS_NORMAL, ls, 0, nullptr, 0, 3};
+  adaflo_b200_operator_ref P = {ADAFLO_B200_OP_JACOBI, ls->ctx, 0, ls->inv_diag, n_owned, 3};
+  adaflo_b200_solver_control c = {4000, 1e-50, fast_computation ? 1e-5 : 1e-7, 0, 0, 0, nullptr, 0, 0};
+  const uint64_t no[3] = {n_owned, n_owned, n_owned}, nl[3] = {n_local, n_local, n_local};
+  const int rc = adaflo_b200_solve_cg(ls->ctx, 3, no, nl, adaflo_b200_apply_operator, &A, adaflo_b200_apply_operator, &P, normal, rhs, &c);
+  if (iterations) *iterations = c.last_step;
+  AB_CHECK(rc);
+  for (int d = 0; d < 3; ++d) AB_CHECK(import_ghosts(ls, ls->dof_ls, normal[d]));  // update_ghost_values, :285
+  return 0;
+}
+
+int adaflo_b200_ls_compute_curvature(adaflo_b200_ls_t ls, double *curvature, const double *level_set, const double *const normal[3],
+                                     int curvature_correction, int projection_operator, int *iterations)
+{
+  if (!ls || !curvature || !level_set || !normal) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(need_diag(ls, "compute_curvature"));
+  const Space &sp = ls->mf->spaces[ls->dof_ls];
+  const uint64_t n_owned = sp.n_owned_entries(), n_local = sp.n_local_entries();
+  Work r(ls->ctx, n_local);
+  if (!r.p) return fail(ADAFLO_B200_ERR_CUDA, "compute_curvature: out of device memory");
+  AB_CHECK(ls_zero(ls, r.p));
+  AB_CHECK(adaflo_b200_ls_compute_curvature_rhs(ls, r.p, normal));
+  // compute_curvature.cc:326-334: ReductionControl(2000, 1e-50, 1e-8).  projection_operator 0: compute_curvature_vmult with
+  // diffusion (ComputeCurvatureMatrix); 1: the operator of the assembled projection_matrix the reference passes to the
+  // solver (mass + damping_scale_factor delta^2 Laplace = one block of compute_normal_vmult)
+  adaflo_b200_operator_ref A = {projection_operator ? ADAFLO_B200_OP_LS_NORMAL_SCALAR : ADAFLO_B200_OP_LS_CURVATURE, ls, 1, nullptr, 0, 1};
+  adaflo_b200_operator_ref P = {ADAFLO_B200_OP_JACOBI, ls->ctx, 0, ls->inv_diag, n_owned, 1};
+  adaflo_b200_solver_control c = {2000, 1e-50, 1e-8, 0, 0, 0, nullptr, 0, 0};
+  double *x[1] = {curvature};
+  const double *b[1] = {r.p};
+  const int rc = adaflo_b200_solve_cg(ls->ctx, 1, &n_owned, &n_local, adaflo_b200_apply_operator, &A, adaflo_b200_apply_operator, &P, x, b, &c);
+  if (iterations) *iterations = c.last_step;
+  AB_CHECK(rc);
+  if (curvature_correction) AB_CHECK(adaflo_b200_ls_curvature_correction(ls, curvature, level_set));  // :340-356
+  return import_ghosts(ls, ls->dof_ls, curvature);
+}
+
+int adaflo_b200_ls_reinitialize(adaflo_b200_ls_t ls, double *solution, double *const normal[3], double dt, unsigned stab_steps, unsigned diff_steps,
+                                const double *last_concentration_range, int *iterations, int *n_steps_done)
+{
+  if (!ls || !solution || !normal) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(need_diag(ls, "reinitialize"));
+  const Space &sp = ls->mf->spaces[ls->dof_ls];
+  const uint64_t n_owned = sp.n_owned_entries(), n_local = sp.n_local_entries();
+  Work rhs(ls->ctx, n_local), inc(ls->ctx, n_local);
+  if (!rhs.p || !inc.p) return fail(ADAFLO_B200_ERR_CUDA, "reinitialize: out of device memory");
+  const double step_size_before = ls->step_size;
+  ls->step_size = dt;  // time_stepping.set_desired_time_step(dt), reinitialization.cc:263
+  unsigned actual_diff_steps = diff_steps;
+  if (last_concentration_range && (last_concentration_range[0] < -1.02 || last_concentration_range[1] > 1.02)) actual_diff_steps += 3;  // :281-283
+  adaflo_b200_operator_ref P = {ADAFLO_B200_OP_JACOBI, ls->ctx, 0, ls->inv_diag, n_owned, 1};
+  int done = 0, rc = 0;
+  for (unsigned tau = 0; tau < actual_diff_steps + stab_steps; ++tau) {
+    const bool diffuse = tau < actual_diff_steps, first_reinit_step = (tau == actual_diff_steps);
+    if (first_reinit_step) {
+      rc = adaflo_b200_ls_compute_normal(ls, normal, solution, 1, nullptr);  // compute_normal(true), :292-293
+      if (rc) break;
+    }
+    if ((rc = ls_zero(ls, rhs.p))) break;
+    if ((rc = adaflo_b200_ls_reinitialization_rhs(ls, rhs.p, solution, diffuse ? nullptr : normal, diffuse ? 1 : 0, first_reinit_step ? 1 : 0))) break;
+    if ((rc = ls_zero(ls, inc.p))) break;
+    adaflo_b200_operator_ref A = {ADAFLO_B200_OP_LS_REINIT, ls, diffuse ? 1 : 0, nullptr, 0, 1};
+    adaflo_b200_solver_control c = {2000, 1e-50, 1e-6, 0, 0, 0, nullptr, 0, 0};  // :331-336
+    double *x[1] = {inc.p};
+    const double *b[1] = {rhs.p};
+    rc = adaflo_b200_solve_cg(ls->ctx, 1, &n_owned, &n_local, adaflo_b200_apply_operator, &A, adaflo_b200_apply_operator, &P, x, b, &c);
+    if (iterations) iterations[done] = c.last_step;
+    ++done;
+    if (rc) break;
+    if ((rc = adaflo_b200_vec_axpy(ls->ctx, solution, 1.0, inc.p, n_owned))) break;  // solution += increment
+    double nn = 0;
+    if ((rc = adaflo_b200_vec_dot(ls->ctx, inc.p, inc.p, n_owned, &nn))) break;
+    if (std::sqrt(nn) < 1e-6) break;  // :352-354
+  }
+  ls->step_size = step_size_before;
+  if (n_steps_done) *n_steps_done = done;
+  AB_CHECK(rc);
+  return import_ghosts(ls, ls->dof_ls, solution);
+}
+
+int adaflo_b200_ls_advance_concentration(adaflo_b200_ls_t ls, double *solution, const double *solution_old, const double *solution_old_old,
+                                         const double *vel_solution, double tol_nl_iteration, double *initial_residual, int *iterations)
+{
+  if (!ls || !solution || !solution_old || !solution_old_old || !vel_solution) return fail(ADAFLO_B200_ERR_ARG, "null argument");
+  AB_CHECK(need_diag(ls, "advance_concentration"));
+  const Space &sp = ls->mf->spaces[ls->dof_ls];
+  const uint64_t n_owned = sp.n_owned_entries(), n_local = sp.n_local_entries();
+  Work rhs(ls->ctx, n_local), inc(ls->ctx, n_local);
+  if (!rhs.p || !inc.p) return fail(ADAFLO_B200_ERR_CUDA, "advance_concentration: out of device memory");
+  AB_CHECK(ls_zero(ls, rhs.p));
+  AB_CHECK(adaflo_b200_ls_advance_concentration_rhs(ls, rhs.p, vel_solution, solution, solution_old, solution_old_old));
+  AB_CHECK(ls_zero(ls, inc.p));
+  adaflo_b200_operator_ref A = {ADAFLO_B200_OP_LS_ADVECT, ls, 0, nullptr, 0, 1};
+  adaflo_b200_operator_ref P = {ADAFLO_B200_OP_JACOBI, ls->ctx, 0, ls->inv_diag, n_owned, 1};
+  double *x[1] = {inc.p};
+  const double *b[1] = {rhs.p};
+  // advance_concentration.cc:626-652: BiCGStab(30, 0.05 tol_nl_iteration, 1e-8), GMRES(3000) if it does not converge
+  adaflo_b200_solver_control c = {30, 0.05 * tol_nl_iteration, 1e-8, 0, 0, 0, nullptr, 0, 0};
+  int rc = adaflo_b200_solve_bicgstab(ls->ctx, 1, &n_owned, &n_local, adaflo_b200_apply_operator, &A, adaflo_b200_apply_operator, &P, x, b, &c);
+  int n_it = c.last_step;
+  const double r0 = c.initial_value;
+  if (rc == ADAFLO_B200_ERR_NO_CONVERGENCE) {
+    adaflo_b200_solver_control g = {3000, 0.05 * tol_nl_iteration, 1e-8, 0, 0, 0, nullptr, 0, 0};
+    rc = adaflo_b200_solve_gmres(ls->ctx, 1, &n_owned, &n_local, adaflo_b200_apply_operator, &A, adaflo_b200_apply_operator, &P, x, b, 28, &g);
+    n_it = 30 + g.last_step;
+  }
+  if (initial_residual) *initial_residual = r0;
+  if (iterations) *iterations = n_it;
+  AB_CHECK(rc);
+  AB_CHECK(adaflo_b200_vec_axpy(ls->ctx, solution, 1.0, inc.p, n_owned));
+  return import_ghosts(ls, ls->dof_ls, solution);
 }
 
 }  // extern "C"

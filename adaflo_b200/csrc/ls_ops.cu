@@ -799,6 +799,12 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
         constexpr bool kGrad = (OP == LS_DAMPED || OP == LS_REINIT || OP == LS_REINIT_DIFFUSE || OP == LS_REINIT_RHS ||
                                 OP == LS_REINIT_RHS_DIFFUSE);
         constexpr bool kVal = (OP != LS_REINIT_RHS && OP != LS_REINIT_RHS_DIFFUSE);
+        double vold[8], voo[8];  // old level sets at the points (advection right-hand side)
+        if (OP == LS_ADVECT_RHS) {
+          double d0[4], d1[4], d2[4];
+          lsq::eval(a0, vold, d0, d1, d2);
+          lsq::eval(a1, voo, d0, d1, d2);
+        }
         double *pd = pdc ? pdc + sub : nullptr;
         const double *pq = pds + sub;  // staged copy (advection / reinitialisation vmult)
 #pragma unroll
@@ -897,8 +903,11 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
 #pragma unroll
             for (int e = 0; e < 3; ++e) tg[e] = -D * g[e];
           } else if (OP == LS_ADVECT_RHS) {
-            const double vo = interp(a0), voo = interp(a1);
-            t = -(A.gamma * vp + uq[p][0] * g[0] + uq[p][1] * g[1] + uq[p][2] * g[2] + A.w_old * vo + A.w_oo * voo);
+            // BDF sum of the three level sets: the old values are evaluated with the same arithmetic as the new one and
+            // the products are rounded individually (no fma contraction), so that equal fields cancel exactly like in the
+            // reference -- the log's "advect [0/0]" of a step with zero velocity is an exact zero
+            const double bdf = __dadd_rn(__dadd_rn(__dmul_rn(A.gamma, vp), __dmul_rn(A.w_old, vold[p])), __dmul_rn(A.w_oo, voo[p]));
+            t = -(bdf + (uq[p][0] * g[0] + uq[p][1] * g[1] + uq[p][2] * g[2]));
 #pragma unroll
             for (int e = 0; e < 3; ++e) pd[(8 * e + p) * S3] = uq[p][e];  // evaluated_convection, :389
           }

@@ -411,6 +411,31 @@ class NavierStokesMatrix:
             return C.c_void_p(t.data_ptr()) if isinstance(t, torch.Tensor) else _np(t)
         check(self.lib.adaflo_b200_ns_vmult_host(self.h, hp(dst_u), hp(dst_p), hp(src_u), hp(src_p)))
 
+    # host-pointer entries of the sub-block operators (the Epetra-side wrappers of navier_stokes_preconditioner.cc)
+    def velocity_vmult_host(self, dst_u, src_u):
+        self._require()
+        check(self.lib.adaflo_b200_ns_velocity_vmult_host(self.h, _host_ptr(dst_u), _host_ptr(src_u)))
+
+    def pressure_poisson_vmult_host(self, dst_p, src_p):
+        self._require()
+        check(self.lib.adaflo_b200_ns_pressure_poisson_vmult_host(self.h, _host_ptr(dst_p), _host_ptr(src_p)))
+
+    def pressure_mass_vmult_host(self, dst_p, src_p):
+        self._require()
+        check(self.lib.adaflo_b200_ns_pressure_mass_vmult_host(self.h, _host_ptr(dst_p), _host_ptr(src_p)))
+
+    def pressure_convdiff_vmult_host(self, dst_p, src_p):
+        self._require()
+        check(self.lib.adaflo_b200_ns_pressure_convdiff_vmult_host(self.h, _host_ptr(dst_p), _host_ptr(src_p)))
+
+    def divergence_vmult_add_host(self, dst_p, src_u, weight_by_viscosity=False):
+        self._require()
+        check(self.lib.adaflo_b200_ns_divergence_vmult_add_host(self.h, _host_ptr(dst_p), _host_ptr(src_u), int(weight_by_viscosity)))
+
+
+def _host_ptr(t):
+    return C.c_void_p(t.data_ptr()) if isinstance(t, torch.Tensor) else _np(t)
+
 
 class NavierStokesMatrix2D:
     """NavierStokesMatrix<2> for Q2/Q1 on Cartesian box meshes (adaflo_b200.mesh.BoxMesh2D).
@@ -581,6 +606,40 @@ class LevelSetOperators:
 
     def compute_heaviside(self, heaviside, level_set):
         check(self.lib.adaflo_b200_ls_compute_heaviside(self.h, _ptr(heaviside), _ptr(level_set)))
+
+    # ---- solver-level routines (the bodies of compute_normal / compute_curvature / reinitialize / advance_concentration
+    # of the reference's level-set classes, matrix-free; csrc/ls_api.cu)
+    def projection_vmult(self, dst, src):
+        """mass + damping_scale_factor delta^2 Laplace on one field: the reference's assembled projection_matrix"""
+        check(self.lib.adaflo_b200_ls_projection_vmult(self.h, _ptr(dst), _ptr(src)))
+
+    def compute_normal(self, normal, level_set, fast_computation=False):
+        """returns the CG iteration count"""
+        its = C.c_int()
+        check(self.lib.adaflo_b200_ls_compute_normal(self.h, self._blocks(normal), _ptr(level_set), int(fast_computation), C.byref(its)))
+        return its.value
+
+    def compute_curvature(self, curvature, level_set, normal, curvature_correction=True, projection_operator=1):
+        its = C.c_int()
+        check(self.lib.adaflo_b200_ls_compute_curvature(self.h, _ptr(curvature), _ptr(level_set), self._blocks(normal), int(curvature_correction),
+                                                        int(projection_operator), C.byref(its)))
+        return its.value
+
+    def reinitialize(self, solution, normal, dt, stab_steps, diff_steps=0, last_concentration_range=None):
+        """returns the CG iteration counts of the pseudo time steps taken (the numbers of the log's 'reinitialize (a + b)')"""
+        n_max = stab_steps + diff_steps + 3
+        its, done = (C.c_int * n_max)(), C.c_int()
+        rng = None if last_concentration_range is None else (C.c_double * 2)(*[float(v) for v in last_concentration_range])
+        check(self.lib.adaflo_b200_ls_reinitialize(self.h, _ptr(solution), self._blocks(normal), float(dt), int(stab_steps), int(diff_steps), rng,
+                                                   its, C.byref(done)))
+        return [its[i] for i in range(done.value)]
+
+    def advance_concentration(self, solution, solution_old, solution_old_old, vel_solution, tol_nl_iteration=1e-8):
+        """returns (initial residual, iterations): the numbers of the log line 'advect [r0/its]'"""
+        r0, its = C.c_double(), C.c_int()
+        check(self.lib.adaflo_b200_ls_advance_concentration(self.h, _ptr(solution), _ptr(solution_old), _ptr(solution_old_old), _ptr(vel_solution),
+                                                            float(tol_nl_iteration), C.byref(r0), C.byref(its)))
+        return r0.value, its.value
 
     def compute_force(self, navier_stokes_matrix, dst_u, heaviside, curvature, surface_tension, gravity, interpolation=None):
         ip = None if interpolation is None else np.ascontiguousarray(interpolation, dtype=np.float64)

@@ -221,17 +221,14 @@ def parity_vs_single_gpu(ctx, rank, world, local_rank):
             "note": "N-rank partition vs single-rank operator on the same global problem (global-id seeded inputs)"}
 
 
-def run_level_set(args):
-    """--workload ls: the level-set operator applications at n^3 cells, FE_Q_iso_Q1(3), one GPU,
-    each with its algorithmic-bytes model.  Extra measurement; the headline line stays the Navier-Stokes vmult."""
+def level_set_timings(ctx, n, steps, warmup):
+    """Level-set operator applications at n^3 cells, FE_Q_iso_Q1(3), one GPU, each with its
+    algorithmic-bytes model; returns (dict per operator, workload description, DoFs)."""
     import torch
     from adaflo_b200 import capi
     from adaflo_b200.mesh import BoxMesh, seeded_uniform
-    from adaflo_b200.operators import Context, LevelSetOperators, MatrixFree
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    ctx = Context(0)
-    n, n_sub = args.n, 3
+    from adaflo_b200.operators import LevelSetOperators, MatrixFree
+    n_sub = 3
     mesh = BoxMesh((n, n, n), build_coords=False)
     mesh.build_ls_space(n_sub, build_coords=False)
     mf = MatrixFree(ctx, mesh, "cartesian")
@@ -248,7 +245,8 @@ def run_level_set(args):
         return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
     src = [dev(seeded_uniform(mesh.ls.global_ids, 1, 100 + k)) for k in range(3)]
     dst = [mf.initialize_dof_vector(2) for _ in range(3)]
-    peak, which_peak = measured_peak()
+    peak, _ = measured_peak()
+    # fp64 work of the cell kernels per DoF (csrc/ls_ops.cu): the projection operator is not HBM-bound on its byte model
     ops = {
         "advance_concentration_vmult": (lambda: A.advance_concentration_vmult(dst[0], src[0]), 16 + idx_per_dof + 24 * pts_per_dof),
         "reinitialization_vmult": (lambda: A.reinitialization_vmult(dst[0], src[0], False), 16 + idx_per_dof + 24 * pts_per_dof),
@@ -256,25 +254,41 @@ def run_level_set(args):
         "compute_curvature_vmult": (lambda: A.compute_curvature_vmult(dst[0], src[0], True), 16 + idx_per_dof),
     }
     out = {}
-    l0 = ctx.lib.adaflo_b200_kernel_launch_count()
     for name, (fn, bpd) in ops.items():
-        for _ in range(max(args.warmup, 3)):
+        for _ in range(max(warmup, 3)):
             fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.steps
+        ms = e0.elapsed_time(e1) / steps
         gbs = bpd * n_dofs / (ms * 1e-3) / 1e9
         out[name] = {"ms": ms, "dofs_per_s": n_dofs / (ms * 1e-3), "bytes_per_dof": bpd, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+    workload = f"level-set operators on {n}^3 cells, FE_Q_iso_Q1({n_sub}), {n_dofs} DoFs, QIterated(QGauss(2),{n_sub}), Cartesian"
+    del A, mf, src, dst
+    return out, workload, n_dofs
+
+
+LS_BYTE_MODEL = ("per level-set DoF: 8 src + 8 dst per component, 4 B x (n_sub+1)^3 indices per cell, 24 B per quadrature point for the "
+                 "stored convection velocity / frozen normal (advection, reinitialisation); the projection operators (normal, curvature) "
+                 "carry no per-point stream and are bound by fp64 issue and the scatter, not by HBM")
+
+
+def run_level_set(args):
+    """--workload ls: the level-set operator timings alone (the default run carries them under the key level_set)."""
+    import torch
+    from adaflo_b200.operators import Context
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    ctx = Context(0)
+    l0 = ctx.lib.adaflo_b200_kernel_launch_count()
+    out, workload, _ = level_set_timings(ctx, args.n, args.steps, args.warmup)
+    peak, which_peak = measured_peak()
     line = {"metric": "ls_operator_dofs_per_s", "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "dtype": "f64",
-            "data": "synthetic", "higher_is_better": True,
-            "config": {"workload": f"level-set operators on {n}^3 cells, FE_Q_iso_Q1({n_sub}), {n_dofs} DoFs, QIterated(QGauss(2),{n_sub}), Cartesian",
-                       "byte_model": "per level-set DoF: 8 src + 8 dst per component, 4 B x (n_sub+1)^3 indices per cell, 24 B per quadrature "
-                                     "point for the stored convection velocity / frozen normal (advection, reinitialisation)"},
+            "data": "synthetic", "higher_is_better": True, "config": {"workload": workload, "byte_model": LS_BYTE_MODEL},
             "peak_gbs": peak, "peak_source": which_peak, "operators": out,
             "gpu_launches": int(ctx.lib.adaflo_b200_kernel_launch_count() - l0)}
     print(json.dumps(line))
@@ -308,6 +322,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--preroll", type=float, default=0.7, help="seconds of untimed load before the timed steps (clock sampling)")
     ap.add_argument("--no-nonlinear-step", action="store_true")
+    ap.add_argument("--no-level-set", action="store_true", help="skip the level-set operator timings of the default line")
     ap.add_argument("--workload", default="ns", choices=["ns", "ls"], help="ns: the headline Navier-Stokes vmult line; ls: level-set operator timings (extra)")
     ap.add_argument("--kernel-only", action="store_true", help="developer A/B mode: kernel timings + checksum only (not a bench line)")
     args = ap.parse_args()
@@ -551,6 +566,11 @@ def main():
                       "roofline_frac": B_PER_DOF_N * n_dofs_rank / b_k / 1e9 / peak,
                       "note": "same K steps right after warm-up, before the GPU reaches its power limit (rank 0 timing)"},
         }
+        if world == 1 and not args.no_level_set:   # extra keys: the level-set operators on the same box, after the timed region
+            del A
+            torch.cuda.empty_cache()
+            ls_ops, ls_workload, _ = level_set_timings(ctx, n, 10, 5)
+            line["level_set"] = {"workload": ls_workload, "byte_model": LS_BYTE_MODEL, "operators": ls_ops}
         if not args.no_cpu_baseline and world == 1:   # cpu_baseline: rank 0 at N = 1 only
             cb, _ = cpu_port_sample(n, max(2, min(n, args.cpu_layers)), 10, 2)
             line["cpu_baseline"] = cb

@@ -41,6 +41,7 @@ extern "C" {
 #define ADAFLO_B200_ERR_UNSUPPORTED 3 /* reference: AssertThrow(.., ExcNotImplemented()) navier_stokes_matrix.cc:68,82 */
 #define ADAFLO_B200_ERR_STATE 4       /* reference: Assert(matrix_free != 0, ExcNotInitialized()) navier_stokes_matrix.cc:228 */
 #define ADAFLO_B200_ERR_COMM 5
+#define ADAFLO_B200_ERR_NO_CONVERGENCE 6 /* reference: SolverControl::NoConvergence */
 
 /* per-component Dirichlet flags live in the top bits of each cell->node index */
 #define ADAFLO_B200_FLAG_SHIFT 29u
@@ -140,6 +141,8 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *desc
 int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf);
 /* vector sizes: MatrixFree::initialize_dof_vector */
 int adaflo_b200_mf_vector_size(adaflo_b200_mf_t mf, int space, uint64_t *n_owned_entries, uint64_t *n_local_entries);
+/* MatrixFree::get_dof_handler(space).get_fe(): kind (ADAFLO_B200_FE_*), degree, components */
+int adaflo_b200_mf_space_info(adaflo_b200_mf_t mf, int space, int *fe_kind, int *degree, int *n_components);
 /* LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) */
 int adaflo_b200_mf_update_ghost_values(adaflo_b200_mf_t mf, int space, double *vec_dev);
 int adaflo_b200_mf_compress_add(adaflo_b200_mf_t mf, int space, double *vec_dev);
@@ -267,6 +270,14 @@ uint64_t adaflo_b200_kernel_launch_count(void);
  * D2H of dst on the context stream, synchronous on return. */
 int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *dst_p_host,
                               const double *src_u_host, const double *src_p_host);
+/* Host-pointer entries of the sub-block operators, for the wrappers that hand them to Trilinos (ML / ILU) with Epetra
+ * vectors: VelocityMatrix::Multiply (source/navier_stokes_preconditioner.cc:332-343), PressurePoissonMatrix::Multiply
+ * (:421-433), PressureMassMatrix (:444-461).  Owned entries, upload + operator + download, synchronous. */
+int adaflo_b200_ns_velocity_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, const double *src_u_host);
+int adaflo_b200_ns_pressure_poisson_vmult_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_p_host);
+int adaflo_b200_ns_pressure_mass_vmult_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_p_host);
+int adaflo_b200_ns_pressure_convdiff_vmult_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_p_host);
+int adaflo_b200_ns_divergence_vmult_add_host(adaflo_b200_ns_t ns, double *dst_p_host, const double *src_u_host, int weight_by_viscosity);
 
 /* ------------------------------------------------------ level-set operators
  * The matrix-free operators of LevelSetOKZSolver{AdvanceConcentration, ComputeNormal,
@@ -303,6 +314,9 @@ int adaflo_b200_ls_advance_concentration_rhs(adaflo_b200_ls_t ls, double *rhs, c
 /* compute_normal_vmult :160-183 ; local_compute_normal_rhs :123-156 */
 int adaflo_b200_ls_compute_normal_vmult(adaflo_b200_ls_t ls, double *const dst[3], const double *const src[3]);
 int adaflo_b200_ls_compute_normal_rhs(adaflo_b200_ls_t ls, double *const rhs[3], const double *level_set);
+/* one block of compute_normal_vmult: mass + damping_scale_factor delta^2 Laplace, the operator of the reference's assembled
+ * projection_matrix (level_set_okz_preconditioner.cc:61-180) which its curvature projection solves with as well */
+int adaflo_b200_ls_projection_vmult(adaflo_b200_ls_t ls, double *dst, const double *src);
 /* compute_curvature_vmult :263-304 ; local_compute_curvature_rhs :212-259 ; correction :362-377 */
 int adaflo_b200_ls_compute_curvature_vmult(adaflo_b200_ls_t ls, double *dst, const double *src, int apply_diffusion);
 int adaflo_b200_ls_compute_curvature_rhs(adaflo_b200_ls_t ls, double *rhs, const double *const normal[3]);
@@ -325,6 +339,26 @@ int adaflo_b200_ls_compute_force(adaflo_b200_ls_t ls, adaflo_b200_ns_t ns, doubl
                                  double surface_tension, double gravity, const double *interpolation_host);
 /* evaluated_convection (which = 0) / evaluated_normal (which = 1): device arrays [cell][3 components][8 points of a sub-cell][n_sub^3 sub-cells] */
 int adaflo_b200_ls_pointdata_ptr(adaflo_b200_ls_t ls, int which, double **dev_ptr, uint64_t *n_doubles);
+
+/* Solver-level routines of the level-set classes: right-hand side + Krylov solve with the diagonal
+ * preconditioner (ls_set_diagonal) + update, matrix-free in place of the reference's assembled projection matrix + ILU.
+ * LevelSetOKZSolverComputeNormal::compute_normal (level_set_okz_compute_normal.cc:211-289): CG(4000, 1e-50, fast ? 1e-5 : 1e-7)
+ * on compute_normal_vmult, initial guess = the normal field passed in */
+int adaflo_b200_ls_compute_normal(adaflo_b200_ls_t ls, double *const normal[3], const double *level_set, int fast_computation, int *iterations);
+/* LevelSetOKZSolverComputeCurvature::compute_curvature (level_set_okz_compute_curvature.cc:305-392): CG(2000, 1e-50, 1e-8);
+ * projection_operator 0: compute_curvature_vmult(apply_diffusion), 1: the reference's projection_matrix operator */
+int adaflo_b200_ls_compute_curvature(adaflo_b200_ls_t ls, double *curvature, const double *level_set, const double *const normal[3],
+                                     int curvature_correction, int projection_operator, int *iterations);
+/* LevelSetOKZSolverReinitialization::reinitialize (level_set_okz_reinitialization.cc:256-367): diff_steps (+3 if the
+ * concentration range left [-1.02, 1.02]; range may be NULL) diffusive and stab_steps compressive pseudo time steps, each a
+ * CG(2000, 1e-50, 1e-6) solve; the normal is recomputed (fast) at the first compressive step.  iterations: one count per step */
+int adaflo_b200_ls_reinitialize(adaflo_b200_ls_t ls, double *solution, double *const normal[3], double dt, unsigned stab_steps, unsigned diff_steps,
+                                const double *last_concentration_range, int *iterations, int *n_steps_done);
+/* LevelSetOKZSolverAdvanceConcentration::advance_concentration (level_set_okz_advance_concentration.cc:503-693) after the
+ * caller has advanced the time weights (ls_set_time) and applied Dirichlet values: rhs, BiCGStab(30, 0.05 tol_nl, 1e-8) with
+ * the GMRES(3000) fallback, solution += increment.  Outputs: the numbers of the log line "advect [r0/its]" */
+int adaflo_b200_ls_advance_concentration(adaflo_b200_ls_t ls, double *solution, const double *solution_old, const double *solution_old_old,
+                                         const double *vel_solution, double tol_nl_iteration, double *initial_residual, int *iterations);
 
 /* ------------------------------------------------- Krylov-step vector kernels
  * The deal.II vector operations the solvers call between two vmults
@@ -353,6 +387,56 @@ int adaflo_b200_vec_add_and_dot(adaflo_b200_ctx_t ctx, double *y, double a, cons
 /* DiagonalPreconditioner::reinit (guarded inverse, :38-60) and ::vmult (:99-124) */
 int adaflo_b200_jacobi_reinit(adaflo_b200_ctx_t ctx, double *inv_diag, const double *diag, uint64_t n);
 int adaflo_b200_jacobi_vmult(adaflo_b200_ctx_t ctx, double *dst, const double *src, const double *inv_diag, uint64_t n, int n_blocks);
+
+/* ------------------------------------------------------------------ Krylov drivers on device vectors
+ * The loops deal.II's SolverCG / SolverBicgstab / SolverFGMRES run around the operators:
+ *   source/level_set_okz_compute_normal.cc:187-217, level_set_okz_compute_curvature.cc:300-330 (CG on the projections),
+ *   source/level_set_okz_reinitialization.cc:334-336 (CG), source/level_set_okz_advance_concentration.cc:626-644 (BiCGStab),
+ *   source/navier_stokes.cc:571-609 (FGMRES with the block preconditioner).
+ * Operators and preconditioners are callbacks on device block vectors (dst/src: n_blocks device pointers); P may be
+ * NULL (identity).  adaflo_b200_apply_operator is a ready-made callback for the library's own operators.
+ * Stopping rule = ReductionControl: ||r|| <= max(abs_tol, rel_tol * ||r_0||); ERR_NO_CONVERGENCE after max_iter steps
+ * (x holds the last iterate, as with deal.II's exception). */
+typedef int (*adaflo_b200_apply_fn)(void *user, double *const *dst, const double *const *src);
+typedef struct {
+  int max_iter;
+  double abs_tol, rel_tol;
+  int last_step;               /* out */
+  double initial_value;        /* out: ||r_0|| */
+  double last_value;           /* out */
+  double *history;             /* host array or NULL: ||r_0||, then the residual (GMRES: its estimate) after every step */
+  int history_capacity;
+  int history_size;            /* out */
+} adaflo_b200_solver_control;
+int adaflo_b200_solve_cg(adaflo_b200_ctx_t ctx, int n_blocks, const uint64_t *n_owned, const uint64_t *n_local, adaflo_b200_apply_fn A, void *A_user,
+                         adaflo_b200_apply_fn P, void *P_user, double *const *x, const double *const *b, adaflo_b200_solver_control *control);
+int adaflo_b200_solve_bicgstab(adaflo_b200_ctx_t ctx, int n_blocks, const uint64_t *n_owned, const uint64_t *n_local, adaflo_b200_apply_fn A,
+                               void *A_user, adaflo_b200_apply_fn P, void *P_user, double *const *x, const double *const *b,
+                               adaflo_b200_solver_control *control);
+/* restarted, right-preconditioned, flexible (the preconditioned basis is stored) */
+int adaflo_b200_solve_gmres(adaflo_b200_ctx_t ctx, int n_blocks, const uint64_t *n_owned, const uint64_t *n_local, adaflo_b200_apply_fn A, void *A_user,
+                            adaflo_b200_apply_fn P, void *P_user, double *const *x, const double *const *b, int max_basis,
+                            adaflo_b200_solver_control *control);
+
+#define ADAFLO_B200_OP_NS_VMULT 0            /* handle: adaflo_b200_ns_t, 2 blocks (u, p) */
+#define ADAFLO_B200_OP_NS_VELOCITY 1
+#define ADAFLO_B200_OP_NS_PRESSURE_POISSON 2
+#define ADAFLO_B200_OP_NS_PRESSURE_MASS 3
+#define ADAFLO_B200_OP_LS_ADVECT 4           /* handle: adaflo_b200_ls_t */
+#define ADAFLO_B200_OP_LS_NORMAL 5           /* 3 blocks */
+#define ADAFLO_B200_OP_LS_CURVATURE 6        /* flag: apply_diffusion */
+#define ADAFLO_B200_OP_LS_REINIT 7           /* flag: diffuse_only */
+#define ADAFLO_B200_OP_LS_NORMAL_SCALAR 9    /* one block of compute_normal_vmult (the assembled projection_matrix of the reference) */
+#define ADAFLO_B200_OP_JACOBI 8              /* handle: adaflo_b200_ctx_t; inv_diag (n entries) applied to each of n_blocks blocks */
+typedef struct {
+  int kind;
+  void *handle;
+  int flag;
+  const double *inv_diag;
+  uint64_t n;
+  int n_blocks;
+} adaflo_b200_operator_ref;
+int adaflo_b200_apply_operator(void *operator_ref, double *const *dst, const double *const *src);
 
 #ifdef __cplusplus
 }

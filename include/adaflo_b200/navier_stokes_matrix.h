@@ -192,20 +192,119 @@ namespace adaflo_b200
     }
   };
 
-  /// The accessors of adaflo::TimeStepping the operator calls (include/adaflo/time_stepping.h:240-295).
+  /// adaflo::TimeSteppingParameters (include/adaflo/time_stepping.h:34-55)
+  struct TimeSteppingParameters
+  {
+    enum class Scheme
+    {
+      implicit_euler,
+      explicit_euler,
+      crank_nicolson,
+      bdf_2
+    };
+    Scheme time_step_scheme     = Scheme::bdf_2;
+    double start_time           = 0.;
+    double end_time             = 1.;
+    double time_step_size_start = 1.;
+    double time_stepping_cfl    = 0.8;
+    double time_stepping_coef2  = 10.;
+    double time_step_tolerance  = 1e-2;
+    double time_step_size_max   = 1.;
+    double time_step_size_min   = 1.;
+  };
+
+  /// adaflo::TimeStepping: the accessors the operators call (include/adaflo/time_stepping.h:240-295) and the step
+  /// control of source/time_stepping.cc:113-192 (next(): BDF-2 weights for variable step sizes, extrapolation factors).
   struct TimeStepping
   {
     double weight_val = 1., weight_old_val = -1., weight_old_old_val = 0., tau1_val = 1.;
     double factor_extrapol_old = 1., factor_extrapol_old_old = 0.;
+    TimeStepping() = default;
+    explicit TimeStepping(const TimeSteppingParameters &p)
+      : weight_val(1. / p.time_step_size_start)
+      , weight_old_val(-1.)
+      , factor_extrapol_old(0.)
+      , scheme(p.time_step_scheme)
+      , start_val(p.start_time)
+      , final_val(p.end_time)
+      , start_step_val(p.time_step_size_start)
+      , max_step_val(p.time_step_size_max)
+      , current_step_val(p.time_step_size_start)
+      , step_val(p.time_step_size_start)
+      , now_val(p.start_time)
+      , prev_val(p.start_time)
+    {
+      tau1_val = scheme == TimeSteppingParameters::Scheme::explicit_euler ? 0. : (scheme == TimeSteppingParameters::Scheme::crank_nicolson ? .5 : 1.);
+    }
     double weight() const { return weight_val; }
     double weight_old() const { return weight_old_val; }
     double weight_old_old() const { return weight_old_old_val; }
     double tau1() const { return tau1_val; }
-    double tau2() const { return 0.; }
+    double tau2() const { return 1. - tau1_val; }
+    double start() const { return start_val; }
+    double now() const { return now_val; }
+    double previous() const { return prev_val; }
+    double step_size() const { return current_step_val; }
+    unsigned int step_no() const { return step_no_val; }
+    bool at_end() const { return at_end_val; }
+    void set_desired_time_step(const double dt) { step_val = dt; current_step_val = dt; }
+    /// time_stepping.cc:113-192
+    double next()
+    {
+      double s = current_step_val;
+      if (now_val != start_val)
+        {
+          last_step_val = current_step_val;
+          if (scheme == TimeSteppingParameters::Scheme::bdf_2 && step_no_val == 1)
+            s = step_val;
+          if (s > max_step_val)
+            s = max_step_val;
+        }
+      double h         = now_val + s;
+      current_step_val = s;
+      if (!at_end_val && h > final_val - .01 * s)
+        {
+          current_step_val = final_val - now_val;
+          h                = final_val;
+          at_end_val       = true;
+        }
+      if (scheme == TimeSteppingParameters::Scheme::bdf_2 && now_val != start_val)
+        {
+          weight_val         = (2. * current_step_val + last_step_val) / (current_step_val * (current_step_val + last_step_val));
+          weight_old_val     = -((current_step_val + last_step_val) / (current_step_val * last_step_val));
+          weight_old_old_val = current_step_val / (last_step_val * (current_step_val + last_step_val));
+        }
+      else
+        {
+          weight_val     = 1. / current_step_val;
+          weight_old_val = -1. / current_step_val;
+        }
+      if (step_no_val > 1)
+        {
+          factor_extrapol_old     = (current_step_val + last_step_val) / last_step_val;
+          factor_extrapol_old_old = -current_step_val / last_step_val;
+        }
+      else
+        {
+          factor_extrapol_old     = 1.;
+          factor_extrapol_old_old = 0.;
+        }
+      prev_val = now_val;
+      now_val  = h;
+      ++step_no_val;
+      return now_val;
+    }
     adaflo_b200_time_weights to_abi() const
     {
       return adaflo_b200_time_weights{weight_val, weight_old_val, weight_old_old_val, tau1_val, factor_extrapol_old, factor_extrapol_old_old};
     }
+
+  private:
+    TimeSteppingParameters::Scheme scheme = TimeSteppingParameters::Scheme::bdf_2;
+    double       start_val = 0., final_val = 1e300, start_step_val = 1., max_step_val = 1e300, current_step_val = 1., last_step_val = 0., step_val = 1.;
+    double       now_val = 0., prev_val = 0.;
+    unsigned int step_no_val = 0;
+    bool         at_end_val  = false;
   };
 
   /// Device mirror of dealii::MatrixFree<dim,double> (what MatrixFree::reinit produced on the host).
@@ -409,12 +508,16 @@ namespace adaflo_b200
   class DiagonalPreconditioner
   {
   public:
+    explicit DiagonalPreconditioner(const Context &ctx) : ctx(ctx) {}
     DiagonalPreconditioner(const Context &ctx, const Vector &diagonal_vector_in) : ctx(ctx) { reinit(diagonal_vector_in); }
     void reinit(const Vector &diagonal_vector_in)
     {
-      inverse_diagonal_vector.reinit(ctx, diagonal_vector_in.locally_owned_size(), diagonal_vector_in.size_with_ghosts());
-      check(adaflo_b200_jacobi_reinit(ctx.handle(), inverse_diagonal_vector.begin(), diagonal_vector_in.begin(),
-                                      diagonal_vector_in.locally_owned_size()));
+      const std::uint64_t n_owned = diagonal_vector_in.locally_owned_size(), n_local = diagonal_vector_in.size_with_ghosts();
+      diagonal_vector.reinit(ctx, n_owned, n_local);
+      check(adaflo_b200_vec_axpy(ctx.handle(), diagonal_vector.begin(), 1.0, diagonal_vector_in.begin(), n_owned));  // copy (vectors are zero initialised)
+      inverse_diagonal_vector.reinit(ctx, n_owned, n_local);
+      check(adaflo_b200_jacobi_reinit(ctx.handle(), inverse_diagonal_vector.begin(), diagonal_vector_in.begin(), n_owned));
+      ++generation_val;
     }
     void vmult(Vector &dst, const Vector &src) const
     {
@@ -422,10 +525,14 @@ namespace adaflo_b200
                                      inverse_diagonal_vector.locally_owned_size(), 1));
     }
     const Vector &get_inverse_vector() const { return inverse_diagonal_vector; }
+    const Vector &get_vector() const { return diagonal_vector; }
+    /// incremented by every reinit: users that hand the diagonal to the library re-send it when this changes
+    unsigned int generation() const { return generation_val; }
 
   private:
     const Context &ctx;
-    Vector         inverse_diagonal_vector;
+    Vector         diagonal_vector, inverse_diagonal_vector;
+    unsigned int   generation_val = 0;
   };
 } // namespace adaflo_b200
 

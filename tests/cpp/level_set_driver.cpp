@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <iostream>
 #include <map>
 #include <string>
 #include <vector>
@@ -151,6 +152,89 @@ int main(int argc, char **argv)
     write_vector(out, "curvature_vmult", dst);
     reinitialization.reinitialization_vmult(dst, src, true);
     write_vector(out, "reinit_vmult_diffuse", dst);
+
+    // ---- the reference's constructor argument lists and solver-level routines (level_set_okz_*.h), the way
+    // LevelSetOKZSolver / SharpInterfaceSolver build and drive the four classes
+    {
+      const CellDiameters cell_diameters(cd, cd + n_cells);
+      const double epsilon_used = prm[1], minimal_edge_length = prm[3], dt = prm[7];
+      DiagonalPreconditioner preconditioner(ctx);
+      preconditioner.reinit(diagonal);
+      AffineConstraints constraints, constraints_curvature, constraints_normals;
+      ConditionalOStream pcout(std::cout, true);
+      std::shared_ptr<BlockMatrixExtension> projection_matrix;
+      std::shared_ptr<BlockILUExtension> ilu_projection_matrix;
+      NormalVector normal_vector_field, normal_vector_rhs;
+      for (NormalVector *nv : {&normal_vector_field, &normal_vector_rhs})
+        for (Vector &v : *nv) {
+          matrix_free.initialize_dof_vector(v, 2);
+          v = 0.;
+        }
+      Vector solution, solution_update, system_rhs, solution_curvature;
+      for (Vector *v : {&solution, &solution_update, &system_rhs, &solution_curvature}) matrix_free.initialize_dof_vector(*v, 2);
+      solution.copy_from_host(in.at("c").as<double>());
+
+      LevelSetOKZSolverComputeNormalParameter normal_parameters;
+      normal_parameters.dof_index_ls = normal_parameters.dof_index_normal = 2;
+      normal_parameters.quad_index = 2;
+      normal_parameters.epsilon = prm[0];
+      normal_parameters.damping_scale_factor = prm[2];
+      LevelSetOKZSolverComputeNormal<3> normal_solver(normal_vector_field, normal_vector_rhs, solution, cell_diameters, epsilon_used, minimal_edge_length,
+                                                      constraints_normals, normal_parameters, matrix_free, preconditioner, projection_matrix,
+                                                      ilu_projection_matrix);
+      normal_solver.compute_normal(false);
+      write_vector(out, "solved_normal_0", normal_vector_field[0]);
+      write_vector(out, "solved_normal_1", normal_vector_field[1]);
+      write_vector(out, "solved_normal_2", normal_vector_field[2]);
+
+      LevelSetOKZSolverComputeCurvatureParameter curvature_parameters;
+      curvature_parameters.dof_index_ls = curvature_parameters.dof_index_curvature = curvature_parameters.dof_index_normal = 2;
+      curvature_parameters.quad_index = 2;
+      curvature_parameters.epsilon = prm[0];
+      curvature_parameters.curvature_correction = false;  // the correction is singular where kappa d = -(dim - 1): tested on equal inputs elsewhere
+      LevelSetOKZSolverComputeCurvature<3> curvature_solver(cell_diameters, normal_vector_field, constraints_curvature, constraints, epsilon_used, system_rhs,
+                                                            curvature_parameters, solution_curvature, solution, matrix_free, preconditioner,
+                                                            projection_matrix, ilu_projection_matrix);
+      curvature_solver.compute_curvature();
+      write_vector(out, "solved_curvature", solution_curvature);
+
+      LevelSetOKZSolverAdvanceConcentrationParameter advance_parameters;
+      advance_parameters.dof_index_ls = 2;
+      advance_parameters.dof_index_vel = 0;
+      advance_parameters.quad_index = 2;
+      advance_parameters.time.time_step_scheme = TimeSteppingParameters::Scheme::bdf_2;
+      advance_parameters.time.time_step_size_start = dt;
+      advance_parameters.time.end_time = 10.;
+      LevelSetOKZSolverAdvanceConcentrationBoundaryDescriptor<3> boundary;
+      Vector advected;
+      matrix_free.initialize_dof_vector(advected, 2);
+      advected.copy_from_host(in.at("c").as<double>());
+      LevelSetOKZSolverAdvanceConcentration<3> advance_solver(advected, c_old, c_old_old, solution_update, system_rhs, vel, vel, vel, cell_diameters, constraints,
+                                                              pcout, boundary, matrix_free, advance_parameters, preconditioner);
+      advance_solver.advance_concentration(dt);  // first step: weights 1/dt, -1/dt, 0
+      std::cout << std::endl;
+      write_vector(out, "advected", advected);
+
+      LevelSetOKZSolverReinitializationParameter reinit_parameters;
+      reinit_parameters.dof_index_ls = reinit_parameters.dof_index_normal = 2;
+      reinit_parameters.quad_index = 2;
+      reinit_parameters.time.time_step_size_start = dt;
+      reinit_parameters.time.end_time = 10.;
+      std::pair<double, double> last_concentration_range(-1., 1.);
+      bool first_reinit_step = true;
+      LevelSetOKZSolverReinitialization<3> reinit_solver(normal_vector_field, cell_diameters, epsilon_used, minimal_edge_length, constraints, solution_update,
+                                                         solution, system_rhs, pcout, preconditioner, last_concentration_range, reinit_parameters,
+                                                         first_reinit_step, matrix_free);
+      reinit_solver.reinitialize(dt, 2, 1);
+      write_vector(out, "reinitialized", solution);
+      Vector counts;  // iteration counts as doubles: normal, curvature, advection, then the reinitialisation steps
+      std::vector<double> cnt = {double(normal_solver.last_iterations()), double(curvature_solver.last_iterations()),
+                                 double(advance_solver.last_iterations())};
+      for (const int i : reinit_solver.last_iterations()) cnt.push_back(double(i));
+      counts.reinit(ctx, cnt.size(), cnt.size());
+      counts.copy_from_host(cnt.data());
+      write_vector(out, "counts", counts);
+    }
     std::printf("level_set_driver: ok\n");
     return 0;
   } catch (const std::exception &e) {

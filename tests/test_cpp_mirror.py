@@ -115,3 +115,43 @@ def test_cpp_level_set_classes_match_oracle(tmp_path):
     assert rel_err(got["normal_rhs_0"], nr[0]) < 1e-12 and rel_err(got["normal_rhs_2"], nr[2]) < 1e-12
     assert rel_err(got["curvature_vmult"], O.compute_curvature_vmult(src, True)) < 1e-12
     assert rel_err(got["reinit_vmult_diffuse"], O.reinitialization_vmult(src, True)) < 1e-12
+
+    # ---- the reference's constructor contracts + solver-level routines, checked against dense solves with the oracle's operators
+    def dense(apply):
+        M = np.zeros((O.n, O.n))
+        e = np.zeros(O.n)
+        for j in range(O.n):
+            e[j] = 1.0
+            M[:, j] = apply(e)
+            e[j] = 0.0
+        return M
+    counts = got["counts"].astype(int)
+    assert len(counts) == 6 and all(1 <= k < 200 for k in counts), counts
+    N = dense(lambda v: O._scalar(0, 4.0, v))                       # one block of compute_normal_vmult = the projection matrix
+    normal = [np.linalg.solve(N, nr[d]) for d in range(3)]
+    for d in range(3):
+        assert rel_err(got[f"solved_normal_{d}"], normal[d]) < 1e-5          # CG stops at 1e-7 relative residual
+    rk = np.zeros(O.n)
+    O.compute_curvature_rhs(rk, [got[f"solved_normal_{d}"].copy() for d in range(3)])
+    kappa = np.linalg.solve(N, rk)
+    assert rel_err(got["solved_curvature"], kappa) < 1e-5
+    # advection, first BDF step: (gamma M + C(u)) dc = rhs with gamma = 1 / dt, c += dc
+    A_adv = dense(lambda v: O.advance_concentration_vmult(v, 1.0 / dt))
+    ra = np.zeros(O.n)
+    O.advance_concentration_rhs(ra, vel, c, c_old, c_oo, 1.0 / dt, -1.0 / dt, 0.0)
+    assert rel_err(got["advected"], c + np.linalg.solve(A_adv, ra)) < 1e-6
+    # reinitialisation: 1 diffusive + 2 compressive pseudo time steps, normal recomputed (fast) at the first compressive one
+    cr = c.copy()
+    O2 = orc.OracleLevelSet(mesh, orc.LSParams(eps, eps_used, 4.0, h_min, dt, 3, 0))
+    O2.diag = O.diag
+    for tau in range(3):
+        diffuse, first = tau < 1, tau == 1
+        if first:
+            nrr = [np.zeros(O.n) for _ in range(3)]
+            O2.compute_normal_rhs(nrr, cr)
+            nfast = [np.linalg.solve(N, nrr[d]) for d in range(3)]
+        rr = np.zeros(O.n)
+        O2.reinitialization_rhs(rr, cr, None if diffuse else nfast, diffuse, first)
+        R = dense(lambda v: O2.reinitialization_vmult(v, diffuse))
+        cr = cr + np.linalg.solve(R, rr)
+    assert rel_err(got["reinitialized"], cr) < 1e-3                        # fast normal: 1e-5, CG: 1e-6 per step, three nonlinear steps

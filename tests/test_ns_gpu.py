@@ -142,6 +142,19 @@ def test_sub_operators(ctx, geometry, var):
         getattr(P.A, name)(g, dev(ctx, sp))
         o = getattr(P.O, name)(sp)
         assert rel_err(g.cpu().numpy(), o) < TOL, name
+        # host-pointer entry (what the Epetra-side wrappers of navier_stokes_preconditioner.cc:421-461 call)
+        gh = np.full_like(sp, 3.0)
+        getattr(P.A, name + "_host")(gh, np.ascontiguousarray(sp))
+        assert rel_err(gh, o) < TOL, name + "_host"
+    duh = np.zeros_like(su)
+    P.A.velocity_vmult_host(duh, np.ascontiguousarray(su))     # VelocityMatrix::Multiply, :332-343
+    assert rel_err(duh, P.O.velocity_vmult(su)) < TOL
+    pre = seeded_uniform(m.p.global_ids, 1, 43)
+    o = pre.copy()
+    P.O.divergence_vmult_add(o, su, True)
+    gh = pre.copy()
+    P.A.divergence_vmult_add_host(gh, np.ascontiguousarray(su), True)
+    assert rel_err(gh, o) < TOL
     P.close()
 
 
