@@ -420,6 +420,8 @@ int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf)
     free_dev(sp.cell_nodes_blk);
     free_dev(sp.hanging_masks);
     free_dev(sp.constrained);
+    free_dev(sp.numbering);
+    free_dev(sp.numbering_stage);
     for (Exchange &x : sp.exchange) {
       free_dev(x.send_dev);
       free_dev(x.send_buf);
@@ -432,6 +434,90 @@ int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf)
     free_dev(q.jxw);
   }
   delete mf;
+  return 0;
+}
+
+// ---- dof numbering of the host application (node-major by default)
+extern "C++" {
+namespace {
+__global__ void k_from_host_order(double *__restrict__ dst, const double *__restrict__ src, const uint32_t *__restrict__ pos, uint64_t n)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[pos[i]];
+}
+__global__ void k_to_host_order(double *__restrict__ dst, const double *__restrict__ src, const uint32_t *__restrict__ pos, uint64_t n)
+{
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[pos[i]] = src[i];
+}
+}  // namespace
+
+namespace ab200 {
+// host vector (owned entries, host numbering) -> device vector in the library's node-major layout, and back; asynchronous
+int upload_owned(adaflo_b200_mf_t mf, int space, double *dev, const double *host, cudaStream_t s)
+{
+  const Space &sp = mf->spaces[space];
+  const uint64_t n = sp.n_owned_entries();
+  if (!sp.numbering) {
+    AB_CUDA(cudaMemcpyAsync(dev, host, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    return 0;
+  }
+  AB_CUDA(cudaMemcpyAsync(sp.numbering_stage, host, n * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (n) k_from_host_order<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, s>>>(dev, sp.numbering_stage, sp.numbering, n);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+int download_owned(adaflo_b200_mf_t mf, int space, double *host, const double *dev, cudaStream_t s)
+{
+  const Space &sp = mf->spaces[space];
+  const uint64_t n = sp.n_owned_entries();
+  if (!sp.numbering) {
+    AB_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return 0;
+  }
+  if (n) k_to_host_order<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, s>>>(sp.numbering_stage, dev, sp.numbering, n);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  AB_CUDA(cudaMemcpyAsync(host, sp.numbering_stage, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+}  // namespace ab200
+}  // extern "C++"
+
+int adaflo_b200_mf_set_dof_numbering(adaflo_b200_mf_t mf, int space, const uint32_t *host_position)
+{
+  if (!mf || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "mf_set_dof_numbering: bad argument");
+  Space &sp = mf->spaces[space];
+  AB_CUDA(cudaSetDevice(mf->ctx->device));
+  free_dev(sp.numbering);
+  free_dev(sp.numbering_stage);
+  sp.numbering = nullptr;
+  sp.numbering_stage = nullptr;
+  if (!host_position) return 0;  // back to the node-major default
+  const uint64_t n = sp.n_owned_entries();
+  std::vector<unsigned char> seen(n, 0);
+  for (uint64_t i = 0; i < n; ++i) {
+    if (host_position[i] >= n || seen[host_position[i]]) return fail(ADAFLO_B200_ERR_ARG, "mf_set_dof_numbering: not a permutation of the owned entries");
+    seen[host_position[i]] = 1;
+  }
+  AB_CUDA(cudaMalloc((void **)&sp.numbering, std::max<uint64_t>(1, n) * sizeof(uint32_t)));
+  AB_CUDA(cudaMalloc((void **)&sp.numbering_stage, std::max<uint64_t>(1, n) * sizeof(double)));
+  AB_CUDA(cudaMemcpy(sp.numbering, host_position, n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int adaflo_b200_mf_upload_vector(adaflo_b200_mf_t mf, int space, double *vec_dev, const double *vec_host)
+{
+  if (!mf || space < 0 || space >= (int)mf->spaces.size() || !vec_dev || !vec_host) return fail(ADAFLO_B200_ERR_ARG, "mf_upload_vector: bad argument");
+  AB_CHECK(upload_owned(mf, space, vec_dev, vec_host, mf->ctx->stream));
+  AB_CUDA(cudaStreamSynchronize(mf->ctx->stream));
+  return 0;
+}
+
+int adaflo_b200_mf_download_vector(adaflo_b200_mf_t mf, int space, double *vec_host, const double *vec_dev)
+{
+  if (!mf || space < 0 || space >= (int)mf->spaces.size() || !vec_dev || !vec_host) return fail(ADAFLO_B200_ERR_ARG, "mf_download_vector: bad argument");
+  AB_CHECK(download_owned(mf, space, vec_host, vec_dev, mf->ctx->stream));
+  AB_CUDA(cudaStreamSynchronize(mf->ctx->stream));
   return 0;
 }
 
@@ -1122,16 +1208,16 @@ int sub_operator_host(adaflo_b200_ns_t ns, int which, double *dst_host, const do
   if (!dst_host || !src_host) return fail(ADAFLO_B200_ERR_ARG, "host sub-operator: null vector");
   AB_CHECK(ensure_stage(ns));
   cudaStream_t s = ns->ctx->stream;
-  const Space &sp = ns->mf->spaces[which == HOST_VELOCITY ? ns->dof_u : ns->dof_p];
   double *src = which == HOST_VELOCITY ? ns->stage_u[0] : ns->stage_p[0], *dst = which == HOST_VELOCITY ? ns->stage_u[1] : ns->stage_p[1];
-  AB_CUDA(cudaMemcpyAsync(src, src_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+  const int space = which == HOST_VELOCITY ? ns->dof_u : ns->dof_p;
+  AB_CHECK(upload_owned(ns->mf, space, src, src_host, s));
   switch (which) {
     case HOST_VELOCITY: AB_CHECK(adaflo_b200_ns_velocity_vmult(ns, dst, src)); break;
     case HOST_POISSON: AB_CHECK(adaflo_b200_ns_pressure_poisson_vmult(ns, dst, src)); break;
     case HOST_MASS: AB_CHECK(adaflo_b200_ns_pressure_mass_vmult(ns, dst, src)); break;
     default: AB_CHECK(adaflo_b200_ns_pressure_convdiff_vmult(ns, dst, src)); break;
   }
-  AB_CUDA(cudaMemcpyAsync(dst_host, dst, sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  AB_CHECK(download_owned(ns->mf, space, dst_host, dst, s));
   AB_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
@@ -1159,12 +1245,12 @@ int adaflo_b200_ns_divergence_vmult_add_host(adaflo_b200_ns_t ns, double *dst_p_
   if (!dst_p_host || !src_u_host) return fail(ADAFLO_B200_ERR_ARG, "divergence_vmult_add_host: null vector");
   AB_CHECK(ensure_stage(ns));
   cudaStream_t s = ns->ctx->stream;
-  const Space &su = ns->mf->spaces[ns->dof_u], &sp = ns->mf->spaces[ns->dof_p];
-  AB_CUDA(cudaMemcpyAsync(ns->stage_u[0], src_u_host, su.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+  const Space &sp = ns->mf->spaces[ns->dof_p];
+  AB_CHECK(upload_owned(ns->mf, ns->dof_u, ns->stage_u[0], src_u_host, s));
   AB_CUDA(cudaMemsetAsync(ns->stage_p[1], 0, sp.n_local_entries() * sizeof(double), s));
-  AB_CUDA(cudaMemcpyAsync(ns->stage_p[1], dst_p_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));  // "add": dst is an input
+  AB_CHECK(upload_owned(ns->mf, ns->dof_p, ns->stage_p[1], dst_p_host, s));  // "add": dst is an input
   AB_CHECK(adaflo_b200_ns_divergence_vmult_add(ns, ns->stage_p[1], ns->stage_u[0], weight_by_viscosity));
-  AB_CUDA(cudaMemcpyAsync(dst_p_host, ns->stage_p[1], sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+  AB_CHECK(download_owned(ns->mf, ns->dof_p, dst_p_host, ns->stage_p[1], s));
   AB_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
@@ -1186,13 +1272,14 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
   static const bool legacy_kernel = [] { const char *k = std::getenv("ADAFLO_B200_VMULT_KERNEL"); return k && !std::strcmp(k, "v1"); }();
   const int mode = mode_of(ns->prm);
   const bool multi = ns->ctx->nranks > 1;
-  if (!pipe_enabled || legacy_kernel || !mf->pipeline_ok || ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin)) {
+  const bool renumbered = su.numbering || sp.numbering;  // host numbering is not node-major: permute on the device, no chunk pipeline
+  if (!pipe_enabled || legacy_kernel || renumbered || !mf->pipeline_ok || ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin)) {
     // plain path: upload, vmult, download
-    AB_CUDA(cudaMemcpyAsync(ns->stage_u[0], src_u_host, su.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
-    AB_CUDA(cudaMemcpyAsync(ns->stage_p[0], src_p_host, sp.n_owned_entries() * sizeof(double), cudaMemcpyHostToDevice, s));
+    AB_CHECK(upload_owned(mf, ns->dof_u, ns->stage_u[0], src_u_host, s));
+    AB_CHECK(upload_owned(mf, ns->dof_p, ns->stage_p[0], src_p_host, s));
     AB_CHECK(vmult_impl(ns, ns->stage_u[1], ns->stage_p[1], ns->stage_u[0], ns->stage_p[0], false));
-    AB_CUDA(cudaMemcpyAsync(dst_u_host, ns->stage_u[1], su.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
-    AB_CUDA(cudaMemcpyAsync(dst_p_host, ns->stage_p[1], sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    AB_CHECK(download_owned(mf, ns->dof_u, dst_u_host, ns->stage_u[1], s));
+    AB_CHECK(download_owned(mf, ns->dof_p, dst_p_host, ns->stage_p[1], s));
     AB_CUDA(cudaStreamSynchronize(s));
     return 0;
   }

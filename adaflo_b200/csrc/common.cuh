@@ -110,6 +110,10 @@ struct Space {
   // prefix that is final after the chunk, and the number of constrained entries inside the final prefix
   std::vector<uint32_t> chunk_need_hi, chunk_final_lo, chunk_constrained_end;
   uint32_t send_lo = 0, send_hi = 0;  // node range covering all nodes this rank exports to its neighbours
+  // dof numbering of the host application where it is not node-major (Cuthill-McKee on the velocity DoFHandler,
+  // source/navier_stokes.cc:208-209): position of library entry i in the host's vector, [n_owned_entries], or null
+  uint32_t *numbering = nullptr;
+  double *numbering_stage = nullptr;  // device staging vector in host order
   uint64_t n_owned_entries() const { return (uint64_t)n_owned_nodes * n_comp; }
   uint64_t n_local_entries() const { return (uint64_t)(n_owned_nodes + n_ghost_nodes) * n_comp; }
 };
@@ -228,6 +232,8 @@ struct NSArgs {
 enum { MODE_STOKES = 0, MODE_NEWTON = 1, MODE_PICARD = 2, MODE_NOCONV = 3 };
 
 int upload_shape_tables(cudaStream_t s);
+int upload_owned(adaflo_b200_mf_t mf, int space, double *dev, const double *host, cudaStream_t s);   // host numbering -> library layout
+int download_owned(adaflo_b200_mf_t mf, int space, double *host, const double *dev, cudaStream_t s);
 void solver_pool_release(adaflo_b200_ctx_t ctx);  // solvers.cu: work vectors of the Krylov drivers
 double *pool_get(adaflo_b200_ctx_t ctx, size_t doubles);  // per-context pool of device work vectors (null: out of memory)
 void pool_put(adaflo_b200_ctx_t ctx, double *p);

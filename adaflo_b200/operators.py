@@ -219,6 +219,18 @@ class MatrixFree:
         check(self.ctx.lib.adaflo_b200_mf_vector_size(self.h, space, C.byref(n_owned), None))
         return n_owned.value
 
+    def set_dof_numbering(self, space, host_position):
+        """host_position[i]: position of library entry i (node-major, components interleaved) in the host application's vector,
+        e.g. after DoFRenumbering::Cuthill_McKee on the velocity DoFHandler (navier_stokes.cc:208-209); None: default"""
+        hp = None if host_position is None else np.ascontiguousarray(host_position, dtype=np.uint32)
+        check(self.ctx.lib.adaflo_b200_mf_set_dof_numbering(self.h, space, _np(hp)))
+
+    def upload_vector(self, space, vec_dev, vec_host):
+        check(self.ctx.lib.adaflo_b200_mf_upload_vector(self.h, space, _ptr(vec_dev), _np(np.ascontiguousarray(vec_host))))
+
+    def download_vector(self, space, vec_host, vec_dev):
+        check(self.ctx.lib.adaflo_b200_mf_download_vector(self.h, space, _np(vec_host), _ptr(vec_dev)))
+
     def update_ghost_values(self, space, vec):
         check(self.ctx.lib.adaflo_b200_mf_update_ghost_values(self.h, space, _ptr(vec)))
 

@@ -322,6 +322,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--preroll", type=float, default=0.7, help="seconds of untimed load before the timed steps (clock sampling)")
     ap.add_argument("--no-nonlinear-step", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: n^3 cells in total, split over the GPUs (default: weak, n^3 per GPU)")
     ap.add_argument("--no-level-set", action="store_true", help="skip the level-set operator timings of the default line")
     ap.add_argument("--workload", default="ns", choices=["ns", "ls"], help="ns: the headline Navier-Stokes vmult line; ls: level-set operator timings (extra)")
     ap.add_argument("--kernel-only", action="store_true", help="developer A/B mode: kernel timings + checksum only (not a bench line)")
@@ -363,7 +364,10 @@ def main():
     n = args.n
     t_setup = time.perf_counter()
     # weak scaling: n x n x (n * world) cells on [-1,1]^2 x [-1, -1 + 2 world]
-    mesh = BoxMesh((n, n, n * world), upper=(1.0, 1.0, -1.0 + 2.0 * world), rank=rank, nranks=world)
+    if args.strong:   # strong scaling (extra measurement): the n^3 box is split into N z-slabs
+        mesh = BoxMesh((n, n, n), rank=rank, nranks=world)
+    else:
+        mesh = BoxMesh((n, n, n * world), upper=(1.0, 1.0, -1.0 + 2.0 * world), rank=rank, nranks=world)
     mf = MatrixFree(ctx, mesh, "cartesian")
     prm = capi.FlowParams(capi.INCOMPRESSIBLE, capi.NEWTON, 0, 0, 1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.5)
     dt = 0.05
@@ -542,9 +546,9 @@ def main():
         achieved = alg_bytes / k_avg / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"ns_vmult Q2/Q1 3D box {n}^3 cells/GPU ({n_dofs_rank} DoFs/GPU, {n_dofs} total), Newton stored linearisation, "
+            "config": {"workload": f"ns_vmult Q2/Q1 3D box {n}^3 cells{' in total' if args.strong else '/GPU'} ({n_dofs_rank} DoFs/GPU, {n_dofs} total), Newton stored linearisation, "
                                    "Cartesian, constant coefficients, Dirichlet u on all faces, pressure mean fixed",
                        "l2": "inputs larger than L2 (vectors 0.42 GB, linearisation data 5.4 GB per GPU)",
                        "partition": f"z-slabs x{world}", "setup_s": round(t_setup, 1), "numa_node_rank0": numa_node},

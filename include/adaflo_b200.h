@@ -141,6 +141,15 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *desc
 int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf);
 /* vector sizes: MatrixFree::initialize_dof_vector */
 int adaflo_b200_mf_vector_size(adaflo_b200_mf_t mf, int space, uint64_t *n_owned_entries, uint64_t *n_local_entries);
+/* Dof numbering of the host application.  The library's vectors are node-major with interleaved components
+ * (entry = n_components * node + component).  deal.II numbers the dofs of FESystem(FE_Q(2), dim) the same way only until
+ * DoFRenumbering::Cuthill_McKee is applied to the velocity DoFHandler, which adaflo does for its ILU (source/navier_stokes.cc:
+ * 208-209).  host_position[i] = position of library entry i in the host's locally owned vector (a permutation, [n_owned
+ * entries]; NULL restores the default).  Used by every host-pointer entry (ns_*_host, mf_upload_vector / mf_download_vector);
+ * device-resident Krylov vectors stay in the library's layout and never see the permutation. */
+int adaflo_b200_mf_set_dof_numbering(adaflo_b200_mf_t mf, int space, const uint32_t *host_position);
+int adaflo_b200_mf_upload_vector(adaflo_b200_mf_t mf, int space, double *vec_dev, const double *vec_host);   /* owned entries, synchronous */
+int adaflo_b200_mf_download_vector(adaflo_b200_mf_t mf, int space, double *vec_host, const double *vec_dev);
 /* MatrixFree::get_dof_handler(space).get_fe(): kind (ADAFLO_B200_FE_*), degree, components */
 int adaflo_b200_mf_space_info(adaflo_b200_mf_t mf, int space, int *fe_kind, int *degree, int *n_components);
 /* LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) */

@@ -155,3 +155,53 @@ def test_cpp_level_set_classes_match_oracle(tmp_path):
         R = dense(lambda v: O2.reinitialization_vmult(v, diffuse))
         cr = cr + np.linalg.solve(R, rr)
     assert rel_err(got["reinitialized"], cr) < 1e-3                        # fast normal: 1e-5, CG: 1e-6 per step, three nonlinear steps
+
+
+def test_cpp_matrix_free_adaptor_with_renumbered_velocity(tmp_path):
+    """include/adaflo_b200/matrix_free_adaptor.h (INTEGRATION.md section 2) fed by a mock of dealii::MatrixFree's batch / lane
+    storage with a velocity numbering scrambled like DoFRenumbering::Cuthill_McKee leaves it (source/navier_stokes.cc:208-209):
+    host vectors in that numbering go through vmult_host / velocity_vmult_host and come back in it"""
+    driver = os.path.join(ROOT, "tests", "cpp", "adaptor_driver")
+    assert os.path.exists(driver), "build the driver with __graft_entry__.build()"
+    mesh = BoxMesh((5, 4, 3))
+    _, oprm = flow_params(damping=-0.2, tau_grad_div=0.3, viscosity=0.7, density=1.3)
+    _, otw = time_weights()
+    O = orc.OracleNavierStokesMatrix(mesh, oprm, otw)
+    u = beltrami_velocity(mesh.u.coords, 0.1).reshape(-1) + 0.1 * seeded_uniform(mesh.u.global_ids, 3, 7)
+    p = seeded_uniform(mesh.p.global_ids, 1, 8)
+    uo, uoo = seeded_uniform(mesh.u.global_ids, 3, 9), seeded_uniform(mesh.u.global_ids, 3, 10)
+    su, sp = seeded_uniform(mesh.u.global_ids, 3, 11), seeded_uniform(mesh.p.global_ids, 1, 12)
+    rng = np.random.default_rng(5)
+    nu, np_ = mesh.u.n_owned * 3, mesh.p.n_owned
+    perm_u = rng.permutation(nu)           # host position of the node-major entry 3 node + c
+    perm_p = rng.permutation(np_)
+    cell_u = mesh.u.cell_nodes.astype(np.int64)                     # [cell][27] node ids
+    dofs_u = np.stack([perm_u[3 * cell_u + c] for c in range(3)], axis=1).reshape(mesh.n_cells, 81)   # component-blocked per cell
+    dofs_p = perm_p[mesh.p.cell_nodes.astype(np.int64)]
+    con = np.sort(perm_u[mesh.u.constrained_dofs().astype(np.int64)])
+
+    def to_host(v, perm):
+        h = np.empty_like(v)
+        h[perm] = v
+        return h
+    inv_h = np.tile(1.0 / mesh.h, (mesh.n_cells, 1)) if np.ndim(mesh.h) == 1 else 1.0 / mesh.h
+    write_dump(tmp_path / "in.bin", {
+        "meta": np.array([mesh.n_cells, nu, np_, len(con), 4], dtype=np.uint32),
+        "params": np.array([oprm.viscosity, oprm.density, oprm.damping, oprm.tau_grad_div, oprm.beta, otw.weight, otw.weight_old,
+                            otw.weight_old_old, otw.tau1, otw.extrapolate_old, otw.extrapolate_old_old]),
+        "plain_dof_indices_u": dofs_u.astype(np.uint32), "plain_dof_indices_p": dofs_p.astype(np.uint32), "constrained_u": con.astype(np.uint32),
+        "inverse_jacobian_diagonal": np.ascontiguousarray(inv_h, dtype=np.float64),
+        "solution_u": to_host(u, perm_u), "solution_p": to_host(p, perm_p), "old_u": to_host(uo, perm_u), "old_old_u": to_host(uoo, perm_u),
+        "src_u": to_host(su, perm_u), "src_p": to_host(sp, perm_p)})
+    r = subprocess.run([driver, str(tmp_path / "in.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0
+    got = read_dump(tmp_path / "out.bin")
+    O.old_u, O.old_old_u = uo, uoo
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, u, p, np.zeros(O.n_u), np.zeros(O.n_p))
+    ou, op = O.vmult(su, sp)
+    assert rel_err(got["residual_u"], to_host(ru, perm_u)) < 1e-12
+    assert rel_err(got["vmult_u"], to_host(ou, perm_u)) < 1e-12 and rel_err(got["vmult_p"], to_host(op, perm_p)) < 1e-12
+    O.fix_linearization_point()
+    assert rel_err(got["velocity_vmult"], to_host(O.velocity_vmult(su), perm_u)) < 1e-12
