@@ -92,7 +92,7 @@ SYMBOLS = [
     "adaflo_b200_last_error", "adaflo_b200_version",
     "adaflo_b200_ctx_create", "adaflo_b200_ctx_destroy", "adaflo_b200_ctx_set_stream", "adaflo_b200_ctx_synchronize",
     "adaflo_b200_comm_unique_id", "adaflo_b200_ctx_init_comm",
-    "adaflo_b200_mf_create", "adaflo_b200_mf_destroy", "adaflo_b200_mf_vector_size", "adaflo_b200_mf_space_info",
+    "adaflo_b200_mf_create", "adaflo_b200_mf_destroy", "adaflo_b200_mf_vector_size", "adaflo_b200_mf_space_info", "adaflo_b200_mf_n_cells",
     "adaflo_b200_mf_set_dof_numbering", "adaflo_b200_mf_upload_vector", "adaflo_b200_mf_download_vector",
     "adaflo_b200_mf_update_ghost_values", "adaflo_b200_mf_compress_add",
     "adaflo_b200_ns_create", "adaflo_b200_ns_destroy", "adaflo_b200_ns_set_flow_params",
@@ -150,6 +150,7 @@ def load():
         "adaflo_b200_mf_destroy": [vp],
         "adaflo_b200_mf_vector_size": [vp, i32, C.POINTER(u64), C.POINTER(u64)],
         "adaflo_b200_mf_space_info": [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+        "adaflo_b200_mf_n_cells": [vp, C.POINTER(C.c_uint32)],
         "adaflo_b200_mf_set_dof_numbering": [vp, i32, vp],
         "adaflo_b200_mf_upload_vector": [vp, i32, vp, vp],
         "adaflo_b200_mf_download_vector": [vp, i32, vp, vp],

@@ -529,6 +529,13 @@ int adaflo_b200_mf_vector_size(adaflo_b200_mf_t mf, int space, uint64_t *n_owned
   return 0;
 }
 
+int adaflo_b200_mf_n_cells(adaflo_b200_mf_t mf, uint32_t *n_cells)
+{
+  if (!mf || !n_cells) return fail(ADAFLO_B200_ERR_ARG, "mf_n_cells: null argument");
+  *n_cells = mf->n_cells;
+  return 0;
+}
+
 int adaflo_b200_mf_space_info(adaflo_b200_mf_t mf, int space, int *fe_kind, int *degree, int *n_components)
 {
   if (!mf || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "mf_space_info: bad argument");

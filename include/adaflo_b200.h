@@ -152,6 +152,7 @@ int adaflo_b200_mf_upload_vector(adaflo_b200_mf_t mf, int space, double *vec_dev
 int adaflo_b200_mf_download_vector(adaflo_b200_mf_t mf, int space, double *vec_host, const double *vec_dev);
 /* MatrixFree::get_dof_handler(space).get_fe(): kind (ADAFLO_B200_FE_*), degree, components */
 int adaflo_b200_mf_space_info(adaflo_b200_mf_t mf, int space, int *fe_kind, int *degree, int *n_components);
+int adaflo_b200_mf_n_cells(adaflo_b200_mf_t mf, uint32_t *n_cells);   /* locally owned cells */
 /* LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) */
 int adaflo_b200_mf_update_ghost_values(adaflo_b200_mf_t mf, int space, double *vec_dev);
 int adaflo_b200_mf_compress_add(adaflo_b200_mf_t mf, int space, double *vec_dev);

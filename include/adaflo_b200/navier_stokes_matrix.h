@@ -438,6 +438,50 @@ namespace adaflo_b200
     double *begin_linearized_velocities() const { return coefficient(ADAFLO_B200_COEF_LINEARIZED_VELOCITY); }
     bool    use_variable_coefficients() const { return parameters.density_diff != 0 || parameters.viscosity_diff != 0; }
 
+    /// The reference's accessors begin_densities(macro_cell) & co. (include/adaflo/navier_stokes_matrix.h:162-178): a pointer to
+    /// the n_q VectorizedArray<double> of one cell batch, i.e. n_q * n_lanes doubles [q][lane] (the linearisation point:
+    /// [q][12 rows][lane]).  They address a HOST mirror in the reference's storage order; external writers
+    /// (LevelSetOKZSolver::local_compute_force level_set_okz.cc:351-364, compute_initial_stokes_field navier_stokes.cc:
+    /// 1178-1196) fill it batch by batch and call update_coefficients_on_device() once.  Reading accessors download first.
+    /// n_lanes = VectorizedArray<double>::size() of the host build; slot_cell maps slot batch * n_lanes + lane to the
+    /// library's cell (empty: identity; 0xffffffff: unused lane), e.g. AdaptedMatrixFree::cell_of.
+    void set_cell_batches(const unsigned int n_lanes_in, const std::vector<std::uint32_t> &slot_cell_in = std::vector<std::uint32_t>())
+    {
+      require();
+      n_lanes   = n_lanes_in;
+      slot_cell = slot_cell_in;
+      std::uint32_t n_cells = 0;
+      check(adaflo_b200_mf_n_cells(matrix_free->handle(), &n_cells));
+      n_batches = slot_cell.empty() ? (n_cells + n_lanes - 1) / n_lanes : static_cast<std::uint32_t>(slot_cell.size() / n_lanes);
+      for (auto &m : host_coefficients) m.clear();
+    }
+    double       *begin_densities(const unsigned int macro_cell) { return host_batch(ADAFLO_B200_COEF_DENSITY, macro_cell, true); }
+    const double *begin_densities(const unsigned int macro_cell) const { return host_batch(ADAFLO_B200_COEF_DENSITY, macro_cell, false); }
+    double       *begin_viscosities(const unsigned int macro_cell) { return host_batch(ADAFLO_B200_COEF_VISCOSITY, macro_cell, true); }
+    const double *begin_viscosities(const unsigned int macro_cell) const { return host_batch(ADAFLO_B200_COEF_VISCOSITY, macro_cell, false); }
+    double       *begin_damping_coeff(const unsigned int macro_cell) { return host_batch(ADAFLO_B200_COEF_DAMPING, macro_cell, true); }
+    const double *begin_damping_coeff(const unsigned int macro_cell) const { return host_batch(ADAFLO_B200_COEF_DAMPING, macro_cell, false); }
+    const double *begin_linearized_velocities(const unsigned int macro_cell) const
+    {
+      return host_batch(ADAFLO_B200_COEF_LINEARIZED_VELOCITY, macro_cell, false);
+    }
+    /// upload the batches handed out for writing since the last call
+    void update_coefficients_on_device()
+    {
+      for (int which = 0; which < 4; ++which)
+        if (host_dirty[which])
+          {
+            check(adaflo_b200_ns_set_coefficient_canonical(h, which, host_coefficients[which].data(), 1, n_batches, n_lanes,
+                                                           slot_cell.empty() ? nullptr : slot_cell.data()));
+            host_dirty[which] = false;
+          }
+    }
+    /// forget the host mirrors (the device arrays have been rewritten, e.g. by residual() or the level-set force kernel)
+    void invalidate_host_coefficients() const
+    {
+      for (auto &m : host_coefficients) m.clear();
+    }
+
     /// (accumulated wall time, number of calls) since the last query; resets the counters.
     /// the C-ABI handle (for the level-set force, which writes rho / mu into this operator)
     adaflo_b200_ns_t handle() const
@@ -502,6 +546,30 @@ namespace adaflo_b200
     const MatrixFreeData *matrix_free   = nullptr;
     const TimeStepping   *time_stepping = nullptr;
     adaflo_b200_ns_t      h             = nullptr;
+    // host mirrors of the per-point coefficient arrays in the reference's [batch][q][(row)][lane] order
+    unsigned int                       n_lanes   = 8;
+    std::uint32_t                      n_batches = 0;
+    std::vector<std::uint32_t>         slot_cell;
+    mutable std::vector<double>        host_coefficients[4];
+    mutable bool                       host_dirty[4] = {false, false, false, false};
+    double *host_batch(const int which, const unsigned int macro_cell, const bool for_writing) const
+    {
+      require();
+      if (n_batches == 0)
+        throw ExcAdafloB200("begin_*(macro_cell): call set_cell_batches(n_lanes) first");
+      const std::size_t n_rows = which == ADAFLO_B200_COEF_LINEARIZED_VELOCITY ? 12 : 1, per_batch = 27 * n_rows * n_lanes;
+      std::vector<double> &m = host_coefficients[which];
+      if (m.empty())
+        {  // first access since the device arrays changed: fetch them
+          m.assign(per_batch * n_batches, 0.);
+          check(adaflo_b200_ns_get_coefficient_canonical(h, which, m.data(), 1, n_batches, n_lanes, slot_cell.empty() ? nullptr : slot_cell.data()));
+        }
+      if (macro_cell >= n_batches)
+        throw ExcAdafloB200("begin_*(macro_cell): cell batch out of range");
+      if (for_writing)
+        host_dirty[which] = true;
+      return m.data() + per_batch * macro_cell;
+    }
   };
 
   /// adaflo::DiagonalPreconditioner<double> (source/diagonal_preconditioner.cc:38-124).

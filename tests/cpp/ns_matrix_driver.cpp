@@ -144,6 +144,15 @@ int main(int argc, char **argv)
     navier_stokes_matrix.apply_pressure_average_projection(system_rhs.block(1));
     navier_stokes_matrix.vmult(dst, src);
     const double dot = dst * src;
+    // begin_linearized_velocities(macro_cell) in the reference's storage order (navier_stokes_matrix.h:162-178): batches of 4
+    // lanes, [q][12 rows][lane] per batch
+    navier_stokes_matrix.set_cell_batches(4);
+    const std::uint32_t n_batches = (n_cells + 3) / 4;
+    std::vector<double> lin_canonical;
+    for (std::uint32_t b = 0; b < n_batches; ++b) {
+      const double *batch = static_cast<const NavierStokesMatrix<3> &>(navier_stokes_matrix).begin_linearized_velocities(b);
+      lin_canonical.insert(lin_canonical.end(), batch, batch + 27 * 12 * 4);
+    }
     const auto stats = navier_stokes_matrix.get_matvec_statistics();
 
     std::vector<double> ru(3 * (std::size_t)n_u), rp(n_p), du(3 * (std::size_t)n_u), dp(n_p);
@@ -152,6 +161,15 @@ int main(int argc, char **argv)
     dst.block(0).copy_to_host(du.data());
     dst.block(1).copy_to_host(dp.data());
     std::ofstream out(argv[2], std::ios::binary);
+    {
+      const std::string name = "lin_canonical";
+      const std::uint32_t len = name.size();
+      const std::uint64_t nbytes = lin_canonical.size() * sizeof(double);
+      out.write(reinterpret_cast<const char *>(&len), 4);
+      out.write(name.data(), len);
+      out.write(reinterpret_cast<const char *>(&nbytes), 8);
+      out.write(reinterpret_cast<const char *>(lin_canonical.data()), nbytes);
+    }
     write_array(out, "residual_u", ru);
     write_array(out, "residual_p", rp);
     write_array(out, "vmult_u", du);

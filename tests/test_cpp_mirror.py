@@ -75,6 +75,12 @@ def test_cpp_navier_stokes_matrix_matches_oracle(tmp_path):
     assert rel_err(got["vmult_u"], ou) < 1e-12 and rel_err(got["vmult_p"], op) < 1e-12
     assert abs(got["scalars"][0] - (ou @ su + op @ sp)) < 1e-10 * abs(ou @ su + op @ sp)
     assert got["scalars"][1] == 1
+    # begin_linearized_velocities(macro_cell): [batch][q][row][lane] with 4 lanes vs the oracle's [cell][row][q]
+    nb = (mesh.n_cells + 3) // 4
+    lin = got["lin_canonical"].reshape(nb, 27, 12, 4)
+    ref = np.zeros((nb * 4, 12, 27))
+    ref[:mesh.n_cells] = O.lin
+    assert rel_err(lin, ref.reshape(nb, 4, 12, 27).transpose(0, 3, 2, 1)) < 1e-12
 
 
 def test_cpp_level_set_classes_match_oracle(tmp_path):
