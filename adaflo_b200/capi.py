@@ -119,6 +119,8 @@ SYMBOLS = [
     "adaflo_b200_vec_dot", "adaflo_b200_vec_multi_dot", "adaflo_b200_vec_multi_axpy", "adaflo_b200_vec_add_and_dot",
     "adaflo_b200_jacobi_reinit", "adaflo_b200_jacobi_vmult",
     "adaflo_b200_solve_cg", "adaflo_b200_solve_bicgstab", "adaflo_b200_solve_gmres", "adaflo_b200_apply_operator",
+    "adaflo_b200_ns_preconditioner_create", "adaflo_b200_ns_preconditioner_destroy", "adaflo_b200_ns_preconditioner_vmult",
+    "adaflo_b200_ns_preconditioner_apply", "adaflo_b200_ns_preconditioner_statistics",
     "adaflo_b200_ls_projection_vmult", "adaflo_b200_ls_compute_normal", "adaflo_b200_ls_compute_curvature", "adaflo_b200_ls_reinitialize",
     "adaflo_b200_ls_advance_concentration",
 ]
@@ -224,6 +226,11 @@ def load():
         "adaflo_b200_solve_gmres": [vp, i32, C.POINTER(u64), C.POINTER(u64), APPLY_FN, vp, APPLY_FN, vp, C.POINTER(vp), C.POINTER(vp), i32,
                                     C.POINTER(SolverControlABI)],
         "adaflo_b200_apply_operator": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "adaflo_b200_ns_preconditioner_create": [vp, C.POINTER(vp)],
+        "adaflo_b200_ns_preconditioner_destroy": [vp],
+        "adaflo_b200_ns_preconditioner_vmult": [vp, vp, vp, vp, vp],
+        "adaflo_b200_ns_preconditioner_apply": [vp, C.POINTER(vp), C.POINTER(vp)],
+        "adaflo_b200_ns_preconditioner_statistics": [vp, C.POINTER(i32), C.POINTER(i32)],
         "adaflo_b200_ls_projection_vmult": [vp, vp, vp],
         "adaflo_b200_ls_compute_normal": [vp, C.POINTER(vp), vp, i32, C.POINTER(i32)],
         "adaflo_b200_ls_compute_curvature": [vp, vp, vp, C.POINTER(vp), i32, i32, C.POINTER(i32)],

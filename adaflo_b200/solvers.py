@@ -52,6 +52,8 @@ class _Solver:
         lib = self.ctx.lib
         if fn is None:
             return C.cast(None, capi.APPLY_FN), None, None
+        if isinstance(fn, tuple):          # (APPLY_FN, user pointer): a callback that lives in the library
+            return fn[0], fn[1], None
         if isinstance(fn, capi.OperatorRef):
             return C.cast(lib.adaflo_b200_apply_operator, capi.APPLY_FN), C.cast(C.pointer(fn), C.c_void_p), fn
         from .operators import device_view

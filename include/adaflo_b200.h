@@ -428,6 +428,18 @@ int adaflo_b200_solve_gmres(adaflo_b200_ctx_t ctx, int n_blocks, const uint64_t 
                             adaflo_b200_apply_fn P, void *P_user, double *const *x, const double *const *b, int max_basis,
                             adaflo_b200_solver_control *control);
 
+/* Block preconditioner of the linearised Navier-Stokes system on the device: NavierStokesPreconditioner::vmult
+ * with inner solves (source/navier_stokes_preconditioner.cc:593-737), lower block-triangular, Cahouet-Chabard Schur complement
+ * from pressure_mass_vmult / pressure_poisson_vmult; inner solves matrix-free with Jacobi preconditioners instead of the
+ * reference's Trilinos ILU / AMG.  Build it after the linearisation point is set (it takes the diagonal of the velocity
+ * block); use adaflo_b200_ns_preconditioner_apply as the P callback of adaflo_b200_solve_gmres. */
+typedef struct adaflo_b200_precond_s *adaflo_b200_precond_t;
+int adaflo_b200_ns_preconditioner_create(adaflo_b200_ns_t ns, adaflo_b200_precond_t *out);
+int adaflo_b200_ns_preconditioner_destroy(adaflo_b200_precond_t precond);
+int adaflo_b200_ns_preconditioner_vmult(adaflo_b200_precond_t precond, double *dst_u, double *dst_p, const double *src_u, const double *src_p);
+int adaflo_b200_ns_preconditioner_apply(void *precond, double *const *dst, const double *const *src);
+int adaflo_b200_ns_preconditioner_statistics(adaflo_b200_precond_t precond, int *n_applications, int inner_iterations[3]);
+
 #define ADAFLO_B200_OP_NS_VMULT 0            /* handle: adaflo_b200_ns_t, 2 blocks (u, p) */
 #define ADAFLO_B200_OP_NS_VELOCITY 1
 #define ADAFLO_B200_OP_NS_PRESSURE_POISSON 2

@@ -195,3 +195,10 @@ def test_block_preconditioner_on_the_first_newton_system_of_beltrami_3d(ctx):
     A.vmult(Ax, upd)
     res = float(((Ax.block(0) - rhs.block(0)).norm() ** 2 + (Ax.block(1) - rhs.block(1)).norm() ** 2).sqrt())
     assert res <= 2e-8 * ctl.history[0]
+    # the same solve entirely inside the library (operator and preconditioner as library callbacks): same iteration
+    upd2 = BlockVector.like(mf)
+    ctl2 = SolverControl(60, 1e-14, 1e-8)
+    from adaflo_b200.solvers import library_operator
+    SolverGMRES(ctx, ctl2, 60).solve(library_operator(capi.OP_NS_VMULT, A.h), [upd2.block(0), upd2.block(1)], [rhs.block(0), rhs.block(1)],
+                                     P.as_library_callback(), [mf.n_owned(0), mf.n_owned(1)])
+    assert abs(ctl2.last_step - ctl.last_step) <= 2 and sum(P.inner_iterations) > 0
