@@ -62,6 +62,9 @@ namespace ab200 {
 #ifndef AB_R1_PLAIN_TICKET  // ticket atomic that ptxas cannot aggregate (see the kernel)
 #define AB_R1_PLAIN_TICKET 1
 #endif
+#ifndef AB_R1_PASYNC  // pressure vertex values by cp.async into their shared-memory slots (see phase A)
+#define AB_R1_PASYNC 1
+#endif
 #ifndef AB_R1_WARPS
 #define AB_R1_WARPS 11
 #endif
@@ -273,6 +276,18 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
     if (t < 2) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) pnode[j] = ld_once(A.cell_p_blk + (g * 4 + j) * 30 + lane, pol);
+#if AB_R1_PASYNC
+      // the 8 vertex values of the cell go straight into their shared-memory slots (cp.async: no registers, nothing waits
+      // for them before the end of phase A); 4 % of the stall samples of profiles/r1_g sat on this gather
+      if (!HANGING) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(sp + t + 2 * j)),
+                       "l"(A.src_p + (pnode[j] & ADAFLO_B200_NODE_MASK))
+                       : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+#endif
     }
     if (A.np_cell == 9) {
       dg0_node = __ldg(A.cell_p + (size_t)cell * 9 + 8);
@@ -357,6 +372,16 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
         }
       }
     }
+#if AB_R1_PASYNC
+    if (WITH_P && !HANGING) {
+      if (t < 2) {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (pnode[j] >> ADAFLO_B200_FLAG_SHIFT) sp[t + 2 * j] = 0.0;  // constrained entries read as zero
+      }
+    } else
+#endif
     if (WITH_P) {
       double pl[4] = {0, 0, 0, 0};
       if (t < 2) {
