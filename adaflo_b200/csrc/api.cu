@@ -106,6 +106,10 @@ static int launch_cells(adaflo_b200_ns_t ns, const NSArgs &a, bool with_p)
   const Quad &q = ns->mf->quads[ns->quad_u];
   const int mode = mode_of(ns->prm);
   cudaStream_t s = ns->ctx->stream;
+  if (ns->generic) {
+    if (a.transpose) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "Tvmult: only the 3-D Q2/Q1 kernels implement the transpose");
+    return launch_ns_generic(a, ns->gen_dim, ns->gen_degree_u, 0, with_p ? 1 : 0, mode, q.geometry_type, s);
+  }
   switch (q.geometry_type) {
     case ADAFLO_B200_GEOM_CARTESIAN: return launch_ns_vmult_cartesian(a, with_p, mode, ns->var, s);
     case ADAFLO_B200_GEOM_AFFINE: return launch_ns_vmult_affine(a, with_p, mode, ns->var, s);
@@ -236,7 +240,7 @@ int adaflo_b200_ctx_init_comm(adaflo_b200_ctx_t ctx, const unsigned char id[128]
 int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, adaflo_b200_mf_t *out)
 {
   if (!ctx || !d || !out) return fail(ADAFLO_B200_ERR_ARG, "mf_create: null argument");
-  if (d->dim != 3) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "mf_create: only dim == 3 is implemented");
+  if (d->dim != 3 && d->dim != 2) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "mf_create: dim must be 2 or 3");
   AB_CUDA(cudaSetDevice(ctx->device));
   adaflo_b200_mf_t mf = new (std::nothrow) adaflo_b200_mf_s();
   if (!mf) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");
@@ -258,7 +262,7 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
       return fail(ADAFLO_B200_ERR_ARG, "mf_create: more than 2^29 nodes per rank");
     AB_CHECK(upload(&sp.cell_nodes, sd.cell_nodes, (size_t)d->n_cells * sd.nodes_per_cell, s));
     if (sd.hanging_masks) AB_CHECK(upload(&sp.hanging_masks, sd.hanging_masks, (size_t)d->n_cells, s));
-    if (sd.nodes_per_cell == 27 || sd.nodes_per_cell == 8 || sd.nodes_per_cell == 9) {
+    if (d->dim == 3 && (sd.nodes_per_cell == 27 || sd.nodes_per_cell == 8 || (sd.nodes_per_cell == 9 && sd.fe_kind == ADAFLO_B200_FE_Q_DG0))) {
       // decade-blocked copy for the vmult kernel: lane 3 cw + iz reads in-plane node j of its plane
       const int n1 = sd.nodes_per_cell == 27 ? 3 : 2, nj = n1 * n1;
       const size_t ng = n_groups(d->n_cells);
@@ -300,10 +304,10 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
     q.n_q_1d = qd.n_q_1d;
     q.geometry_type = qd.geometry_type;
     q.n_rows = qd.n_table_rows;
-    const size_t nq = (size_t)qd.n_q_1d * qd.n_q_1d * qd.n_q_1d;
+    const size_t nq = (size_t)qd.n_q_1d * qd.n_q_1d * (d->dim == 3 ? qd.n_q_1d : 1);
     if (qd.geometry_type == ADAFLO_B200_GEOM_GENERAL) {
       if (!qd.inv_jacobian || !qd.jxw) return fail(ADAFLO_B200_ERR_ARG, "mf_create: general geometry needs inv_jacobian and jxw");
-      if (qd.n_q_1d == 3) {  // decade blocked (see coef_index)
+      if (qd.n_q_1d == 3 && d->dim == 3) {  // decade blocked (see coef_index)
         const size_t ng = n_groups(d->n_cells);
         std::vector<double> kb(ng * 9 * 270, 0.0), jb(ng * 270, 1.0);
         for (uint32_t c = 0; c < d->n_cells; ++c)
@@ -568,9 +572,27 @@ int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   const Space &su = mf->spaces[dof_u], &sp = mf->spaces[dof_p];
   // EXPAND_OPERATIONS, navier_stokes_matrix.cc:64-82: the reference dispatches pressure degree 1..5;
   // this library implements degree_p == 1 (Q2/Q1 and Q2/(Q1+DG0))
-  if (su.degree != 2 || su.n_comp != 3 || su.nodes_per_cell != 27 || sp.degree != 1 || sp.n_comp != 1 ||
-      !(sp.nodes_per_cell == 8 || sp.nodes_per_cell == 9) || mf->quads[quad_u].n_q_1d != 3 || mf->quads[quad_p].n_q_1d != 2)
-    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: only 3-D Taylor-Hood Q2/Q1(+DG0) with QGauss(3)/QGauss(2) is implemented");
+  // 3-D Q2/Q1(+DG0) runs on the tuned kernels; every other Taylor-Hood pair (velocity degree 2..5, dim 2 or 3) on the generic
+  // sum-factorisation kernel of ns_generic.cu.  ADAFLO_B200_NS_GENERIC=1 forces the generic path (tests).
+  const char *force_env = std::getenv("ADAFLO_B200_NS_GENERIC");  // read at every create: tests switch it at run time
+  const bool force_generic = force_env && force_env[0] == '1';
+  const bool tuned = mf->dim == 3 && su.degree == 2 && su.n_comp == 3 && su.nodes_per_cell == 27 && sp.degree == 1 && sp.n_comp == 1 &&
+                     (sp.nodes_per_cell == 8 || sp.nodes_per_cell == 9) && mf->quads[quad_u].n_q_1d == 3 && mf->quads[quad_p].n_q_1d == 2;
+  const bool generic = !tuned || (force_generic && sp.nodes_per_cell == 8 && !su.hanging_masks && prm->density_diff == 0 && prm->viscosity_diff == 0 &&
+                                  (prm->linearization == ADAFLO_B200_COUPLED_IMPLICIT_NEWTON || prm->linearization == ADAFLO_B200_COUPLED_IMPLICIT_PICARD));
+  if (generic) {
+    const int K = su.degree, dim = mf->dim;
+    const uint32_t nn = dim == 2 ? (K + 1) * (K + 1) : (K + 1) * (K + 1) * (K + 1), npn = dim == 2 ? K * K : K * K * K;
+    if (K < 2 || K > 5 || sp.degree != K - 1 || su.fe_kind != ADAFLO_B200_FE_Q || sp.fe_kind != ADAFLO_B200_FE_Q || su.n_comp != dim ||
+        sp.n_comp != 1 || su.nodes_per_cell != nn || sp.nodes_per_cell != npn || mf->quads[quad_u].n_q_1d != K + 1)
+      return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: Taylor-Hood Q_k/Q_(k-1) with k = 2..5, FE_Q spaces, QGauss(k+1), dim 2 or 3 "
+                                               "(navier_stokes_matrix.cc:64-82); the element-constant pressure needs 3-D Q2/Q1");
+    if (su.hanging_masks || sp.hanging_masks || prm->density_diff != 0 || prm->viscosity_diff != 0 || prm->augmented_taylor_hood)
+      return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: hanging nodes, variable coefficients and the augmented pressure are implemented "
+                                               "for 3-D Q2/Q1 only");
+    if (prm->linearization != ADAFLO_B200_COUPLED_IMPLICIT_NEWTON && prm->linearization != ADAFLO_B200_COUPLED_IMPLICIT_PICARD)
+      return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: the generic-degree path implements the coupled implicit Newton and Picard linearisations");
+  }
   if ((su.hanging_masks != nullptr) != (sp.hanging_masks != nullptr))
     return fail(ADAFLO_B200_ERR_ARG, "ns_create: hanging-node masks must be given for both spaces or for none");
   AB_CUDA(cudaSetDevice(ctx->device));
@@ -586,9 +608,17 @@ int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   ns->quad_u = quad_u;
   ns->quad_p = quad_p;
   ns->n_q = 27;
+  ns->generic = generic;
+  ns->gen_dim = mf->dim;
+  ns->gen_degree_u = su.degree;
   ns->var = prm->density_diff != 0 || prm->viscosity_diff != 0;  // :97-98
   cudaStream_t s = ctx->stream;
-  const size_t size = n_groups(mf->n_cells) * 270;  // decade-blocked per-point arrays
+  size_t size = n_groups(mf->n_cells) * 270;  // decade-blocked per-point arrays
+  if (generic) {  // plain [cell][row][q] with dim + dim^2 rows; size * 12 below covers it
+    const int n1 = su.degree + 1;
+    ns->n_q = mf->dim == 2 ? n1 * n1 : n1 * n1 * n1;
+    size = ((size_t)mf->n_cells * ns->n_q * (mf->dim + mf->dim * mf->dim) + 11) / 12;
+  }
   if (ns->var) {  // :100-106
     AB_CUDA(cudaMalloc((void **)&ns->rho, size * sizeof(double)));
     AB_CUDA(cudaMalloc((void **)&ns->mu, size * sizeof(double)));
@@ -616,7 +646,16 @@ int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
     pa.dst = pres_mass;
     pa.c0 = 1.0;
     fill_geometry(pa, mf->quads[quad_p]);
-    AB_CHECK(launch_pressure_op(pa, 2, 2, s));
+    if (generic) {  // integrals of the pressure shape functions with the velocity quadrature (exact for them)
+      NSArgs ga = make_args(ns, false);
+      ga.dst_p = pres_mass;
+      if (mf->quads[quad_p].n_q_1d == su.degree) {  // the pressure quadrature QGauss(degree_p + 1), like the reference
+        fill_geometry(ga, mf->quads[quad_p]);
+        AB_CHECK(launch_ns_generic(ga, mf->dim, su.degree - 1, 3, 1, 0, mf->quads[quad_p].geometry_type, s));
+      } else
+        AB_CHECK(launch_ns_generic(ga, mf->dim, su.degree, 2, 1, 0, mf->quads[quad_u].geometry_type, s));
+    } else
+      AB_CHECK(launch_pressure_op(pa, 2, 2, s));
     AB_CHECK(comm_compress_add(mf, dof_p, pres_mass));
     std::vector<double> pm(n_p_local), m(n_p_local), w(n_p_local);
     AB_CUDA(cudaMemcpyAsync(pm.data(), pres_mass, n_p_local * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -751,7 +790,7 @@ static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const d
     const char *k = std::getenv("ADAFLO_B200_VMULT_KERNEL"), *o = std::getenv("ADAFLO_B200_HALO_OVERLAP");
     return !(k && !std::strcmp(k, "v1")) && (o && !std::strcmp(o, "1"));  // the legacy v1 kernel has no decade range
   }();
-  const bool overlap = overlap_enabled && ctx->nranks > 1 && mf->ghost_range_valid && ctx->comm_stream;
+  const bool overlap = overlap_enabled && !ns->generic && ctx->nranks > 1 && mf->ghost_range_valid && ctx->comm_stream;
   if (ctx->nranks > 1) {
     const int spaces[2] = {ns->dof_u, ns->dof_p};
     double *vecs[2] = {const_cast<double *>(src_u), const_cast<double *>(in_p)};
@@ -862,7 +901,10 @@ int adaflo_b200_ns_residual(adaflo_b200_ns_t ns, double *rhs_u, double *rhs_p, c
   a.old_old_u = ns->old_old_u;
   a.dst_u = rhs_u;
   a.dst_p = rhs_p;
-  AB_CHECK(launch_ns_residual(a, mf->quads[ns->quad_u].geometry_type, ns->var, s));
+  if (ns->generic)
+    AB_CHECK(launch_ns_generic(a, ns->gen_dim, ns->gen_degree_u, 1, 1, mode_of(ns->prm), mf->quads[ns->quad_u].geometry_type, s));
+  else
+    AB_CHECK(launch_ns_residual(a, mf->quads[ns->quad_u].geometry_type, ns->var, s));
   if (ctx->nranks > 1) {
     AB_CHECK(comm_compress_add(mf, ns->dof_u, rhs_u));
     AB_CHECK(comm_compress_add(mf, ns->dof_p, rhs_p));
@@ -893,6 +935,7 @@ int adaflo_b200_ns_velocity_vmult(adaflo_b200_ns_t ns, double *dst_u, const doub
 
 int adaflo_b200_ns_divergence_vmult_add(adaflo_b200_ns_t ns, double *dst_p, const double *src_u, int weight_by_viscosity)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "divergence_vmult_add: operator not initialised");
   if (!dst_p || !src_u) return fail(ADAFLO_B200_ERR_ARG, "divergence_vmult_add: null vector");
   adaflo_b200_mf_t mf = ns->mf;
@@ -942,6 +985,7 @@ static int pressure_common(adaflo_b200_ns_t ns, double *dst_p, const double *src
 
 int adaflo_b200_ns_pressure_mass_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_mass_vmult: operator not initialised");
   if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_mass_vmult: null vector");
   PArgs pa{};
@@ -968,6 +1012,7 @@ int adaflo_b200_ns_pressure_mass_vmult(adaflo_b200_ns_t ns, double *dst_p, const
 
 int adaflo_b200_ns_pressure_poisson_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_poisson_vmult: operator not initialised");
   if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_poisson_vmult: null vector");
   PArgs pa{};
@@ -998,6 +1043,7 @@ int adaflo_b200_ns_pressure_poisson_vmult(adaflo_b200_ns_t ns, double *dst_p, co
 
 int adaflo_b200_ns_pressure_convdiff_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_convdiff_vmult: operator not initialised");
   if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_convdiff_vmult: null vector");
   if (!ns->lin) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "pressure_convdiff_vmult needs linearized velocities (:1111)");
@@ -1014,6 +1060,7 @@ int adaflo_b200_ns_pressure_convdiff_vmult(adaflo_b200_ns_t ns, double *dst_p, c
 
 int adaflo_b200_ns_compute_diagonal(adaflo_b200_ns_t ns, double *diag_u, double *diag_p)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   // Exact diagonal of vmult.  Velocity block: diag(C^T A_cell C) summed over cells (one unit-source pass per
   // cell-local slot inside the cell kernel), 1 on constrained rows.  Pressure block: the operator has no
   // pressure-pressure coupling and the mean projection removes a multiple of (A^T w)_p = 0, so the diagonal is
@@ -1040,7 +1087,8 @@ int adaflo_b200_ns_fix_linearization_point(adaflo_b200_ns_t ns)
 {
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "operator not initialised");
   cudaStream_t s = ns->ctx->stream;
-  const size_t size = n_groups(ns->mf->n_cells) * 270;
+  size_t size = n_groups(ns->mf->n_cells) * 270;
+  if (ns->generic) size = ((size_t)ns->mf->n_cells * ns->n_q * (ns->gen_dim + ns->gen_dim * ns->gen_dim) + 11) / 12;
   struct { double **dst; double *src; size_t n; } items[] = {{&ns->lin_prec, ns->lin, size * 12},
                                                              {&ns->rho_prec, ns->rho, size},
                                                              {&ns->mu_prec, ns->mu, size},
@@ -1073,6 +1121,7 @@ int adaflo_b200_ns_apply_pressure_shift(adaflo_b200_ns_t ns, double shift, doubl
 
 int adaflo_b200_ns_coefficient_ptr(adaflo_b200_ns_t ns, int which, double **dev_ptr, uint64_t *n)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns || !dev_ptr) return fail(ADAFLO_B200_ERR_ARG, "null argument");
   const uint64_t size = (uint64_t)n_groups(ns->mf->n_cells) * 270;
   double *p = nullptr;
@@ -1136,12 +1185,14 @@ static int coef_canonical(adaflo_b200_ns_t ns, int which, double *canonical, int
 int adaflo_b200_ns_set_coefficient_canonical(adaflo_b200_ns_t ns, int which, const double *canonical, int on_host, uint32_t n_batches,
                                              uint32_t lanes, const uint32_t *slot_cell_host)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   return coef_canonical(ns, which, const_cast<double *>(canonical), on_host, n_batches, lanes, slot_cell_host, false);
 }
 
 int adaflo_b200_ns_get_coefficient_canonical(adaflo_b200_ns_t ns, int which, double *canonical, int on_host, uint32_t n_batches,
                                              uint32_t lanes, const uint32_t *slot_cell_host)
 {
+  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   return coef_canonical(ns, which, canonical, on_host, n_batches, lanes, slot_cell_host, true);
 }
 
@@ -1280,7 +1331,7 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
   const int mode = mode_of(ns->prm);
   const bool multi = ns->ctx->nranks > 1;
   const bool renumbered = su.numbering || sp.numbering;  // host numbering is not node-major: permute on the device, no chunk pipeline
-  if (!pipe_enabled || legacy_kernel || renumbered || !mf->pipeline_ok || ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin)) {
+  if (!pipe_enabled || legacy_kernel || renumbered || ns->generic || !mf->pipeline_ok || ((mode == MODE_NEWTON || mode == MODE_PICARD) && !ns->lin)) {
     // plain path: upload, vmult, download
     AB_CHECK(upload_owned(mf, ns->dof_u, ns->stage_u[0], src_u_host, s));
     AB_CHECK(upload_owned(mf, ns->dof_p, ns->stage_p[0], src_p_host, s));

@@ -167,6 +167,10 @@ struct adaflo_b200_ns_s {
   adaflo_b200_time_weights tw;
   int dof_u, dof_p, quad_u, quad_p;
   int n_q;  // points of quad_u
+  // degree / dimension dispatch (ns_generic.cu): anything but 3-D Q2/Q1 runs through the generic kernel with plain
+  // per-point arrays [cell][row][q]
+  bool generic;
+  int gen_dim, gen_degree_u;
   // per-quadrature-point coefficient arrays (owned)
   double *lin, *rho, *mu, *damp;
   double *lin_prec, *rho_prec, *mu_prec, *damp_prec;  // fix_linearization_point snapshots
@@ -243,7 +247,8 @@ int launch_ns_vmult_cartesian(const NSArgs &a, bool with_p, int mode, bool var, 
 int launch_ns_vmult_affine(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
 int launch_ns_vmult_general(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
 int launch_ns_residual(const NSArgs &a, int geom, bool var, cudaStream_t s);
-int launch_ns_residual_r1(const NSArgs &a, int geom, bool var, cudaStream_t s);  // Newton / Picard / Stokes, vmult mapping
+int launch_ns_residual_r1(const NSArgs &a, int geom, bool var, cudaStream_t s);
+int launch_ns_generic(const NSArgs &a, int dim, int degree_u, int kind, int with_p, int mode, int geom, cudaStream_t s);  // ns_generic.cu  // Newton / Picard / Stokes, vmult mapping
 
 struct PArgs {
   uint32_t n_cells;

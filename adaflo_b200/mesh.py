@@ -755,3 +755,80 @@ class RefinedBoxMesh:
         qz, qy, qx = np.meshgrid(np.arange(n_q_1d), np.arange(n_q_1d), np.arange(n_q_1d), indexing="ij")
         xi = np.stack([qp[qx.reshape(-1)], qp[qy.reshape(-1)], qp[qz.reshape(-1)]], axis=1)
         return self.origin[:, None, :] + self.h_cell[:, None, :] * xi[None, :, :]
+
+
+class TensorMesh:
+    """Uniform box of n cells per direction in dim = 2 or 3 with Taylor-Hood Q_k / Q_(k-1) spaces (k = degree >= 2):
+    the meshes of the degree / dimension dispatch (csrc/ns_generic.cu), e.g. Q4/Q3 in 2-D like tests/beltrami_2d.prm.
+    Nodes are global tensor grids (lexicographic, x fastest), cell-local nodes lexicographic; FE_Q(k) nodes sit on the
+    Gauss-Lobatto points of each cell (deal.II's FE_Q).  Velocity entry (node, c) = dim node + c; homogeneous Dirichlet flags on
+    all boundary faces."""
+
+    def __init__(self, dim, n, degree, lower=None, upper=None):
+        assert dim in (2, 3) and degree >= 2
+        self.dim, self.degree = dim, degree
+        self.n = tuple(int(v) for v in n)
+        assert len(self.n) == dim
+        self.lower = np.asarray(lower if lower is not None else (-1.0,) * dim, dtype=np.float64)
+        self.upper = np.asarray(upper if upper is not None else (1.0,) * dim, dtype=np.float64)
+        self.h = (self.upper - self.lower) / np.asarray(self.n, dtype=np.float64)
+        self.n_cells = int(np.prod(self.n))
+        self.cell_u, self.n_u_nodes, self.u_coords, self.u_boundary = self._space(degree)
+        self.cell_p, self.n_p_nodes, self.p_coords, _ = self._space(degree - 1)
+        self.u_dirichlet = np.repeat(self.u_boundary[:, None], dim, axis=1)
+        self.u_ids = np.arange(self.n_u_nodes, dtype=np.int64)
+        self.p_ids = np.arange(self.n_p_nodes, dtype=np.int64)
+
+    @staticmethod
+    def _gll(n):
+        from numpy.polynomial import legendre as npleg
+        if n == 2:
+            return np.array([0.0, 1.0])
+        c = np.zeros(n)
+        c[-1] = 1.0
+        return 0.5 * (np.concatenate([[-1.0], np.sort(npleg.legroots(npleg.legder(c))), [1.0]]) + 1.0)
+
+    def _space(self, k):
+        dim, n = self.dim, self.n
+        N = [n[d] * k + 1 for d in range(dim)]
+        gll = self._gll(k + 1)
+        # node index along direction d of local node a in cell i: i k + a
+        local = np.arange(k + 1)
+        axes = [np.arange(n[d])[:, None] * k + local[None, :] for d in range(dim)]          # [cell_d, a]
+        x1d = []
+        for d in range(dim):
+            x = np.zeros(N[d])
+            for i in range(n[d]):
+                x[i * k: i * k + k + 1] = self.lower[d] + self.h[d] * (i + gll)
+            x1d.append(x)
+        if dim == 2:
+            g = axes[0][None, :, None, :] + N[0] * axes[1][:, None, :, None]                # [cy, cx, b, a]
+            cells = g.reshape(n[1] * n[0], (k + 1) ** 2)
+            X, Y = np.meshgrid(x1d[0], x1d[1], indexing="xy")
+            coords = np.stack([X.reshape(-1), Y.reshape(-1)], axis=1)
+            ix, iy = np.meshgrid(np.arange(N[0]), np.arange(N[1]), indexing="xy")
+            bnd = ((ix == 0) | (ix == N[0] - 1) | (iy == 0) | (iy == N[1] - 1)).reshape(-1)
+        else:
+            g = (axes[0][None, None, :, None, None, :] + N[0] * axes[1][None, :, None, None, :, None]
+                 + N[0] * N[1] * axes[2][:, None, None, :, None, None])                     # [cz, cy, cx, c, b, a]
+            cells = g.reshape(n[2] * n[1] * n[0], (k + 1) ** 3)
+            Z, Y, X = np.meshgrid(x1d[2], x1d[1], x1d[0], indexing="ij")
+            coords = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], axis=1)
+            iz, iy, ix = np.meshgrid(np.arange(N[2]), np.arange(N[1]), np.arange(N[0]), indexing="ij")
+            bnd = ((ix == 0) | (ix == N[0] - 1) | (iy == 0) | (iy == N[1] - 1) | (iz == 0) | (iz == N[2] - 1)).reshape(-1)
+        return cells.astype(np.int64), int(np.prod(N)), coords, bnd
+
+    def encoded_cell_u(self):
+        """cell lists with the constraint flag bits of the C ABI (bit 29 + c: component c constrained)"""
+        flags = np.zeros(self.n_u_nodes, dtype=np.uint32)
+        for c in range(self.dim):
+            flags |= (self.u_dirichlet[:, c].astype(np.uint32) << np.uint32(29 + c))
+        return (self.cell_u.astype(np.uint32) | flags[self.cell_u]).astype(np.uint32)
+
+    def constrained_u(self):
+        return np.nonzero(self.u_dirichlet.reshape(-1))[0].astype(np.uint32)
+
+    def cartesian_geometry(self):
+        inv = np.ones(3)
+        inv[: self.dim] = 1.0 / self.h
+        return np.array([[inv[0], inv[1], inv[2], float(np.prod(self.h))]]), np.zeros(self.n_cells, dtype=np.uint32)

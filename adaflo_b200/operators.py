@@ -801,3 +801,51 @@ class LevelSetOperators2D:
         self.L.close()
         if self._own_mf:
             self.mf.close()
+
+
+class MatrixFreeGeneric:
+    """Device mirror of MatrixFree for the degree / dimension dispatch: Taylor-Hood Q_k / Q_(k-1) on an
+    adaflo_b200.mesh.TensorMesh (dim 2 or 3), dof handlers {0: u, 1: p}, quadratures {0: QGauss(k+1), 1: QGauss(k)}."""
+
+    def __init__(self, ctx: Context, mesh):
+        self.ctx, self.mesh = ctx, mesh
+        k, dim = mesh.degree, mesh.dim
+        cu = np.ascontiguousarray(mesh.encoded_cell_u())
+        cp = np.ascontiguousarray(mesh.cell_p.astype(np.uint32))
+        con = np.ascontiguousarray(mesh.constrained_u())
+        spaces = (capi.SpaceDesc * 2)()
+        for i, (cells, n_nodes, n_comp, deg) in enumerate([(cu, mesh.n_u_nodes, dim, k), (cp, mesh.n_p_nodes, 1, k - 1)]):
+            d = spaces[i]
+            d.fe_kind, d.degree, d.n_components = capi.FE_Q, deg, n_comp
+            d.n_owned_nodes, d.n_ghost_nodes, d.nodes_per_cell = n_nodes, 0, cells.shape[1]
+            d.cell_nodes = cells.ctypes.data
+            d.hanging_masks = None
+            d.n_constrained = len(con) if i == 0 else 0
+            d.constrained_dofs = con.ctypes.data if (i == 0 and len(con)) else None
+            d.n_exchange, d.exchange = 0, None
+        table, row = mesh.cartesian_geometry()
+        table, row = np.ascontiguousarray(table), np.ascontiguousarray(row)
+        quads = (capi.QuadDesc * 2)()
+        for i, nq1 in enumerate((k + 1, k)):
+            q = quads[i]
+            q.n_q_1d, q.geometry_type, q.n_table_rows = nq1, capi.GEOM_CARTESIAN, table.shape[0]
+            q.table, q.cell_row = table.ctypes.data, row.ctypes.data
+        desc = capi.MFDesc(dim, mesh.n_cells, 2, spaces, 2, quads)
+        h = C.c_void_p()
+        check(ctx.lib.adaflo_b200_mf_create(ctx.h, C.byref(desc), C.byref(h)))
+        self.h = h
+
+    def initialize_dof_vector(self, space):
+        n_owned, n_local = C.c_uint64(), C.c_uint64()
+        check(self.ctx.lib.adaflo_b200_mf_vector_size(self.h, space, C.byref(n_owned), C.byref(n_local)))
+        return torch.zeros(n_local.value, dtype=torch.float64, device=self.ctx.device)
+
+    def n_owned(self, space):
+        n_owned = C.c_uint64()
+        check(self.ctx.lib.adaflo_b200_mf_vector_size(self.h, space, C.byref(n_owned), None))
+        return n_owned.value
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.adaflo_b200_mf_destroy(self.h)
+            self.h = C.c_void_p()
