@@ -505,12 +505,13 @@ struct LsCellTraits {
 template <int OP, int S>
 __host__ __device__ constexpr int ls_cell_warps()  // warps per block: the double-buffered per-point stream of n_sub = 4 is 24 KB per warp
 {
-  return (LsCellTraits<OP>::tma_pd && S == 4) ? 4 : 8;
+  // n_sub = 3: 15 KB per warp with the stream buffers -> 7 warps per block let two blocks (14 warps) share an SM
+  return LsCellTraits<OP>::tma_pd ? (S == 4 ? 4 : 7) : 8;
 }
 template <int OP, int S>
 __host__ __device__ constexpr int ls_cell_warp_doubles()
 {
-  constexpr int NP = ((S + 1) * (S + 1) * (S + 1) + 7) / 8 * 8;
+  constexpr int NP = ((S + 1) * (S + 1) * (S + 1) + (S + 1) + 7) / 8 * 8;  // node planes padded by one entry (bank conflicts)
   return LsCellTraits<OP>::n_in * NP + LsCellTraits<OP>::n_out * 8 * NP + (LsCellTraits<OP>::has_u ? 88 : 0) +
          (LsCellTraits<OP>::tma_pd ? 2 * S * S * S * 24 + 2 : 0);
 }
@@ -555,8 +556,11 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
     ls_cell_kernel(const LSArgs A)
 {
   using T = LsCellTraits<OP>;
-  constexpr int S3 = S * S * S, n1 = S + 1, N = n1 * n1 * n1, NP = (N + 7) / 8 * 8;
+  // shared-memory arrays of nodal values: node (ix, iy, iz) at ix + n1 iy + PS iz with the plane stride PS = n1^2 + 1 -- with
+  // PS = n1^2 = 16 (n_sub = 3) the sub-cells (sx, sy, 0..2) of a warp hit one bank (3-way conflicts on every corner access)
+  constexpr int S3 = S * S * S, n1 = S + 1, N = n1 * n1 * n1, PS = n1 * n1 + 1, NP = (N + n1 + 7) / 8 * 8;
   constexpr int NIT = (S3 + 31) / 32, NSL = (N + 31) / 32, WARPS = ls_cell_warps<OP, S>();
+  auto sidx = [](const int slot) { return slot + slot / (n1 * n1); };  // cell slot (list order) -> shared-memory index
   constexpr unsigned kPdBytes = S3 * 24 * 8;
   extern __shared__ __align__(16) double ls_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -657,7 +661,7 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
                 v = rd(A.src[f], i, T::resolve);
               else
                 v = (T::resolve && (nd[i] >> ADAFLO_B200_FLAG_SHIFT)) ? 0.0 : val[f][i];
-              cin[f * NP + lane + 32 * i] = v;
+              cin[f * NP + sidx(lane + 32 * i)] = v;
             }
         }
     }
@@ -705,9 +709,9 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
             a1 = nn > 1e-2 ? a1 / nn : 0.0;
             a2 = nn > 1e-2 ? a2 / nn : 0.0;
           }
-          cin[(T::n_src + 0) * NP + lane + 32 * i] = a0;
-          cin[(T::n_src + 1) * NP + lane + 32 * i] = a1;
-          cin[(T::n_src + 2) * NP + lane + 32 * i] = a2;
+          cin[(T::n_src + 0) * NP + sidx(lane + 32 * i)] = a0;
+          cin[(T::n_src + 1) * NP + sidx(lane + 32 * i)] = a1;
+          cin[(T::n_src + 2) * NP + sidx(lane + 32 * i)] = a2;
         }
     }
     if (T::has_u) {  // Q2 velocity of the cell (read_dof_values_plain of a distributed vector = the interpolated values)
@@ -744,13 +748,13 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
         const int sub = lane + 32 * it;
         if (sub >= S3) continue;
         const int sx = sub % S, sy = (sub / S) % S, sz = sub / (S * S);
-        const int nb = sx + n1 * (sy + n1 * sz);  // corner (0,0,0) of the sub-cell in the cell's node numbering
+        const int nb = sx + n1 * sy + PS * sz;  // corner (0,0,0) of the sub-cell in the shared-memory node numbering
         double out[T::n_out][8];
         double cv[8], v[8], dx[4], dy[4], dz[4];
         if (T::has_src) {
           const double *cf = cin + (OP == LS_DAMPED ? f : 0) * NP;
 #pragma unroll
-          for (int n = 0; n < 8; ++n) cv[n] = cf[nb + (n & 1) + n1 * (((n >> 1) & 1) + n1 * (n >> 2))];
+          for (int n = 0; n < 8; ++n) cv[n] = cf[nb + (n & 1) + n1 * ((n >> 1) & 1) + PS * (n >> 2)];
         }
         if (OP == LS_DAMPED && CART) {  // constant coefficients: tensor product of 2x2 matrices, no quadrature loop
           const double vol = 8.0 * jxw;
@@ -762,7 +766,7 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
         if (T::has_aux) {
 #pragma unroll
           for (int n = 0; n < 8; ++n) {
-            const int nn = nb + (n & 1) + n1 * (((n >> 1) & 1) + n1 * (n >> 2));
+            const int nn = nb + (n & 1) + n1 * ((n >> 1) & 1) + PS * (n >> 2);
             a0[n] = cin[(T::n_src + 0) * NP + nn];
             a1[n] = cin[(T::n_src + 1) * NP + nn];
             a2[n] = cin[(T::n_src + 2) * NP + nn];
@@ -942,7 +946,7 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
 #pragma unroll
         for (int o = 0; o < T::n_out; ++o)
 #pragma unroll
-          for (int n = 0; n < 8; ++n) cbuf[(o * 8 + n) * NP + nb + (n & 1) + n1 * (((n >> 1) & 1) + n1 * (n >> 2))] = out[o][n];
+          for (int n = 0; n < 8; ++n) cbuf[(o * 8 + n) * NP + nb + (n & 1) + n1 * ((n >> 1) & 1) + PS * (n >> 2)] = out[o][n];
       }
       __syncwarp();
       // cell vector: sum of the 8 corner buffers; scatter it
@@ -953,9 +957,9 @@ __global__ void __launch_bounds__(ls_cell_warps<OP, S>() * 32, (OP == LS_ADVECT_
           double sum[T::n_out];
 #pragma unroll
           for (int o = 0; o < T::n_out; ++o) {
-            sum[o] = cbuf[(o * 8) * NP + slot];
+            sum[o] = cbuf[(o * 8) * NP + sidx(slot)];
 #pragma unroll
-            for (int n = 1; n < 8; ++n) sum[o] += cbuf[(o * 8 + n) * NP + slot];
+            for (int n = 1; n < 8; ++n) sum[o] += cbuf[(o * 8 + n) * NP + sidx(slot)];
           }
           constexpr bool skip = OP != LS_MASS_DIAG;
           if (OP == LS_NORMAL_RHS) {

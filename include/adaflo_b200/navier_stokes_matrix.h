@@ -334,7 +334,7 @@ namespace adaflo_b200
   class NavierStokesMatrix
   {
   public:
-    static_assert(dim == 3, "only dim == 3 is implemented (the reference instantiates 1, 2, 3)");
+    static_assert(dim == 2 || dim == 3, "dim 2 and 3 are implemented (the reference also instantiates dim 1, source/navier_stokes_matrix.cc:1210)");
 
     NavierStokesMatrix(const FlowParameters &parameters,
                        const unsigned int   &dof_index_u,
