@@ -18,6 +18,7 @@ using namespace ab200;
 
 struct adaflo_b200_precond_s {
   adaflo_b200_ns_t ns;
+  int device;  // kept here: the preconditioner may outlive the operator it was built for (destruction order of a host language)
   double *inv_diag_u, *inv_lump_p, *ones_p, *temp, *temp2;
   uint64_t nu_owned, nu_local, np_owned, np_local;
   int inner_iterations[3];  // velocity, pressure mass, pressure Poisson (accumulated)
@@ -43,6 +44,7 @@ int adaflo_b200_ns_preconditioner_create(adaflo_b200_ns_t ns, adaflo_b200_precon
   adaflo_b200_precond_t P = new (std::nothrow) adaflo_b200_precond_s();
   if (!P) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");
   P->ns = ns;
+  P->device = ctx->device;
   const Space &su = ns->mf->spaces[ns->dof_u], &sp = ns->mf->spaces[ns->dof_p];
   P->nu_owned = su.n_owned_entries(); P->nu_local = su.n_local_entries();
   P->np_owned = sp.n_owned_entries(); P->np_local = sp.n_local_entries();
@@ -72,8 +74,8 @@ int adaflo_b200_ns_preconditioner_create(adaflo_b200_ns_t ns, adaflo_b200_precon
 int adaflo_b200_ns_preconditioner_destroy(adaflo_b200_precond_t P)
 {
   if (!P) return 0;
-  cudaSetDevice(P->ns->ctx->device);
-  cudaStreamSynchronize(P->ns->ctx->stream);
+  cudaSetDevice(P->device);
+  cudaDeviceSynchronize();
   cudaFree(P->inv_diag_u);
   cudaFree(P->inv_lump_p);
   cudaFree(P->ones_p);

@@ -43,8 +43,4 @@ class NavierStokesPreconditioner:
             self.ctx.lib.adaflo_b200_ns_preconditioner_destroy(self.h)
             self.h = C.c_void_p()
 
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+    # no __del__: the handle refers to the operator; at interpreter shutdown the destruction order is arbitrary.  Call close().

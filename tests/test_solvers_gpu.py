@@ -202,3 +202,4 @@ def test_block_preconditioner_on_the_first_newton_system_of_beltrami_3d(ctx):
     SolverGMRES(ctx, ctl2, 60).solve(library_operator(capi.OP_NS_VMULT, A.h), [upd2.block(0), upd2.block(1)], [rhs.block(0), rhs.block(1)],
                                      P.as_library_callback(), [mf.n_owned(0), mf.n_owned(1)])
     assert abs(ctl2.last_step - ctl.last_step) <= 2 and sum(P.inner_iterations) > 0
+    P.close()
