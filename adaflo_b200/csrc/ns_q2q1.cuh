@@ -555,11 +555,9 @@ int launch_vmult_inst(const NSArgs &a, cudaStream_t s)
 {
   auto kern = ns_vmult_kernel<WITH_P, MODE, GEOM, VAR, TRANSPOSE>;
   const size_t smem = sizeof(double) * kWarpsPerBlock * kWarpSmem;
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (a process may drive several GPUs)
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured = true;
   }
   const size_t cells_per_block = (size_t)kWarpsPerBlock * kCellsPerWarp;
   const unsigned grid = (unsigned)((a.n_cells + cells_per_block - 1) / cells_per_block);

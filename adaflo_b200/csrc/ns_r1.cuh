@@ -826,16 +826,17 @@ int launch_vmult_r1_hn(const NSArgs &a, cudaStream_t s)
 {
   auto kern = ns_vmult_r1_kernel<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>;
   const size_t smem = sizeof(double) * kR1Warps * kR1WarpSmem;
-  static bool configured = false;
-  static int n_sm = 0;
-  if (!configured) {
+  // function attributes and the SM count are per device: a process may drive several GPUs through several contexts
+  static int n_sm_of[64] = {};
+  int dev = 0;
+  AB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(ADAFLO_B200_ERR_ARG, "ns_vmult_r1: device ordinal out of range");
+  if (!n_sm_of[dev]) {
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int dev = 0;
-    AB_CUDA(cudaGetDevice(&dev));
-    AB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
+    AB_CUDA(cudaDeviceGetAttribute(&n_sm_of[dev], cudaDevAttrMultiProcessorCount, dev));
   }
+  const int n_sm = n_sm_of[dev];
   if (!a.work_counter) return fail(ADAFLO_B200_ERR_STATE, "ns_vmult_r1: no work counter");
   NSArgs b = a;
   const size_t n_dec = n_groups(a.n_cells);

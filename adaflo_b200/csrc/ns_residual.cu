@@ -238,10 +238,8 @@ static int launch_res_inst(const NSArgs &a, cudaStream_t s)
 {
   auto kern = ns_residual_kernel<GEOM, VAR, EXTRAP>;
   const size_t smem = sizeof(double) * kWarpsPerBlock * kWarpSmem;
-  static bool configured = false;
-  if (!configured) {
+  {  // per device and cheap: set on every launch (a process may drive several GPUs)
     AB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   const size_t cells_per_block = (size_t)kWarpsPerBlock * kCellsPerWarp;
   const unsigned grid = (unsigned)((a.n_cells + cells_per_block - 1) / cells_per_block);

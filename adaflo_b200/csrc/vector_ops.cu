@@ -21,16 +21,17 @@ static inline unsigned grid_for(uint64_t n, int sm_count, int per_thread = 4)
   return (unsigned)blocks;
 }
 
-static int sm_count_cached()
+static int sm_count_cached()  // per device: a process may drive several GPUs
 {
-  static int sm = 0;
-  if (!sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev);
-    if (sm <= 0) sm = 148;
+  static int sm[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!sm[dev]) {
+    cudaDeviceGetAttribute(&sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sm[dev] <= 0) sm[dev] = 148;
   }
-  return sm;
+  return sm[dev];
 }
 
 __global__ void k_set(double *x, double v, uint64_t n)
