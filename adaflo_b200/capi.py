@@ -27,7 +27,9 @@ class SpaceDesc(C.Structure):
                 ("n_owned_nodes", C.c_uint32), ("n_ghost_nodes", C.c_uint32), ("nodes_per_cell", C.c_uint32),
                 ("cell_nodes", C.c_void_p), ("hanging_masks", C.c_void_p),
                 ("n_constrained", C.c_uint32), ("constrained_dofs", C.c_void_p),
-                ("n_exchange", C.c_int32), ("exchange", C.POINTER(Exchange))]
+                ("n_exchange", C.c_int32), ("exchange", C.POINTER(Exchange)),
+                ("n_hanging_nodes", C.c_uint32), ("hanging_row_ptr", C.c_void_p), ("hanging_cols", C.c_void_p),
+                ("hanging_weights", C.c_void_p)]
 
 
 class QuadDesc(C.Structure):
@@ -94,7 +96,7 @@ SYMBOLS = [
     "adaflo_b200_comm_unique_id", "adaflo_b200_ctx_init_comm",
     "adaflo_b200_mf_create", "adaflo_b200_mf_destroy", "adaflo_b200_mf_vector_size", "adaflo_b200_mf_space_info", "adaflo_b200_mf_n_cells",
     "adaflo_b200_mf_set_dof_numbering", "adaflo_b200_mf_upload_vector", "adaflo_b200_mf_download_vector",
-    "adaflo_b200_mf_update_ghost_values", "adaflo_b200_mf_compress_add",
+    "adaflo_b200_mf_update_ghost_values", "adaflo_b200_mf_compress_add", "adaflo_b200_mf_distribute_constraints",
     "adaflo_b200_ns_create", "adaflo_b200_ns_destroy", "adaflo_b200_ns_set_flow_params",
     "adaflo_b200_ns_set_time_weights", "adaflo_b200_ns_set_old_solutions",
     "adaflo_b200_ns_vmult", "adaflo_b200_ns_Tvmult", "adaflo_b200_ns_residual", "adaflo_b200_ns_velocity_vmult",
@@ -158,6 +160,7 @@ def load():
         "adaflo_b200_mf_download_vector": [vp, i32, vp, vp],
         "adaflo_b200_mf_update_ghost_values": [vp, i32, vp],
         "adaflo_b200_mf_compress_add": [vp, i32, vp],
+        "adaflo_b200_mf_distribute_constraints": [vp, i32, vp],
         "adaflo_b200_ns_create": [vp, vp, C.POINTER(FlowParams), i32, i32, i32, i32, i32, C.POINTER(vp)],
         "adaflo_b200_ns_destroy": [vp],
         "adaflo_b200_ns_set_flow_params": [vp, C.POINTER(FlowParams)],

@@ -76,6 +76,17 @@ static NSArgs make_args(adaflo_b200_ns_t ns, bool use_prec)
   a.cell_p_blk = mf->spaces[ns->dof_p].cell_nodes_blk;
   a.hn_u = mf->spaces[ns->dof_u].hanging_masks;
   a.hn_p = mf->spaces[ns->dof_p].hanging_masks;
+  {
+    const Space &su = mf->spaces[ns->dof_u], &sp = mf->spaces[ns->dof_p];
+    a.gc_first_u = su.hn_first;
+    a.gc_ptr_u = su.hn_row_ptr;
+    a.gc_cols_u = su.hn_cols;
+    a.gc_w_u = su.hn_weights;
+    a.gc_first_p = sp.hn_first;
+    a.gc_ptr_p = sp.hn_row_ptr;
+    a.gc_cols_p = sp.hn_cols;
+    a.gc_w_p = sp.hn_weights;
+  }
   const bool prec = use_prec && ns->lin_prec;
   a.lin = prec ? ns->lin_prec : ns->lin;
   a.rho = (use_prec && ns->rho_prec) ? ns->rho_prec : ns->rho;
@@ -277,6 +288,18 @@ int adaflo_b200_mf_create(adaflo_b200_ctx_t ctx, const adaflo_b200_mf_desc *d, a
     }
     sp.n_constrained = sd.n_constrained;
     AB_CHECK(upload(&sp.constrained, sd.constrained_dofs, (size_t)sd.n_constrained, s));
+    if (sd.n_hanging_nodes) {  // general constraint rows (generic-degree path)
+      if (!sd.hanging_row_ptr || !sd.hanging_cols || !sd.hanging_weights || sd.n_hanging_nodes > sd.n_owned_nodes)
+        return fail(ADAFLO_B200_ERR_ARG, "mf_create: n_hanging_nodes needs hanging_row_ptr / hanging_cols / hanging_weights");
+      const uint32_t first = sd.n_owned_nodes - sd.n_hanging_nodes, nnz = sd.hanging_row_ptr[sd.n_hanging_nodes];
+      for (uint32_t k = 0; k < nnz; ++k)  // rows are resolved: parents are unconstrained nodes (AffineConstraints::close)
+        if ((sd.hanging_cols[k] & ADAFLO_B200_NODE_MASK) >= first && (sd.hanging_cols[k] & ADAFLO_B200_NODE_MASK) < sd.n_owned_nodes)
+          return fail(ADAFLO_B200_ERR_ARG, "mf_create: a constraint row refers to another constrained node (rows must be closed)");
+      sp.hn_first = first;
+      AB_CHECK(upload(&sp.hn_row_ptr, sd.hanging_row_ptr, (size_t)sd.n_hanging_nodes + 1, s));
+      AB_CHECK(upload(&sp.hn_cols, sd.hanging_cols, (size_t)nnz, s));
+      AB_CHECK(upload(&sp.hn_weights, sd.hanging_weights, (size_t)nnz, s));
+    }
     if (sd.fe_kind == ADAFLO_B200_FE_Q_DG0) {
       sp.dg0_dofs.resize(d->n_cells);
       for (uint32_t c = 0; c < d->n_cells; ++c)
@@ -424,6 +447,9 @@ int adaflo_b200_mf_destroy(adaflo_b200_mf_t mf)
     free_dev(sp.cell_nodes_blk);
     free_dev(sp.hanging_masks);
     free_dev(sp.constrained);
+    free_dev(sp.hn_row_ptr);
+    free_dev(sp.hn_cols);
+    free_dev(sp.hn_weights);
     free_dev(sp.numbering);
     free_dev(sp.numbering_stage);
     for (Exchange &x : sp.exchange) {
@@ -561,6 +587,32 @@ int adaflo_b200_mf_compress_add(adaflo_b200_mf_t mf, int space, double *vec)
   return comm_compress_add(mf, space, vec);
 }
 
+namespace ab200 {
+__global__ void k_distribute_constraints(double *vec, const uint32_t first, const uint32_t n_rows, const int n_comp, const uint32_t *ptr,
+                                         const uint32_t *cols, const double *w)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * n_comp) return;
+  const uint32_t r = i / n_comp, c = i % n_comp;
+  double v = 0.0;
+  for (uint32_t k = ptr[r], end = ptr[r + 1]; k < end; ++k) v = fma(w[k], vec[(size_t)n_comp * (cols[k] & ADAFLO_B200_NODE_MASK) + c], v);
+  vec[(size_t)n_comp * (first + r) + c] = v;  // rows are closed: no parent is a constrained node
+}
+}  // namespace ab200
+
+int adaflo_b200_mf_distribute_constraints(adaflo_b200_mf_t mf, int space, double *vec)
+{
+  if (!mf || !vec || space < 0 || space >= (int)mf->spaces.size()) return fail(ADAFLO_B200_ERR_ARG, "distribute_constraints: bad argument");
+  const Space &sp = mf->spaces[space];
+  if (!sp.hn_row_ptr) return 0;
+  AB_CUDA(cudaSetDevice(mf->ctx->device));
+  const uint32_t n_rows = sp.n_owned_nodes - sp.hn_first, n = n_rows * sp.n_comp;
+  k_distribute_constraints<<<(n + 127) / 128, 128, 0, mf->ctx->stream>>>(vec, sp.hn_first, n_rows, sp.n_comp, sp.hn_row_ptr, sp.hn_cols, sp.hn_weights);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------- NavierStokesMatrix
 int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaflo_b200_flow_params *prm, int dof_u, int dof_p,
                           int quad_u, int quad_p, int pressure_average_fix, adaflo_b200_ns_t *out)
@@ -595,6 +647,8 @@ int adaflo_b200_ns_create(adaflo_b200_ctx_t ctx, adaflo_b200_mf_t mf, const adaf
   }
   if ((su.hanging_masks != nullptr) != (sp.hanging_masks != nullptr))
     return fail(ADAFLO_B200_ERR_ARG, "ns_create: hanging-node masks must be given for both spaces or for none");
+  if (!generic && (su.hn_row_ptr || sp.hn_row_ptr))
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "ns_create: the tuned 3-D Q2/Q1 kernels take hanging_masks, not general constraint rows");
   AB_CUDA(cudaSetDevice(ctx->device));
   adaflo_b200_ns_t ns = new (std::nothrow) adaflo_b200_ns_s();
   if (!ns) return fail(ADAFLO_B200_ERR_ARG, "out of host memory");

@@ -104,6 +104,10 @@ struct Space {
   uint32_t *hanging_masks;   // device [n_cells] or null
   uint32_t n_constrained;
   uint32_t *constrained;     // device
+  // general constraint rows of the generic-degree path (adaflo_b200_space_desc::hanging_*): nodes >= hn_first are constrained
+  uint32_t hn_first = 0xffffffffu;
+  uint32_t *hn_row_ptr = nullptr, *hn_cols = nullptr;  // device
+  double *hn_weights = nullptr;                        // device
   std::vector<Exchange> exchange;
   std::vector<uint32_t> dg0_dofs;  // host: element-constant dofs (FE_Q_DG0)
   // host-vector pipeline (vmult_host): per cell chunk, the node prefix the chunk needs as source, the node
@@ -208,6 +212,10 @@ struct NSArgs {
   const uint32_t *cell_p_blk;
   const uint32_t *hn_u;  // per-cell refinement masks (null on conforming meshes)
   const uint32_t *hn_p;
+  // generic-degree path: constraint rows (Space::hn_*); first = 0xffffffff on conforming meshes
+  uint32_t gc_first_u, gc_first_p;
+  const uint32_t *gc_ptr_u, *gc_cols_u, *gc_ptr_p, *gc_cols_p;
+  const double *gc_w_u, *gc_w_p;
   const double *src_u;
   const double *src_p;
   const double *old_u;

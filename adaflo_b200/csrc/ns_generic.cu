@@ -10,7 +10,8 @@
 //   -> per-point physics (source/navier_stokes_matrix.cc:702-893, the formulas of ns_r1.cuh for any dim) -> transposed sweeps
 //   -> red.global.add scatter.
 // FE_Q(K) of deal.II is the Lagrange basis on the Gauss-Lobatto points (equidistant for K <= 2); cell-local nodes are
-// lexicographic, x fastest.  Conforming meshes, constant coefficients, Cartesian / affine / general geometry.  This is the
+// lexicographic, x fastest.  Conforming meshes or general constraint rows (hanging nodes: gc_read / gc_add), constant coefficients,
+// Cartesian / affine / general geometry.  This is the
 // correctness path for the configurations outside the benchmark (<= 10^4 cells in the reference's tests), not a tuned one.
 #include <cmath>
 #include <vector>
@@ -58,6 +59,28 @@ __device__ void sweep(const double *M, const int m_stride, const int n_out, cons
   __syncthreads();
 }
 
+// General constraint rows (hanging nodes of any degree; adaflo_b200_space_desc::hanging_*): what FEEvaluation::read_dof_values and
+// distribute_local_to_global do with an AffineConstraints row.  A flagged (homogeneous Dirichlet) component of a parent is read as
+// zero and never written.
+template <int NC>
+__device__ __forceinline__ double gc_read(const double *vec, const uint32_t row, const int c, const uint32_t *ptr, const uint32_t *cols, const double *w)
+{
+  double v = 0.0;
+  for (uint32_t k = __ldg(ptr + row), end = __ldg(ptr + row + 1); k < end; ++k) {
+    const uint32_t pe = __ldg(cols + k);
+    if (!((pe >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) v = fma(__ldg(w + k), vec[(size_t)NC * (pe & ADAFLO_B200_NODE_MASK) + c], v);
+  }
+  return v;
+}
+template <int NC>
+__device__ __forceinline__ void gc_add(double *vec, const uint32_t row, const int c, const uint32_t *ptr, const uint32_t *cols, const double *w, const double val)
+{
+  for (uint32_t k = __ldg(ptr + row), end = __ldg(ptr + row + 1); k < end; ++k) {
+    const uint32_t pe = __ldg(cols + k);
+    if (!((pe >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) red_add(vec + (size_t)NC * (pe & ADAFLO_B200_NODE_MASK) + c, __ldg(w + k) * val);
+  }
+}
+
 enum { GEN_VMULT = 0, GEN_RESIDUAL = 1, GEN_PRESSURE_MASS = 2, GEN_NODAL_MASS = 3 };
 // GEN_NODAL_MASS: integrals of the degree-K shape functions with QGauss(K + 1), scattered through cell_p into dst_p.  Instantiated
 // with K = pressure degree it gives the integrals of the pressure shape functions with the PRESSURE quadrature QGauss(degree_p + 1),
@@ -95,10 +118,13 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       if (fld > 0 && (!vec || A.physical_type != ADAFLO_B200_INCOMPRESSIBLE)) continue;  // block-uniform
       for (int c = 0; c < DIM; ++c) {
         for (int i = tid; i < NN; i += blockDim.x) {
-          const uint32_t e = __ldg(cu + i);
-          const double v = vec[(size_t)DIM * (e & ADAFLO_B200_NODE_MASK) + c];
-          // vmult resolves the constraints (read_dof_values), the residual reads plainly (read_dof_values_plain, :663-664)
-          work[0][i] = (KIND == GEN_VMULT && ((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) ? 0.0 : v;
+          const uint32_t e = __ldg(cu + i), node = e & ADAFLO_B200_NODE_MASK;
+          // vmult resolves the constraints (read_dof_values), the residual reads plainly (read_dof_values_plain, :663-664:
+          // also the entry of a hanging node, which AffineConstraints::distribute has filled, navier_stokes.cc:1252)
+          if (KIND == GEN_VMULT && node >= A.gc_first_u)
+            work[0][i] = gc_read<DIM>(vec, node - A.gc_first_u, c, A.gc_ptr_u, A.gc_cols_u, A.gc_w_u);
+          else
+            work[0][i] = (KIND == GEN_VMULT && ((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) ? 0.0 : vec[(size_t)DIM * node + c];
         }
         __syncthreads();
         int cur = 0;
@@ -119,9 +145,11 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
     // ---- pressure at the points
     if (with_p) {
       for (int i = tid; i < NPN; i += blockDim.x) {
-        const uint32_t e = __ldg(cp + i);
-        const double v = A.src_p[e & ADAFLO_B200_NODE_MASK];
-        work[0][i] = (KIND == GEN_VMULT && (e >> ADAFLO_B200_FLAG_SHIFT)) ? 0.0 : v;
+        const uint32_t e = __ldg(cp + i), node = e & ADAFLO_B200_NODE_MASK;
+        if (KIND == GEN_VMULT && node >= A.gc_first_p)
+          work[0][i] = gc_read<1>(A.src_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p);
+        else
+          work[0][i] = (KIND == GEN_VMULT && (e >> ADAFLO_B200_FLAG_SHIFT)) ? 0.0 : A.src_p[node];
       }
       __syncthreads();
       int cur = 0, ext[3] = {K, K, K};
@@ -251,8 +279,11 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
         cur ^= 1;
       }
       for (int i = tid; i < NN; i += blockDim.x) {
-        const uint32_t e = __ldg(cu + i);
-        if (!((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) red_add(A.dst_u + (size_t)DIM * (e & ADAFLO_B200_NODE_MASK) + c, work[cur][i]);
+        const uint32_t e = __ldg(cu + i), node = e & ADAFLO_B200_NODE_MASK;
+        if (node >= A.gc_first_u)
+          gc_add<DIM>(A.dst_u, node - A.gc_first_u, c, A.gc_ptr_u, A.gc_cols_u, A.gc_w_u, work[cur][i]);
+        else if (!((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u))
+          red_add(A.dst_u + (size_t)DIM * node + c, work[cur][i]);
       }
       __syncthreads();
     }
@@ -265,7 +296,13 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       sweep<DIM, true, false>(tabN, n1, n1, n1, d, ext_q, work[cur], work[cur ^ 1]);
       cur ^= 1;
     }
-    for (int i = tid; i < NN; i += blockDim.x) red_add(A.dst_p + (__ldg(A.cell_p + (size_t)cell * NN + i) & ADAFLO_B200_NODE_MASK), work[cur][i]);
+    for (int i = tid; i < NN; i += blockDim.x) {
+      const uint32_t node = __ldg(A.cell_p + (size_t)cell * NN + i) & ADAFLO_B200_NODE_MASK;
+      if (node >= A.gc_first_p)
+        gc_add<1>(A.dst_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p, work[cur][i]);
+      else
+        red_add(A.dst_p + node, work[cur][i]);
+    }
   } else if (KIND == GEN_PRESSURE_MASS || (with_p && !A.skip_p_test)) {
     int cur = 0, ext[3] = {n1, n1, n1};
     for (int i = tid; i < NQ; i += blockDim.x) work[0][i] = pq[i];
@@ -276,8 +313,11 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       cur ^= 1;
     }
     for (int i = tid; i < NPN; i += blockDim.x) {
-      const uint32_t e = __ldg(cp + i);
-      if (KIND == GEN_PRESSURE_MASS || !(e >> ADAFLO_B200_FLAG_SHIFT)) red_add(A.dst_p + (e & ADAFLO_B200_NODE_MASK), work[cur][i]);
+      const uint32_t e = __ldg(cp + i), node = e & ADAFLO_B200_NODE_MASK;
+      if (node >= A.gc_first_p)
+        gc_add<1>(A.dst_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p, work[cur][i]);
+      else if (KIND == GEN_PRESSURE_MASS || !(e >> ADAFLO_B200_FLAG_SHIFT))
+        red_add(A.dst_p + node, work[cur][i]);
     }
   }
 }

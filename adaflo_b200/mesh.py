@@ -378,6 +378,9 @@ def beltrami_velocity(x: np.ndarray, t=0.0, nu=1.0):
     """Ethier-Steinman Beltrami flow, the analytic field of tests/beltrami.cc:82-115."""
     a = 0.25 * np.pi
     d = 2.0 * a
+    if x.shape[-1] == 2:   # the 2-D Taylor vortex of the same file, tests/beltrami.cc:109-114
+        e = np.exp(-2.0 * nu * a * a * t)
+        return np.stack([-a * np.cos(a * x[..., 0]) * np.sin(a * x[..., 1]) * e, a * np.sin(a * x[..., 0]) * np.cos(a * x[..., 1]) * e], axis=-1)
     X, Y, Z = x[..., 0], x[..., 1], x[..., 2]
     e = np.exp(-nu * d * d * t)
     u0 = -a * (np.exp(a * X) * np.sin(a * Y + d * Z) + np.exp(a * Z) * np.cos(a * X + d * Y)) * e
@@ -390,6 +393,8 @@ def beltrami_pressure(x: np.ndarray, t=0.0, nu=1.0):
     """Pressure of the Beltrami flow, tests/beltrami.cc:140-160."""
     a = 0.25 * np.pi
     d = 2.0 * a
+    if x.shape[-1] == 2:   # tests/beltrami.cc:161-164
+        return -a * a * 0.25 * (np.cos(2 * a * x[..., 0]) + np.cos(2 * a * x[..., 1])) * np.exp(-4.0 * nu * a * a * t)
     X, Y, Z = x[..., 0], x[..., 1], x[..., 2]
     val = -a * a * 0.5 * (np.exp(2 * a * X) + np.exp(2 * a * Y) + np.exp(2 * a * Z)
                           + 2 * np.sin(a * X + d * Y) * np.cos(a * Z + d * X) * np.exp(a * (Y + Z))
@@ -832,3 +837,184 @@ class TensorMesh:
         inv = np.ones(3)
         inv[: self.dim] = 1.0 / self.h
         return np.array([[inv[0], inv[1], inv[2], float(np.prod(self.h))]]), np.zeros(self.n_cells, dtype=np.uint32)
+
+
+class RefinedTensorMesh2D:
+    """2-D box of n coarse cells per direction whose rectangular block `refine` = ((x0, x1), (y0, y1)) of coarse cells is refined
+    once more (2:1 hanging nodes on the block's faces towards active coarse cells), with Taylor-Hood Q_k / Q_(k-1) spaces of any
+    degree: the mesh of tests/beltrami_2d (tests/beltrami.cc:385-412: a 4 x 4 grid refined twice, active cells #2 and #3 flagged,
+    one more global refinement = a 32 x 32 grid whose cells [0, 4) x [2, 4) are refined; Q4/Q3).
+
+    Like deal.II, every cell keeps its own dofs on a hanging face (the coarse cell's k + 1 face nodes; the two fine cells' 2 k + 1
+    nodes, of which the two end points are the coarse vertices): the 2 k - 1 remaining fine nodes are *constrained* dofs that exist
+    in the vectors (the DoF counts of beltrami_2d.output:3 include them) and carry one constraint row each,
+    value = sum_j L_j(s) * coarse face node j, L_j = the Lagrange basis of the coarse face on the Gauss-Lobatto points and s the
+    node's position on it -- the rows AffineConstraints holds after DoFTools::make_hanging_node_constraints.  Constrained nodes
+    are numbered last (adaflo_b200_space_desc::n_hanging_nodes).  Cells: coarse cells lexicographically (without the refined
+    ones), then the fine cells of the block lexicographically."""
+
+    def __init__(self, n, refine, degree, lower=(-1.0, -1.0), upper=(1.0, 1.0)):
+        assert degree >= 2
+        self.dim, self.degree = 2, degree
+        self.n = (int(n[0]), int(n[1]))
+        (x0, x1), (y0, y1) = refine
+        assert 0 <= x0 < x1 <= self.n[0] and 0 <= y0 < y1 <= self.n[1]
+        self.refine = ((x0, x1), (y0, y1))
+        self.lower, self.upper = np.asarray(lower, dtype=np.float64), np.asarray(upper, dtype=np.float64)
+        self.h = (self.upper - self.lower) / np.asarray(self.n, dtype=np.float64)      # coarse cell size
+        # cells in units of the fine cell size: (origin x, origin y, size)
+        cells = [(2 * i, 2 * j, 2) for j in range(self.n[1]) for i in range(self.n[0]) if not (x0 <= i < x1 and y0 <= j < y1)]
+        self.n_coarse = len(cells)
+        cells += [(i, j, 1) for j in range(2 * y0, 2 * y1) for i in range(2 * x0, 2 * x1)]
+        self.cells = np.asarray(cells, dtype=np.int64)
+        self.n_cells = len(cells)
+        self.h_cell = self.cells[:, 2:3] * (0.5 * self.h)[None, :]
+        self.origin = self.lower[None, :] + self.cells[:, 0:2] * (0.5 * self.h)[None, :]
+        self.cell_u, self.n_u_nodes, self.u_coords, self.u_boundary, self.u_rows = self._space(degree)
+        self.cell_p, self.n_p_nodes, self.p_coords, _, self.p_rows = self._space(degree - 1)
+        self.u_dirichlet = np.repeat(self.u_boundary[:, None], 2, axis=1)
+        self.u_ids = np.arange(self.n_u_nodes, dtype=np.int64)
+        self.p_ids = np.arange(self.n_p_nodes, dtype=np.int64)
+
+    @staticmethod
+    def _gll(n):
+        """n Gauss-Lobatto points on [0, 1], exactly symmetric about 1/2"""
+        from numpy.polynomial import legendre as npleg
+        if n == 2:
+            return np.array([0.0, 1.0])
+        c = np.zeros(n)
+        c[-1] = 1.0
+        z = np.concatenate([[-1.0], np.sort(npleg.legroots(npleg.legder(c))), [1.0]])
+        z = 0.5 * (z - z[::-1])
+        return 0.5 * (z + 1.0)
+
+    def _space(self, k):
+        gll = self._gll(k + 1)
+        (x0, x1), (y0, y1) = self.refine
+        nx, ny = self.n
+        scale = float(2 ** 40)
+        key = lambda px, py: (int(round(px * scale)), int(round(py * scale)))
+        coarse, fine = {}, {}
+        pos = []                                                    # node position in fine-cell units
+        lists = np.zeros((self.n_cells, (k + 1) ** 2), dtype=np.int64)
+        for c in range(self.n_coarse):
+            ox, oy, s = self.cells[c]
+            for b in range(k + 1):
+                for a in range(k + 1):
+                    kk = key(ox + s * gll[a], oy + s * gll[b])
+                    if kk not in coarse:
+                        coarse[kk] = len(pos)
+                        pos.append((ox + s * gll[a], oy + s * gll[b]))
+                    lists[c, a + (k + 1) * b] = coarse[kk]
+        hanging = {}                                                # node -> (parents, weights)
+        for c in range(self.n_coarse, self.n_cells):
+            ox, oy, s = self.cells[c]
+            for b in range(k + 1):
+                for a in range(k + 1):
+                    px, py = ox + gll[a], oy + gll[b]
+                    kk = key(px, py)
+                    at_coarse_vertex = (a in (0, k)) and (b in (0, k)) and (ox + a // k) % 2 == 0 and (oy + b // k) % 2 == 0
+                    if at_coarse_vertex and kk in coarse:           # a vertex shared with an active coarse cell: one dof
+                        lists[c, a + (k + 1) * b] = coarse[kk]
+                        continue
+                    if kk not in fine:
+                        fine[kk] = len(pos)
+                        pos.append((px, py))
+                        # on a face of the block with an active coarse neighbour?  (never at a corner of the block: those are
+                        # coarse vertices, and a block face on the domain boundary has no neighbour)
+                        face = None
+                        if a == 0 and ox == 2 * x0 and x0 > 0:
+                            face = (0, 2 * x0)
+                        elif a == k and ox + 1 == 2 * x1 and x1 < nx:
+                            face = (0, 2 * x1)
+                        elif b == 0 and oy == 2 * y0 and y0 > 0:
+                            face = (1, 2 * y0)
+                        elif b == k and oy + 1 == 2 * y1 and y1 < ny:
+                            face = (1, 2 * y1)
+                        if face is not None:
+                            d, X = face                              # face normal direction, its coordinate
+                            t = py if d == 0 else px                 # position along the face
+                            jc = int(np.floor(t / 2.0 + 1e-12))
+                            if abs(t - 2 * jc) < 1e-12 and abs(t - round(t)) < 1e-12 and int(round(t)) % 2 == 0:
+                                raise AssertionError("coarse vertex on a hanging face must have been merged")
+                            sloc = (t - 2 * jc) / 2.0
+                            wts = lagrange_values(gll, np.array([sloc]))[0][0]
+                            par = []
+                            for j in range(k + 1):
+                                tj = 2 * jc + 2 * gll[j]
+                                par.append(coarse[key(X, tj) if d == 0 else key(tj, X)])
+                            keep = np.abs(wts) > 1e-14
+                            hanging[fine[kk]] = (np.asarray(par)[keep], wts[keep])
+                    lists[c, a + (k + 1) * b] = fine[kk]
+        n_nodes = len(pos)
+        # constrained nodes last
+        is_h = np.zeros(n_nodes, dtype=bool)
+        is_h[list(hanging.keys())] = True
+        order = np.concatenate([np.nonzero(~is_h)[0], np.nonzero(is_h)[0]])
+        new_id = np.empty(n_nodes, dtype=np.int64)
+        new_id[order] = np.arange(n_nodes)
+        lists = new_id[lists]
+        P = np.asarray(pos)[order]
+        coords = self.lower[None, :] + P * (0.5 * self.h)[None, :]
+        bnd = (np.abs(P[:, 0]) < 1e-12) | (np.abs(P[:, 0] - 2 * nx) < 1e-12) | (np.abs(P[:, 1]) < 1e-12) | (np.abs(P[:, 1] - 2 * ny) < 1e-12)
+        n_h = int(is_h.sum())
+        ptr, cols, wts = [0], [], []
+        for old in order[n_nodes - n_h:]:
+            par, w = hanging[int(old)]
+            cols += [int(new_id[q]) for q in par]
+            wts += [float(v) for v in w]
+            ptr.append(len(cols))
+        assert not bnd[n_nodes - n_h:].any()
+        rows = (np.asarray(ptr, dtype=np.uint32), np.asarray(cols, dtype=np.uint32), np.asarray(wts, dtype=np.float64))
+        return lists, n_nodes, coords, bnd, rows
+
+    @property
+    def n_hanging_u(self):
+        return len(self.u_rows[0]) - 1
+
+    @property
+    def n_hanging_p(self):
+        return len(self.p_rows[0]) - 1
+
+    def encoded_cell_u(self):
+        flags = np.zeros(self.n_u_nodes, dtype=np.uint32)
+        for c in range(2):
+            flags |= (self.u_dirichlet[:, c].astype(np.uint32) << np.uint32(29 + c))
+        return (self.cell_u.astype(np.uint32) | flags[self.cell_u]).astype(np.uint32)
+
+    def encoded_rows_u(self):
+        """constraint rows with the Dirichlet flag bits on the parents"""
+        ptr, cols, w = self.u_rows
+        flags = np.zeros(self.n_u_nodes, dtype=np.uint32)
+        for c in range(2):
+            flags |= (self.u_dirichlet[:, c].astype(np.uint32) << np.uint32(29 + c))
+        return ptr, (cols | flags[cols]).astype(np.uint32), w
+
+    def constrained_u(self):
+        """MatrixFree::get_constrained_dofs: Dirichlet entries and the entries of the hanging nodes, sorted"""
+        con = self.u_dirichlet.copy()
+        con[self.n_u_nodes - self.n_hanging_u:, :] = True
+        return np.nonzero(con.reshape(-1))[0].astype(np.uint32)
+
+    def constrained_p(self):
+        return np.arange(self.n_p_nodes - self.n_hanging_p, self.n_p_nodes, dtype=np.uint32)
+
+    def distribute(self, vec, space):
+        """AffineConstraints::distribute for the hanging-node rows of a nodal vector ([n_nodes * n_comp], node-major)"""
+        ptr, cols, w = self.u_rows if space == 0 else self.p_rows
+        n_nodes = self.n_u_nodes if space == 0 else self.n_p_nodes
+        v = vec.reshape(n_nodes, -1)
+        first = n_nodes - (len(ptr) - 1)
+        for r in range(len(ptr) - 1):
+            v[first + r] = (w[ptr[r]:ptr[r + 1], None] * v[cols[ptr[r]:ptr[r + 1]]]).sum(axis=0)
+        return vec
+
+    def cartesian_geometry(self):
+        table = np.array([[2.0 / self.h[0] * f, 2.0 / self.h[1] * f, 1.0, self.h[0] * self.h[1] / (4.0 * f * f)] for f in (0.5, 1.0)])
+        return table, (self.cells[:, 2] == 1).astype(np.uint32)
+
+    def quadrature_points(self, n_q_1d):
+        qp, _ = gauss_legendre_01(n_q_1d)
+        qx, qy = np.meshgrid(qp, qp, indexing="xy")
+        xi = np.stack([qx.reshape(-1), qy.reshape(-1)], axis=1)
+        return self.origin[:, None, :] + self.h_cell[:, None, :] * xi[None, :, :]

@@ -812,17 +812,25 @@ class MatrixFreeGeneric:
         k, dim = mesh.degree, mesh.dim
         cu = np.ascontiguousarray(mesh.encoded_cell_u())
         cp = np.ascontiguousarray(mesh.cell_p.astype(np.uint32))
-        con = np.ascontiguousarray(mesh.constrained_u())
+        con_u = np.ascontiguousarray(mesh.constrained_u())
+        con_p = np.ascontiguousarray(mesh.constrained_p()) if hasattr(mesh, "constrained_p") else np.zeros(0, dtype=np.uint32)
+        # hanging nodes: general constraint rows (adaflo_b200_space_desc::hanging_*), e.g. mesh.RefinedTensorMesh2D
+        rows_u = tuple(np.ascontiguousarray(a) for a in mesh.encoded_rows_u()) if hasattr(mesh, "encoded_rows_u") else None
+        rows_p = tuple(np.ascontiguousarray(a) for a in mesh.p_rows) if hasattr(mesh, "p_rows") else None
         spaces = (capi.SpaceDesc * 2)()
-        for i, (cells, n_nodes, n_comp, deg) in enumerate([(cu, mesh.n_u_nodes, dim, k), (cp, mesh.n_p_nodes, 1, k - 1)]):
+        for i, (cells, n_nodes, n_comp, deg, con, rows) in enumerate([(cu, mesh.n_u_nodes, dim, k, con_u, rows_u),
+                                                                      (cp, mesh.n_p_nodes, 1, k - 1, con_p, rows_p)]):
             d = spaces[i]
             d.fe_kind, d.degree, d.n_components = capi.FE_Q, deg, n_comp
             d.n_owned_nodes, d.n_ghost_nodes, d.nodes_per_cell = n_nodes, 0, cells.shape[1]
             d.cell_nodes = cells.ctypes.data
             d.hanging_masks = None
-            d.n_constrained = len(con) if i == 0 else 0
-            d.constrained_dofs = con.ctypes.data if (i == 0 and len(con)) else None
+            d.n_constrained = len(con)
+            d.constrained_dofs = con.ctypes.data if len(con) else None
             d.n_exchange, d.exchange = 0, None
+            if rows is not None and len(rows[0]) > 1:
+                d.n_hanging_nodes = len(rows[0]) - 1
+                d.hanging_row_ptr, d.hanging_cols, d.hanging_weights = rows[0].ctypes.data, rows[1].ctypes.data, rows[2].ctypes.data
         table, row = mesh.cartesian_geometry()
         table, row = np.ascontiguousarray(table), np.ascontiguousarray(row)
         quads = (capi.QuadDesc * 2)()
@@ -844,6 +852,10 @@ class MatrixFreeGeneric:
         n_owned = C.c_uint64()
         check(self.ctx.lib.adaflo_b200_mf_vector_size(self.h, space, C.byref(n_owned), None))
         return n_owned.value
+
+    def distribute_constraints(self, space, vec):
+        """AffineConstraints::distribute for the hanging-node rows (navier_stokes.cc:643-644, 1252)"""
+        check(self.ctx.lib.adaflo_b200_mf_distribute_constraints(self.h, space, _ptr(vec)))
 
     def close(self):
         if self.h:

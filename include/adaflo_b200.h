@@ -110,6 +110,18 @@ typedef struct {
   const uint32_t *constrained_dofs;
   int32_t n_exchange;
   const adaflo_b200_exchange *exchange;
+  /* General homogeneous constraint rows (dealii::AffineConstraints as MatrixFree resolves them inside
+   * read_dof_values / distribute_local_to_global; hanging nodes of any degree), used by the degree / dimension dispatch
+   * (csrc/ns_generic.cu): the LAST n_hanging_nodes owned nodes are constrained nodes; row r belongs to node
+   * n_owned_nodes - n_hanging_nodes + r and reads  value = sum_k hanging_weights[k] * value(hanging_cols[k]),
+   * k in [hanging_row_ptr[r], hanging_row_ptr[r + 1]).  hanging_cols are node indices with the Dirichlet flag bits of
+   * cell_nodes (a flagged component of a parent is read as 0 and never written).  Cell lists name the constrained node
+   * itself; read_dof_values_plain (residual, navier_stokes_matrix.cc:663-664) reads its vector entry.  All zero / NULL on
+   * conforming meshes.  The tuned 3-D Q2/Q1 kernels use hanging_masks instead. */
+  uint32_t n_hanging_nodes;
+  const uint32_t *hanging_row_ptr; /* host [n_hanging_nodes + 1] */
+  const uint32_t *hanging_cols;    /* host [hanging_row_ptr[n_hanging_nodes]] */
+  const double *hanging_weights;   /* host, same length */
 } adaflo_b200_space_desc;
 
 enum adaflo_b200_geometry_type {
@@ -156,6 +168,12 @@ int adaflo_b200_mf_n_cells(adaflo_b200_mf_t mf, uint32_t *n_cells);   /* locally
 /* LinearAlgebra::distributed::Vector::update_ghost_values / compress(add) */
 int adaflo_b200_mf_update_ghost_values(adaflo_b200_mf_t mf, int space, double *vec_dev);
 int adaflo_b200_mf_compress_add(adaflo_b200_mf_t mf, int space, double *vec_dev);
+/* AffineConstraints::distribute for the general constraint rows of the space (hanging_row_ptr / cols / weights): every
+ * constrained node gets sum_k weight_k * value(parent_k), per component -- what the reference calls after every update of a
+ * solution vector (hanging_node_constraints_u.distribute, source/navier_stokes.cc:1252; constraints_u.distribute on the Newton
+ * update, :643-644, where the Dirichlet entries of the update are zero: flagged parent components are read as they stand in
+ * the vector).  No-op for spaces without rows. */
+int adaflo_b200_mf_distribute_constraints(adaflo_b200_mf_t mf, int space, double *vec_dev);
 
 /* ------------------------------------------------------- NavierStokesMatrix
  * Enumerations and PODs mirror adaflo::FlowParameters

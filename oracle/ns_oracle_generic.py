@@ -79,34 +79,79 @@ class OracleNavierStokesGeneric:
         self.dphi_u = np.stack([tensor(dim, [du if f == d else vu for d in range(dim)]) for f in range(dim)], axis=-1)   # [q, n, f]
         self.phi_p = tensor(dim, [vp] * dim)
         self.wq = tensor(dim, [wq[:, None]] * dim)[:, 0]
-        self.K = 1.0 / np.asarray(mesh.h)
-        self.jxw = self.wq * np.prod(mesh.h)
+        h_cell = getattr(mesh, "h_cell", None)                                                 # meshes with two cell sizes
+        if h_cell is None:
+            h_cell = np.tile(np.asarray(mesh.h, dtype=np.float64)[None, :], (mesh.n_cells, 1))
+        self.K = 1.0 / h_cell                                                                  # [c, e]
+        self.jxw = self.wq[None, :] * np.prod(h_cell, axis=1)[:, None]                         # [c, q]
         self.n_u, self.n_p = mesh.n_u_nodes * dim, mesh.n_p_nodes
         self.n_q = len(self.wq)
+        # hanging nodes: constraint rows (row_ptr, parents, weights) of the last nodes of each space, applied exactly as
+        # FEEvaluation::read_dof_values / distribute_local_to_global apply an AffineConstraints row: expansion matrices
+        # E [cell-local slot, node] with E = identity pick for plain nodes
+        self.Eu = self._expansion(mesh.cell_u, mesh.n_u_nodes, getattr(mesh, "u_rows", None))
+        self.Ep = self._expansion(mesh.cell_p, mesh.n_p_nodes, getattr(mesh, "p_rows", None))
+        self.p_constrained = np.zeros(self.n_p, dtype=bool)
+        if getattr(mesh, "p_rows", None) is not None:
+            self.p_constrained[mesh.n_p_nodes - (len(mesh.p_rows[0]) - 1):] = True
+        self.u_constrained = mesh.u_dirichlet.copy()
+        if getattr(mesh, "u_rows", None) is not None:
+            self.u_constrained[mesh.n_u_nodes - (len(mesh.u_rows[0]) - 1):, :] = True
         self.lin = np.zeros((mesh.n_cells, dim + dim * dim, self.n_q))
         self.old_u = np.zeros(self.n_u)
         self.old_old_u = np.zeros(self.n_u)
         self.mode_w = None
         if pressure_average_fix:
-            wv = np.zeros(self.n_p)                                                            # pressure mass matrix applied to 1
-            np.add.at(wv, mesh.cell_p.reshape(-1), np.tile(self.phi_p.T @ self.jxw, mesh.n_cells))
+            # integrals of the pressure shape functions, distributed through the constraints (navier_stokes_matrix.cc:117-133);
+            # the constant mode is 1 on the unconstrained dofs (:158-163)
+            wv = self._scatter(self.Ep, np.einsum("qn,cq->cn", self.phi_p, self.jxw)[:, :, None], None)[:, 0]
             self.mode_w = wv
+            self.mode = (~self.p_constrained).astype(np.float64)
 
-    def _gather(self, vec, cells, n_comp, dirichlet=None):
-        v = vec.reshape(-1, n_comp)[cells]
+    @staticmethod
+    def _expansion(cells, n_nodes, rows):
+        import scipy.sparse as sps
+        n_slots = cells.size
+        flat = cells.reshape(-1)
+        if rows is None:
+            return sps.csr_matrix((np.ones(n_slots), (np.arange(n_slots), flat)), shape=(n_slots, n_nodes))
+        ptr, cols, w = (np.asarray(a) for a in rows)
+        first = n_nodes - (len(ptr) - 1)
+        ri, ci, vi = [], [], []
+        for slot, node in enumerate(flat):
+            if node < first:
+                ri.append(slot), ci.append(node), vi.append(1.0)
+            else:
+                for k in range(ptr[node - first], ptr[node - first + 1]):
+                    ri.append(slot), ci.append(int(cols[k])), vi.append(float(w[k]))
+        return sps.csr_matrix((vi, (ri, ci)), shape=(n_slots, n_nodes))
+
+    def _gather(self, vec, cells, n_comp, E=None, dirichlet=None):
+        """plain read of the vector entries (E None: read_dof_values_plain), or the constraint-resolving read (read_dof_values):
+        hanging rows expanded, homogeneous Dirichlet entries read as zero"""
+        v = vec.reshape(-1, n_comp)
+        if E is None:
+            return v[cells]
         if dirichlet is not None:
-            v = np.where(dirichlet[cells], 0.0, v)
-        return v
+            v = np.where(dirichlet, 0.0, v)
+        return (E @ v).reshape(cells.shape[0], cells.shape[1], n_comp)
+
+    def _scatter(self, E, local, dirichlet):
+        """distribute_local_to_global: E^T local, rows of homogeneous Dirichlet entries dropped; returns [n_nodes, n_comp]"""
+        out = E.T @ local.reshape(-1, local.shape[-1])
+        if dirichlet is not None:
+            out = np.where(dirichlet, 0.0, out)
+        return out
 
     def _loop(self, op, src_u, src_p, dst_u, dst_p):
         m, dim = self.m, self.dim
         resolve = op != "residual"
-        ul = self._gather(src_u, m.cell_u, dim, m.u_dirichlet if resolve else None)
+        ul = self._gather(src_u, m.cell_u, dim, self.Eu if resolve else None, m.u_dirichlet)
         val = np.einsum("qn,cnd->cqd", self.phi_u, ul)
-        grad = np.einsum("qnf,cnd->cqdf", self.dphi_u, ul) * self.K[None, None, None, :]          # [c, q, d, e]
+        grad = np.einsum("qnf,cnd->cqdf", self.dphi_u, ul) * self.K[:, None, None, :]             # [c, q, d, e]
         pres = 0.0
         if op != "vmult_velocity":
-            pres = np.einsum("qn,cn->cq", self.phi_p, self._gather(src_p, m.cell_p, 1)[:, :, 0])
+            pres = np.einsum("qn,cn->cq", self.phi_p, self._gather(src_p, m.cell_p, 1, self.Ep if resolve else None)[:, :, 0])
         div = np.einsum("cqdd->cq", grad)
         stokes = self.physical_type == STOKES
         gamma = self.weight if self.physical_type == INCOMPRESSIBLE else 0.0
@@ -116,7 +161,7 @@ class OracleNavierStokesGeneric:
             conv = gamma * val
             if op == "residual":
                 if self.physical_type != STATIONARY:
-                    uo = np.einsum("qn,cnd->cqd", self.phi_u, self._gather(self.old_u, m.cell_u, dim))
+                    uo = np.einsum("qn,cnd->cqd", self.phi_u, self._gather(self.old_u, m.cell_u, dim))       # plain reads
                     uoo = np.einsum("qn,cnd->cqd", self.phi_u, self._gather(self.old_old_u, m.cell_u, dim))
                     conv = conv + self.w_old * uo + self.w_oo * uoo
                 res = self.beta * div[:, :, None] * val + np.einsum("cqe,cqde->cqd", val, grad)
@@ -142,33 +187,57 @@ class OracleNavierStokesGeneric:
         S = tmu * (grad + grad.transpose(0, 1, 3, 2))
         for d in range(dim):
             S[:, :, d, d] = 2 * tmu * grad[:, :, d, d] + self.tau_gd * div - (pres if op != "vmult_velocity" else 0.0)
-        Sref = S * self.K[None, None, None, :] * self.jxw[None, :, None, None]
+        Sref = S * self.K[:, None, None, :] * self.jxw[:, :, None, None]
         out_u = np.einsum("qnf,cqdf->cnd", self.dphi_u, Sref)
         if not stokes:
-            out_u = out_u + np.einsum("qn,cqd->cnd", self.phi_u, conv * self.jxw[None, :, None])
-        keep = ~m.u_dirichlet[m.cell_u]
-        idx = (dim * m.cell_u[:, :, None] + np.arange(dim)[None, None, :])
-        np.add.at(dst_u, idx[keep], out_u[keep])
+            out_u = out_u + np.einsum("qn,cqd->cnd", self.phi_u, conv * self.jxw[:, :, None])
+        dst_u += self._scatter(self.Eu, out_u, m.u_dirichlet).reshape(-1)
         if op != "vmult_velocity":
-            out_p = np.einsum("qn,cq->cn", self.phi_p, -div * self.jxw[None, :])
-            np.add.at(dst_p, m.cell_p.reshape(-1), out_p.reshape(-1))
+            out_p = np.einsum("qn,cq->cn", self.phi_p, -div * self.jxw)
+            dst_p += self._scatter(self.Ep, out_p[:, :, None], None)[:, 0]
+
+    def l2_error(self, space, vec, exact, n_q_1d):
+        """sqrt(int |u_h - exact|^2) with QGauss(n_q_1d) per direction (VectorTools::integrate_difference + L2 norm,
+        tests/beltrami.cc:254-283: QGauss(degree + 2)); space 0: velocity, 1: pressure; exact(x[c, q, dim]) -> [c, q, n_comp];
+        the vector entries are read plainly (hanging nodes hold their distributed / interpolated values)"""
+        m, dim = self.m, self.dim
+        k = m.degree if space == 0 else m.degree - 1
+        xq, wq = gauss(n_q_1d)
+        v1, _ = lagrange_tables(gauss_lobatto(k + 1), xq)
+        phi = tensor(dim, [v1] * dim)
+        w = tensor(dim, [wq[:, None]] * dim)[:, 0]
+        grids = np.meshgrid(*([xq] * dim), indexing="ij")
+        pts = np.stack([g.T.reshape(-1) if dim == 2 else g.transpose(2, 1, 0).reshape(-1) for g in grids], axis=1)   # x fastest
+        h_cell = getattr(m, "h_cell", None)
+        if h_cell is None:
+            h_cell = np.tile(np.asarray(m.h, dtype=np.float64)[None, :], (m.n_cells, 1))
+        origin = getattr(m, "origin", None)
+        if origin is None:
+            idx = np.stack(np.unravel_index(np.arange(m.n_cells), m.n[::-1]), axis=1)[:, ::-1]
+            origin = np.asarray(m.lower)[None, :] + idx * np.asarray(m.h)[None, :]
+        x = origin[:, None, :] + h_cell[:, None, :] * pts[None, :, :]
+        cells, n_comp = (m.cell_u, dim) if space == 0 else (m.cell_p, 1)
+        uh = np.einsum("qn,cnd->cqd", phi, vec.reshape(-1, n_comp)[cells])
+        diff = uh - exact(x).reshape(uh.shape)
+        return float(np.sqrt(np.einsum("cqd,cqd,q,c->", diff, diff, w, np.prod(h_cell, axis=1))))
 
     def apply_pressure_average_projection(self, p):
         if self.mode_w is not None and self.physical_type != STATIONARY:
-            p -= float(self.mode_w @ p) / float(self.mode_w.sum())
+            p -= float(self.mode_w @ p) / float(self.mode_w @ self.mode) * self.mode
 
     def vmult(self, src_u, src_p):
         dst_u, dst_p = np.zeros(self.n_u), np.zeros(self.n_p)
         self._loop("vmult", src_u, src_p, dst_u, dst_p)
-        c = self.m.u_dirichlet.reshape(-1)
+        c = self.u_constrained.reshape(-1)                     # constrained rows, :247-256
         dst_u[c] = src_u[c]
+        dst_p[self.p_constrained] = -src_p[self.p_constrained]
         self.apply_pressure_average_projection(dst_p)
         return dst_u, dst_p
 
     def velocity_vmult(self, src_u):
         dst_u = np.zeros(self.n_u)
         self._loop("vmult_velocity", src_u, None, dst_u, None)
-        c = self.m.u_dirichlet.reshape(-1)
+        c = self.u_constrained.reshape(-1)
         dst_u[c] = src_u[c]
         return dst_u
 

@@ -65,7 +65,7 @@ def test_higher_degrees_integrate_exactly_and_vmult_is_the_jacobian(dim, k):
     m = TensorMesh(dim, n, k)
     O = og.OracleNavierStokesGeneric(m, og.INCOMPRESSIBLE, og.NEWTON, 1.3, 0.7, 0.0, 0.0, 0.5, (10.0, -10.0, 0.0, 1.0))
     # partition of unity and exact quadrature: sum_n phi_n = 1, the weights integrate 1 over the cell
-    assert np.allclose(O.phi_u.sum(axis=1), 1.0) and np.allclose(O.phi_p.sum(axis=1), 1.0) and abs(O.jxw.sum() - np.prod(m.h)) < 1e-14
+    assert np.allclose(O.phi_u.sum(axis=1), 1.0) and np.allclose(O.phi_p.sum(axis=1), 1.0) and abs(O.jxw[0].sum() - np.prod(m.h)) < 1e-14
     # a polynomial of degree k in every variable is reproduced at the quadrature points
     x = m.u_coords
     f = np.prod(1.0 + 0.3 * x ** k - 0.2 * x, axis=1)
@@ -91,3 +91,106 @@ def test_higher_degrees_integrate_exactly_and_vmult_is_the_jacobian(dim, k):
     ju, jp = O.vmult(du, dp)
     free = ~m.u_dirichlet.reshape(-1)
     assert rel_err((-(ru1 - ru0) / (2 * eps))[free], ju[free]) < 1e-7 and rel_err(-(rp1 - rp0) / (2 * eps), jp) < 1e-7
+
+
+# ---------------------------------------------------------------- hanging nodes of any degree: tests/beltrami_2d.output (Q4/Q3)
+import json
+import os
+
+from adaflo_b200.mesh import RefinedTensorMesh2D, beltrami_pressure, beltrami_velocity
+
+with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "beltrami_2d_output.json")) as _f:
+    GOLDEN_2D = json.load(_f)   # numbers of the reference's golden log tests/beltrami_2d.output
+
+
+@pytest.fixture(scope="module")
+def beltrami_2d():
+    par = GOLDEN_2D["parameters"]
+    n = par["coarse_cells_per_direction"]
+    mesh = RefinedTensorMesh2D((n, n), par["refined_block"], par["velocity_degree"])     # tests/beltrami.cc:385-412
+    dt = par["dt"]
+    # time step #1 of BDF-2: implicit Euler weights (time_stepping.cc:158-198); Newton, beta = 0.5, nu = rho = 1
+    O = og.OracleNavierStokesGeneric(mesh, og.INCOMPRESSIBLE, og.NEWTON, 1.0, par["viscosity"], 0.0, 0.0, 0.5, (1 / dt, -1 / dt, 0.0, 1.0))
+    return mesh, O, dt
+
+
+def test_beltrami_2d_dof_counts_match_the_golden_log(beltrami_2d):
+    mesh, _, _ = beltrami_2d
+    # beltrami_2d.output:2-3; deal.II counts the constrained (hanging) dofs
+    assert mesh.n_cells == GOLDEN_2D["n_active_cells"]["value"] == 1048
+    assert 2 * mesh.n_u_nodes == GOLDEN_2D["n_dofs"]["velocity"] == 34158
+    assert mesh.n_p_nodes == GOLDEN_2D["n_dofs"]["pressure"] == 9663
+    # 10 coarse faces carry hanging nodes (4 above, 4 below, 2 right of the block; the left side is the boundary): 2 k - 1 each
+    assert mesh.n_hanging_u == 10 * 7 and mesh.n_hanging_p == 10 * 5
+
+
+def test_beltrami_2d_interpolation_errors_match_the_golden_log(beltrami_2d):
+    mesh, O, _ = beltrami_2d
+    u0 = beltrami_velocity(mesh.u_coords, 0.0).reshape(-1)
+    p0 = beltrami_pressure(mesh.p_coords, 0.0)
+    e_u = O.l2_error(0, u0, lambda x: beltrami_velocity(x, 0.0), 6)          # QGauss(degree + 2), tests/beltrami.cc:254
+    e_p = O.l2_error(1, p0, lambda x: beltrami_pressure(x, 0.0)[..., None], 6)
+    # beltrami_2d.output:5 -- this pins the Gauss-Lobatto support points and the Q4 / Q3 shape functions
+    assert f"{e_p:.3e}" == GOLDEN_2D["l2_errors_t0"]["e_p"] == "9.507e-09"
+    assert f"{e_u:.3e}" == GOLDEN_2D["l2_errors_t0"]["e_u"] == "8.461e-12"
+
+
+def test_beltrami_2d_first_nonlinear_residual_matches_the_golden_log(beltrami_2d):
+    mesh, O, dt = beltrami_2d
+    u0 = beltrami_velocity(mesh.u_coords, 0.0).reshape(-1)
+    p0 = beltrami_pressure(mesh.p_coords, 0.0)                       # interpolate_pressure_field: nodal values, also at hanging nodes
+    u = u0.copy()
+    d = mesh.u_dirichlet.reshape(-1)
+    u[d] = beltrami_velocity(mesh.u_coords, dt).reshape(-1)[d]       # apply_boundary_conditions, navier_stokes.cc:1216-1251
+    mesh.distribute(u, 0)                                            # hanging_node_constraints_u.distribute, :1252
+    O.old_u, O.old_old_u = u0.copy(), np.zeros_like(u0)
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, u, p0, np.zeros(O.n_u), np.zeros(O.n_p))
+    O.apply_pressure_average_projection(rp)
+    # beltrami_2d.output:13: "4.149e-01   1.021e-03" -- Q4/Q3, hanging nodes through the constraint rows, two cell sizes
+    assert f"{np.linalg.norm(ru):.3e}" == GOLDEN_2D["first_nonlinear_residual"]["1"]["u"] == "4.149e-01"
+    assert f"{np.linalg.norm(rp):.3e}" == GOLDEN_2D["first_nonlinear_residual"]["1"]["p"] == "1.021e-03"
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
+def test_constraint_rows_reproduce_polynomials_and_keep_the_operator_consistent(k):
+    """the hanging-node rows interpolate degree-k polynomials exactly; on distributed vectors the constraint-resolving read of
+    vmult equals the plain read, so vmult stays the Jacobian of the residual on the refined mesh"""
+    mesh = RefinedTensorMesh2D((4, 3), ((1, 3), (0, 2)), k, lower=(-1.0, -0.5), upper=(1.0, 0.75))
+    f = lambda x: (0.3 + x[:, 0]) ** k * (1.1 - 0.7 * x[:, 1]) ** k
+    for space, coords in ((0, mesh.u_coords), (1, mesh.p_coords)):
+        kk = k - space
+        v = ((0.3 + coords[:, 0]) ** kk * (1.1 - 0.7 * coords[:, 1]) ** kk).copy()
+        assert np.abs(mesh.distribute(v.copy(), space) - v).max() < 1e-13
+    O = og.OracleNavierStokesGeneric(mesh, og.INCOMPRESSIBLE, og.NEWTON, 1.3, 0.7, 0.0, 0.0, 0.5, (10.0, -10.0, 0.0, 1.0))
+    rng = np.random.default_rng(k)
+    free_u = ~O.u_constrained.reshape(-1)
+
+    def consistent(seed):
+        r = np.random.default_rng(seed)
+        u = r.uniform(-1, 1, O.n_u)
+        p = r.uniform(-1, 1, O.n_p)
+        return mesh.distribute(u, 0), mesh.distribute(p, 1)
+
+    u, p = consistent(1)
+    du, dp = consistent(2)
+    du[~free_u] = 0.0
+    mesh.distribute(du, 0)
+    O.old_u, O.old_old_u = consistent(3)[0], consistent(4)[0]
+
+    def R(uu, pp):
+        ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+        O.residual(ru, rp, uu, pp, np.zeros(O.n_u), np.zeros(O.n_p))
+        return -ru, -rp
+
+    eps = 1e-6
+    (rpu, rpp), (rmu, rmp) = R(u + eps * du, p + eps * dp), R(u - eps * du, p - eps * dp)
+    R(u, p)                                                        # linearisation point = (u, p)
+    O.mode_w = None                                                # compare the cell integrals
+    ju, jp = O.vmult(du, dp)
+    fd_u, fd_p = (rpu - rmu) / (2 * eps), (rpp - rmp) / (2 * eps)
+    free_p = ~O.p_constrained
+    assert np.abs(ju[free_u] - fd_u[free_u]).max() < 1e-6 * max(1.0, np.abs(fd_u).max())
+    assert np.abs(jp[free_p] - fd_p[free_p]).max() < 1e-6 * max(1.0, np.abs(fd_p).max())
+    # constrained rows: identity / minus identity (navier_stokes_matrix.cc:247-256)
+    assert np.array_equal(ju[~free_u], du[~free_u]) and np.array_equal(jp[~free_p], -dp[~free_p])

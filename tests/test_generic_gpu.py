@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from adaflo_b200 import capi
-from adaflo_b200.mesh import BoxMesh, TensorMesh, seeded_uniform
+from adaflo_b200.mesh import BoxMesh, RefinedTensorMesh2D, TensorMesh, seeded_uniform
 from adaflo_b200.operators import BlockVector, Context, MatrixFree, MatrixFreeGeneric, NavierStokesMatrix
 from oracle import ns_oracle_generic as og
 from oracle import oracle as orc
@@ -113,6 +113,58 @@ def test_taylor_hood_degrees_and_native_2d(ctx, dim, k, n, linearization):
     hu, hp = np.zeros_like(su), np.zeros_like(sp)
     A.vmult_host(hu, hp, np.ascontiguousarray(su), np.ascontiguousarray(sp))
     assert rel_err(hu, ou) < TOL and rel_err(hp, op) < TOL
+    A.clear()
+    mf.close()
+
+
+@pytest.mark.parametrize("k", [2, 3, 4, 5])
+@pytest.mark.parametrize("linearization", [capi.NEWTON, capi.PICARD])
+def test_hanging_nodes_of_any_degree(ctx, k, linearization):
+    """2:1 hanging nodes on Q_k / Q_(k-1) in 2-D through general constraint rows (adaflo_b200_space_desc::hanging_*): the mesh
+    type of tests/beltrami_2d (Q4/Q3).  vmult resolves the rows in the read and in the scatter, the residual reads the vector
+    entries plainly (read_dof_values_plain) and scatters through the rows; the constrained rows are +-identity."""
+    mesh = RefinedTensorMesh2D((4, 3), ((1, 3), (0, 2)), k, lower=(-1.0, -0.5), upper=(1.0, 0.75))
+    assert mesh.n_hanging_u > 0 and mesh.n_hanging_p > 0
+    mf = MatrixFreeGeneric(ctx, mesh)
+    dt = 0.05
+    tw = (1.5 / dt, -2.0 / dt, 0.5 / dt, 1.0)
+    dprm = capi.FlowParams(capi.INCOMPRESSIBLE, linearization, 0, 0, 1.3, 0.7, 0.0, 0.0, -0.2, 0.3, 0.5)
+    old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+    A = NavierStokesMatrix(dprm, 0, 1, 0, 1, old, old_old)
+    A.initialize(mf, capi.TimeWeights(tw[0], tw[1], tw[2], tw[3], 2.0, -1.0), True)
+    O = og.OracleNavierStokesGeneric(mesh, og.INCOMPRESSIBLE, og.NEWTON if linearization == capi.NEWTON else og.PICARD, 1.3, 0.7, -0.2, 0.3, 0.5, tw)
+    u, p = seeded_uniform(mesh.u_ids, 2, 1), seeded_uniform(mesh.p_ids, 1, 2)          # NOT distributed: the residual must read plainly
+    uo, uoo = seeded_uniform(mesh.u_ids, 2, 3), seeded_uniform(mesh.u_ids, 2, 4)
+    old.block(0).copy_(dev(ctx, uo))
+    old_old.block(0).copy_(dev(ctx, uoo))
+    O.old_u, O.old_old_u = uo, uoo
+    ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+    O.residual(ru, rp, u, p, np.zeros(O.n_u), np.zeros(O.n_p))
+    O.apply_pressure_average_projection(rp)
+    rhs, zero = BlockVector.like(mf), BlockVector.like(mf)
+    A.residual(rhs, BlockVector(dev(ctx, u), dev(ctx, p)), zero)
+    A.apply_pressure_average_projection(rhs.block(1))
+    assert rel_err(rhs.block(0).cpu().numpy(), ru) < TOL and rel_err(rhs.block(1).cpu().numpy(), rp) < TOL
+    su, sp = seeded_uniform(mesh.u_ids, 2, 11), seeded_uniform(mesh.p_ids, 1, 12)
+    ou, op = O.vmult(su, sp)
+    dst = BlockVector.like(mf)
+    A.vmult(dst, BlockVector(dev(ctx, su), dev(ctx, sp)))
+    du, dp = dst.block(0).cpu().numpy(), dst.block(1).cpu().numpy()
+    assert rel_err(du, ou) < TOL and rel_err(dp, op) < TOL
+    cu, cp = O.u_constrained.reshape(-1), O.p_constrained
+    assert np.array_equal(du[cu], su[cu])                                               # navier_stokes_matrix.cc:247-256
+    assert cp.sum() == mesh.n_hanging_p
+    dv = mf.initialize_dof_vector(0)
+    A.velocity_vmult(dv, dev(ctx, su))
+    assert rel_err(dv.cpu().numpy(), O.velocity_vmult(su)) < TOL
+    hu, hp = np.zeros_like(su), np.zeros_like(sp)
+    A.vmult_host(hu, hp, np.ascontiguousarray(su), np.ascontiguousarray(sp))
+    assert rel_err(hu, ou) < TOL and rel_err(hp, op) < TOL
+    # AffineConstraints::distribute on the device
+    for space, vec in ((0, u), (1, p)):
+        d = dev(ctx, vec.copy())
+        mf.distribute_constraints(space, d)
+        assert rel_err(d.cpu().numpy(), mesh.distribute(vec.copy(), space)) < 1e-15
     A.clear()
     mf.close()
 

@@ -137,3 +137,77 @@ def test_device_time_stepping_on_the_refined_augmented_mesh_reproduces_the_golde
     e_p = O.l2_error(1, p_h, beltrami_pressure(xq, 0.2)[..., None], n_q_1d=4)
     assert f"{e_u:.4g}" == gold["l2_errors_t0.2"]["e_u"], e_u
     assert f"{e_p:.4g}" == gold["l2_errors_t0.2"]["e_p"], e_p
+
+
+def test_device_time_stepping_of_beltrami_2d_q4q3_reproduces_the_golden_log():
+    """tests/beltrami_2d.output: 2-D Taylor vortex, Q4/Q3 on 1048 cells with 2:1 hanging nodes -- the degree / dimension dispatch
+    (csrc/ns_generic.cu) with general constraint rows.  Four BDF-2 steps on the device (Newton on residual / vmult,
+    unpreconditioned device GMRES, AffineConstraints::distribute by adaflo_b200_mf_distribute_constraints, fix_pressure_constant
+    restated); the first nonlinear residuals of time steps #1 - #4 are compared digit by digit."""
+    from adaflo_b200.mesh import RefinedTensorMesh2D, gauss_lobatto_01, lagrange_values
+    from adaflo_b200.operators import MatrixFreeGeneric
+    gold = golden("beltrami_2d_output.json")
+    par = gold["parameters"]
+    n, k = par["coarse_cells_per_direction"], par["velocity_degree"]
+    mesh = RefinedTensorMesh2D((n, n), par["refined_block"], k)                       # tests/beltrami.cc:385-412
+    assert mesh.n_cells == gold["n_active_cells"]["value"]
+    assert (2 * mesh.n_u_nodes, mesh.n_p_nodes) == (gold["n_dofs"]["velocity"], gold["n_dofs"]["pressure"])
+    ctx = Context(0)
+    mf = MatrixFreeGeneric(ctx, mesh)
+    dt = par["dt"]
+    prm = capi.FlowParams(capi.INCOMPRESSIBLE, capi.NEWTON, 0, 0, 1.0, par["viscosity"], 0.0, 0.0, 0.0, 0.0, 0.5)
+    euler = capi.TimeWeights(1 / dt, -1 / dt, 0.0, 1.0, 1.0, 0.0)
+    bdf2 = capi.TimeWeights(1.5 / dt, -2 / dt, 0.5 / dt, 1.0, 2.0, -1.0)
+    sol, old, old_old = BlockVector.like(mf), BlockVector.like(mf), BlockVector.like(mf)
+    A = NavierStokesMatrix(prm, 0, 1, 0, 1, old, old_old)
+    A.initialize(mf, euler, True)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    sol.block(0).copy_(dev(beltrami_velocity(mesh.u_coords, 0.0).reshape(-1)))
+    sol.block(1).copy_(dev(beltrami_pressure(mesh.p_coords, 0.0)))                   # nodal values, also at the hanging nodes
+    dirichlet = torch.from_numpy(np.nonzero(mesh.u_dirichlet.reshape(-1))[0]).to(ctx.device)
+    nu, npp = mf.n_owned(0), mf.n_owned(1)
+    rhs, zero, upd = BlockVector.like(mf), BlockVector.like(mf), BlockVector.like(mf)
+    # fix_pressure_constant (navier_stokes.cc:982-1043): first boundary face of the first cell = the face x = -1 of the coarse cell
+    # at the corner; the Q3 pressure at its midpoint
+    w_mid = torch.from_numpy(lagrange_values(gauss_lobatto_01(k), np.array([0.5]))[0][0]).to(ctx.device)
+    face_nodes = torch.from_numpy(mesh.cell_p[0].reshape(k, k)[:, 0].astype(np.int64)).to(ctx.device)
+    mid = np.array([[-1.0, -1.0 + 0.5 * mesh.h[1]]])
+    for step in range(1, 5):
+        for b in range(2):                                                           # init_time_advance, navier_stokes.cc:659-685
+            old_old.block(b).copy_(old.block(b))
+            old.block(b).copy_(sol.block(b))
+            if step >= 3:
+                sol.block(b).mul_(2.0).sub_(old_old.block(b))
+        A.set_time_stepping(euler if step == 1 else bdf2)
+        sol.block(0)[dirichlet] = dev(beltrami_velocity(mesh.u_coords, step * dt).reshape(-1))[dirichlet]
+        mf.distribute_constraints(0, sol.block(0))                                   # :1252
+        for it in range(10):
+            rhs.block(0).zero_()
+            rhs.block(1).zero_()
+            A.residual(rhs, sol, zero)
+            A.apply_pressure_average_projection(rhs.block(1))
+            ru, rp = float(rhs.block(0).norm()), float(rhs.block(1).norm())
+            if it == 0:
+                g = gold["first_nonlinear_residual"][str(step)]
+                assert (f"{ru:.3e}", f"{rp:.3e}") == (g["u"], g["p"]), (step, ru, rp)
+            if (ru * ru + rp * rp) ** 0.5 < 1e-9:
+                break
+            upd.block(0).zero_()
+            upd.block(1).zero_()
+            ctl = SolverControl(8000, 2e-10, 1e-7)
+            try:
+                SolverGMRES(ctx, ctl, 300).solve(lambda d, s: A.vmult(BlockVector(*d), BlockVector(*s)), [upd.block(0), upd.block(1)],
+                                                 [rhs.block(0), rhs.block(1)], None, [nu, npp])
+            except NoConvergence:
+                pass
+            mf.distribute_constraints(0, upd.block(0))                               # :643-644
+            mf.distribute_constraints(1, upd.block(1))
+            sol.block(0).add_(upd.block(0))
+            sol.block(1).add_(upd.block(1))
+        else:
+            pytest.fail(f"Newton did not converge in time step {step}")
+        p_mid = float((w_mid * sol.block(1)[face_nodes]).sum())
+        A.apply_pressure_shift(float(beltrami_pressure(mid, step * dt)[0]) - p_mid, sol.block(1))
+        mf.distribute_constraints(1, sol.block(1))                                   # :1042
+    A.clear()
+    mf.close()
