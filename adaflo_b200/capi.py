@@ -14,7 +14,11 @@ LIB_PATH = os.environ.get("ADAFLO_B200_LIB") or os.path.join(_HERE, "lib", "liba
 
 
 class AdafloB200Error(RuntimeError):
-    pass
+    """a non-zero return code of the C ABI; .code is the ADAFLO_B200_ERR_* value"""
+
+    def __init__(self, message, code=None):
+        super().__init__(message)
+        self.code = code
 
 
 class Exchange(C.Structure):
@@ -81,7 +85,7 @@ class OperatorRef(C.Structure):
 APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p))
 OP_NS_VMULT, OP_NS_VELOCITY, OP_NS_PRESSURE_POISSON, OP_NS_PRESSURE_MASS, OP_LS_ADVECT, OP_LS_NORMAL, OP_LS_CURVATURE, OP_LS_REINIT, OP_JACOBI, \
     OP_LS_NORMAL_SCALAR = range(10)
-ERR_NO_CONVERGENCE = 6
+ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_COMM, ERR_NO_CONVERGENCE = 1, 2, 3, 4, 5, 6
 
 INCOMPRESSIBLE, INCOMPRESSIBLE_STATIONARY, STOKES = 0, 1, 2
 NEWTON, PICARD, SEMI_IMPLICIT, EXPLICIT, PROJECTION = 0, 1, 2, 3, 4
@@ -254,4 +258,4 @@ def load():
 
 def check(rc):
     if rc != 0:
-        raise AdafloB200Error(f"adaflo_b200 error {rc}: {load().adaflo_b200_last_error().decode()}")
+        raise AdafloB200Error(f"adaflo_b200 error {rc}: {load().adaflo_b200_last_error().decode()}", rc)

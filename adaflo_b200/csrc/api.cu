@@ -189,6 +189,9 @@ int adaflo_b200_ctx_create(adaflo_b200_ctx_t *out, int device, void *stream)
   c->nccl_comm = nullptr;
   c->rank = 0;
   c->nranks = 1;
+  c->ev_watch = nullptr;
+  c->comm_timeout_s = 0.0;  // single rank: plain synchronisation; comm_init arms the watchdog (120 s)
+  if (const char *t = std::getenv("ADAFLO_B200_COMM_TIMEOUT")) c->comm_timeout_s = std::atof(t);  // seconds; also arms it without a communicator
   AB_CUDA(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
   c->red_capacity = 64 + (size_t)8 * c->sm_count * 8 + 64;
   AB_CUDA(cudaMalloc((void **)&c->red_dev, c->red_capacity * sizeof(double)));
@@ -213,6 +216,7 @@ int adaflo_b200_ctx_destroy(adaflo_b200_ctx_t ctx)
   cudaFree(ctx->work_counter);
   cudaEventDestroy(ctx->ev_a);
   cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_watch) cudaEventDestroy(ctx->ev_watch);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   delete ctx;
   return 0;
@@ -228,8 +232,8 @@ int adaflo_b200_ctx_set_stream(adaflo_b200_ctx_t ctx, void *stream)
 int adaflo_b200_ctx_synchronize(adaflo_b200_ctx_t ctx)
 {
   if (!ctx) return fail(ADAFLO_B200_ERR_ARG, "null context");
-  AB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
+  AB_CUDA(cudaSetDevice(ctx->device));
+  return stream_wait(ctx, ctx->stream);
 }
 
 int adaflo_b200_comm_unique_id(unsigned char id[128]) { return comm_unique_id(id); }
@@ -539,7 +543,7 @@ int adaflo_b200_mf_upload_vector(adaflo_b200_mf_t mf, int space, double *vec_dev
 {
   if (!mf || space < 0 || space >= (int)mf->spaces.size() || !vec_dev || !vec_host) return fail(ADAFLO_B200_ERR_ARG, "mf_upload_vector: bad argument");
   AB_CHECK(upload_owned(mf, space, vec_dev, vec_host, mf->ctx->stream));
-  AB_CUDA(cudaStreamSynchronize(mf->ctx->stream));
+  AB_CHECK(stream_wait(mf->ctx, mf->ctx->stream));
   return 0;
 }
 
@@ -547,7 +551,7 @@ int adaflo_b200_mf_download_vector(adaflo_b200_mf_t mf, int space, double *vec_h
 {
   if (!mf || space < 0 || space >= (int)mf->spaces.size() || !vec_dev || !vec_host) return fail(ADAFLO_B200_ERR_ARG, "mf_download_vector: bad argument");
   AB_CHECK(download_owned(mf, space, vec_host, vec_dev, mf->ctx->stream));
-  AB_CUDA(cudaStreamSynchronize(mf->ctx->stream));
+  AB_CHECK(stream_wait(mf->ctx, mf->ctx->stream));
   return 0;
 }
 
@@ -1497,8 +1501,8 @@ int adaflo_b200_ns_vmult_host(adaflo_b200_ns_t ns, double *dst_u_host, double *d
         AB_CHECK(vec_project(ns->ctx, dp, ns->mode_weights[m], ns->modes[m], ns->inv_weights[m], sp.n_owned_entries(), sp.n_local_entries()));
   AB_CUDA(cudaMemcpyAsync(dst_p_host, dp, sp.n_owned_entries() * sizeof(double), cudaMemcpyDeviceToHost, s));
   stats_end(ns, t0);
-  AB_CUDA(cudaStreamSynchronize(ns->down_stream));
-  AB_CUDA(cudaStreamSynchronize(s));
+  AB_CHECK(stream_wait(ns->ctx, ns->down_stream));
+  AB_CHECK(stream_wait(ns->ctx, s));
   return 0;
 }
 
@@ -1533,7 +1537,7 @@ int adaflo_b200_vec_download(adaflo_b200_ctx_t ctx, double *host, const double *
 {
   if (!ctx || (n && (!dev || !host))) return fail(ADAFLO_B200_ERR_ARG, "vec_download: null argument");
   AB_CUDA(cudaMemcpyAsync(host, dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  AB_CUDA(cudaStreamSynchronize(ctx->stream));
+  AB_CHECK(stream_wait(ctx, ctx->stream));
   return 0;
 }
 int adaflo_b200_vec_set(adaflo_b200_ctx_t ctx, double *x, double v, uint64_t n) { return vec_set(ctx->stream, x, v, n); }

@@ -8,7 +8,11 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -27,6 +31,8 @@ struct NcclApi {
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;                          // optional
+  ncclResult_t (*CommGetAsyncError)(ncclComm_t, ncclResult_t *) = nullptr;  // optional
 };
 NcclApi g_nccl;
 
@@ -52,6 +58,8 @@ int load_nccl()
   AB_SYM(AllReduce, "ncclAllReduce")
   AB_SYM(GetErrorString, "ncclGetErrorString")
 #undef AB_SYM
+  *(void **)(&g_nccl.CommAbort) = dlsym(g_nccl.handle, "ncclCommAbort");
+  *(void **)(&g_nccl.CommGetAsyncError) = dlsym(g_nccl.handle, "ncclCommGetAsyncError");
   return 0;
 }
 }  // namespace
@@ -84,7 +92,47 @@ int comm_init(adaflo_b200_ctx_t ctx, const unsigned char id[128], int rank, int 
   ctx->nccl_comm = comm;
   ctx->rank = rank;
   ctx->nranks = nranks;
+  if (ctx->comm_timeout_s <= 0) ctx->comm_timeout_s = 120.0;  // default with a communicator; ADAFLO_B200_COMM_TIMEOUT overrides (ctx_create)
   return 0;
+}
+
+int stream_wait(adaflo_b200_ctx_t ctx, cudaStream_t s)
+{
+  if (ctx->comm_timeout_s <= 0) {
+    AB_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
+  if (!ctx->ev_watch) AB_CUDA(cudaEventCreateWithFlags(&ctx->ev_watch, cudaEventDisableTiming));
+  AB_CUDA(cudaEventRecord(ctx->ev_watch, s));
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spin = 0;; ++spin) {
+    const cudaError_t e = cudaEventQuery(ctx->ev_watch);
+    if (e == cudaSuccess) return 0;
+    if (e != cudaErrorNotReady) return fail(ADAFLO_B200_ERR_CUDA, std::string("stream_wait: ") + cudaGetErrorString(e));
+    if (spin < 2000) continue;  // short waits (a reduction of a Krylov step) never leave the spin
+    const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (ctx->nccl_comm && g_nccl.CommGetAsyncError && (spin & 1023u) == 0) {
+      ncclResult_t async = ncclSuccess;
+      if (g_nccl.CommGetAsyncError((ncclComm_t)ctx->nccl_comm, &async) == ncclSuccess && async != ncclSuccess && async != ncclInProgress) {
+        if (g_nccl.CommAbort) g_nccl.CommAbort((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+        return fail(ADAFLO_B200_ERR_COMM, std::string("asynchronous NCCL error: ") + g_nccl.GetErrorString(async));
+      }
+    }
+    if (waited > ctx->comm_timeout_s) {
+      // the stream does not drain: most likely a collective whose peers never arrived.  Abort the communicator so that the
+      // stuck NCCL kernel ends and the process can report the error instead of spinning until an external timeout.
+      if (ctx->nccl_comm && g_nccl.CommAbort) {
+        g_nccl.CommAbort((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+      }
+      char msg[256];
+      std::snprintf(msg, sizeof(msg), "rank %d of %d: the stream did not drain within %.1f s (a collective whose peers never arrived? every rank "
+                                      "must issue the same sequence of operator calls); communicator aborted", ctx->rank, ctx->nranks, ctx->comm_timeout_s);
+      return fail(ADAFLO_B200_ERR_COMM, msg);
+    }
+    if (waited > 2e-3) std::this_thread::sleep_for(std::chrono::microseconds(50));
+  }
 }
 
 int comm_destroy(adaflo_b200_ctx_t ctx)

@@ -147,6 +147,9 @@ struct adaflo_b200_ctx_s {
   // communicator
   void *nccl_comm;
   int rank, nranks;
+  // stall watchdog of the host-side waits (comm.cu stream_wait): seconds, 0 = plain cudaStreamSynchronize
+  double comm_timeout_s;
+  cudaEvent_t ev_watch;
 };
 
 struct adaflo_b200_mf_s {
@@ -308,5 +311,10 @@ int comm_allreduce(adaflo_b200_ctx_t ctx, double *dev, int k, int op_max);
 int comm_unique_id(unsigned char id[128]);
 int comm_init(adaflo_b200_ctx_t ctx, const unsigned char id[128], int rank, int nranks);
 int comm_destroy(adaflo_b200_ctx_t ctx);
+// Host wait for everything queued on `s` (a stream of this context).  With a communicator (or ADAFLO_B200_COMM_TIMEOUT set) the wait
+// is a watchdog: it polls an event, checks the communicator's asynchronous error state and gives up after comm_timeout_s seconds
+// with ADAFLO_B200_ERR_COMM (the communicator is aborted) -- a rank that issued a different number of collective-bearing calls
+// than its peers then fails loudly instead of hanging (MatrixFree::cell_loop is collective, navier_stokes_matrix.cc:236-242).
+int stream_wait(adaflo_b200_ctx_t ctx, cudaStream_t s);
 
 }  // namespace ab200

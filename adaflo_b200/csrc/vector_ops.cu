@@ -280,7 +280,7 @@ static int finish_to_host(adaflo_b200_ctx_t ctx, int k, int n_partial, int op_ma
   if (ctx->nranks > 1) AB_CHECK(comm_allreduce(ctx, ctx->red_dev + result_offset, k, op_max));
   if (to_host) {
     AB_CUDA(cudaMemcpyAsync(ctx->red_host, ctx->red_dev + result_offset, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
-    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AB_CHECK(stream_wait(ctx, ctx->stream));
     for (int j = 0; j < k; ++j) results_host[j] = ctx->red_host[j];
   }
   return 0;
@@ -316,7 +316,7 @@ int vec_multi_dot(adaflo_b200_ctx_t ctx, const double *x, const double *const *y
   if (ctx->nranks > 1) AB_CHECK(comm_allreduce(ctx, ctx->red_dev, k, 0));
   if (to_host) {
     AB_CUDA(cudaMemcpyAsync(ctx->red_host, ctx->red_dev, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
-    AB_CUDA(cudaStreamSynchronize(ctx->stream));
+    AB_CHECK(stream_wait(ctx, ctx->stream));
     for (int j = 0; j < k; ++j) results_host[j] = ctx->red_host[j];
   }
   return 0;

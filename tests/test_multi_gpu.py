@@ -22,3 +22,17 @@ def test_partitioned_vmult_matches_global_oracle(world, overlap):
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
     assert r.returncode == 0
+
+
+def test_rank_mismatch_fails_loudly_instead_of_hanging():
+    """one rank issues a collective-bearing vmult its peer never issues: the stall watchdog of the library (csrc/comm.cu
+    stream_wait) aborts the communicator and returns ADAFLO_B200_ERR_COMM within the time-out"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(HERE, "mismatch_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    print(r.stdout[-3000:])
+    print(r.stderr[-3000:])
+    assert r.returncode == 0

@@ -239,4 +239,4 @@ def test_golden_fixtures_match_the_reference_logs():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     report, bad = mod.check_all(root)
-    assert len(report) == 6 and not bad, "\n".join(bad)
+    assert len(report) == 7 and not bad, "\n".join(bad)

@@ -203,3 +203,30 @@ def test_block_preconditioner_on_the_first_newton_system_of_beltrami_3d(ctx):
                                      P.as_library_callback(), [mf.n_owned(0), mf.n_owned(1)])
     assert abs(ctl2.last_step - ctl.last_step) <= 2 and sum(P.inner_iterations) > 0
     P.close()
+
+
+def test_stall_watchdog_reports_a_stream_that_does_not_drain():
+    """csrc/comm.cu stream_wait: with ADAFLO_B200_COMM_TIMEOUT armed, a host-side wait that outlasts the time-out returns
+    ADAFLO_B200_ERR_COMM instead of blocking (the multi-rank case -- a collective whose peer never arrives -- is
+    tests/test_multi_gpu.py::test_rank_mismatch_fails_loudly_instead_of_hanging; here the stream is kept busy by a spin kernel)"""
+    import os
+    import time
+    from adaflo_b200.operators import Context
+    os.environ["ADAFLO_B200_COMM_TIMEOUT"] = "0.2"
+    try:
+        wctx = Context(0)
+    finally:
+        os.environ.pop("ADAFLO_B200_COMM_TIMEOUT")
+    wctx.synchronize()                                   # an idle stream: returns at once
+    torch.cuda._sleep(int(4e9))                          # about 2 s of spinning on the (default) stream of the context
+    t0 = time.time()
+    with pytest.raises(capi.AdafloB200Error) as info:
+        wctx.synchronize()
+    waited = time.time() - t0
+    assert info.value.code == capi.ERR_COMM and 0.15 < waited < 1.5, (info.value, waited)
+    torch.cuda.synchronize()
+    wctx.synchronize()                                   # drained: fine again
+    # without the variable a single-rank context waits plainly
+    plain = Context(0)
+    torch.cuda._sleep(int(1e9))
+    plain.synchronize()
