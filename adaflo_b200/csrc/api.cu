@@ -993,9 +993,15 @@ int adaflo_b200_ns_velocity_vmult(adaflo_b200_ns_t ns, double *dst_u, const doub
 
 int adaflo_b200_ns_divergence_vmult_add(adaflo_b200_ns_t ns, double *dst_p, const double *src_u, int weight_by_viscosity)
 {
-  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "divergence_vmult_add: operator not initialised");
   if (!dst_p || !src_u) return fail(ADAFLO_B200_ERR_ARG, "divergence_vmult_add: null vector");
+  if (ns->generic) {  // degree / dimension dispatch: constant coefficients, single rank
+    NSArgs a = make_args(ns, false);
+    a.src_u = src_u;
+    a.dst_p = dst_p;
+    a.div_weight = weight_by_viscosity ? -ns->prm.viscosity : -1.0;  // :948-953
+    return launch_ns_generic(a, ns->gen_dim, ns->gen_degree_u, 4, 0, mode_of(ns->prm), ns->mf->quads[ns->quad_u].geometry_type, ns->ctx->stream);
+  }
   adaflo_b200_mf_t mf = ns->mf;
   cudaStream_t s = ns->ctx->stream;
   const Space &sp = mf->spaces[ns->dof_p];
@@ -1041,13 +1047,32 @@ static int pressure_common(adaflo_b200_ns_t ns, double *dst_p, const double *src
   return 0;
 }
 
+// pressure mass / Poisson of the degree / dimension dispatch: constant coefficient c0, the pressure quadrature QGauss(degree_p + 1)
+static int generic_pressure_op(adaflo_b200_ns_t ns, double *dst_p, const double *src_p, int kind, double c0)
+{
+  adaflo_b200_mf_t mf = ns->mf;
+  cudaStream_t s = ns->ctx->stream;
+  const Space &sp = mf->spaces[ns->dof_p];
+  if (mf->quads[ns->quad_p].n_q_1d != sp.degree + 1)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "generic pressure operators: the pressure quadrature must be QGauss(degree_p + 1) (navier_stokes_matrix.cc:1003-1005)");
+  AB_CUDA(cudaMemsetAsync(dst_p, 0, sp.n_local_entries() * sizeof(double), s));
+  NSArgs a = make_args(ns, false);
+  fill_geometry(a, mf->quads[ns->quad_p]);
+  a.src_p = src_p;
+  a.dst_p = dst_p;
+  a.scalar_c0 = c0;
+  AB_CHECK(launch_ns_generic_scalar(a, ns->gen_dim, sp.degree, kind, mf->quads[ns->quad_p].geometry_type, s));
+  return vec_copy_indexed(s, dst_p, src_p, sp.constrained, sp.n_constrained, 1.0);  // :411-415, :443-446
+}
+
 int adaflo_b200_ns_pressure_mass_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
 {
-  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_mass_vmult: operator not initialised");
   if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_mass_vmult: null vector");
   PArgs pa{};
   const auto &p = ns->prm;
+  if (ns->generic)  // :1059-1063 with constant coefficients
+    return generic_pressure_op(ns, dst_p, src_p, 0, p.physical_type == ADAFLO_B200_INCOMPRESSIBLE_STATIONARY ? 1.0 : 1.0 / (p.viscosity + p.tau_grad_div));
   if (p.linearization == ADAFLO_B200_PROJECTION || p.physical_type == ADAFLO_B200_INCOMPRESSIBLE_STATIONARY) {
     pa.coeff_mode = 0;
     pa.c0 = 1.0;  // :1059-1062
@@ -1070,11 +1095,12 @@ int adaflo_b200_ns_pressure_mass_vmult(adaflo_b200_ns_t ns, double *dst_p, const
 
 int adaflo_b200_ns_pressure_poisson_vmult(adaflo_b200_ns_t ns, double *dst_p, const double *src_p)
 {
-  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   if (!ns) return fail(ADAFLO_B200_ERR_STATE, "pressure_poisson_vmult: operator not initialised");
   if (!dst_p || !src_p) return fail(ADAFLO_B200_ERR_ARG, "pressure_poisson_vmult: null vector");
   PArgs pa{};
   const auto &p = ns->prm;
+  if (ns->generic)  // :1003-1028 with constant coefficients
+    return generic_pressure_op(ns, dst_p, src_p, 1, p.physical_type == ADAFLO_B200_INCOMPRESSIBLE_STATIONARY ? 1.0 : 1.0 / (ns->tw.weight * p.density));
   const bool var = ns->var && p.linearization != ADAFLO_B200_PROJECTION;  // :975-977
   const double *rho = ns->rho_prec ? ns->rho_prec : ns->rho;             // :398-399
   const bool stationary = p.physical_type == ADAFLO_B200_INCOMPRESSIBLE_STATIONARY;
@@ -1118,7 +1144,6 @@ int adaflo_b200_ns_pressure_convdiff_vmult(adaflo_b200_ns_t ns, double *dst_p, c
 
 int adaflo_b200_ns_compute_diagonal(adaflo_b200_ns_t ns, double *diag_u, double *diag_p)
 {
-  if (ns && ns->generic) return fail(ADAFLO_B200_ERR_UNSUPPORTED, "this entry point is implemented for the 3-D Q2/Q1 operator only (generic-degree path: vmult, residual, velocity_vmult, projection)");
   // Exact diagonal of vmult.  Velocity block: diag(C^T A_cell C) summed over cells (one unit-source pass per
   // cell-local slot inside the cell kernel), 1 on constrained rows.  Pressure block: the operator has no
   // pressure-pressure coupling and the mean projection removes a multiple of (A^T w)_p = 0, so the diagonal is
@@ -1134,7 +1159,14 @@ int adaflo_b200_ns_compute_diagonal(adaflo_b200_ns_t ns, double *diag_u, double 
   a.src_u = diag_u;  // not read in diagonal mode
   a.dst_u = diag_u;
   a.diag = 1;
-  AB_CHECK(launch_cells(ns, a, false));
+  if (ns->generic) {  // one pass per cell-local slot (the meshes of this path are small); on hanging nodes see ns_generic.cu
+    const int n1 = ns->gen_degree_u + 1, nn = ns->gen_dim == 2 ? n1 * n1 : n1 * n1 * n1;
+    for (int slot = 0; slot < nn * ns->gen_dim; ++slot) {
+      a.diag = slot + 1;
+      AB_CHECK(launch_cells(ns, a, false));
+    }
+  } else
+    AB_CHECK(launch_cells(ns, a, false));
   if (ns->ctx->nranks > 1) AB_CHECK(comm_compress_add(mf, ns->dof_u, diag_u));
   AB_CHECK(vec_set_indexed(s, diag_u, su.constrained, su.n_constrained, 1.0));
   AB_CHECK(vec_set_indexed(s, diag_p, sp.constrained, sp.n_constrained, -1.0));

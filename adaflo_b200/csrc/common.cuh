@@ -241,6 +241,8 @@ struct NSArgs {
   size_t decade_begin, decade_end;  // range of cell decades of this launch (end == 0: all); halo overlap
   int diag;           // compute_diagonal: unit sources per cell-local slot (velocity block)
   int skip_p_test;    // linearization == projection: pressure block not integrated (:902-907)
+  double div_weight;  // generic divergence_vmult_add: -1 or -viscosity (:948-953)
+  double scalar_c0;   // generic pressure mass / Poisson: constant coefficient
 };
 
 // mode of the convective block in a matrix-vector product
@@ -259,6 +261,7 @@ int launch_ns_vmult_affine(const NSArgs &a, bool with_p, int mode, bool var, cud
 int launch_ns_vmult_general(const NSArgs &a, bool with_p, int mode, bool var, cudaStream_t s);
 int launch_ns_residual(const NSArgs &a, int geom, bool var, cudaStream_t s);
 int launch_ns_residual_r1(const NSArgs &a, int geom, bool var, cudaStream_t s);
+int launch_ns_generic_scalar(const NSArgs &a, int dim, int degree_p, int kind, int geom, cudaStream_t s);  // ns_generic.cu: 0 mass, 1 Laplace
 int launch_ns_generic(const NSArgs &a, int dim, int degree_u, int kind, int with_p, int mode, int geom, cudaStream_t s);  // ns_generic.cu  // Newton / Picard / Stokes, vmult mapping
 
 struct PArgs {

@@ -81,7 +81,8 @@ __device__ __forceinline__ void gc_add(double *vec, const uint32_t row, const in
   }
 }
 
-enum { GEN_VMULT = 0, GEN_RESIDUAL = 1, GEN_PRESSURE_MASS = 2, GEN_NODAL_MASS = 3 };
+enum { GEN_VMULT = 0, GEN_RESIDUAL = 1, GEN_PRESSURE_MASS = 2, GEN_NODAL_MASS = 3, GEN_DIVERGENCE = 4 };
+// GEN_DIVERGENCE: local_divergence (navier_stokes_matrix.cc:920-962): dst_p += int q (weight div u), velocity quadrature.
 // GEN_NODAL_MASS: integrals of the degree-K shape functions with QGauss(K + 1), scattered through cell_p into dst_p.  Instantiated
 // with K = pressure degree it gives the integrals of the pressure shape functions with the PRESSURE quadrature QGauss(degree_p + 1),
 // which is what the reference uses for the null-space weights (navier_stokes_matrix.cc:110-168).
@@ -99,6 +100,9 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
   __shared__ double pq[NQ];                     // pressure at the points, then the pressure test integrand
   const uint32_t cell = blockIdx.x;
   const int tid = threadIdx.x;
+  constexpr bool RESOLVE = KIND == GEN_VMULT || KIND == GEN_DIVERGENCE;  // read_dof_values; the residual reads plainly
+  // compute_diagonal: unit source in cell-local slot (node dslot % NN, component dslot / NN), only that slot's row is scattered
+  const int dslot = KIND == GEN_VMULT ? A.diag - 1 : -1;
   for (int i = tid; i < n1 * n1; i += blockDim.x) {
     tabN[i] = T.N[(i / n1) * kGenMaxN1 + i % n1];
     tabD[i] = T.Dq[(i / n1) * kGenMaxN1 + i % n1];
@@ -121,10 +125,12 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
           const uint32_t e = __ldg(cu + i), node = e & ADAFLO_B200_NODE_MASK;
           // vmult resolves the constraints (read_dof_values), the residual reads plainly (read_dof_values_plain, :663-664:
           // also the entry of a hanging node, which AffineConstraints::distribute has filled, navier_stokes.cc:1252)
-          if (KIND == GEN_VMULT && node >= A.gc_first_u)
+          if (dslot >= 0)
+            work[0][i] = (i == dslot % NN && c == dslot / NN) ? 1.0 : 0.0;
+          else if (RESOLVE && node >= A.gc_first_u)
             work[0][i] = gc_read<DIM>(vec, node - A.gc_first_u, c, A.gc_ptr_u, A.gc_cols_u, A.gc_w_u);
           else
-            work[0][i] = (KIND == GEN_VMULT && ((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) ? 0.0 : vec[(size_t)DIM * node + c];
+            work[0][i] = (RESOLVE && ((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) ? 0.0 : vec[(size_t)DIM * node + c];
         }
         __syncthreads();
         int cur = 0;
@@ -146,10 +152,10 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
     if (with_p) {
       for (int i = tid; i < NPN; i += blockDim.x) {
         const uint32_t e = __ldg(cp + i), node = e & ADAFLO_B200_NODE_MASK;
-        if (KIND == GEN_VMULT && node >= A.gc_first_p)
+        if (RESOLVE && node >= A.gc_first_p)
           work[0][i] = gc_read<1>(A.src_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p);
         else
-          work[0][i] = (KIND == GEN_VMULT && (e >> ADAFLO_B200_FLAG_SHIFT)) ? 0.0 : A.src_p[node];
+          work[0][i] = (RESOLVE && (e >> ADAFLO_B200_FLAG_SHIFT)) ? 0.0 : A.src_p[node];
       }
       __syncthreads();
       int cur = 0, ext[3] = {K, K, K};
@@ -201,6 +207,9 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       }
       double div = 0;
       for (int d = 0; d < DIM; ++d) div += g[d][d];
+      if (KIND == GEN_DIVERGENCE) {
+        pq[q] = A.div_weight * div * jxw;
+      } else {
       double conv[DIM];
       for (int d = 0; d < DIM; ++d) conv[d] = 0;
       double *lin = A.lin ? A.lin + (size_t)cell * NROWS * NQ + q : nullptr;  // row r at lin[r * NQ]
@@ -263,12 +272,13 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
         }
       }
       pq[q] = -div * jxw;
+      }  // KIND != GEN_DIVERGENCE
     }
   }
   __syncthreads();
 
   // ---- integrate and scatter
-  if (KIND != GEN_PRESSURE_MASS && KIND != GEN_NODAL_MASS) {
+  if (KIND != GEN_PRESSURE_MASS && KIND != GEN_NODAL_MASS && KIND != GEN_DIVERGENCE) {
     for (int c = 0; c < DIM; ++c) {
       for (int d = 0; d < DIM; ++d) sweep<DIM, true, true>(tabD, n1, n1, n1, d, ext_q, grad[c][d], val[c]);  // val += Dq^T grad_d
       int cur = 0;
@@ -280,6 +290,18 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       }
       for (int i = tid; i < NN; i += blockDim.x) {
         const uint32_t e = __ldg(cu + i), node = e & ADAFLO_B200_NODE_MASK;
+        if (dslot >= 0) {
+          if (i != dslot % NN || c != dslot / NN) continue;
+          if (node >= A.gc_first_u) {  // a constrained slot adds w_k^2 a_ii to parent k (couplings between two slots of one parent are left out)
+            for (uint32_t k = __ldg(A.gc_ptr_u + node - A.gc_first_u), end = __ldg(A.gc_ptr_u + node - A.gc_first_u + 1); k < end; ++k) {
+              const uint32_t pe = __ldg(A.gc_cols_u + k);
+              const double w = __ldg(A.gc_w_u + k);
+              if (!((pe >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u)) red_add(A.dst_u + (size_t)DIM * (pe & ADAFLO_B200_NODE_MASK) + c, w * w * work[cur][i]);
+            }
+          } else if (!((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u))
+            red_add(A.dst_u + (size_t)DIM * node + c, work[cur][i]);
+          continue;
+        }
         if (node >= A.gc_first_u)
           gc_add<DIM>(A.dst_u, node - A.gc_first_u, c, A.gc_ptr_u, A.gc_cols_u, A.gc_w_u, work[cur][i]);
         else if (!((e >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u))
@@ -303,7 +325,7 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       else
         red_add(A.dst_p + node, work[cur][i]);
     }
-  } else if (KIND == GEN_PRESSURE_MASS || (with_p && !A.skip_p_test)) {
+  } else if (KIND == GEN_PRESSURE_MASS || KIND == GEN_DIVERGENCE || (with_p && !A.skip_p_test && dslot < 0)) {
     int cur = 0, ext[3] = {n1, n1, n1};
     for (int i = tid; i < NQ; i += blockDim.x) work[0][i] = pq[i];
     __syncthreads();
@@ -319,6 +341,97 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       else if (KIND == GEN_PRESSURE_MASS || !(e >> ADAFLO_B200_FLAG_SHIFT))
         red_add(A.dst_p + node, work[cur][i]);
     }
+  }
+}
+
+// ---------------------------------------------------------------- scalar operators on the pressure space
+// local_pressure_mass / local_pressure_poisson with constant coefficients (navier_stokes_matrix.cc:966-1073): a scalar field of
+// degree K with QGauss(K + 1) -- for the pressure of Q_(K+1)/Q_K this is the reference's pressure quadrature quad_index_p.
+//   SC_MASS:    dst += int phi (c0 p);   SC_POISSON: dst += int grad phi . (c0 grad p)
+enum { SC_MASS = 0, SC_POISSON = 1 };
+template <int DIM, int K, int KIND>
+__global__ void gen_scalar_kernel(const NSArgs A, const GenTables T, const int geom)
+{
+  constexpr int n1 = K + 1, NN = DIM == 2 ? n1 * n1 : n1 * n1 * n1, NQ = NN;
+  __shared__ double tabN[n1 * n1], tabD[n1 * n1];
+  __shared__ double work[2][NN], val[NQ], grad[DIM][NQ];
+  const uint32_t cell = blockIdx.x;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n1 * n1; i += blockDim.x) {
+    tabN[i] = T.N[(i / n1) * kGenMaxN1 + i % n1];
+    tabD[i] = T.Dq[(i / n1) * kGenMaxN1 + i % n1];
+  }
+  const uint32_t *cp = A.cell_p + (size_t)cell * NN;
+  const int ext_q[3] = {n1, n1, n1};
+  for (int i = tid; i < NN; i += blockDim.x) {
+    const uint32_t e = __ldg(cp + i), node = e & ADAFLO_B200_NODE_MASK;
+    if (node >= A.gc_first_p)
+      work[0][i] = gc_read<1>(A.src_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p);
+    else
+      work[0][i] = (e >> ADAFLO_B200_FLAG_SHIFT) ? 0.0 : A.src_p[node];
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int d = 0; d < DIM; ++d) {
+    sweep<DIM, false, false>(tabN, n1, n1, n1, d, ext_q, work[cur], work[cur ^ 1]);
+    cur ^= 1;
+  }
+  for (int i = tid; i < NQ; i += blockDim.x) val[i] = work[cur][i];
+  __syncthreads();
+  if (KIND == SC_POISSON)
+    for (int d = 0; d < DIM; ++d) sweep<DIM, false, false>(tabD, n1, n1, n1, d, ext_q, val, grad[d]);
+  if (tid < NQ) {
+    const int q = tid;
+    const int qi[3] = {q % n1, (q / n1) % n1, DIM == 3 ? q / (n1 * n1) : 0};
+    double Kj[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, jxw;
+    const double wq = T.W[qi[0]] * T.W[qi[1]] * (DIM == 3 ? T.W[qi[2]] : 1.0);
+    if (geom == ADAFLO_B200_GEOM_CARTESIAN) {
+      const double *row = A.geom_table + 4 * (size_t)__ldg(A.geom_row + cell);
+      for (int f = 0; f < DIM; ++f) Kj[f][f] = row[f];
+      jxw = row[3] * wq;
+    } else if (geom == ADAFLO_B200_GEOM_AFFINE) {
+      const double *row = A.geom_table + 10 * (size_t)__ldg(A.geom_row + cell);
+      for (int f = 0; f < DIM; ++f)
+        for (int e = 0; e < DIM; ++e) Kj[f][e] = row[3 * f + e];
+      jxw = row[9] * wq;
+    } else {
+      for (int f = 0; f < DIM; ++f)
+        for (int e = 0; e < DIM; ++e) Kj[f][e] = __ldg(A.inv_jac + ((size_t)cell * 9 + 3 * f + e) * NQ + q);
+      jxw = __ldg(A.jxw + (size_t)cell * NQ + q);
+    }
+    if (KIND == SC_MASS)
+      val[q] *= A.scalar_c0 * jxw;
+    else {
+      double g[DIM];
+      for (int e = 0; e < DIM; ++e) {
+        double s = 0;
+        for (int f = 0; f < DIM; ++f) s = fma(grad[f][q], Kj[f][e], s);
+        g[e] = s * A.scalar_c0 * jxw;
+      }
+      for (int f = 0; f < DIM; ++f) {
+        double s = 0;
+        for (int e = 0; e < DIM; ++e) s = fma(Kj[f][e], g[e], s);
+        grad[f][q] = s;
+      }
+      val[q] = 0.0;
+    }
+  }
+  __syncthreads();
+  if (KIND == SC_POISSON)
+    for (int d = 0; d < DIM; ++d) sweep<DIM, true, true>(tabD, n1, n1, n1, d, ext_q, grad[d], val);
+  cur = 0;
+  for (int i = tid; i < NQ; i += blockDim.x) work[0][i] = val[i];
+  __syncthreads();
+  for (int d = 0; d < DIM; ++d) {
+    sweep<DIM, true, false>(tabN, n1, n1, n1, d, ext_q, work[cur], work[cur ^ 1]);
+    cur ^= 1;
+  }
+  for (int i = tid; i < NN; i += blockDim.x) {
+    const uint32_t e = __ldg(cp + i), node = e & ADAFLO_B200_NODE_MASK;
+    if (node >= A.gc_first_p)
+      gc_add<1>(A.dst_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p, work[cur][i]);
+    else if (!(e >> ADAFLO_B200_FLAG_SHIFT))
+      red_add(A.dst_p + node, work[cur][i]);
   }
 }
 
@@ -425,15 +538,43 @@ int launch_dk(const NSArgs &a, int kind, int with_p, int mode, int geom, cudaStr
     case GEN_VMULT: ns_generic_kernel<DIM, K, GEN_VMULT><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
     case GEN_RESIDUAL: ns_generic_kernel<DIM, K, GEN_RESIDUAL><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
     case GEN_NODAL_MASS: ns_generic_kernel<DIM, K, GEN_NODAL_MASS><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
+    case GEN_DIVERGENCE: ns_generic_kernel<DIM, K, GEN_DIVERGENCE><<<a.n_cells, threads, 0, s>>>(a, T, 0, mode, geom); break;
     default: ns_generic_kernel<DIM, K, GEN_PRESSURE_MASS><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
   }
   AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());
   return 0;
 }
+template <int DIM, int K>
+int launch_scalar_dk(const NSArgs &a, int kind, int geom, cudaStream_t s)
+{
+  static const GenTables T = make_tables(K);
+  constexpr int n1 = K + 1, NQ = DIM == 2 ? n1 * n1 : n1 * n1 * n1;
+  const int threads = (NQ + 31) / 32 * 32;
+  if (!a.n_cells) return 0;
+  if (kind == SC_MASS)
+    gen_scalar_kernel<DIM, K, SC_MASS><<<a.n_cells, threads, 0, s>>>(a, T, geom);
+  else
+    gen_scalar_kernel<DIM, K, SC_POISSON><<<a.n_cells, threads, 0, s>>>(a, T, geom);
+  AB_COUNT_LAUNCH();
+  AB_CUDA(cudaGetLastError());
+  return 0;
+}
 }  // namespace
 
-// kind: 0 vmult (with_p = 0: velocity block), 1 residual, 2 integrals of the pressure shape functions into dst_p
+// scalar operators on the pressure space of degree degree_p with QGauss(degree_p + 1): kind 0 mass, 1 Laplace; coefficient a.scalar_c0
+int launch_ns_generic_scalar(const NSArgs &a, int dim, int degree_p, int kind, int geom, cudaStream_t s)
+{
+  if (geom == ADAFLO_B200_GEOM_GENERAL && dim == 3 && degree_p == 2)
+    return fail(ADAFLO_B200_ERR_UNSUPPORTED, "generic pressure operators: per-point geometry of QGauss(3) in 3-D is stored for the tuned kernels");
+#define AB_G(D, K) \
+  if (dim == D && degree_p == K) return launch_scalar_dk<D, K>(a, kind, geom, s);
+  AB_G(2, 1) AB_G(2, 2) AB_G(2, 3) AB_G(2, 4) AB_G(3, 1) AB_G(3, 2) AB_G(3, 3) AB_G(3, 4)
+#undef AB_G
+  return fail(ADAFLO_B200_ERR_UNSUPPORTED, "generic pressure operators: pressure degree 1..4 in 2 or 3 dimensions");
+}
+
+// kind: 0 vmult (with_p = 0: velocity block), 1 residual, 2 integrals of the pressure shape functions into dst_p, 4 divergence
 int launch_ns_generic(const NSArgs &a, int dim, int degree_u, int kind, int with_p, int mode, int geom, cudaStream_t s)
 {
   if (geom == ADAFLO_B200_GEOM_GENERAL && dim == 3 && degree_u == 2) geom = 3;  // QGauss(3) in 3-D: decade-blocked arrays (api.cu mf_create)

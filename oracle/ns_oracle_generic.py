@@ -241,6 +241,50 @@ class OracleNavierStokesGeneric:
         dst_u[c] = src_u[c]
         return dst_u
 
+    # ---- sub-block operators of the block preconditioner (navier_stokes_matrix.cc:300-483, cell kernels :920-1073), constant
+    # coefficients
+    def divergence_vmult_add(self, dst_p, src_u, weight_by_viscosity=False):
+        """dst_p += int q (weight div u), weight = -1 or -viscosity, velocity quadrature, constraints resolved (:920-962)"""
+        m, dim = self.m, self.dim
+        ul = self._gather(src_u, m.cell_u, dim, self.Eu, m.u_dirichlet)
+        grad = np.einsum("qnf,cnd->cqdf", self.dphi_u, ul) * self.K[:, None, None, :]
+        div = np.einsum("cqdd->cq", grad)
+        w = -self.mu if weight_by_viscosity else -1.0
+        out_p = np.einsum("qn,cq->cn", self.phi_p, w * div * self.jxw)
+        dst_p += self._scatter(self.Ep, out_p[:, :, None], None)[:, 0]
+
+    def _pressure_quadrature(self):
+        """pressure shape data on the pressure quadrature QGauss(degree_p + 1) (quad_index_p)"""
+        k, dim = self.m.degree, self.dim
+        xq, wq = gauss(k)
+        vp, dp = lagrange_tables(gauss_lobatto(k), xq)
+        phi = tensor(dim, [vp] * dim)
+        dphi = np.stack([tensor(dim, [dp if f == d else vp for d in range(dim)]) for f in range(dim)], axis=-1)
+        w = tensor(dim, [wq[:, None]] * dim)[:, 0]
+        jxw = w[None, :] / np.prod(self.K, axis=1)[:, None]
+        return phi, dphi, jxw
+
+    def pressure_mass_vmult(self, src_p):
+        """int phi (p / (mu + tau_grad_div)) on the pressure quadrature, constrained rows = identity (:420-455, :1041-1073)"""
+        phi, _, jxw = self._pressure_quadrature()
+        c = 1.0 if self.physical_type == STATIONARY else 1.0 / (self.mu + self.tau_gd)
+        pl = self._gather(src_p, self.m.cell_p, 1, self.Ep)[:, :, 0]
+        out = np.einsum("qn,cq->cn", phi, c * np.einsum("qn,cn->cq", phi, pl) * jxw)
+        dst = self._scatter(self.Ep, out[:, :, None], None)[:, 0]
+        dst[self.p_constrained] = src_p[self.p_constrained]
+        return dst
+
+    def pressure_poisson_vmult(self, src_p):
+        """int grad phi . grad p / (weight rho) on the pressure quadrature, constrained rows = identity (:386-415, :966-1038)"""
+        phi, dphi, jxw = self._pressure_quadrature()
+        c = 1.0 if self.physical_type == STATIONARY else 1.0 / (self.weight * self.rho)
+        pl = self._gather(src_p, self.m.cell_p, 1, self.Ep)[:, :, 0]
+        g = np.einsum("qnf,cn->cqf", dphi, pl) * self.K[:, None, :]
+        out = np.einsum("qnf,cqf->cn", dphi, c * g * self.K[:, None, :] * jxw[:, :, None])
+        dst = self._scatter(self.Ep, out[:, :, None], None)[:, 0]
+        dst[self.p_constrained] = src_p[self.p_constrained]
+        return dst
+
     def residual(self, rhs_u, rhs_p, src_u, src_p, user_u, user_p):
         """rhs = user - cell integrals, navier_stokes_matrix.cc:266-293"""
         self._loop("residual", src_u, src_p, rhs_u, rhs_p)

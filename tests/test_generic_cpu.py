@@ -57,6 +57,14 @@ def test_generic_oracle_equals_the_pinned_3d_oracle_for_q2q1():
     su, sp = fields(mt, 10)
     (au, ap), (bu, bp) = A.vmult(su, sp), B.vmult(su, sp)
     assert rel_err(bu, au) < 1e-13 and rel_err(bp, ap) < 1e-13
+    # sub-block operators of the block preconditioner (navier_stokes_matrix.cc:300-483)
+    for weight in (False, True):
+        da, db = np.zeros(A.n_p), np.zeros(B.n_p)
+        A.divergence_vmult_add(da, su, weight)
+        B.divergence_vmult_add(db, su, weight)
+        assert rel_err(db, da) < 1e-13
+    assert rel_err(B.pressure_mass_vmult(sp), A.pressure_mass_vmult(sp)) < 1e-13
+    assert rel_err(B.pressure_poisson_vmult(sp), A.pressure_poisson_vmult(sp)) < 1e-13
 
 
 @pytest.mark.parametrize("dim,k", [(2, 3), (2, 4), (3, 3)])

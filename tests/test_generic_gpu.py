@@ -67,11 +67,49 @@ def test_generic_kernel_on_3d_q2q1_matches_the_pinned_oracle(ctx, geometry, line
     dv = mf.initialize_dof_vector(0)
     A.velocity_vmult(dv, dev(ctx, su))
     assert rel_err(dv.cpu().numpy(), O.velocity_vmult(su)) < TOL
+    # sub-block operators of the block preconditioner on the generic path vs the pinned oracle
+    for weight in (False, True):
+        dp, od = dev(ctx, sp.copy()), sp.copy()
+        A.divergence_vmult_add(dp, dev(ctx, su), weight)
+        O.divergence_vmult_add(od, su, weight)
+        assert rel_err(dp.cpu().numpy(), od) < TOL
+    dp = mf.initialize_dof_vector(1)
+    A.pressure_mass_vmult(dp, dev(ctx, sp))
+    assert rel_err(dp.cpu().numpy(), O.pressure_mass_vmult(sp)) < TOL
+    A.pressure_poisson_vmult(dp, dev(ctx, sp))
+    assert rel_err(dp.cpu().numpy(), O.pressure_poisson_vmult(sp)) < TOL
     # entry points that exist for the tuned 3-D Q2/Q1 kernels only fail loudly
     with pytest.raises(capi.AdafloB200Error):
-        A.pressure_mass_vmult(mf.initialize_dof_vector(1), dev(ctx, sp))
+        A.pressure_convdiff_vmult(mf.initialize_dof_vector(1), dev(ctx, sp))
     A.clear()
     mf.close()
+
+
+def check_sub_blocks_and_diagonal(ctx, mf, A, O, mesh, su, sp, exact_diagonal):
+    """divergence_vmult_add (both weights, adds into dst), pressure_mass_vmult, pressure_poisson_vmult, compute_diagonal of
+    the degree / dimension dispatch against the generic oracle"""
+    dim = mesh.dim
+    for weight in (False, True):
+        dp, od = dev(ctx, sp.copy()), sp.copy()
+        A.divergence_vmult_add(dp, dev(ctx, su), weight)
+        O.divergence_vmult_add(od, su, weight)
+        assert rel_err(dp.cpu().numpy(), od) < TOL
+    dp = mf.initialize_dof_vector(1)
+    A.pressure_mass_vmult(dp, dev(ctx, sp))
+    assert rel_err(dp.cpu().numpy(), O.pressure_mass_vmult(sp)) < TOL
+    A.pressure_poisson_vmult(dp, dev(ctx, sp))
+    assert rel_err(dp.cpu().numpy(), O.pressure_poisson_vmult(sp)) < TOL
+    diag = BlockVector.like(mf)
+    A.compute_diagonal(diag)
+    du = diag.block(0).cpu().numpy()
+    con = O.u_constrained.reshape(-1)
+    assert np.all(du[con] == 1.0) and np.all(du[~con] > 0.0)
+    if exact_diagonal:                                    # e_i^T A e_i for a sample of free dofs
+        rng = np.random.default_rng(5)
+        for i in rng.choice(np.nonzero(~con)[0], 12, replace=False):
+            e = np.zeros(O.n_u)
+            e[i] = 1.0
+            assert abs(O.velocity_vmult(e)[i] - du[i]) < 1e-12 * abs(du[i])
 
 
 @pytest.mark.parametrize("dim,k,n", [(2, 2, (6, 5)), (2, 3, (4, 3)), (2, 4, (4, 4)), (2, 5, (2, 3)), (3, 3, (3, 2, 2)), (3, 4, (2, 2, 2))])
@@ -113,6 +151,7 @@ def test_taylor_hood_degrees_and_native_2d(ctx, dim, k, n, linearization):
     hu, hp = np.zeros_like(su), np.zeros_like(sp)
     A.vmult_host(hu, hp, np.ascontiguousarray(su), np.ascontiguousarray(sp))
     assert rel_err(hu, ou) < TOL and rel_err(hp, op) < TOL
+    check_sub_blocks_and_diagonal(ctx, mf, A, O, mesh, su, sp, exact_diagonal=True)
     A.clear()
     mf.close()
 
@@ -165,6 +204,7 @@ def test_hanging_nodes_of_any_degree(ctx, k, linearization):
         d = dev(ctx, vec.copy())
         mf.distribute_constraints(space, d)
         assert rel_err(d.cpu().numpy(), mesh.distribute(vec.copy(), space)) < 1e-15
+    check_sub_blocks_and_diagonal(ctx, mf, A, O, mesh, su, sp, exact_diagonal=False)
     A.clear()
     mf.close()
 
