@@ -1015,6 +1015,195 @@ int launch_ls_cell(const LSArgs &a, cudaStream_t s)
   return cart ? launch_ls_cell_sc<OP, 4, true>(a, s) : launch_ls_cell_sc<OP, 4, false>(a, s);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Projection operator (mass + delta Laplace: compute_normal_vmult / compute_curvature_vmult, LS_DAMPED) on Cartesian cells
+// without hanging nodes, applied at CELL level: with constant coefficients the cell matrix of FE_Q_iso_Q1(S) is
+//   alpha [ M (x) M (x) M + kx K (x) M (x) M + ky M (x) K (x) M + kz M (x) M (x) K ],      alpha = |sub-cell| / 216, k_d = 6 delta / h_d^2
+// with the assembled 1-D matrices of the S sub-intervals, M = tridiag(1, [2, 4, .., 4, 2], 1), K = tridiag(-1, [1, 2, .., 2, 1], -1)
+// (what the 2-point Gauss rule integrates exactly on every sub-interval, compute_normal.cc:82-119).  Sum factorisation on the
+// (S + 1)^3 nodal array: one lane per grid line, three register sweeps
+//   x: a = M u, b = kx K u          y: c = M a, e = c + M b + ky K a          z: out = alpha (M e + kz K c)
+// with two transposes through shared memory (for S = 3: two cells per warp, a 4 x 4 x 4 array per cell stored bank-swizzled so
+// that every phase is conflict free).  Per cell and field: 2 (S + 1)^3 shared-memory stores and loads and about 70 flops per line,
+// instead of 8 loads + 8 stores per sub-cell plus the 8-fold corner sum per node, and 98 flops per sub-cell.
+template <int S>
+struct LsLineCfg {
+  static constexpr int n1 = S + 1, lines = n1 * n1, N = n1 * n1 * n1;
+  static constexpr int cpw = 32 / lines;          // cells per warp
+  static constexpr int group = S == 3 ? 16 : 32;  // lanes per cell
+  static constexpr int PN = S == 3 ? 64 : (n1 * n1 + 1) * n1;  // doubles per array
+  __device__ static __forceinline__ int addr(int ix, int iy, int iz)
+  {
+    if (S == 3) return ((ix + iz) & 3) + 4 * ((iy + iz) & 3) + 16 * iz;  // every plane of the 4^3 array covers the 16 8-byte banks once
+    return ix + n1 * iy + (n1 * n1 + 1) * iz;
+  }
+};
+template <int n1>
+__device__ __forceinline__ void tri_m(const double (&x)[n1], double (&y)[n1])
+{
+  y[0] = 2.0 * x[0] + x[1];
+#pragma unroll
+  for (int i = 1; i < n1 - 1; ++i) y[i] = fma(4.0, x[i], x[i - 1] + x[i + 1]);
+  y[n1 - 1] = 2.0 * x[n1 - 1] + x[n1 - 2];
+}
+template <int n1>
+__device__ __forceinline__ void tri_k(const double (&x)[n1], double (&y)[n1])
+{
+  y[0] = x[0] - x[1];
+#pragma unroll
+  for (int i = 1; i < n1 - 1; ++i) y[i] = fma(2.0, x[i], -(x[i - 1] + x[i + 1]));
+  y[n1 - 1] = x[n1 - 1] - x[n1 - 2];
+}
+
+// 4 x 4 transpose of r[0..3] across the four lanes {base, base + d, base + 2 d, base + 3 d} of a warp (d = 1 or 4; t = the lane's
+// index in that group): afterwards r[j] holds what lane j of the group had in r[t].  Two exchange stages, two 64-bit shuffles each:
+// half the L1 data-pipe wavefronts of the same transpose through shared memory (4 STS.64 + 4 LDS.64).
+__device__ __forceinline__ void transpose4(double (&r)[4], const int t, const int d)
+{
+  {
+    const bool up = t & 2;
+    const double x0 = up ? r[0] : r[2], x1 = up ? r[1] : r[3];
+    const double y0 = __shfl_xor_sync(0xffffffffu, x0, 2 * d), y1 = __shfl_xor_sync(0xffffffffu, x1, 2 * d);
+    if (up) { r[0] = y0; r[1] = y1; } else { r[2] = y0; r[3] = y1; }
+  }
+  {
+    const bool up = t & 1;
+    const double x0 = up ? r[0] : r[1], x1 = up ? r[2] : r[3];
+    const double y0 = __shfl_xor_sync(0xffffffffu, x0, d), y1 = __shfl_xor_sync(0xffffffffu, x1, d);
+    if (up) { r[0] = y0; r[2] = y1; } else { r[1] = y0; r[3] = y1; }
+  }
+}
+
+template <int S>
+__global__ void __launch_bounds__(256, 4) ls_damped_lines_kernel(const LSArgs A)
+{
+  using C = LsLineCfg<S>;
+  constexpr int n1 = C::n1, WARPS = 8;
+  __shared__ double sm[WARPS][C::cpw][2][C::PN];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane / C::group, l = lane % C::group;  // cell of the warp's bundle, line within the cell
+  const bool line_ok = sub < C::cpw && l < C::lines;
+  const int p = l % n1, q = l / n1;
+  const size_t n_bundles = ((size_t)A.n_cells + C::cpw - 1) / C::cpw;
+  for (size_t bundle = (size_t)blockIdx.x * WARPS + warp; bundle < n_bundles; bundle += (size_t)gridDim.x * WARPS) {
+    const size_t cell = bundle * C::cpw + sub;
+    const bool ok = line_ok && cell < A.n_cells;
+    double *sa = sm[warp][ok ? sub : 0][0], *sb = sm[warp][ok ? sub : 0][1];
+    uint32_t nx[n1], nz[n1];  // node entries of the x line (iy, iz) = (p, q) and of the z line (ix, iy) = (p, q)
+    double alpha = 0, kx = 0, ky = 0, kz = 0;
+    if (ok) {
+      const uint32_t *cl = A.cell_ls + cell * C::N;
+      if (S == 3) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(cl) + l);
+        nx[0] = v.x; nx[1] = v.y; nx[2] = v.z; nx[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < n1; ++i) nx[i] = __ldg(cl + i + n1 * l);
+      }
+#pragma unroll
+      for (int i = 0; i < n1; ++i) nz[i] = __ldg(cl + l + n1 * n1 * i);
+      const double *tr = A.geom_table + 4 * (size_t)__ldg(A.geom_row + cell);
+      const double gx = S * __ldg(tr), gy = S * __ldg(tr + 1), gz = S * __ldg(tr + 2), vol = __ldg(tr + 3) / (S * S * S);
+      const double h_rel = (A.cell_diameters ? __ldg(A.cell_diameters + cell) : 0.0) / S;
+      const double dd = fmax(A.eps_ratio, h_rel);
+      const double delta = A.delta_scale * dd * dd;  // compute_normal.cc:105-108, compute_curvature.cc:112-117
+      alpha = vol / 216.0;
+      kx = 6.0 * delta * gx * gx;
+      ky = 6.0 * delta * gy * gy;
+      kz = 6.0 * delta * gz * gz;
+    }
+    if constexpr (S == 3) {  // transposes by warp shuffles: no shared memory, no barriers (idle lanes take part with zeros)
+      for (int f = 0; f < A.n_comp; ++f) {
+        double u[4] = {0, 0, 0, 0}, a[4], b[4], c[4], e[4], t1[4], t2[4];
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) u[i] = (nx[i] >> ADAFLO_B200_FLAG_SHIFT) ? 0.0 : A.src[f][nx[i] & ADAFLO_B200_NODE_MASK];
+        }
+        tri_m<4>(u, a);
+        tri_k<4>(u, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b[i] *= kx;
+        transpose4(a, p, 1);  // lane (iy, iz) = (p, q), index ix  ->  lane (ix, iz) = (p, q), index iy
+        transpose4(b, p, 1);
+        tri_m<4>(a, c);
+        tri_m<4>(b, t1);
+        tri_k<4>(a, t2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = c[i] + fma(ky, t2[i], t1[i]);
+        transpose4(c, q, 4);  // lane (ix, iz) = (p, q), index iy  ->  lane (ix, iy) = (p, q), index iz
+        transpose4(e, q, 4);
+        tri_m<4>(e, t1);
+        tri_k<4>(c, t2);
+        if (ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (!(nz[i] >> ADAFLO_B200_FLAG_SHIFT)) red_add(A.dst[f] + (nz[i] & ADAFLO_B200_NODE_MASK), alpha * fma(kz, t2[i], t1[i]));
+        }
+      }
+    } else {
+    for (int f = 0; f < A.n_comp; ++f) {
+      if (ok) {
+        double u[n1], a[n1], b[n1];
+#pragma unroll
+        for (int i = 0; i < n1; ++i) u[i] = (nx[i] >> ADAFLO_B200_FLAG_SHIFT) ? 0.0 : A.src[f][nx[i] & ADAFLO_B200_NODE_MASK];
+        tri_m<n1>(u, a);
+        tri_k<n1>(u, b);
+#pragma unroll
+        for (int i = 0; i < n1; ++i) {
+          sa[C::addr(i, p, q)] = a[i];
+          sb[C::addr(i, p, q)] = kx * b[i];
+        }
+      }
+      __syncwarp();
+      if (ok) {  // y lines: lane (ix, iz) = (p, q); the lane rewrites exactly the entries it has read
+        double a[n1], b[n1], c[n1], mb[n1], ka[n1];
+#pragma unroll
+        for (int i = 0; i < n1; ++i) {
+          a[i] = sa[C::addr(p, i, q)];
+          b[i] = sb[C::addr(p, i, q)];
+        }
+        tri_m<n1>(a, c);
+        tri_m<n1>(b, mb);
+        tri_k<n1>(a, ka);
+#pragma unroll
+        for (int i = 0; i < n1; ++i) {
+          sa[C::addr(p, i, q)] = c[i];
+          sb[C::addr(p, i, q)] = c[i] + fma(ky, ka[i], mb[i]);
+        }
+      }
+      __syncwarp();
+      if (ok) {  // z lines: lane (ix, iy) = (p, q)
+        double c[n1], e[n1], me[n1], kc[n1];
+#pragma unroll
+        for (int i = 0; i < n1; ++i) {
+          c[i] = sa[C::addr(p, q, i)];
+          e[i] = sb[C::addr(p, q, i)];
+        }
+        tri_m<n1>(e, me);
+        tri_k<n1>(c, kc);
+#pragma unroll
+        for (int i = 0; i < n1; ++i)
+          if (!(nz[i] >> ADAFLO_B200_FLAG_SHIFT)) red_add(A.dst[f] + (nz[i] & ADAFLO_B200_NODE_MASK), alpha * fma(kz, kc[i], me[i]));
+      }
+      __syncwarp();
+    }
+    }  // S != 3
+  }
+}
+
+template <int S>
+int launch_ls_damped_lines(const LSArgs &a, cudaStream_t s)
+{
+  constexpr int cpw = LsLineCfg<S>::cpw;
+  int dev = 0, n_sm = 0;
+  AB_CUDA(cudaGetDevice(&dev));
+  AB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const size_t needed = (((size_t)a.n_cells + cpw - 1) / cpw + 7) / 8;
+  const size_t resident = (size_t)n_sm * 8;  // up to 8 blocks of 8 warps per SM
+  ls_damped_lines_kernel<S><<<(unsigned)(needed < resident ? needed : resident), 256, 0, s>>>(a);
+  return 0;
+}
+
 static bool ls_use_subcell_kernel()
 {
   static const bool v1 = [] {
@@ -1030,6 +1219,16 @@ int launch_ls(const LSArgs &a, int op, cudaStream_t s)
   if (threads == 0) return 0;
   const unsigned grid = (unsigned)((threads + 127) / 128);
   const bool cell_kernel = a.n_sub >= 3 && !ls_use_subcell_kernel();  // n_sub <= 2: too few sub-cells for a warp per cell
+  static const bool no_lines = [] { const char *e = getenv("ADAFLO_B200_LS_DAMPED_LINES"); return e && e[0] == '0'; }();  // A/B switch
+  if (op == LS_DAMPED && cell_kernel && !no_lines && a.geom == ADAFLO_B200_GEOM_CARTESIAN && !a.hn && (a.n_sub == 3 || a.n_sub == 4)) {
+    if (a.n_sub == 3)
+      AB_CHECK(launch_ls_damped_lines<3>(a, s));
+    else
+      AB_CHECK(launch_ls_damped_lines<4>(a, s));
+    AB_COUNT_LAUNCH();
+    AB_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define AB_L(O) case O: if (cell_kernel) { AB_CHECK(launch_ls_cell<O>(a, s)); } else ls_subcell_kernel<O><<<grid, 128, 0, s>>>(a); break;
   switch (op) {
     AB_L(LS_ADVECT) AB_L(LS_DAMPED) AB_L(LS_REINIT) AB_L(LS_REINIT_DIFFUSE) AB_L(LS_NORMAL_RHS) AB_L(LS_CURV_RHS)
