@@ -65,6 +65,9 @@ namespace ab200 {
 #ifndef AB_R1_PASYNC  // pressure vertex values by cp.async into their shared-memory slots (see phase A)
 #define AB_R1_PASYNC 1
 #endif
+#ifndef AB_R1_LEAN   // lean per-point physics on Cartesian cells and predicated scatter (round 2: fewer instructions per cell)
+#define AB_R1_LEAN 1
+#endif
 #ifndef AB_R1_WARPS
 #define AB_R1_WARPS 11
 #endif
@@ -269,6 +272,11 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
     }
   }
 #endif
+#if AB_R1_LEAN
+  // does any lane of the decade see a constrained velocity entry?  (interior decades: no -> no selects, no predicates)
+  const bool any_con =
+    __any_sync(mask, ((node[0] | node[1] | node[2] | node[3] | node[4] | node[5] | node[6] | node[7] | node[8]) >> ADAFLO_B200_FLAG_SHIFT) != 0u);
+#endif
   uint32_t pnode[4] = {0, 0, 0, 0};
   double p_dg0 = 0;
   uint32_t dg0_node = 0;
@@ -305,6 +313,23 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   const int dg_c = pass / 27, dg_t = (pass % 27) / 9, dg_j = pass % 9;
   {
     double P[3][9];
+#if AB_R1_LEAN
+    if (!kDiagCapable) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        const size_t n = node[j] & ADAFLO_B200_NODE_MASK;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) P[c][j] = A.src_u[3 * n + c];
+      }
+      if (any_con) {  // warp-uniform: interior decades skip the 27 selects
+#pragma unroll
+        for (int j = 0; j < 9; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            if ((node[j] >> (ADAFLO_B200_FLAG_SHIFT + c)) & 1u) P[c][j] = 0.0;
+      }
+    } else
+#endif
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const size_t n = node[j] & ADAFLO_B200_NODE_MASK;
@@ -433,6 +458,9 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   // writes of line j, the tile reads and the z contraction of line j + 1 -- at no cost in registers (the rows of line
   // j are dead by then); the rows of line 0 are requested before the pressure interpolation.
   double LQ[3][12];
+#if AB_R1_LEAN
+  const double cA = fma(A.gamma, A.rho0, -A.damp0), cB = A.tau1 * A.rho0, tmu0 = A.mu0 * A.tau1;  // constant coefficients
+#endif
   pol = policy_evict_first();
 #if AB_R1_RING
 #pragma unroll
@@ -445,6 +473,9 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
 #endif
   for (int j = 0; j < 3; ++j) {
     const double wj = (j == 1) ? W[1] : W[0];
+#if AB_R1_LEAN
+    const double wline = G.det * (wj * wt);
+#endif
 #if !AB_R1_RING
 #pragma unroll
     for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, 3 * j + qz, pol);
@@ -479,6 +510,83 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
     for (int qz = 0; qz < 3; ++qz) {
       const size_t slot = cbase + (size_t)qz * 30;
       const double(&L)[12] = LQ[qz];
+#if AB_R1_LEAN
+      if constexpr (GEOM == ADAFLO_B200_GEOM_CARTESIAN && !TRANSPOSE) {
+        // Lean formulation of the per-point physics for axis-aligned cells (same terms as the general branch below,
+        // navier_stokes_matrix.cc:702-893, with the constant factors folded): the kernel is bound by its instruction
+        // count, and the general branch spends 110 fp64 instructions per point where 71 suffice:
+        //   value part   w [(gamma rho - damping) u + tau1 rho res]      = wA u + wB res
+        //   flux part    K_ee w S_de with S = tmu (grad + grad^T) + (tau_gd div - p) I
+        const double w = wline * W[qz];  // JxW
+        const double g0 = G.K[0][0] * w, g1 = G.K[1][1] * w, g2 = G.K[2][2] * w;
+        double gr[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          gr[d][kAxX] = dx[d][qz] * G.K[kAxX][kAxX];
+          gr[d][kAxY] = dy[d][qz] * G.K[kAxY][kAxY];
+          gr[d][kAxZ] = dz[d][qz] * G.K[kAxZ][kAxZ];
+        }
+        const double div = gr[0][0] + gr[1][1] + gr[2][2];
+        if (MODE != MODE_STOKES) {
+          const double u[3] = {val[0][qz], val[1][qz], val[2][qz]};
+          double wA, wB;
+          if (VAR) {
+            const double rho = __ldg(A.rho + g * 270 + slot), damping = __ldg(A.damp + g * 270 + slot);
+            wA = fma(A.gamma, rho, -damping) * w;
+            wB = (A.tau1 * rho) * w;
+          } else {
+            wA = cA * w;
+            wB = cB * w;
+          }
+          if (MODE == MODE_NEWTON) {
+            const double ltr = L[3] + L[7] + L[11];
+            const double f1 = A.beta * div, f2 = A.beta * ltr;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              double res = f1 * L[d];
+              res = fma(f2, u[d], res);
+#pragma unroll
+              for (int e = 0; e < 3; ++e) res = fma(L[e], gr[d][e], fma(u[e], L[3 + 3 * d + e], res));
+              val[d][qz] = fma(wB, res, wA * u[d]);
+            }
+          } else if (MODE == MODE_PICARD) {
+            const double f2 = A.beta * L[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              double res = f2 * u[d];
+#pragma unroll
+              for (int e = 0; e < 3; ++e) res = fma(L[e], gr[d][e], res);
+              val[d][qz] = fma(wB, res, wA * u[d]);
+            }
+          } else {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) val[d][qz] = wA * u[d];
+          }
+        }
+        const double tmu = VAR ? __ldg(A.mu + g * 270 + slot) * A.tau1 : tmu0;
+        const double tmu2 = tmu + tmu;
+        const double q = WITH_P ? fma(A.tau_gd, div, -pv[qz]) : A.tau_gd * div;
+        const double s01 = tmu * (gr[0][1] + gr[1][0]), s02 = tmu * (gr[0][2] + gr[2][0]), s12 = tmu * (gr[1][2] + gr[2][1]);
+        double tr[3][3];  // [d][mesh axis]
+        tr[0][0] = g0 * fma(tmu2, gr[0][0], q);
+        tr[1][1] = g1 * fma(tmu2, gr[1][1], q);
+        tr[2][2] = g2 * fma(tmu2, gr[2][2], q);
+        tr[0][1] = g1 * s01;
+        tr[1][0] = g0 * s01;
+        tr[0][2] = g2 * s02;
+        tr[2][0] = g0 * s02;
+        tr[1][2] = g2 * s12;
+        tr[2][1] = g1 * s12;
+        tp[qz] = -div * w;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          dx[d][qz] = tr[d][kAxX];
+          dy[d][qz] = tr[d][kAxY];
+          dz[d][qz] = tr[d][kAxZ];
+        }
+        continue;
+      }
+#endif
       const double jxw = G.at_blk(A, g, slot, wj * W[qz] * wt);
       double gr[3][3];
 #pragma unroll
@@ -664,6 +772,13 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
           if (hn.line(0, i, t, 3)) hn_q2_t(hn.sub(0), o[3 * i], o[3 * i + 1], o[3 * i + 2]);
       }
     }
+#if AB_R1_LEAN
+    if (!kDiagCapable && !any_con && !AB_R1_MERGE) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) red_add(A.dst_u + 3 * (size_t)(node[j] & ADAFLO_B200_NODE_MASK) + c, o[j]);
+      continue;
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
       const uint32_t nd = node[j];
