@@ -849,10 +849,18 @@ static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const d
     return !(k && !std::strcmp(k, "v1")) && (o && !std::strcmp(o, "1"));  // the legacy v1 kernel has no decade range
   }();
   const bool overlap = overlap_enabled && !ns->generic && ctx->nranks > 1 && mf->ghost_range_valid && ctx->comm_stream;
+  // Default on several GPUs: the import runs on the communication stream next to the zero-fill of dst (0.42 GB per GPU at
+  // 128^3 cells: 65-100 us, longer than the import), and the cell kernel -- ONE launch -- waits for both.  This hides the
+  // import without the second launch that made the split overlap above slower (ADAFLO_B200_FILL_OVERLAP=0 switches it off).
+  static const bool fill_overlap_enabled = [] {
+    const char *o = std::getenv("ADAFLO_B200_FILL_OVERLAP");
+    return !(o && !std::strcmp(o, "0"));
+  }();
+  const bool fill_overlap = !overlap && fill_overlap_enabled && ctx->nranks > 1 && ctx->comm_stream;
   if (ctx->nranks > 1) {
     const int spaces[2] = {ns->dof_u, ns->dof_p};
     double *vecs[2] = {const_cast<double *>(src_u), const_cast<double *>(in_p)};
-    if (overlap) {
+    if (overlap || fill_overlap) {
       AB_CUDA(cudaEventRecord(ctx->ev_a, s));
       AB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_a, 0));
       cudaStream_t keep = ctx->stream;
@@ -866,6 +874,7 @@ static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const d
   }
   AB_CUDA(cudaMemsetAsync(dst_u, 0, su.n_local_entries() * sizeof(double), s));  // dst = 0, :229
   AB_CUDA(cudaMemsetAsync(dst_p, 0, sp.n_local_entries() * sizeof(double), s));
+  if (fill_overlap) AB_CUDA(cudaStreamWaitEvent(s, ctx->ev_b, 0));
   NSArgs a = make_args(ns, false);
   a.src_u = src_u;
   a.src_p = in_p;

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("overlap", ["1", "0"])
+@pytest.mark.parametrize("overlap", ["1", "0", "serial"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_partitioned_vmult_matches_global_oracle(world, overlap):
     import torch
@@ -17,7 +17,10 @@ def test_partitioned_vmult_matches_global_oracle(world, overlap):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + world), os.path.join(HERE, "mgpu_worker.py")]
-    env = dict(os.environ, ADAFLO_B200_HALO_OVERLAP=overlap)  # import overlapped with interior decades / serial
+    # "1": import overlapped with interior decades (two launches); "0": the default, import next to the zero-fill of dst
+    # on the communication stream; "serial": everything on the compute stream
+    env = dict(os.environ, ADAFLO_B200_HALO_OVERLAP="1" if overlap == "1" else "0",
+               ADAFLO_B200_FILL_OVERLAP="0" if overlap == "serial" else "1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout[-3000:])
     print(r.stderr[-3000:])
