@@ -881,6 +881,13 @@ static int vmult_impl(adaflo_b200_ns_t ns, double *dst_u, double *dst_p, const d
   a.dst_u = dst_u;
   a.dst_p = dst_p;
   a.transpose = transpose ? 1 : 0;
+  {  // paced source prefetch (ns_r1.cuh): stride in doubles, even, so that 16-byte aligned vectors give aligned requests
+    const size_t n_dec = n_groups(mf->n_cells);
+    const uint64_t stride = n_dec ? ((su.n_local_entries() + n_dec - 1) / n_dec + 1) & ~(uint64_t)1 : 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(src_u) & 15u) == 0;
+    a.pf_stride = aligned ? stride : 0;
+    a.pf_u_entries = su.n_local_entries();
+  }
   if (ns->time_kernel) {
     if (ns->kernel_events_used == ns->kernel_events->size()) {
       cudaEvent_t e0, e1;

@@ -243,6 +243,8 @@ struct NSArgs {
   int skip_p_test;    // linearization == projection: pressure block not integrated (:902-907)
   double div_weight;  // generic divergence_vmult_add: -1 or -viscosity (:948-953)
   double scalar_c0;   // generic pressure mass / Poisson: constant coefficient
+  // paced L2 prefetch of the source vector by the persistent vmult kernel (doubles per decade, length of src_u; 0: off)
+  uint64_t pf_stride, pf_u_entries;
 };
 
 // mode of the convective block in a matrix-vector product

@@ -68,6 +68,9 @@ namespace ab200 {
 #ifndef AB_R1_LEAN   // lean per-point physics on Cartesian cells and predicated scatter (round 2: fewer instructions per cell)
 #define AB_R1_LEAN 1
 #endif
+#ifndef AB_R1_PFSRC  // paced L2 prefetch of src_u this many decades ahead of the ticket (0: off)
+#define AB_R1_PFSRC 0
+#endif
 #ifndef AB_R1_WARPS
 #define AB_R1_WARPS 11
 #endif
@@ -927,6 +930,14 @@ __global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
     }
 #else
     if (lane == 0) i_n2 = atomicAdd(A.work_counter, 1u);
+#endif
+#if AB_R1_PFSRC
+    // paced L2 prefetch of the source vector: where node numbers follow the cell order, the entries first touched by the
+    // decades AB_R1_PFSRC tickets ahead lie about that many strides ahead (a hint only: any numbering stays correct)
+    if (lane == 0 && A.pf_stride) {
+      const size_t off = (A.decade_begin + i + AB_R1_PFSRC) * A.pf_stride;
+      if (off + A.pf_stride <= A.pf_u_entries) l2_prefetch(A.src_u + off, (unsigned)(A.pf_stride * 8));
+    }
 #endif
     r1_decade<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>(A, A.decade_begin + i, warp_smem, lane);
     __syncwarp();
