@@ -232,6 +232,73 @@ __device__ __forceinline__ void r1_residual_decade(const NSArgs &A, const size_t
 #pragma unroll
     for (int qz = 0; qz < 3; ++qz) {
       const size_t slot = cbase + (size_t)qz * 30;
+#if AB_R1_LEAN
+      if constexpr (GEOM == ADAFLO_B200_GEOM_CARTESIAN) {
+        // lean formulation on axis-aligned cells, constant factors folded (see ns_r1.cuh, same terms as the general branch)
+        const double w = G.det * (wj * wt) * W[qz];
+        const double g0 = G.K[0][0] * w, g1 = G.K[1][1] * w, g2 = G.K[2][2] * w;
+        double gr[3][3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          gr[d][kAxX] = dx[d][qz] * G.K[kAxX][kAxX];
+          gr[d][kAxY] = dy[d][qz] * G.K[kAxY][kAxY];
+          gr[d][kAxZ] = dz[d][qz] * G.K[kAxZ][kAxZ];
+        }
+        const double div = gr[0][0] + gr[1][1] + gr[2][2];
+        if (!stokes) {
+          const double u[3] = {val[0][qz], val[1][qz], val[2][qz]};
+          if (lin_lane) {  // linearized_velocities (:791-798)
+            double *l = lin_lane + (3 * j + qz) * kLinPointStride;
+            if (newton) {
+              st_pair(l, u[0], u[1]);
+              st_pair(l + kLinPairStride, u[2], gr[0][0]);
+              st_pair(l + 2 * kLinPairStride, gr[0][1], gr[0][2]);
+              st_pair(l + 3 * kLinPairStride, gr[1][0], gr[1][1]);
+              st_pair(l + 4 * kLinPairStride, gr[1][2], gr[2][0]);
+              st_pair(l + 5 * kLinPairStride, gr[2][1], gr[2][2]);
+            } else {
+              st_pair(l, u[0], u[1]);
+              st_pair(l + kLinPairStride, u[2], div);
+            }
+          }
+          const double rho = VAR ? __ldg(A.rho + g * 270 + slot) : A.rho0;
+          const double damping = VAR ? __ldg(A.damp + g * 270 + slot) : A.damp0;
+          const double wR = w * rho, wA = fma(A.gamma, wR, -damping * w), wB = A.tau1 * wR, f1 = A.beta * div;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            double res = f1 * u[d];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) res = fma(u[e], gr[d][e], res);
+            val[d][qz] = fma(wB, res, fma(wR, hist[d][qz], wA * u[d]));  // :727-732, :783-790
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < 3; ++d) val[d][qz] = 0.0;
+        }
+        const double tmu = (VAR ? __ldg(A.mu + g * 270 + slot) : A.mu0) * A.tau1;
+        const double tmu2 = tmu + tmu;
+        const double q = fma(A.tau_gd, div, -pv[qz]);
+        const double s01 = tmu * (gr[0][1] + gr[1][0]), s02 = tmu * (gr[0][2] + gr[2][0]), s12 = tmu * (gr[1][2] + gr[2][1]);
+        double tr[3][3];  // [d][mesh axis]
+        tr[0][0] = g0 * fma(tmu2, gr[0][0], q);
+        tr[1][1] = g1 * fma(tmu2, gr[1][1], q);
+        tr[2][2] = g2 * fma(tmu2, gr[2][2], q);
+        tr[0][1] = g1 * s01;
+        tr[1][0] = g0 * s01;
+        tr[0][2] = g2 * s02;
+        tr[2][0] = g0 * s02;
+        tr[1][2] = g2 * s12;
+        tr[2][1] = g1 * s12;
+        tp[qz] = -div * w;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          dx[d][qz] = tr[d][kAxX];
+          dy[d][qz] = tr[d][kAxY];
+          dz[d][qz] = tr[d][kAxZ];
+        }
+        continue;
+      }
+#endif
       const double jxw = G.at_blk(A, g, slot, wj * W[qz] * wt);
       double gr[3][3];
 #pragma unroll

@@ -416,3 +416,44 @@ def test_device_poiseuille_is_a_discrete_stokes_solution(ctx):
     assert np.abs(ru[~interior]).max() > 1e-3      # the traction integral of the exact solution on the open faces
     A.clear()
     mf.close()
+
+
+def test_amr_cycle_reupload(ctx):
+    """What adaflo does after refine_grid (navier_stokes.cc:414-451 runs again: MatrixFree::reinit, operator
+    re-initialised): the device mirror and the operator of the old mesh are destroyed, the refined mesh is uploaded on the
+    same context, and the solution, transferred by the host (SolutionTransfer), is used as the linearisation point.  Three
+    cycles; every cycle is checked against the oracle and the device memory of the destroyed cycles is returned."""
+    from adaflo_b200.mesh import RefinedBoxMesh
+    dprm, oprm = flow_params(damping=0.1, tau_grad_div=0.2)
+    dtw, otw = time_weights()
+    free_after = []
+    for cycle, mesh in enumerate([BoxMesh((4, 4, 4)), RefinedBoxMesh((4, 4, 4), ((1, 3), (1, 3), (0, 2))),
+                                  RefinedBoxMesh((4, 4, 4), ((0, 2), (2, 4), (1, 4)))]):
+        mf = MatrixFree(ctx, mesh, "cartesian")
+        old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+        A = NavierStokesMatrix(dprm, 0, 1, 0, 1, old, old_old)
+        A.initialize(mf, dtw, True)
+        lists = (mesh.u_lists, mesh.p_lists) if hasattr(mesh, "u_lists") else (None, None)
+        O = orc.OracleNavierStokesMatrix(mesh, oprm, otw, None, True, *lists)
+        u = beltrami_velocity(mesh.u.coords, 0.1).reshape(-1)  # the "transferred" solution: the same field on every mesh
+        p = beltrami_pressure(mesh.p.coords, 0.1).reshape(-1)
+        uo, uoo = seeded_uniform(mesh.u.global_ids, 3, 9), seeded_uniform(mesh.u.global_ids, 3, 10)
+        O.old_u, O.old_old_u = uo.copy(), uoo.copy()
+        old.block(0).copy_(dev(ctx, uo))
+        old_old.block(0).copy_(dev(ctx, uoo))
+        ru, rp = np.zeros(O.n_u), np.zeros(O.n_p)
+        O.residual(ru, rp, u, p, np.zeros(O.n_u), np.zeros(O.n_p))
+        rhs = BlockVector.like(mf)
+        A.residual(rhs, BlockVector(dev(ctx, u), dev(ctx, p)), BlockVector.like(mf))
+        assert rel_err(rhs.block(0).cpu().numpy(), ru) < TOL and rel_err(rhs.block(1).cpu().numpy(), rp) < TOL, cycle
+        su, sp = seeded_uniform(mesh.u.global_ids, 3, 31), seeded_uniform(mesh.p.global_ids, 1, 32)
+        ou, op = O.vmult(su, sp)
+        dst = BlockVector.like(mf)
+        A.vmult(dst, BlockVector(dev(ctx, su), dev(ctx, sp)))
+        assert rel_err(dst.block(0).cpu().numpy(), ou) < TOL and rel_err(dst.block(1).cpu().numpy(), op) < TOL, cycle
+        A.clear()
+        mf.close()
+        ctx.synchronize()
+        free_after.append(torch.cuda.mem_get_info()[0])
+    # nothing of a destroyed cycle stays allocated by the library (cudaMalloc'ed mirrors are freed; slack for the work pool)
+    assert abs(free_after[2] - free_after[0]) < 64 << 20
