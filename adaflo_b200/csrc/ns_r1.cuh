@@ -71,6 +71,12 @@ namespace ab200 {
 #ifndef AB_R1_PFSRC  // paced L2 prefetch of src_u this many decades ahead of the ticket (0: off)
 #define AB_R1_PFSRC 0
 #endif
+#ifndef AB_R1_RING0  // rows of the first point of a line requested one line ahead (24 registers stay live)
+#define AB_R1_RING0 0
+#endif
+#ifndef AB_R1_STAGE  // cell->node lists of the warp's next decade staged through dead tile slots (see phase A)
+#define AB_R1_STAGE 0
+#endif
 #ifndef AB_R1_WARPS
 #define AB_R1_WARPS 11
 #endif
@@ -220,8 +226,12 @@ __device__ __forceinline__ void r1_prefetch(const NSArgs &A, const size_t g)
 
 // One decade (10 cells) of the cell loop, executed by one warp: 3 lanes per cell.  x, y, z, ix, qx ... below are
 // KERNEL axes (common.cuh: kernel (X, Y, Z) = mesh (y, z, x)); only the geometry sees mesh axes.
+// idx_staged: the cell->node lists of this decade were staged into shared memory by the previous decade of this warp;
+// g_next: the warp's next decade (kNoDecade: none), whose lists are staged during phase C (AB_R1_STAGE)
+constexpr size_t kNoDecade = ~(size_t)0;
 template <bool WITH_P, int MODE, int GEOM, bool VAR, bool TRANSPOSE, bool HANGING>
-__device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, double *warp_smem, const int lane)
+__device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, double *warp_smem, const int lane, const bool idx_staged = false,
+                                          const size_t g_next = kNoDecade)
 {
   AB_TABLES_Q2G3
   const int cw = lane / 3;
@@ -260,6 +270,19 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   // ---------------------------------------------------------------- phase A
   uint32_t node[9];
   uint64_t pol = policy_evict_first();  // re-created where it is needed: it must not occupy registers across the phases
+#if AB_R1_STAGE
+  // Staged lists: lane (cell, t) keeps the 9 + 4 words of its NEXT decade in tile slots that are private to it once it
+  // has read them in phase C (entries with k = t of component 0: value array for the velocity nodes, d/dx array for the
+  // pressure vertices).  The list loads -- first touches, i.e. HBM latency, 10 % of the stall samples of profiles/r2_i --
+  // then overlap two thirds of phase C instead of opening the decade.
+  constexpr bool kStage = !(HANGING && !WITH_P);
+  const uint32_t *stage_u = reinterpret_cast<const uint32_t *>(s + t);
+  if (kStage && idx_staged) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 9; ++j) node[j] = stage_u[2 * (3 * (j % 3) + kR1QyStride * (j / 3))];
+  } else
+#endif
 #pragma unroll
   for (int j = 0; j < 9; ++j) node[j] = ld_once(A.cell_u_blk + (g * 9 + j) * 30 + lane, pol);
 #if AB_R1_MERGE
@@ -285,6 +308,12 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
   uint32_t dg0_node = 0;
   if (WITH_P) {
     if (t < 2) {
+#if AB_R1_STAGE
+      if (kStage && idx_staged) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pnode[j] = stage_u[2 * (9 + 3 * j)];
+      } else
+#endif
 #pragma unroll
       for (int j = 0; j < 4; ++j) pnode[j] = ld_once(A.cell_p_blk + (g * 4 + j) * 30 + lane, pol);
 #if AB_R1_PASYNC
@@ -469,6 +498,9 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
 #pragma unroll
   for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, qz, pol);
 #endif
+#if AB_R1_RING0
+  load_lin<MODE>(LQ[0], lin_lane, 0, pol);
+#endif
 #if AB_R1_UNROLLJ
 #pragma unroll
 #else
@@ -479,7 +511,11 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
 #if AB_R1_LEAN
     const double wline = G.det * (wj * wt);
 #endif
-#if !AB_R1_RING
+#if AB_R1_RING0
+    // rows of point qz = 0 were requested a line ago (see the end of its physics below); qz = 1, 2 now
+#pragma unroll
+    for (int qz = 1; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, 3 * j + qz, pol);
+#elif !AB_R1_RING
 #pragma unroll
     for (int qz = 0; qz < 3; ++qz) load_lin<MODE>(LQ[qz], lin_lane, 3 * j + qz, pol);
 #endif
@@ -587,6 +623,11 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
           dy[d][qz] = tr[d][kAxY];
           dz[d][qz] = tr[d][kAxZ];
         }
+#if AB_R1_RING0
+        // the rows of this point are consumed: request the same point of the next line now, a whole line ahead of its
+        // use (the first consumer of a line's rows otherwise waits for them: 23 % of the stall samples of profiles/r2_i)
+        if (qz == 0 && j < 2) load_lin<MODE>(LQ[0], lin_lane, 3 * (j + 1), pol);
+#endif
         continue;
       }
 #endif
@@ -690,6 +731,9 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
         dy[d][qz] = tr[kAxY];
         dz[d][qz] = tr[kAxZ];
       }
+#if AB_R1_RING0
+      if (qz == 0 && j < 2) load_lin<MODE>(LQ[0], lin_lane, 3 * (j + 1), pol);
+#endif
     }
 #if AB_R1_RING
     if (j < 2) {  // all rows of this line are consumed: request the next line's now
@@ -751,6 +795,24 @@ __device__ __forceinline__ void r1_decade(const NSArgs &A, const size_t g, doubl
       q2::der_t_add(Tx[0], Tx[1], Tx[2], Y[qy][0], Y[qy][1], Y[qy][2]);
       q2::val_t(Ty[0], Ty[1], Ty[2], Yd[qy][0], Yd[qy][1], Yd[qy][2]);
     }
+#if AB_R1_STAGE
+    if (kStage && c == 0 && g_next != kNoDecade && g_next * kGroup + cw < A.n_cells) {
+      // this lane's entries of component 0 are dead now: stage the lists of its next decade into them
+      const unsigned dst0 = (unsigned)__cvta_generic_to_shared(s + t);
+#pragma unroll
+      for (int j = 0; j < 9; ++j)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 8u * (3 * (j % 3) + kR1QyStride * (j / 3))),
+                     "l"(A.cell_u_blk + (g_next * 9 + j) * 30 + lane)
+                     : "memory");
+      if (WITH_P && t < 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst0 + 8u * (9 + 3 * j)), "l"(A.cell_p_blk + (g_next * 4 + j) * 30 + lane)
+                       : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#endif
     double o[9];  // o[3 iy + ix] = N^T Y + D^T Yd along y
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -920,6 +982,9 @@ __global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
   }
   i = __shfl_sync(0xffffffffu, i, 0);
   i_n1 = __shfl_sync(0xffffffffu, i_n1, 0);
+#if AB_R1_STAGE
+  bool staged = false;
+#endif
   while (i < n_dec) {
     unsigned i_n2 = 0;
 #if AB_R1_PLAIN_TICKET
@@ -939,7 +1004,13 @@ __global__ void __maxnreg__(kR1MaxReg) ns_vmult_r1_kernel(const NSArgs A)
       if (off + A.pf_stride <= A.pf_u_entries) l2_prefetch(A.src_u + off, (unsigned)(A.pf_stride * 8));
     }
 #endif
+#if AB_R1_STAGE
+    r1_decade<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>(A, A.decade_begin + i, warp_smem, lane, staged,
+                                                           i_n1 < n_dec ? A.decade_begin + i_n1 : kNoDecade);
+    staged = i_n1 < n_dec;
+#else
     r1_decade<WITH_P, MODE, GEOM, VAR, TRANSPOSE, HANGING>(A, A.decade_begin + i, warp_smem, lane);
+#endif
     __syncwarp();
     i = i_n1;
     i_n1 = __shfl_sync(0xffffffffu, i_n2, 0);

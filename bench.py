@@ -36,21 +36,28 @@ METRIC = "ns_vmult_dofs_per_s"
 UNIT = "DoF/s"
 
 
+TRAFFIC_FILES = ("r2_i_ns_key_metrics.txt", "r2_f_ns_key_metrics.txt", "r1_g_ns_vmult_r1_key_metrics.txt")
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the cell kernel at the bench workload, from the committed
     summary of the latest `ncu --set full` capture (profiles/); None if the summary is missing."""
-    path = os.path.join(ROOT, "profiles", "r1_g_ns_vmult_r1_key_metrics.txt")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-    total, seen = 0.0, 0
-    try:
-        for line in open(path):
-            f = line.split()
-            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                total += float(f[2]) * scale[f[1]]
-                seen += 1
-    except OSError:
-        return None
-    return total if seen == 2 else None
+    for name in TRAFFIC_FILES:  # newest capture first
+        total, seen = 0.0, 0
+        try:
+            for line in open(os.path.join(ROOT, "profiles", name)):
+                f = line.split()
+                if line.startswith("==") and seen:
+                    break  # first launch of the file only
+                if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    total += float(f[2]) * scale[f[1]]
+                    seen += 1
+        except OSError:
+            continue
+        if seen == 2:
+            return total, name
+    return None, None
 
 
 def bind_to_gpu_numa_node(device_index):
@@ -553,8 +560,8 @@ def main():
                        "l2": "inputs larger than L2 (vectors 0.42 GB, linearisation data 5.4 GB per GPU)",
                        "partition": f"z-slabs x{world}", "setup_s": round(t_setup, 1), "numa_node_rank0": numa_node},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic() if n == 128 and world == 1 else None,
-                         "traffic_source": "profiles/r1_g_ns_vmult_r1_key_metrics.txt (ncu --set full, same workload, 1 GPU)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
+                         "traffic": ncu_traffic()[0] if n == 128 and world == 1 else None,
+                         "traffic_source": f"profiles/{ncu_traffic()[1]} (ncu --set full, same workload, 1 GPU)", "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({which})",
                          "kernel": "ns_vmult_r1_kernel<with_p, newton, cartesian> (persistent, 148 blocks x 11 warps)", "kernel_ms": k_avg * 1e3,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_dof": B_PER_DOF_N},
             "e2e": {"value": n_dofs / e2e_t, "unit": UNIT, "h2d_bytes_per_step": 8 * n_dofs, "d2h_bytes_per_step": 8 * n_dofs,   # all ranks
