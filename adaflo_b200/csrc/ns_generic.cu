@@ -87,18 +87,35 @@ enum { GEN_VMULT = 0, GEN_RESIDUAL = 1, GEN_PRESSURE_MASS = 2, GEN_NODAL_MASS = 
 // with K = pressure degree it gives the integrals of the pressure shape functions with the PRESSURE quadrature QGauss(degree_p + 1),
 // which is what the reference uses for the null-space weights (navier_stokes_matrix.cc:110-168).
 
+// Cells per block: the block is (points of a cell) x (cells), about 128 threads, so that the small cells of the 2-D / low-degree
+// configurations fill warps (2-D Q2: 14 cells x 9 points instead of one 9-thread block per cell).  All barriers of the kernel sit
+// in block-uniform control flow (conditions on kernel arguments only), so the cells of a block simply run in lock step.
+template <int NQ>
+struct GenCellsPerBlock {
+  static constexpr int value = NQ >= 64 ? 1 : 128 / NQ;  // measured: two 64-point cells per block are slower than one (3-D Q3: 9.6 vs 11.0 GDoF/s)
+};
+
 template <int DIM, int K, int KIND>
 __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int with_p, const int mode, const int geom)
 {
   constexpr int n1 = K + 1, NN = DIM == 2 ? n1 * n1 : n1 * n1 * n1, NQ = NN, NPN = DIM == 2 ? K * K : K * K * K;
   constexpr int NROWS = DIM + DIM * DIM;
+  constexpr int CPB = GenCellsPerBlock<NQ>::value;
   __shared__ double tabN[n1 * n1], tabD[n1 * n1], tabP[n1 * K];
-  __shared__ double work[2][NN];                // ping-pong arrays of the sweeps
-  __shared__ double val[DIM][NQ];               // values at the points, then the value test integrands
-  __shared__ double grad[DIM][DIM][NQ];         // reference gradients [component][direction], then the gradient test integrands
-  __shared__ double hist[DIM][NQ];              // residual: w_old u_old + w_oo u_old_old at the points
-  __shared__ double pq[NQ];                     // pressure at the points, then the pressure test integrand
-  const uint32_t cell = blockIdx.x;
+  __shared__ double work_[CPB][2][NN];          // ping-pong arrays of the sweeps
+  __shared__ double val_[CPB][DIM][NQ];         // values at the points, then the value test integrands
+  __shared__ double grad_[CPB][DIM][DIM][NQ];   // reference gradients [component][direction], then the gradient test integrands
+  __shared__ double hist_[CPB][DIM][NQ];        // residual: w_old u_old + w_oo u_old_old at the points
+  __shared__ double pq_[CPB][NQ];               // pressure at the points, then the pressure test integrand
+  const int slot = threadIdx.y;
+  double(*work)[NN] = work_[slot];
+  double(*val)[NQ] = val_[slot];
+  double(*grad)[DIM][NQ] = grad_[slot];
+  double(*hist)[NQ] = hist_[slot];
+  double *pq = pq_[slot];
+  // a block's last slots may lie beyond the mesh: they follow the barriers on the last cell's data and write nothing
+  const bool active = (size_t)blockIdx.x * CPB + slot < A.n_cells;
+  const uint32_t cell = active ? blockIdx.x * CPB + slot : A.n_cells - 1;
   const int tid = threadIdx.x;
   constexpr bool RESOLVE = KIND == GEN_VMULT || KIND == GEN_DIVERGENCE;  // read_dof_values; the residual reads plainly
   // compute_diagonal: unit source in cell-local slot (node dslot % NN, component dslot / NN), only that slot's row is scattered
@@ -248,7 +265,7 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
           for (int e = 0; e < DIM; ++e) res += u[e] * g[d][e];
           conv[d] = A.gamma * u[d] + (A.physical_type == ADAFLO_B200_INCOMPRESSIBLE ? hist[d][q] : 0.0) + A.tau1 * res;
         }
-        if (lin) {
+        if (lin && active) {
           for (int d = 0; d < DIM; ++d) lin[d * NQ] = u[d];
           if (A.linearization == ADAFLO_B200_COUPLED_IMPLICIT_NEWTON) {
             for (int d = 0; d < DIM; ++d)
@@ -288,7 +305,7 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
         sweep<DIM, true, false>(tabN, n1, n1, n1, d, ext_q, work[cur], work[cur ^ 1]);
         cur ^= 1;
       }
-      for (int i = tid; i < NN; i += blockDim.x) {
+      for (int i = tid; i < NN && active; i += blockDim.x) {
         const uint32_t e = __ldg(cu + i), node = e & ADAFLO_B200_NODE_MASK;
         if (dslot >= 0) {
           if (i != dslot % NN || c != dslot / NN) continue;
@@ -318,7 +335,7 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       sweep<DIM, true, false>(tabN, n1, n1, n1, d, ext_q, work[cur], work[cur ^ 1]);
       cur ^= 1;
     }
-    for (int i = tid; i < NN; i += blockDim.x) {
+    for (int i = tid; i < NN && active; i += blockDim.x) {
       const uint32_t node = __ldg(A.cell_p + (size_t)cell * NN + i) & ADAFLO_B200_NODE_MASK;
       if (node >= A.gc_first_p)
         gc_add<1>(A.dst_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p, work[cur][i]);
@@ -334,7 +351,7 @@ __global__ void ns_generic_kernel(const NSArgs A, const GenTables T, const int w
       ext[d] = K;
       cur ^= 1;
     }
-    for (int i = tid; i < NPN; i += blockDim.x) {
+    for (int i = tid; i < NPN && active; i += blockDim.x) {
       const uint32_t e = __ldg(cp + i), node = e & ADAFLO_B200_NODE_MASK;
       if (node >= A.gc_first_p)
         gc_add<1>(A.dst_p, node - A.gc_first_p, 0, A.gc_ptr_p, A.gc_cols_p, A.gc_w_p, work[cur][i]);
@@ -531,15 +548,16 @@ template <int DIM, int K>
 int launch_dk(const NSArgs &a, int kind, int with_p, int mode, int geom, cudaStream_t s)
 {
   static const GenTables T = make_tables(K);
-  constexpr int n1 = K + 1, NQ = DIM == 2 ? n1 * n1 : n1 * n1 * n1;
-  const int threads = (NQ + 31) / 32 * 32;
+  constexpr int n1 = K + 1, NQ = DIM == 2 ? n1 * n1 : n1 * n1 * n1, CPB = GenCellsPerBlock<NQ>::value;
   if (!a.n_cells) return 0;
+  const dim3 threads(NQ, CPB);
+  const unsigned blocks = (a.n_cells + CPB - 1) / CPB;
   switch (kind) {
-    case GEN_VMULT: ns_generic_kernel<DIM, K, GEN_VMULT><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
-    case GEN_RESIDUAL: ns_generic_kernel<DIM, K, GEN_RESIDUAL><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
-    case GEN_NODAL_MASS: ns_generic_kernel<DIM, K, GEN_NODAL_MASS><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
-    case GEN_DIVERGENCE: ns_generic_kernel<DIM, K, GEN_DIVERGENCE><<<a.n_cells, threads, 0, s>>>(a, T, 0, mode, geom); break;
-    default: ns_generic_kernel<DIM, K, GEN_PRESSURE_MASS><<<a.n_cells, threads, 0, s>>>(a, T, with_p, mode, geom); break;
+    case GEN_VMULT: ns_generic_kernel<DIM, K, GEN_VMULT><<<blocks, threads, 0, s>>>(a, T, with_p, mode, geom); break;
+    case GEN_RESIDUAL: ns_generic_kernel<DIM, K, GEN_RESIDUAL><<<blocks, threads, 0, s>>>(a, T, with_p, mode, geom); break;
+    case GEN_NODAL_MASS: ns_generic_kernel<DIM, K, GEN_NODAL_MASS><<<blocks, threads, 0, s>>>(a, T, with_p, mode, geom); break;
+    case GEN_DIVERGENCE: ns_generic_kernel<DIM, K, GEN_DIVERGENCE><<<blocks, threads, 0, s>>>(a, T, 0, mode, geom); break;
+    default: ns_generic_kernel<DIM, K, GEN_PRESSURE_MASS><<<blocks, threads, 0, s>>>(a, T, with_p, mode, geom); break;
   }
   AB_COUNT_LAUNCH();
   AB_CUDA(cudaGetLastError());

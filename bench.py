@@ -301,6 +301,59 @@ def run_level_set(args):
     print(json.dumps(line))
 
 
+def run_generic(args):
+    """--workload generic: the degree / dimension dispatch path (csrc/ns_generic.cu, navier_stokes_matrix.cc:64-82) -- Newton vmult
+    of Q_k/Q_(k-1) on uniform meshes with the pairs of the reference's 2-D configurations (tests/beltrami_2d.prm: Q4/Q3).  Extra
+    line, not the headline: the path is the correctness path for the small configurations."""
+    import torch
+    from adaflo_b200 import capi
+    from adaflo_b200.mesh import TensorMesh, seeded_uniform
+    from adaflo_b200.operators import BlockVector, Context, MatrixFreeGeneric, NavierStokesMatrix
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    ctx = Context(0)
+    l0 = ctx.lib.adaflo_b200_kernel_launch_count()
+    peak, which_peak = measured_peak()
+    out = {}
+    for dim, k, n in ((2, 2, (512, 512)), (2, 4, (256, 256)), (3, 3, (32, 32, 32))):
+        mesh = TensorMesh(dim, n, k)
+        mf = MatrixFreeGeneric(ctx, mesh)
+        old, old_old = BlockVector.like(mf), BlockVector.like(mf)
+        A = NavierStokesMatrix(capi.FlowParams(capi.INCOMPRESSIBLE, capi.NEWTON, 0, 0, 1.0, 0.01, 0.0, 0.0, 0.0, 0.0, 0.5), 0, 1, 0, 1, old, old_old)
+        A.initialize(mf, capi.TimeWeights(30.0, -40.0, 10.0, 1.0, 2.0, -1.0), True)
+
+        def dev(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+        sol = BlockVector(dev(seeded_uniform(mesh.u_ids, dim, 1)), dev(seeded_uniform(mesh.p_ids, 1, 2)))
+        rhs, zero, dst = BlockVector.like(mf), BlockVector.like(mf), BlockVector.like(mf)
+        A.residual(rhs, sol, zero)   # stores the linearisation point
+        src = BlockVector(dev(seeded_uniform(mesh.u_ids, dim, 11)), dev(seeded_uniform(mesh.p_ids, 1, 12)))
+        for _ in range(max(args.warmup, 3)):
+            A.vmult(dst, src)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            A.vmult(dst, src)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        n_dofs = int(sol.block(0).numel() + sol.block(1).numel())
+        n_cells = int(np.prod(n))
+        # algorithmic bytes: src + dst, 4-byte cell->dof lists, dim + dim^2 doubles per Gauss point (Newton linearisation point)
+        alg = 16.0 * n_dofs + n_cells * (4.0 * ((k + 1) ** dim + k ** dim) + 8.0 * (dim + dim * dim) * (k + 1) ** dim)
+        gbs = alg / (ms * 1e-3) / 1e9
+        out[f"{dim}d_Q{k}Q{k - 1}_{'x'.join(map(str, n))}"] = {"ms": ms, "dofs": n_dofs, "dofs_per_s": n_dofs / (ms * 1e-3), "bytes_per_dof": alg / n_dofs,
+                                                             "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+        A.clear()
+        mf.close()
+    line = {"metric": "ns_generic_vmult_dofs_per_s", "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "dtype": "f64",
+            "data": "synthetic", "higher_is_better": True,
+            "config": {"workload": "Newton vmult of Taylor-Hood Q_k/Q_(k-1) on uniform Cartesian meshes, generic sum-factorisation kernel (one block per cell)"},
+            "peak_gbs": peak, "peak_source": which_peak, "operators": out, "gpu_launches": int(ctx.lib.adaflo_b200_kernel_launch_count() - l0)}
+    print(json.dumps(line))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -331,7 +384,8 @@ def main():
     ap.add_argument("--no-nonlinear-step", action="store_true")
     ap.add_argument("--strong", action="store_true", help="strong scaling: n^3 cells in total, split over the GPUs (default: weak, n^3 per GPU)")
     ap.add_argument("--no-level-set", action="store_true", help="skip the level-set operator timings of the default line")
-    ap.add_argument("--workload", default="ns", choices=["ns", "ls"], help="ns: the headline Navier-Stokes vmult line; ls: level-set operator timings (extra)")
+    ap.add_argument("--workload", default="ns", choices=["ns", "ls", "generic"],
+                    help="ns: the headline Navier-Stokes vmult line; ls: level-set operator timings (extra); generic: the degree-dispatch path (extra)")
     ap.add_argument("--kernel-only", action="store_true", help="developer A/B mode: kernel timings + checksum only (not a bench line)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -340,6 +394,8 @@ def main():
         return run_reference(args)
     if args.workload == "ls":
         return run_level_set(args)
+    if args.workload == "generic":
+        return run_generic(args)
 
     import torch
     import torch.distributed as dist
