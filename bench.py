@@ -80,6 +80,18 @@ def bind_to_gpu_numa_node(device_index):
             return node
     except Exception:
         pass
+    try:  # sysfs has no NUMA node for the device (virtualised boxes): ask NVML for the CPUs next to the GPU
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return f"nvml:{len(cpus)} cpus"
+    except Exception:
+        pass
     return None
 
 
