@@ -36,7 +36,7 @@ METRIC = "ns_vmult_dofs_per_s"
 UNIT = "DoF/s"
 
 
-TRAFFIC_FILES = ("r2_i_ns_key_metrics.txt", "r2_f_ns_key_metrics.txt", "r1_g_ns_vmult_r1_key_metrics.txt")
+TRAFFIC_FILES = ("r2_j_ns_key_metrics.txt", "r2_i_ns_key_metrics.txt", "r2_f_ns_key_metrics.txt", "r1_g_ns_vmult_r1_key_metrics.txt")
 
 
 def ncu_traffic():
