@@ -13,6 +13,9 @@
 // The extrapolating linearisations (semi-implicit, explicit, projection) need a third field with gradients; they are
 // not on the hot path and stay on the round-1 kernel (launch_ns_residual dispatches).
 #include "ns_r1.cuh"
+#ifndef AB_RES_ROLLJ  // line loop of phase B rolled (2280 instead of 3152 instructions: the unrolled kernel loses 6 % to instruction fetch)
+#define AB_RES_ROLLJ 0
+#endif
 
 namespace ab200 {
 
@@ -196,7 +199,11 @@ __device__ __forceinline__ void r1_residual_decade(const NSArgs &A, const size_t
   const double wt = (t == 1) ? W[1] : W[0];
   double dg0_sum = 0;
   double *lin_lane = A.lin ? A.lin + g * kLinDecade + 2 * lane : nullptr;
+#if AB_RES_ROLLJ
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int j = 0; j < 3; ++j) {  // unrolled: no loop-carried register constraints (ns_r1.cuh)
     const double wj = (j == 1) ? W[1] : W[0];
     double val[3][3], dx[3][3], dy[3][3], dz[3][3], hist[3][3];  // [c][qz]
