@@ -13,14 +13,14 @@ class PortArgs(C.Structure):
     _fields_ = [("n_cells", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32), ("cell_u", C.c_void_p), ("cell_p", C.c_void_p),
                 ("inv_h", C.c_double * 3), ("det", C.c_double), ("mode", C.c_int32),
                 ("gamma", C.c_double), ("tau1", C.c_double), ("beta", C.c_double), ("rho", C.c_double),
-                ("mu", C.c_double), ("damping", C.c_double), ("tau_gd", C.c_double), ("lin", C.c_void_p)]
+                ("mu", C.c_double), ("damping", C.c_double), ("tau_gd", C.c_double), ("lin", C.c_void_p), ("lin_b", C.c_void_p)]
 
 
 def build(force=False):
     so = os.path.join(_HERE, "libcpu_port.so")
     src = os.path.join(_HERE, "ns_cpu_port.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-ffp-contract=fast", "-fopenmp", "-fPIC", "-std=c11", "-shared", "-o", so, src, "-lm"])
     return so
 
 
@@ -53,6 +53,14 @@ class CpuPortVmult:
         a.mode = mode
         a.gamma, a.tau1, a.beta, a.rho, a.mu, a.damping, a.tau_gd = gamma, tau1, beta, rho, mu, damping, tau_gd
         a.lin = None if self.lin is None else self.lin.ctypes.data
+        # the linearisation point in MatrixFree's layout: batches of 4 x-adjacent cells, [row][nx // 4][12 rows][27 points][4 lanes]
+        self.lin_b = None
+        nb = mesh.n[0] // 4
+        if self.lin is not None and nb > 0:
+            rows = mesh.n_cells // mesh.n[0]
+            l4 = self.lin.reshape(rows, mesh.n[0], 12, 27)[:, :4 * nb].reshape(rows, nb, 4, 12, 27)
+            self.lin_b = np.ascontiguousarray(l4.transpose(0, 1, 3, 4, 2))
+        a.lin_b = None if self.lin_b is None else self.lin_b.ctypes.data
         self.args = a
 
     def cells(self, src_u, src_p, dst_u, dst_p):

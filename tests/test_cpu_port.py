@@ -31,8 +31,9 @@ def test_port_matches_dense_oracle(lin, mode):
     assert rel_err(gu, ou) < 1e-13 and rel_err(gp, op) < 1e-13
 
 
-def test_port_stokes():
-    mesh = BoxMesh((3, 3, 3))
+@pytest.mark.parametrize("n", [(3, 3, 3), (9, 3, 2)])   # scalar cells only / two SIMD batches of 4 cells and a scalar remainder per row
+def test_port_stokes(n):
+    mesh = BoxMesh(n)
     _, oprm = flow_params(physical_type=capi.STOKES, viscosity=0.7)
     _, tw = time_weights()
     ns = orc.OracleNavierStokesMatrix(mesh, oprm, tw)
