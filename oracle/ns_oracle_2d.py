@@ -156,3 +156,50 @@ class OracleNavierStokes2D:
         rhs_u += user_u
         rhs_p *= -1.0
         rhs_p += user_p
+
+
+class OracleNavierStokes2DVariable(OracleNavierStokes2D):
+    """The same operator with density and viscosity given per quadrature point (rho_q, mu_q: [cell, 9], the arrays
+    LevelSetOKZSolver::local_compute_force fills, level_set_okz.cc:333-334; variable_densities / variable_viscosities of
+    navier_stokes_matrix.h:293-395), time-dependent Newton linearisation.  Parity status: pinned through the second time step
+    of tests/rising_bubble_ls.output (tests/test_2d_cpu.py: the Newton solve of step 1 with this operator leads to the
+    printed advection residual, iteration counts and first Navier-Stokes residual of step 2)."""
+
+    def __init__(self, mesh2d, rho_q, mu_q, damping, tau_grad_div, beta, tw):
+        super().__init__(mesh2d, INCOMPRESSIBLE, NEWTON, 1.0, 1.0, damping, tau_grad_div, beta, tw, pressure_average_fix=False)
+        self.rho_q, self.mu_q = np.asarray(rho_q), np.asarray(mu_q)
+
+    def _loop(self, op, src_u, src_p, dst_u, dst_p):
+        assert op in ("vmult", "residual")
+        m = self.m
+        resolve = op != "residual"
+        ul = self._gather(src_u, m.cell_u, 2, m.u_dirichlet if resolve else None)
+        val = np.einsum("qn,cnd->cqd", self.phi_u, ul)
+        grad = np.einsum("qnf,cnd->cqdf", self.dphi_u, ul) * self.K[None, None, None, :]
+        pres = np.einsum("qn,cn->cq", self.phi_p, self._gather(src_p, m.cell_p, 1)[:, :, 0])
+        div = grad[:, :, 0, 0] + grad[:, :, 1, 1]
+        conv = self.weight * val
+        if op == "residual":
+            uo = np.einsum("qn,cnd->cqd", self.phi_u, self._gather(self.old_u, m.cell_u, 2))
+            uoo = np.einsum("qn,cnd->cqd", self.phi_u, self._gather(self.old_old_u, m.cell_u, 2))
+            conv = conv + self.w_old * uo + self.w_oo * uoo
+            conv = conv + self.tau1 * (self.beta * div[:, :, None] * val + np.einsum("cqe,cqde->cqd", val, grad))
+            self.lin[:, 0:2, :] = val.transpose(0, 2, 1)
+            self.lin[:, 2:6, :] = grad.reshape(grad.shape[0], 9, 4).transpose(0, 2, 1)
+        else:
+            lu = self.lin[:, 0:2, :].transpose(0, 2, 1)
+            lg = self.lin[:, 2:6, :].transpose(0, 2, 1).reshape(-1, 9, 2, 2)
+            ltr = lg[:, :, 0, 0] + lg[:, :, 1, 1]
+            conv = conv + self.tau1 * (self.beta * div[:, :, None] * lu + self.beta * ltr[:, :, None] * val
+                                       + np.einsum("cqe,cqde->cqd", lu, grad) + np.einsum("cqe,cqde->cqd", val, lg))
+        conv = conv * self.rho_q[:, :, None] - self.damping * val
+        tmu = self.mu_q * self.tau1                                              # [cell, q]
+        S = tmu[:, :, None, None] * (grad + grad.transpose(0, 1, 3, 2))
+        for d in range(2):
+            S[:, :, d, d] = 2 * tmu * grad[:, :, d, d] + self.tau_gd * div - pres
+        Sref = S * self.K[None, None, None, :] * self.jxw[None, :, None, None]
+        out_u = np.einsum("qnf,cqdf->cnd", self.dphi_u, Sref) + np.einsum("qn,cqd->cnd", self.phi_u, conv * self.jxw[None, :, None])
+        keep = ~m.u_dirichlet[m.cell_u]
+        idx = (2 * m.cell_u[:, :, None] + np.arange(2)[None, None, :])
+        np.add.at(dst_u, idx[keep], out_u[keep])
+        np.add.at(dst_p, m.cell_p.reshape(-1), np.einsum("qn,cq->cn", self.phi_p, -div * self.jxw[None, :]).reshape(-1))

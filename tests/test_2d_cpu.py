@@ -345,3 +345,157 @@ def test_level_set_oracle_reproduces_the_first_step_of_the_spurious_currents_log
     compute_force_2d(m, n_sub, H, kappa, prm["surface_tension"], prm["gravity"], prm["density"], prm["density_difference"],
                      prm["viscosity"], prm["viscosity_difference"], True, f, interpolate=True)
     assert f"{np.linalg.norm(f):.3g}" == gold["time_step_1_first_navier_stokes_residual"]["value"]
+
+
+# --------------------------------------------------------------------- second time step of the rising-bubble log
+def bicgstab_iterations(A, b, P, max_iter, abs_tol, rel_tol):
+    """deal.II SolverBicgstab (exact_residual = false) with ReductionControl(max_iter, abs_tol, rel_tol), zero start vector,
+    right-preconditioned directions as in deal.II: solution, last_step(), initial_value()"""
+    x, r = np.zeros_like(b), b.copy()
+    rbar = r.copy()
+    res0 = res = np.linalg.norm(r)
+    tol = max(abs_tol, rel_tol * res)
+    rho = alpha = omega = 1.0
+    p = v = None
+    it = 0
+    while res > tol and it < max_iter:
+        it += 1
+        rhobar = r @ rbar
+        beta = rhobar * alpha / (rho * omega)
+        rho = rhobar
+        p = r.copy() if p is None else r + beta * p - beta * omega * v
+        y = P(p)
+        v = A(y)
+        alpha = rho / (rbar @ v)
+        r = r - alpha * v
+        res = np.linalg.norm(r)
+        if res <= tol:
+            x += alpha * y
+            break
+        z = P(r)
+        t = A(z)
+        omega = (t @ r) / (t @ t)
+        x += alpha * y + omega * z
+        r = r - omega * t
+        res = np.linalg.norm(r)
+    return x, it, res0
+
+
+def newton_with_probed_jacobian(A, m, f, tol=1e-9):
+    """Solve the nonlinear Navier-Stokes system of one time step with the oracle operator A (residual / vmult): the Jacobian
+    is recovered exactly from 75 coloured applications of vmult (two nodes of the Q2 grid couple only within +-2 grid lines, so
+    the columns with equal coordinates mod 5 are probed together) and factorised; one pressure dof is pinned (closed
+    container).  Returns (u, p, residual norms)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    nu, npr = A.n_u, A.n_p
+    h = np.asarray(m.h)
+    iu = np.rint((m.u_coords - m.u_coords.min(axis=0)) / (0.5 * h)).astype(int)
+    ip = np.rint((m.p_coords - m.u_coords.min(axis=0)) / (0.5 * h)).astype(int)
+    nx, ny = iu[:, 0].max() + 1, iu[:, 1].max() + 1
+    u_of = -np.ones((nx, ny), dtype=int)
+    u_of[iu[:, 0], iu[:, 1]] = np.arange(len(iu))
+    p_of = -np.ones((nx, ny), dtype=int)
+    p_of[ip[:, 0], ip[:, 1]] = np.arange(len(ip))
+    row_ij = np.concatenate([np.repeat(iu, 2, axis=0), ip])
+
+    def jacobian():
+        rows, cols, vals = [], [], []
+        for kind in range(3):                                       # columns: u_x, u_y, p
+            ij = iu if kind < 2 else ip
+            for gi in range(5):
+                for gj in range(5):
+                    sel = np.nonzero((ij[:, 0] % 5 == gi) & (ij[:, 1] % 5 == gj))[0]
+                    if len(sel) == 0:
+                        continue
+                    eu, ep = np.zeros(nu), np.zeros(npr)
+                    if kind < 2:
+                        eu[2 * sel + kind] = 1.0
+                    else:
+                        ep[sel] = 1.0
+                    y = np.concatenate(A.vmult(eu, ep))
+                    nz = np.nonzero(y)[0]
+                    ci = row_ij[nz, 0] + ((gi - row_ij[nz, 0] + 2) % 5) - 2
+                    cj = row_ij[nz, 1] + ((gj - row_ij[nz, 1] + 2) % 5) - 2
+                    node = (u_of if kind < 2 else p_of)[ci, cj]
+                    assert (node >= 0).all()
+                    rows.append(nz)
+                    cols.append(2 * node + kind if kind < 2 else nu + node)
+                    vals.append(y[nz])
+        return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nu + npr, nu + npr))
+
+    u, p, history = np.zeros(nu), np.zeros(npr), []
+    for _ in range(8):
+        ru, rp = np.zeros(nu), np.zeros(npr)
+        A.residual(ru, rp, u, p, f, np.zeros(npr))
+        history.append(float(np.sqrt(ru @ ru + rp @ rp)))
+        if history[-1] < tol:
+            break
+        J = jacobian().tolil()
+        J.rows[nu], J.data[nu] = [nu], [1.0]
+        b = np.concatenate([ru, rp])
+        b[nu] = 0.0
+        d = spla.spsolve(J.tocsc(), b)
+        u += d[:nu]
+        p += d[nu:]
+    return u, p, history
+
+
+def test_oracle_chain_reproduces_the_second_time_step_of_the_rising_bubble_log():
+    """tests/rising_bubble_ls.output:21-22 -- 'Concentration advance: advect [0.000471/9] and reinitialize (11 + 10)' and
+    'Residual/iterations: [0.00581/...': the first quantities of the log that depend on a converged two-phase Navier-Stokes
+    solution.  Chain: time step 1 (reinitialisation, curvature, Heaviside, force, variable density / viscosity, Newton on the
+    oracle's residual / vmult solved to 1e-9 with an exactly recovered Jacobian); time step 2: level set extrapolated
+    (two_phase_base.cc:443-456), velocity not (TimeStepping::next, time_stepping.cc:182-193), BDF-2 weights,
+    local_advance_concentration_rhs, BiCGStab on advance_concentration_vmult with the inverse mass diagonal
+    (level_set_okz_advance_concentration.cc:217-258, 300-420, 626-640), reinitialisation, force, residual.  This pins the
+    advection operator and right-hand side, which no other log reaches, and the variable-coefficient
+    Navier-Stokes operator incl. its Jacobian."""
+    from oracle.ls_oracle_2d import OracleLevelSet2D, compute_force_2d
+    from oracle.ns_oracle_2d import OracleNavierStokes2DVariable
+    gold, m, eps_used, c = rising_bubble_setup()
+    prm = gold["parameters"]
+    n_sub, dt = prm["concentration_subdivisions"], prm["step_size"]
+    O = OracleLevelSet2D(m, n_sub, prm["epsilon"], eps_used, prm["h"], dt, np.full(m.n_cells, prm["h"]))
+    O.diag = O.mass_diagonal()
+    x = m.u_coords
+    dirichlet = np.zeros_like(m.u_dirichlet)
+    dirichlet[(np.abs(x[:, 1]) < 1e-12) | (np.abs(x[:, 1] - 2) < 1e-12), :] = True      # set_no_slip_boundary(0)
+    dirichlet[(np.abs(x[:, 0]) < 1e-12) | (np.abs(x[:, 0] - 1) < 1e-12), 0] = True      # set_symmetry_boundary(2)
+    m.u_dirichlet = dirichlet
+
+    def force(level_set):
+        kappa = corrected_curvature(O, level_set, eps_used)
+        H = orc.compute_heaviside(m.cell_ls, level_set, prm["epsilon"], n_sub)
+        f = np.zeros(m.n_u_nodes * 2)
+        rho_q, mu_q = compute_force_2d(m, n_sub, H, kappa, prm["surface_tension"], prm["gravity"], prm["density"], prm["density_difference"],
+                                       prm["viscosity"], prm["viscosity_difference"], True, f, interpolate=True, u_dirichlet=dirichlet)
+        return f, rho_q, mu_q
+
+    # ---- set-up and time step 1 (zero velocity: 'advect [0/0]')
+    c, _ = reinitialize(O, c, 2)
+    c_old = c.copy()
+    c1, counts = reinitialize(O, c, 2)
+    assert counts == gold["time_step_1_reinitialization_cg_iterations"]["value"]
+    f, rho_q, mu_q = force(c1)
+    A = OracleNavierStokes2DVariable(m, rho_q, mu_q, 0.0, 0.0, 0.5, (1.0 / dt, -1.0 / dt, 0.0, 1.0))   # BDF-2 start-up step
+    u1, p1, history = newton_with_probed_jacobian(A, m, f)
+    assert f"{history[0]:.3g}" == gold["time_step_1_first_navier_stokes_residual"]["value"]
+    assert len(history) == 3 and history[1] < 1e-5 and history[2] < 1e-9     # the log: [0.0198] [4.61e-06] [3.05e-10/conv.] (inexact solves)
+
+    # ---- time step 2
+    g2 = gold["time_step_2_concentration_advance"]
+    c_star = 2.0 * c1 - c_old
+    rhs = np.zeros(O.n)
+    O.advance_concentration_rhs(rhs, u1, c_star, c1, c_old, 1.5 / dt, -2.0 / dt, 0.5 / dt)
+    inc, n_it, res0 = bicgstab_iterations(lambda v: O.advance_concentration_vmult(v, 1.5 / dt), rhs, lambda r: r / O.diag, 30, 0.05 * 1e-9, 1e-8)
+    assert f"{res0:.3g}" == g2["advection_initial_residual"]
+    assert n_it == g2["advection_bicgstab_iterations"]
+    c2, counts = reinitialize(O, c_star + inc, 2)
+    assert counts == g2["reinitialization_cg_iterations"]
+    f2, rho_q, mu_q = force(c2)
+    A2 = OracleNavierStokes2DVariable(m, rho_q, mu_q, 0.0, 0.0, 0.5, (1.5 / dt, -2.0 / dt, 0.5 / dt, 1.0))
+    A2.old_u, A2.old_old_u = u1.copy(), np.zeros(A2.n_u)
+    ru, rp = np.zeros(A2.n_u), np.zeros(A2.n_p)
+    A2.residual(ru, rp, u1, p1, f2, np.zeros(A2.n_p))
+    assert f"{np.sqrt(ru @ ru + rp @ rp):.3g}" == gold["time_step_2_first_navier_stokes_residual"]["value"]
