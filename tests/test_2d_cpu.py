@@ -381,7 +381,7 @@ def bicgstab_iterations(A, b, P, max_iter, abs_tol, rel_tol):
     return x, it, res0
 
 
-def newton_with_probed_jacobian(A, m, f, tol=1e-9):
+def newton_with_probed_jacobian(A, m, f, tol=1e-9, start=None):
     """Solve the nonlinear Navier-Stokes system of one time step with the oracle operator A (residual / vmult): the Jacobian
     is recovered exactly from 75 coloured applications of vmult (two nodes of the Q2 grid couple only within +-2 grid lines, so
     the columns with equal coordinates mod 5 are probed together) and factorised; one pressure dof is pinned (closed
@@ -424,7 +424,7 @@ def newton_with_probed_jacobian(A, m, f, tol=1e-9):
                     vals.append(y[nz])
         return sp.csr_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(nu + npr, nu + npr))
 
-    u, p, history = np.zeros(nu), np.zeros(npr), []
+    u, p, history = (np.zeros(nu), np.zeros(npr), []) if start is None else (start[0].copy(), start[1].copy(), [])
     for _ in range(8):
         ru, rp = np.zeros(nu), np.zeros(npr)
         A.residual(ru, rp, u, p, f, np.zeros(npr))
@@ -441,10 +441,10 @@ def newton_with_probed_jacobian(A, m, f, tol=1e-9):
     return u, p, history
 
 
-def test_oracle_chain_reproduces_the_second_time_step_of_the_rising_bubble_log():
+def test_oracle_chain_reproduces_the_second_and_third_time_step_of_the_rising_bubble_log():
     """tests/rising_bubble_ls.output:21-22 -- 'Concentration advance: advect [0.000471/9] and reinitialize (11 + 10)' and
-    'Residual/iterations: [0.00581/...': the first quantities of the log that depend on a converged two-phase Navier-Stokes
-    solution.  Chain: time step 1 (reinitialisation, curvature, Heaviside, force, variable density / viscosity, Newton on the
+    'Residual/iterations: [0.00581/...' -- and :29-30 -- 'advect [0.00108/10] and reinitialize (11 + 11)', '[0.000246/...': the
+    first quantities of the log that depend on a converged two-phase Navier-Stokes solution.  Chain: time step 1 (reinitialisation, curvature, Heaviside, force, variable density / viscosity, Newton on the
     oracle's residual / vmult solved to 1e-9 with an exactly recovered Jacobian); time step 2: level set extrapolated
     (two_phase_base.cc:443-456), velocity not (TimeStepping::next, time_stepping.cc:182-193), BDF-2 weights,
     local_advance_concentration_rhs, BiCGStab on advance_concentration_vmult with the inverse mass diagonal
@@ -499,3 +499,23 @@ def test_oracle_chain_reproduces_the_second_time_step_of_the_rising_bubble_log()
     ru, rp = np.zeros(A2.n_u), np.zeros(A2.n_p)
     A2.residual(ru, rp, u1, p1, f2, np.zeros(A2.n_p))
     assert f"{np.sqrt(ru @ ru + rp @ rp):.3g}" == gold["time_step_2_first_navier_stokes_residual"]["value"]
+
+    # ---- time step 3 (lines 29-30): now the velocity and the pressure are extrapolated too (step_no > 1)
+    g3 = gold["time_step_3_concentration_advance"]
+    u2, p2, history = newton_with_probed_jacobian(A2, m, f2, start=(u1, p1))
+    assert len(history) == 3 and history[2] < 1e-9
+    assert f"{history[1]:.3g}" == "4.08e-06"       # line 22 prints [4.08e-06/14] after its first (inexact, 1e-4) linear solve: same to 3 digits
+    u_star, p_star, c_star = 2.0 * u2 - u1, 2.0 * p2 - p1, 2.0 * c2 - c1
+    rhs = np.zeros(O.n)
+    O.advance_concentration_rhs(rhs, u_star, c_star, c2, c1, 1.5 / dt, -2.0 / dt, 0.5 / dt)
+    inc, n_it, res0 = bicgstab_iterations(lambda v: O.advance_concentration_vmult(v, 1.5 / dt), rhs, lambda r: r / O.diag, 30, 0.05 * 1e-9, 1e-8)
+    assert f"{res0:.3g}" == g3["advection_initial_residual"]
+    assert n_it == g3["advection_bicgstab_iterations"]
+    c3, counts = reinitialize(O, c_star + inc, 2)
+    assert counts == g3["reinitialization_cg_iterations"]
+    f3, rho_q, mu_q = force(c3)
+    A3 = OracleNavierStokes2DVariable(m, rho_q, mu_q, 0.0, 0.0, 0.5, (1.5 / dt, -2.0 / dt, 0.5 / dt, 1.0))
+    A3.old_u, A3.old_old_u = u2.copy(), u1.copy()
+    ru, rp = np.zeros(A3.n_u), np.zeros(A3.n_p)
+    A3.residual(ru, rp, u_star, p_star, f3, np.zeros(A3.n_p))
+    assert f"{np.sqrt(ru @ ru + rp @ rp):.3g}" == gold["time_step_3_first_navier_stokes_residual"]["value"]
