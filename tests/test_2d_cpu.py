@@ -523,3 +523,53 @@ def test_oracle_chain_reproduces_the_second_and_third_time_step_of_the_rising_bu
     ru, rp = np.zeros(A3.n_u), np.zeros(A3.n_p)
     A3.residual(ru, rp, u_star, p_star, f3, np.zeros(A3.n_p))
     assert f"{np.sqrt(ru @ ru + rp @ rp):.3g}" == gold["time_step_3_first_navier_stokes_residual"]["value"]
+
+
+def test_oracle_chain_reproduces_the_second_time_step_of_the_spurious_currents_log():
+    """tests/spurious_currents_ls.output:15-16 -- 'advect [0.000803/8] and reinitialize (7 + 7)', '[0.00024/...': the same chain
+    as for the rising bubble on the surface-tension dominated problem (80 x 80 cells, no-slip everywhere, constant density,
+    no initial reinitialisation): the spurious velocity of step 1 (3.8e-5) advects the level set in step 2."""
+    import json
+    import os
+    from oracle.ls_oracle_2d import OracleLevelSet2D, compute_force_2d
+    from oracle.ns_oracle_2d import OracleNavierStokes2DVariable
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spurious_currents_ls_output.json")) as f:
+        gold = json.load(f)
+    prm = gold["parameters"]
+    n_sub, h, dt = prm["concentration_subdivisions"], prm["h"], prm["step_size"]
+    m = BoxMesh2D((80, 80), lower=(-2.5, -2.5), upper=(2.5, 2.5))
+    m.build_ls_space(n_sub)
+    eps_used = prm["epsilon"] / n_sub * h
+    dist = np.linalg.norm(m.ls_coords - np.array(prm["bubble_centre"]), axis=1) - prm["bubble_radius"]
+    c_old = -np.tanh(dist / (2.0 * eps_used))
+    O = OracleLevelSet2D(m, n_sub, prm["epsilon"], eps_used, h, dt, np.full(m.n_cells, h))
+    O.diag = O.mass_diagonal()
+
+    def force(level_set):
+        kappa = corrected_curvature(O, level_set, eps_used)
+        H = orc.compute_heaviside(m.cell_ls, level_set, prm["epsilon"], n_sub)
+        f = np.zeros(m.n_u_nodes * 2)
+        rho_q, mu_q = compute_force_2d(m, n_sub, H, kappa, prm["surface_tension"], prm["gravity"], prm["density"], prm["density_difference"],
+                                       prm["viscosity"], prm["viscosity_difference"], True, f, interpolate=True)
+        return f, rho_q, mu_q
+
+    c1, counts = reinitialize(O, c_old, 2)
+    assert counts == gold["time_step_1_reinitialization_cg_iterations"]["value"]
+    f, rho_q, mu_q = force(c1)
+    A = OracleNavierStokes2DVariable(m, rho_q, mu_q, 0.0, 0.0, 0.5, (1.0 / dt, -1.0 / dt, 0.0, 1.0))
+    u1, p1, history = newton_with_probed_jacobian(A, m, f)
+    assert f"{history[0]:.3g}" == gold["time_step_1_first_navier_stokes_residual"]["value"] and history[-1] < 1e-9
+    g2 = gold["time_step_2_concentration_advance"]
+    c_star = 2.0 * c1 - c_old
+    rhs = np.zeros(O.n)
+    O.advance_concentration_rhs(rhs, u1, c_star, c1, c_old, 1.5 / dt, -2.0 / dt, 0.5 / dt)
+    inc, n_it, res0 = bicgstab_iterations(lambda v: O.advance_concentration_vmult(v, 1.5 / dt), rhs, lambda r: r / O.diag, 30, 0.05 * 1e-9, 1e-8)
+    assert f"{res0:.3g}" == g2["advection_initial_residual"] and n_it == g2["advection_bicgstab_iterations"]
+    c2, counts = reinitialize(O, c_star + inc, 2)
+    assert counts == g2["reinitialization_cg_iterations"]
+    f2, rho_q, mu_q = force(c2)
+    A2 = OracleNavierStokes2DVariable(m, rho_q, mu_q, 0.0, 0.0, 0.5, (1.5 / dt, -2.0 / dt, 0.5 / dt, 1.0))
+    A2.old_u, A2.old_old_u = u1.copy(), np.zeros(A2.n_u)
+    ru, rp = np.zeros(A2.n_u), np.zeros(A2.n_p)
+    A2.residual(ru, rp, u1, p1, f2, np.zeros(A2.n_p))
+    assert f"{np.sqrt(ru @ ru + rp @ rp):.3g}" == gold["time_step_2_first_navier_stokes_residual"]["value"]
