@@ -561,7 +561,8 @@ def test_oracle_chain_reproduces_the_second_and_third_time_step_of_the_rising_bu
 def test_oracle_chain_reproduces_the_second_time_step_of_the_spurious_currents_log():
     """tests/spurious_currents_ls.output:15-16 -- 'advect [0.000803/8] and reinitialize (7 + 7)', '[0.00024/...': the same chain
     as for the rising bubble on the surface-tension dominated problem (80 x 80 cells, no-slip everywhere, constant density,
-    no initial reinitialisation): the spurious velocity of step 1 (3.8e-5) advects the level set in step 2."""
+    no initial reinitialisation): the spurious velocity of step 1 advects the level set in step 2.  The size of that velocity,
+    printed with 7 digits (3.776641e-05, line 12), is reproduced to 2.5e-7: a pin of the converged velocity field itself."""
     import json
     import os
     from oracle.ls_oracle_2d import OracleLevelSet2D, compute_force_2d
@@ -592,6 +593,12 @@ def test_oracle_chain_reproduces_the_second_time_step_of_the_spurious_currents_l
     A = OracleNavierStokes2DVariable(m, rho_q, mu_q, 0.0, 0.0, 0.5, (1.0 / dt, -1.0 / dt, 0.0, 1.0))
     u1, p1, history = newton_with_probed_jacobian(A, m, f)
     assert f"{history[0]:.3g}" == gold["time_step_1_first_navier_stokes_residual"]["value"] and history[-1] < 1e-9
+    # 'Size spurious currents, absolute: 3.776641e-05' (line 12): the velocity field itself, to 6 digits
+    from oracle.ns_oracle_2d import _q2
+    v1 = _q2(np.linspace(0.0, 1.0, 5))[0]
+    phi = np.einsum("bj,ai->baji", v1, v1).reshape(25, 9)
+    size = np.linalg.norm(np.einsum("qn,cnd->cqd", phi, u1.reshape(-1, 2)[m.cell_u]), axis=2).max()
+    assert abs(size / float(gold["time_step_1_size_spurious_currents"]["value"]) - 1.0) < 1e-6
     g2 = gold["time_step_2_concentration_advance"]
     c_star = 2.0 * c1 - c_old
     rhs = np.zeros(O.n)
