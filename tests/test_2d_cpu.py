@@ -599,6 +599,20 @@ def test_oracle_chain_reproduces_the_second_time_step_of_the_spurious_currents_l
     phi = np.einsum("bj,ai->baji", v1, v1).reshape(25, 9)
     size = np.linalg.norm(np.einsum("qn,cnd->cqd", phi, u1.reshape(-1, 2)[m.cell_u]), axis=2).max()
     assert abs(size / float(gold["time_step_1_size_spurious_currents"]["value"]) - 1.0) < 1e-6
+    # 'Error in pressure jump: 0.57390569 %' (line 11, spurious_currents.cc:152-215): mean pressure of the 12 cells around the
+    # centre against the mean over the boundary faces (Q1: vertex means), relative to 2 sigma -- the pressure field, to 3e-7
+    X, pc = m.p_coords, p1[m.cell_p]
+    inner = np.linalg.norm(X[m.cell_p].mean(axis=1), axis=1) < 0.1
+    face_means = []
+    for a, b in ((0, 1), (2, 3), (0, 2), (1, 3)):            # the four faces of a cell as vertex pairs (x fastest)
+        xa, xb = X[m.cell_p[:, a]], X[m.cell_p[:, b]]
+        for d in range(2):
+            on = (np.abs(np.abs(xa[:, d]) - 2.5) < 1e-12) & (xa[:, d] == xb[:, d])
+            face_means.append(0.5 * (pc[on, a] + pc[on, b]))
+    face_means = np.concatenate(face_means)
+    assert inner.sum() == 12 and len(face_means) == 320
+    jump_error = ((pc[inner].mean() - face_means.mean()) - 2.0 * prm["surface_tension"]) / (2.0 * prm["surface_tension"]) * 100.0
+    assert abs(jump_error - float(gold["time_step_1_pressure_jump_error_percent"]["value"])) < 1e-6
     g2 = gold["time_step_2_concentration_advance"]
     c_star = 2.0 * c1 - c_old
     rhs = np.zeros(O.n)
