@@ -627,3 +627,49 @@ def test_oracle_chain_reproduces_the_second_time_step_of_the_spurious_currents_l
     ru, rp = np.zeros(A2.n_u), np.zeros(A2.n_p)
     A2.residual(ru, rp, u1, p1, f2, np.zeros(A2.n_p))
     assert f"{np.sqrt(ru @ ru + rp @ rp):.3g}" == gold["time_step_2_first_navier_stokes_residual"]["value"]
+
+
+def test_2d_variable_coefficient_oracle_equals_extruded_3d_oracle():
+    """OracleNavierStokes2DVariable (the operator of the golden-log chains above) against the pinned 3-D oracle with
+    per-point density / viscosity on the one-cell extrusion, and against the constant-coefficient 2-D oracle."""
+    from oracle.ns_oracle_2d import OracleNavierStokes2DVariable
+    m = BoxMesh2D((5, 4))
+    _, oprm = flow_params(linearization=capi.NEWTON, damping=-0.2, tau_grad_div=0.3, density=1.3, viscosity=0.7, density_diff=9.0, viscosity_diff=0.5)
+    _, otw = time_weights()
+    tw = (otw.weight, otw.weight_old, otw.weight_old_old, otw.tau1)
+    # a smooth two-phase-like field at the 9 points of every cell
+    H = 0.5 * (1.0 + np.tanh((0.6 - np.linalg.norm(m.u_coords[m.cell_u].mean(axis=1), axis=1)) / 0.2))[:, None] * (1.0 + 0.05 * np.arange(9)[None, :])
+    rho_q, mu_q = 1.3 + 9.0 * H, 0.7 + 0.5 * H
+    O3 = orc.OracleNavierStokesMatrix(m.mesh3d, oprm, otw, None, False)
+    O3.rho[:], O3.muq[:], O3.damp[:] = np.tile(rho_q, (1, 3)), np.tile(mu_q, (1, 3)), -0.2   # points q = qx + 3 qy + 9 qz
+    O2 = OracleNavierStokes2DVariable(m, rho_q, mu_q, -0.2, 0.3, 0.5, tw)
+    u, p = fields(m, 3)
+    uo, _ = fields(m, 5)
+    uoo, _ = fields(m, 7)
+    O2.old_u, O2.old_old_u = uo.copy(), uoo.copy()
+    O3.old_u, _ = m.extend(uo, np.zeros(m.n_p_nodes))
+    O3.old_old_u, _ = m.extend(uoo, np.zeros(m.n_p_nodes))
+    r2u, r2p = np.zeros(O2.n_u), np.zeros(O2.n_p)
+    O2.residual(r2u, r2p, u, p, np.zeros(O2.n_u), np.zeros(O2.n_p))
+    r3u, r3p = np.zeros(O3.n_u), np.zeros(O3.n_p)
+    O3.residual(r3u, r3p, *m.extend(u, p), np.zeros(O3.n_u), np.zeros(O3.n_p))
+    ru, rp = m.restrict(r3u, r3p)
+    assert rel_err(ru, r2u) < 1e-13 and rel_err(rp, r2p) < 1e-13
+    su, sp = fields(m, 11)
+    d2u, d2p = O2.vmult(su, sp)
+    d3u, d3p = O3.vmult(*m.extend(su, sp))
+    du, dp = m.restrict(d3u, d3p)
+    c = m.u_dirichlet.reshape(-1)
+    du[c] = su[c]
+    assert rel_err(du, d2u) < 1e-13 and rel_err(dp, d2p) < 1e-13
+    # constant coefficients: identical to the base class
+    Oc = OracleNavierStokes2DVariable(m, np.full((m.n_cells, 9), 1.3), np.full((m.n_cells, 9), 0.7), -0.2, 0.3, 0.5, tw)
+    Ob = OracleNavierStokes2D(m, capi.INCOMPRESSIBLE, capi.NEWTON, 1.3, 0.7, -0.2, 0.3, 0.5, tw, pressure_average_fix=False)
+    for O in (Oc, Ob):
+        O.old_u, O.old_old_u = uo.copy(), uoo.copy()
+    ra, rb = [np.zeros(Oc.n_u), np.zeros(Oc.n_p)], [np.zeros(Oc.n_u), np.zeros(Oc.n_p)]
+    Oc.residual(ra[0], ra[1], u, p, np.zeros(Oc.n_u), np.zeros(Oc.n_p))
+    Ob.residual(rb[0], rb[1], u, p, np.zeros(Oc.n_u), np.zeros(Oc.n_p))
+    assert rel_err(ra[0], rb[0]) < 1e-14 and rel_err(ra[1], rb[1]) < 1e-14
+    va, vb = Oc.vmult(su, sp), Ob.vmult(su, sp)
+    assert rel_err(va[0], vb[0]) < 1e-14 and rel_err(va[1], vb[1]) < 1e-14
