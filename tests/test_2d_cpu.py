@@ -673,3 +673,32 @@ def test_2d_variable_coefficient_oracle_equals_extruded_3d_oracle():
     assert rel_err(ra[0], rb[0]) < 1e-14 and rel_err(ra[1], rb[1]) < 1e-14
     va, vb = Oc.vmult(su, sp), Ob.vmult(su, sp)
     assert rel_err(va[0], vb[0]) < 1e-14 and rel_err(va[1], vb[1]) < 1e-14
+
+
+def rising_bubble_first_step(fixture):
+    """Oracle chain of set-up and time step 1 of a rising-bubble log (shared with tests/test_2d_gpu.py): returns the golden
+    values, the mesh, eps_used and the fields that enter time step 2 -- level sets c_0 (after set-up), c_1 (after step 1)
+    and the converged velocity / pressure (u_1, p_1)."""
+    from oracle.ls_oracle_2d import OracleLevelSet2D, compute_force_2d
+    from oracle.ns_oracle_2d import OracleNavierStokes2DVariable
+    gold, m, eps_used, c = rising_bubble_setup(fixture)
+    prm = gold["parameters"]
+    n_sub, dt = prm["concentration_subdivisions"], prm["step_size"]
+    O = OracleLevelSet2D(m, n_sub, prm["epsilon"], eps_used, prm["h"], dt, np.full(m.n_cells, prm["h"]))
+    O.diag = O.mass_diagonal()
+    x = m.u_coords
+    dirichlet = np.zeros_like(m.u_dirichlet)
+    dirichlet[(np.abs(x[:, 1]) < 1e-12) | (np.abs(x[:, 1] - 2) < 1e-12), :] = True
+    dirichlet[(np.abs(x[:, 0]) < 1e-12) | (np.abs(x[:, 0] - 1) < 1e-12), 0] = True
+    m.u_dirichlet = dirichlet
+    c0, _ = reinitialize(O, c, 2)
+    c1, _ = reinitialize(O, c0, 2)
+    kappa = corrected_curvature(O, c1, eps_used)
+    H = orc.compute_heaviside(m.cell_ls, c1, prm["epsilon"], n_sub)
+    f = np.zeros(m.n_u_nodes * 2)
+    rho_q, mu_q = compute_force_2d(m, n_sub, H, kappa, prm["surface_tension"], prm["gravity"], prm["density"], prm["density_difference"],
+                                   prm["viscosity"], prm["viscosity_difference"], True, f, interpolate=True, u_dirichlet=dirichlet)
+    A = OracleNavierStokes2DVariable(m, rho_q, mu_q, 0.0, 0.0, 0.5, (1.0 / dt, -1.0 / dt, 0.0, 1.0))
+    u1, p1, history = newton_with_probed_jacobian(A, m, f)
+    assert history[-1] < 1e-9
+    return gold, m, eps_used, c0, c1, u1, p1

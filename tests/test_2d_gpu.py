@@ -207,3 +207,35 @@ def test_device_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log(
     assert counts[:2] == gold["initial_reinitialization_cg_iterations"]["value"], counts
     assert counts[2:] == gold["time_step_1_reinitialization_cg_iterations"]["value"], counts
     L.close()
+
+
+@pytest.mark.parametrize("fixture", ["rising_bubble_ls_picard_output.json", "rising_bubble_ls_output.json"])
+def test_device_reproduces_the_advection_of_time_step_2_of_the_rising_bubble_log(ctx, fixture):
+    """tests/rising_bubble_ls_picard.output:21 and tests/rising_bubble_ls.output:21 on the device: 'advect [0.000546/10]'
+    (FE_Q_iso_Q1(3)) and 'advect [0.000471/9]' (FE_Q_iso_Q1(4)).  The fields that enter time step 2 (level
+    sets after set-up and after step 1, converged velocity of step 1) come from the oracle chain on the CPU
+    (tests/test_2d_cpu.py); local_advance_concentration_rhs, advance_concentration_vmult and the BiCGStab solve with the
+    inverse mass diagonal (level_set_okz_advance_concentration.cc:217-258, 300-420, 626-640) run in the library."""
+    from adaflo_b200.operators import LevelSetOperators2D
+    from adaflo_b200.solvers import SolverBicgstab, SolverControl
+    from test_2d_cpu import rising_bubble_first_step
+    gold, m, eps_used, c0, c1, u1, _ = rising_bubble_first_step(fixture)
+    prm = gold["parameters"]
+    dt = prm["step_size"]
+    L = LevelSetOperators2D(ctx, m, capi.LSParams(2, prm["concentration_subdivisions"], 0, 0, prm["epsilon"], eps_used, 4.0, prm["h"]),
+                            cell_diameters=np.full(m.n_cells, prm["h"]))
+    L.set_time(1.5 / dt, -2.0 / dt, 0.5 / dt, dt)                    # BDF-2 weights of the second step
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(ctx.device)
+    rhs = L.new_vector()
+    # level set extrapolated (two_phase_base.cc:443-456), velocity not (TimeStepping::next, time_stepping.cc:182-193)
+    L.advance_concentration_rhs(rhs, dev(u1), dev(2.0 * c1 - c0), dev(c1), dev(c0))
+    g2 = gold["time_step_2_concentration_advance"]
+    assert f"{float(rhs.norm()):.3g}" == g2["advection_initial_residual"]
+    inv_diag = 1.0 / L.diag
+    x = L.new_vector()
+    ctl = SolverControl(30, 0.05 * 1e-9, 1e-8)
+    SolverBicgstab(ctx, ctl).solve(lambda dst, src: L.advance_concentration_vmult(dst, src), x, rhs,
+                                   lambda dst, src: torch.mul(src, inv_diag, out=dst))
+    assert ctl.last_step == g2["advection_bicgstab_iterations"]
+    assert f"{ctl.initial_value:.3g}" == g2["advection_initial_residual"]
+    L.close()
