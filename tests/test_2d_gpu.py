@@ -211,8 +211,8 @@ def test_device_reproduces_the_reinitialisation_counts_of_the_rising_bubble_log(
 
 @pytest.mark.parametrize("fixture", ["rising_bubble_ls_picard_output.json", "rising_bubble_ls_output.json"])
 def test_device_reproduces_the_advection_of_time_step_2_of_the_rising_bubble_log(ctx, fixture):
-    """tests/rising_bubble_ls_picard.output:21 and tests/rising_bubble_ls.output:21 on the device: 'advect [0.000546/10]'
-    (FE_Q_iso_Q1(3)) and 'advect [0.000471/9]' (FE_Q_iso_Q1(4)).  The fields that enter time step 2 (level
+    """tests/rising_bubble_ls_picard.output:21 and tests/rising_bubble_ls.output:21 on the device: 'advect [0.000546/10] and
+    reinitialize (10 + 10)' (FE_Q_iso_Q1(3)) and 'advect [0.000471/9] and reinitialize (11 + 10)' (FE_Q_iso_Q1(4)).  The fields that enter time step 2 (level
     sets after set-up and after step 1, converged velocity of step 1) come from the oracle chain on the CPU
     (tests/test_2d_cpu.py); local_advance_concentration_rhs, advance_concentration_vmult and the BiCGStab solve with the
     inverse mass diagonal (level_set_okz_advance_concentration.cc:217-258, 300-420, 626-640) run in the library."""
@@ -238,4 +238,35 @@ def test_device_reproduces_the_advection_of_time_step_2_of_the_rising_bubble_log
                                    lambda dst, src: torch.mul(src, inv_diag, out=dst))
     assert ctl.last_step == g2["advection_bicgstab_iterations"]
     assert f"{ctl.initial_value:.3g}" == g2["advection_initial_residual"]
+    # ... 'and reinitialize (11 + 10)' / '(10 + 10)': the two reinitialisation steps of the advected level set on the device
+    from adaflo_b200.solvers import SolverCG
+    L.set_time(1.0 / dt, -1.0 / dt, 0.0, dt)    # the reinitialisation uses the step size only
+    c = dev(2.0 * c1 - c0) + x
+    zero = L.new_vector()
+
+    def solve(A, b, P, rel_tol, max_iter):
+        y = L.new_vector()
+        control = SolverControl(max_iter, 1e-50, rel_tol)
+        SolverCG(ctx, control).solve(A, y, b, P)
+        return y, control.last_step
+
+    def normal_component(d, rhs_d):
+        def A(dst, src):
+            out = [L.new_vector(), L.new_vector()]
+            L.compute_normal_vmult(out, [src, zero] if d == 0 else [zero, src])
+            dst.copy_(out[d])
+        return solve(A, rhs_d, None, 1e-5, 4000)[0]
+
+    counts = []
+    for tau in range(2):
+        if tau == 0:
+            rhs_n = [L.new_vector(), L.new_vector()]
+            L.compute_normal_rhs(rhs_n, c)
+            normal = [normal_component(d, rhs_n[d]) for d in range(2)]
+        r = L.new_vector()
+        L.reinitialization_rhs(r, c, normal, False, tau == 0)
+        inc, it = solve(lambda dst, src: L.reinitialization_vmult(dst, src, False), r, lambda dst, src: torch.mul(src, inv_diag, out=dst), 1e-6, 2000)
+        counts.append(it)
+        c = c + inc
+    assert counts == g2["reinitialization_cg_iterations"], counts
     L.close()
