@@ -106,6 +106,45 @@ def test_2d_oracle_reproduces_the_first_residual_of_the_couette_log():
     assert np.linalg.norm(rp) < 1e-14               # the lid field is divergence free
 
 
+def test_2d_oracle_reproduces_the_second_time_step_of_the_couette_log():
+    """tests/couette.output:10,31 -- the Newton increment 5.83e+01 of time step #1, and the first nonlinear residual 1.930e-01 and
+    increment 1.60e+01 of time step #2, which need the converged solution of step #1: Newton on the oracle's residual / vmult with
+    an exactly recovered Jacobian (open boundaries fix the pressure level: nothing is pinned).  Step #2 uses BDF-2 weights,
+    does not extrapolate (time_stepping.cc:182-193), and its solution_old_old is the ZERO start vector -- the lid values enter
+    'solution' only (with the lid field there the residual would be 1.919e-01)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "couette_output.json")) as f:
+        gold = json.load(f)
+    prm = gold["parameters"]
+    m = BoxMesh2D((64, 16), lower=(-2.0, -1.0), upper=(2.0, 0.0))
+    x = m.u_coords
+    bottom, top = np.abs(x[:, 1] + 1) < 1e-12, np.abs(x[:, 1]) < 1e-12
+    sides = (np.abs(x[:, 0] - 2) < 1e-12) | (np.abs(x[:, 0] + 2) < 1e-12)
+    dirichlet = np.zeros_like(m.u_dirichlet)
+    dirichlet[bottom | top, :] = True
+    dirichlet[sides, 1] = True
+    m.u_dirichlet = dirichlet
+    dt = prm["dt"]
+
+    def operator(tw):
+        return OracleNavierStokes2D(m, capi.INCOMPRESSIBLE, capi.NEWTON, prm["density"], prm["viscosity"], 0.0, 0.0, 0.5, tw, pressure_average_fix=False)
+    O = operator((1 / dt, -1 / dt, 0.0, 1.0))
+    u0 = np.zeros(O.n_u)
+    u0.reshape(-1, 2)[top] = prm["lid_velocity"]
+    zero_u, zero_p = np.zeros(O.n_u), np.zeros(O.n_p)
+    increments = []
+    u1, p1, history = newton_with_probed_jacobian(O, m, zero_u, tol=1e-11, start=(u0, zero_p), pin_pressure=False, increments=increments)
+    assert f"{history[0]:.3e}" == gold["first_nonlinear_residual"]["value"] and history[-1] < 1e-11
+    assert f"{increments[0]:.2e}" == gold["time_step_1_first_newton_increment"]["value"]
+    O2 = operator((1.5 / dt, -2.0 / dt, 0.5 / dt, 1.0))
+    O2.old_u, O2.old_old_u = u1.copy(), zero_u.copy()
+    increments = []
+    _, _, history = newton_with_probed_jacobian(O2, m, zero_u, tol=1e-11, start=(u1, p1), pin_pressure=False, increments=increments)
+    assert f"{history[0]:.3e}" == gold["time_step_2_first_nonlinear_residual"]["value"] and history[-1] < 1e-11
+    assert f"{increments[0]:.2e}" == gold["time_step_2_first_nonlinear_residual"]["increment"]
+
+
 # ---------------------------------------------------------------------------------------------- level set
 def ls_setup(n=(4, 3), n_sub=3, dirichlet_edges=()):
     from oracle.ls_oracle_2d import OracleLevelSet2D
@@ -410,7 +449,7 @@ def bicgstab_iterations(A, b, P, max_iter, abs_tol, rel_tol):
     return x, it, res0
 
 
-def newton_with_probed_jacobian(A, m, f, tol=1e-9, start=None):
+def newton_with_probed_jacobian(A, m, f, tol=1e-9, start=None, pin_pressure=True, increments=None):
     """Solve the nonlinear Navier-Stokes system of one time step with the oracle operator A (residual / vmult): the Jacobian
     is recovered exactly from 75 coloured applications of vmult (two nodes of the Q2 grid couple only within +-2 grid lines, so
     the columns with equal coordinates mod 5 are probed together) and factorised; one pressure dof is pinned (closed
@@ -463,12 +502,16 @@ def newton_with_probed_jacobian(A, m, f, tol=1e-9, start=None):
             break
         if lu is None:    # the first update is an exact Newton step; later ones reuse its factorisation (the velocities are
             J = jacobian().tocoo()    # small against the viscous and mass terms: every further step gains two to three digits)
-            keep = J.row != nu                               # pinned pressure dof: identity row
-            J = sp.csc_matrix((np.append(J.data[keep], 1.0), (np.append(J.row[keep], nu), np.append(J.col[keep], nu))), shape=J.shape)
-            lu = spla.splu(J)
+            if pin_pressure:                                 # closed container: one pressure dof pinned (identity row)
+                keep = J.row != nu
+                J = sp.csc_matrix((np.append(J.data[keep], 1.0), (np.append(J.row[keep], nu), np.append(J.col[keep], nu))), shape=J.shape)
+            lu = spla.splu(sp.csc_matrix(J))
         b = np.concatenate([ru, rp])
-        b[nu] = 0.0
+        if pin_pressure:
+            b[nu] = 0.0
         d = lu.solve(b)
+        if increments is not None:
+            increments.append(float(np.linalg.norm(d)))
         u += d[:nu]
         p += d[nu:]
     return u, p, history
